@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py — pages/sec through tile -> filter -> merge -> columns (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 path (this repo)
+    python bench.py --impl reference --steps K --warmup W    # reference's CPU algorithm (oracle port)
+
+A "step" is one pass of the whole hot path over one batch of synthetic pages.  Default workload
+= BASELINE.json configs[2] ("cfg3"): 8000x6000 px broadsheet scans, 4x4 overlapped grid,
+10k synthetic detections/page, page-sharded over the GPUs with no collective (weak scaling:
+pages per GPU fixed).  `--workload cfg2` runs configs[1] (the 19 fixture page sizes, 2x2 grid,
+2k detections/page).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "pages/sec tile->filter->merge->columns"
+UNIT = "pages/s"
+
+
+def workload_spec(name: str):
+    if name == "cfg3":
+        return {"name": "cfg3: synthetic 8000x6000 px scans, 4x4 grid @20% overlap, 10k detections/page",
+                "sizes": [(8000, 6000)], "grid": (4, 4), "boxes": 10000}
+    if name == "cfg2":
+        from multimodal_embeddings_b200.synth import FIXTURE_PAGE_SIZES
+        return {"name": "cfg2: the 19 newspaper_images page sizes, 2x2 grid @20% overlap, 2k detections/page",
+                "sizes": list(FIXTURE_PAGE_SIZES), "grid": (2, 2), "boxes": 2000}
+    raise SystemExit(f"unknown workload {name}")
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML), runs during the timed region
+class ClockSampler:
+    def __init__(self, device_index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.004)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's algorithm on the host cores
+_W = {}
+
+
+def _cpu_worker_init(w, h, rows, cols, n_boxes, seed):
+    import numpy as np
+    from multimodal_embeddings_b200 import synth
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+    except Exception:
+        pass
+    rng = np.random.default_rng(seed + os.getpid())
+    _W["page"] = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    _W["det"] = synth.page_detections(w, h, rows, cols, 20.0, n_boxes, seed)
+    _W["cfg"] = (w, h, rows, cols)
+
+
+def _cpu_one_page(_):
+    """Reference algorithm for one page, function level: grid split + cv2
+    letterbox + /255, translate + edge filter, pooled pure-Python NMS, width median, columns."""
+    from multimodal_embeddings_b200 import synth
+    from oracle import boxes as ob
+    from oracle import tiler as ot
+    w, h, rows, cols = _W["cfg"]
+    d = _W["det"]
+    t0 = time.perf_counter()
+    tiles = ot.tile_page(_W["page"], rows, cols, 20.0)
+    cells = [{"coordinates": c["coordinates"]} for c, _ in tiles]
+    boxes_page = []
+    for b, ci in zip(d["boxes_local"].tolist(), d["box_cell"].tolist()):
+        boxes_page.append(ot.translate_boxes([b], cells[ci]["coordinates"])[0])
+    keep = [i for i, b in enumerate(boxes_page)
+            if not ob.touches_internal_edge(b, ob.cell_tuple(cells[d["box_cell"][i]]["coordinates"], w, h), w, h, 10)]
+    kb = [boxes_page[i] for i in keep]
+    ks = [float(d["scores"][i]) for i in keep]
+    kc = [float(d["classes"][i]) for i in keep]
+    order = ob.nms_pick_order(kb, ks, kc, 0.5)
+    fb, fs, fc = [kb[i] for i in order], [ks[i] for i in order], [kc[i] for i in order]
+    names = synth.class_names_of(fc)
+    med, _ = ob.median_width(fb, names, w, 0.2)
+    cols_out = ob.column_centers(fb, names, fs, w, h, med, 0.3) if med > 0 else ([], [])
+    return time.perf_counter() - t0, len(fb), len(cols_out[0])
+
+
+def run_cpu_arm(spec, steps, warmup, budget_s=150.0, pages_per_step=None):
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    w, h = spec["sizes"][0]
+    rows, cols = spec["grid"]
+    ctx = mp.get_context("fork")
+    pps = pages_per_step or cores
+    times = []
+    with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(w, h, rows, cols, spec["boxes"], 0xB200)) as pool:
+        done = 0
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_one_page, range(pps), chunksize=1)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append((dt, pps))
+            done += 1
+            if it == 0 and pages_per_step is None:
+                # keep the whole run inside the budget: shrink the per-step sample if needed
+                remaining = warmup + steps - 1
+                if remaining * dt > budget_s:
+                    pps = max(1, int(pps * budget_s / (remaining * dt)))
+    total_pages = sum(p for _, p in times)
+    total_t = sum(t for t, _ in times)
+    return {"value": total_pages / total_t, "cores": cores, "pages_per_step": times[-1][1] if times else pps,
+            "ms_per_step": 1e3 * total_t / max(1, len(times)), "single_page_s": res[0][0]}
+
+
+def print_reference_line(args, spec):
+    r = run_cpu_arm(spec, args.steps, args.warmup)
+    sample = (f"{r['pages_per_step']} page(s) per step, one per worker process on {r['cores']} host cores; "
+              "oracle port of the reference scripts at function level: cv2 letterbox tiles, translate+edge "
+              "filter, pure-Python greedy NMS, width median, column peaks (no PNG/JSON codec time)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 boxes / u8 pixels", "data": "synthetic",
+        "config": {"workload": spec["name"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2"])
+    ap.add_argument("--pages-per-gpu", type=int, default=64)
+    ap.add_argument("--e2e-pages", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--corpus-stats", action="store_true", help="accumulate + all-reduce corpus histograms (cfg5)")
+    ap.add_argument("--tiler-only", action="store_true", help="profiling helper: time the tiler alone")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    spec = workload_spec(args.workload)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            print_reference_line(args, spec)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from multimodal_embeddings_b200 import build as pg_build
+    from multimodal_embeddings_b200 import ops, synth
+    from multimodal_embeddings_b200.pipeline import KERNELS_PER_STEP, PagePipeline
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pg_build.build()
+
+    rows, cols = spec["grid"]
+    ppg = args.pages_per_gpu
+    first_page = rank * ppg
+    # group pages by size (cfg3: one size; cfg2: 19 sizes round-robin) -> one plan/pipeline per size
+    sizes = spec["sizes"]
+    groups = {}
+    for i in range(ppg):
+        groups.setdefault(sizes[(first_page + i) % len(sizes)], []).append(first_page + i)
+    stream = torch.cuda.current_stream()
+    pipes = []
+    alg_bytes_step = 0
+    for (w, h), idxs in groups.items():
+        plan = ops.TilePlan(w, h, [(rows, cols)], 20.0)
+        pages = plan.alloc_pages(len(idxs))
+        for j, gi in enumerate(idxs):  # page content depends on the global page index only
+            ops.synth_pages(plan, 1, synth.PAGE_SEED0, first_page=gi, out=pages[j:j + 1])
+        dets = [synth.page_detections(w, h, rows, cols, 20.0, spec["boxes"], synth.PAGE_SEED0 + gi) for gi in idxs]
+        pipe = PagePipeline(plan, len(idxs), corpus_stats=args.corpus_stats)
+        host = pipe.set_detections(dets)
+        pipes.append((plan, pipe, pages, host, dets))
+        alg_bytes_step += plan.algorithmic_bytes * len(idxs) + 48 * pipe.n_boxes
+    torch.cuda.synchronize()
+
+    def step(ev=None):
+        for k, (plan, pipe, pages, _, _) in enumerate(pipes):
+            if args.tiler_only:
+                plan.run(pages, out=pipe.tiles_out)
+            else:
+                pipe.run(pages, tiler_events=ev[k] if ev is not None else None)
+        if args.corpus_stats:
+            for _, pipe, _, _, _ in pipes:
+                pipe.allreduce_corpus_stats()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    for _, pipe, _, _, _ in pipes:
+        if not args.tiler_only:
+            pipe.check_status()
+
+    tiler_ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in pipes]
+                for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0.record(stream)
+    for s_i in range(args.steps):
+        step(None if args.tiler_only else tiler_ev[s_i])
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    for _, pipe, _, _, _ in pipes:
+        if not args.tiler_only:
+            pipe.check_status()
+    pages_total = ppg * world * args.steps
+    value = pages_total / (ms * 1e-3)
+
+    # roofline of the dominant kernel (tiler): algorithmic bytes / live CUDA-event duration
+    peak, peak_src = measured_peak_hbm()
+    if args.tiler_only:
+        tiler_ms = ms / args.steps
+    else:
+        tiler_ms = sum(a.elapsed_time(b) for evs in tiler_ev for (a, b) in evs) / args.steps
+    tiler_bytes = sum(plan.algorithmic_bytes * pipe.n_pages for plan, pipe, _, _, _ in pipes)
+    achieved = tiler_bytes / (tiler_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "tiler_traffic.json")) as f:
+            tj = json.load(f)
+            if tj.get("workload") == args.workload and tj.get("pages_per_launch") == ppg:
+                traffic = tj.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "tile_letterbox_kernel", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": tiler_bytes, "kernel_ms_per_launch": tiler_ms / max(1, len(pipes)),
+                "kernel_share_of_step": tiler_ms / (ms / args.steps)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 pixels -> f16 tiles (11-bit fixed point), f64 boxes", "data": "synthetic",
+        "config": {"workload": spec["name"], "pages_per_gpu": ppg, "global_pages_per_step": ppg * world,
+                   "parallelism": f"page-sharded x{world}, no collective" + (" + hist all-reduce" if args.corpus_stats else ""),
+                   "l2": f"inputs {sum(p[2].numel() for p in pipes) / 1e9:.1f} GB/step per GPU >> 126 MB L2 (no flush needed)",
+                   "stages": "tiler only" if args.tiler_only else "tile+letterbox, translate+edge filter, NMS merge, width median, column peaks"},
+        "roofline": roofline, "clocks": clocks,
+        "gpu_launches": (len(pipes) if args.tiler_only else KERNELS_PER_STEP * len(pipes)) * args.steps,
+    }
+
+    # ---- e2e: same metric through the host-buffer API, H2D of pages+detections and D2H of results timed
+    if rank == 0 or world > 1:
+        plan, pipe0, pages0, host0, dets0 = pipes[0]
+        n_e = min(args.e2e_pages, pipe0.n_pages)
+        epipe = PagePipeline(plan, n_e)
+        ehost = epipe.set_detections(dets0[:n_e])
+        pin_pages = torch.empty((n_e, plan.page_h, plan.pitch), dtype=torch.uint8).pin_memory()
+        pin_pages.copy_(pages0[:n_e])
+        pin_in = {k: torch.from_numpy(v).pin_memory() for k, v in ehost.items()}
+        pin_out = {n: torch.empty_like(getattr(epipe, n), device="cpu").pin_memory()
+                   for n in ("kept2", "n_kept2", "median", "n_bins", "centers", "col_widths", "n_cols")}
+        dev_pages = plan.alloc_pages(n_e)
+
+        def e2e_step():
+            dev_pages.copy_(pin_pages, non_blocking=True)
+            nb = epipe.upload_detections(ehost, pinned=pin_in)
+            epipe.run(dev_pages)
+            epipe.results_to_host(pinned=pin_out)
+            return nb
+
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_steps = max(3, min(args.steps, 10))
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        a.record(stream)
+        for _ in range(e2e_steps):
+            box_bytes = e2e_step()
+        b.record(stream)
+        torch.cuda.synchronize()
+        e_ms = max(a.elapsed_time(b), (time.perf_counter() - t_wall) * 1e3)
+        if world > 1:
+            t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        epipe.check_status()
+        line["e2e"] = {"value": n_e * world * e2e_steps / (e_ms * 1e-3), "unit": UNIT,
+                       "h2d_bytes_per_step": int(pin_pages.numel() + box_bytes), "d2h_bytes_per_step": epipe.result_bytes(),
+                       "pages_per_step": n_e * world, "steps": e2e_steps,
+                       "note": "pinned host pages+detections -> H2D -> 11 kernels -> D2H kept indices/medians/columns; "
+                               "fp16 tiles stay in HBM for the detector"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del pipes
+        torch.cuda.empty_cache()
+        r = run_cpu_arm(workload_spec("cfg3") if args.workload == "cfg3" else spec, steps=2, warmup=1, budget_s=40.0)
+        line["cpu_baseline"] = {
+            "value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+            "sample": f"2 timed steps of {r['pages_per_step']} page(s), one page per worker process on {r['cores']} cores; "
+                      f"oracle port of the reference at function level (cv2 tiles, edge filter, pure-Python NMS, median, "
+                      f"columns); {r['single_page_s']:.1f} s per page per core"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,174 @@
+/* pagegeom.h — C ABI of libpagegeom.so, the B200 (sm_100a) implementation of the
+ * page-geometry hot path of calhounpaul/multimodal_embeddings:
+ *
+ *     tile -> edge filter -> cross-tile NMS merge -> width median -> column centres
+ *
+ * The reference is a set of Python scripts with no FFI seam; each entry point
+ * below names the reference function(s) (file:line, relative to the upstream repo
+ * root) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes stubs a
+ * maintainer of the reference would add to call them from the numbered scripts.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "dev" is a CUDA device pointer owned
+ *     by the caller, everything else is host memory;
+ *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: PG_OK or an error code; pg_last_error() gives the text
+ *     (thread-local).  Nothing throws, nothing falls back to the CPU;
+ *   - batching: boxes of many pages are concatenated; `page_off[P+1]` (dev, int64)
+ *     gives each page's slice; a stage may restrict itself to a subset through
+ *     `sel_idx` (dev, int32 global box indices, page p's entries stored from
+ *     page_off[p]) and `n_sel[P]` (dev) — exactly what the previous stage emitted —
+ *     so the stages chain on-device without host round trips;
+ *   - all box arithmetic is IEEE fp64 in the reference's operation order with FMA
+ *     contraction disabled (bit-exact against the Python doubles).
+ */
+#ifndef PAGEGEOM_H_
+#define PAGEGEOM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_OK 0
+#define PG_ERR_INVALID 1     /* bad argument */
+#define PG_ERR_CUDA 2        /* CUDA runtime error (text in pg_last_error) */
+#define PG_ERR_WORKSPACE 3   /* caller workspace too small */
+#define PG_ERR_UNSUPPORTED 4 /* shape outside what the kernels handle */
+
+#define PG_FLAG_PLAIN_TEXT 1u /* class_name == 'plain_text' (4_extract_median_widths.py:136) */
+#define PG_FLAG_TITLE 2u      /* class_name == 'title'      (5_detect_column_centers.py:111) */
+
+#define PG_WIDTH_HIST_BINS 16384 /* corpus width histogram: 1-px bins            */
+#define PG_COL_HIST_BINS 1001    /* corpus column histogram: per-mille of page W */
+
+const char* pg_last_error(void);
+int pg_version(void);
+/* SM count / compute capability of the current device. */
+int pg_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ------------------------------------------------------------------ K1 tiler
+ * Replaces split_image_into_grid (1_doclayout_bboxes.py:366-444) and the front half
+ * of YOLODocumentLayoutDetector.detect_regions (1_doclayout_bboxes.py:191-210:
+ * third-party LetterBox -> cv2.resize(INTER_LINEAR) -> pad 114 -> BGR->RGB -> CHW
+ * -> /255), without the PNG round trip of 1_doclayout_bboxes.py:568,202.
+ */
+typedef struct PgTilePlan PgTilePlan;
+
+typedef struct PgTileInfo {
+  double x_start, y_start, x_end, y_end; /* un-truncated cell rectangle (:401-421)  */
+  int32_t grid_rows, grid_cols;          /* grid this tile belongs to               */
+  int32_t row, col;                      /* 1-indexed (:440-441)                    */
+  int32_t x0, y0, x1, y1;                /* int()-truncated slice (:424-430)        */
+  int32_t new_w, new_h;                  /* resized size inside the letterbox       */
+  int32_t pad_l, pad_t;                  /* 114-valued border, left / top           */
+  int32_t out_w, out_h;                  /* tile tensor is [3, out_h, out_w] fp16   */
+  int64_t out_offset;                    /* in fp16 elements from the page's output */
+} PgTileInfo;
+
+/* One plan per page size.  `grid_rows/grid_cols[n_grids]` lists the grids applied to
+ * every page (a 1x1 grid is the reference's full-page pass, :446-482).  Tiles are
+ * enumerated grid-major, then row-major like the reference.  Host-only; no device
+ * work happens until the first pg_tile_letterbox call. */
+int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t* grid_rows,
+                        const int32_t* grid_cols, int32_t n_grids, double overlap_percentage,
+                        int32_t imgsz, int32_t stride, int32_t auto_pad, int32_t scaleup,
+                        PgTilePlan** plan);
+void pg_tile_plan_destroy(PgTilePlan* plan);
+int32_t pg_tile_plan_num_tiles(const PgTilePlan* plan);
+int pg_tile_plan_tile(const PgTilePlan* plan, int32_t tile, PgTileInfo* info);
+int64_t pg_tile_plan_out_elems(const PgTilePlan* plan);      /* fp16 elements per page  */
+int64_t pg_tile_plan_algorithmic_bytes(const PgTilePlan* plan); /* 3WH + 2*out_elems    */
+
+/* pages: dev uint8 BGR, HWC, `n_pages` pages `page_stride` bytes apart, rows `pitch`
+ * bytes apart (pitch % 16 == 0, base 16-byte aligned — bulk-copy alignment).
+ * out: dev fp16, page p's tiles start at out + p*out_page_stride (elements).
+ * Persistent warp-specialised kernel: TMA bulk copies stage the two source rows of
+ * each output row in shared memory behind an mbarrier ring. */
+int pg_tile_letterbox(PgTilePlan* plan, const uint8_t* pages, int32_t n_pages, int64_t pitch,
+                      int64_t page_stride, void* out_f16, int64_t out_page_stride, void* stream);
+/* Validation twin: same arithmetic with plain global loads, no staging.  Used by the
+ * tests as an independent on-device cross-check at full size. */
+int pg_tile_letterbox_direct(PgTilePlan* plan, const uint8_t* pages, int32_t n_pages, int64_t pitch,
+                             int64_t page_stride, void* out_f16, int64_t out_page_stride, void* stream);
+
+/* Synthetic newspaper-like pages generated on the device (counter-based hash of
+ * (seed0 + first_page + p, y, x)); used by bench.py so inputs are HBM-resident. */
+int pg_synth_pages(uint8_t* pages, int32_t n_pages, int32_t page_w, int32_t page_h, int64_t pitch,
+                   int64_t page_stride, uint64_t seed0, int64_t first_page, void* stream);
+
+/* ------------------------------------------------------------------ K2 edge filter
+ * Replaces translate_coordinates_to_original (1_doclayout_bboxes.py:484-511) and
+ * is_box_touching_internal_edge / filter_grid_info (2_edge_box_filter.py:44-90,
+ * 206-217).  boxes_are_local != 0: `boxes` are cell-local detector outputs and
+ * the float cell origin is added first (result optionally stored to boxes_page_out);
+ * else `boxes` are already page coordinates.  kept_idx keeps input order. */
+int pg_edge_filter(const double* boxes /*dev [N,4]*/, int32_t boxes_are_local,
+                   const int32_t* box_cell /*dev [N] index into cells*/,
+                   const double* cells /*dev [C,4] x_start,y_start,x_end,y_end*/,
+                   const int32_t* page_wh /*dev [P,2] width,height*/,
+                   const int64_t* page_off /*dev [P+1]*/, int32_t n_pages, double threshold,
+                   double* boxes_page_out /*dev [N,4] or NULL*/, uint8_t* keep /*dev [N] or NULL*/,
+                   int32_t* kept_idx /*dev [N]*/, int32_t* n_kept /*dev [P]*/, void* stream);
+
+/* ------------------------------------------------------------------ K3 NMS merge
+ * Replaces calculate_iou / apply_non_max_suppression (3_combine_grids.py:46-138) on
+ * the pooled boxes of combine_boxes_for_image (3_combine_grids.py:222-267).
+ * Output: kept_idx = global box indices in pick order (score descending, earlier
+ * pooled position first on ties), page p's picks stored from page_off[p]. */
+size_t pg_nms_workspace_bytes(int64_t n_boxes, int32_t n_pages, int32_t pairs_per_block);
+int pg_nms_merge(const double* boxes /*dev [N,4]*/, const double* scores /*dev [N]*/,
+                 const double* classes /*dev [N]*/, const int32_t* sel_idx /*dev or NULL*/,
+                 const int64_t* page_off /*dev [P+1]*/, const int32_t* n_sel /*dev [P] or NULL*/,
+                 int32_t n_pages, int64_t n_boxes, int32_t max_boxes_per_page, double iou_threshold,
+                 int32_t* kept_idx /*dev [N]*/, int32_t* n_kept /*dev [P]*/,
+                 void* workspace /*dev*/, size_t workspace_bytes, void* stream);
+/* After the stream has been synchronised: status word + counters the merge left in
+ * its workspace. stats[0]=status (PG_OK/PG_ERR_*), [1]=candidate block pairs,
+ * [2]=resolve rounds (max over pages), [3]=box pairs tested. */
+int pg_nms_stats(const void* workspace /*dev*/, int64_t stats[4]);
+
+/* ------------------------------------------------------------------ K4 width median
+ * Replaces bin_widths / calculate_median_width and the plain_text width extraction
+ * (4_extract_median_widths.py:49-101, 135-141).  flags: dev [N] PG_FLAG_* per box. */
+int pg_class_flags(const double* classes /*dev [N]*/, int64_t n, double plain_text_id,
+                   double title_id, uint8_t* flags /*dev [N]*/, void* stream);
+int pg_width_median(const double* boxes, const uint8_t* flags, const int32_t* sel_idx,
+                    const int64_t* page_off, const int32_t* n_sel, int32_t n_pages,
+                    const int32_t* page_wh, double min_margin_percent,
+                    double* median /*dev [P]*/, int32_t* n_bins /*dev [P]*/,
+                    double* ws_keys /*dev [N]*/, int32_t* ws_counts /*dev [N]*/,
+                    uint32_t* width_hist /*dev [PG_WIDTH_HIST_BINS] or NULL*/, void* stream);
+
+/* ------------------------------------------------------------------ K5 column centres
+ * Replaces find_column_centers (5_detect_column_centers.py:91-224) including the
+ * scipy.signal.find_peaks(height, distance, prominence) step order and np.convolve
+ * ('same').  gauss_table holds, for every odd window length M = 2k+1 <= max_window,
+ * the normalised scipy.signal.windows.gaussian(M, std=M/6) starting at
+ * gauss_off[k] (host-built so that np.exp rounding is shared with the reference).
+ * Outputs per page: up to max_cols centres (px, = peak*resolution) and widths. */
+int pg_column_peaks(const double* boxes, const uint8_t* flags, const double* scores,
+                    const int32_t* sel_idx, const int64_t* page_off, const int32_t* n_sel,
+                    int32_t n_pages, const int32_t* page_wh, const double* median /*dev [P]*/,
+                    const double* gauss_table /*dev*/, const int64_t* gauss_off /*dev*/,
+                    int32_t max_window, double min_confidence, int32_t max_cols,
+                    int32_t* centers /*dev [P,max_cols]*/, double* widths /*dev [P,max_cols]*/,
+                    int32_t* n_cols /*dev [P]; <0 = unsupported shape*/,
+                    double* ws /*dev [P, 2*max_bins]*/, int32_t max_bins,
+                    uint32_t* col_hist /*dev [PG_COL_HIST_BINS] or NULL*/, void* stream);
+
+/* ------------------------------------------------------------------ test hooks
+ * Host evaluations of the same inline arithmetic the kernels are compiled from
+ * (csrc/pg_math.h).  Used by the CPU test-suite only; not a compute path. */
+double pg_hostcheck_iou(const double* a, const double* b);
+int32_t pg_hostcheck_edge_touch(const double* box, const double* cell, int32_t w, int32_t h, double thr);
+double pg_hostcheck_density_weight(int32_t bin, int32_t left, int32_t right, int32_t center);
+int pg_hostcheck_resize_row(const uint8_t* row0, const uint8_t* row1, int32_t src_w, int32_t src_h,
+                            int32_t dst_w, int32_t dst_h, int32_t dy, uint8_t* out_bgr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAGEGEOM_H_ */

@@ -1,0 +1,676 @@
+// pg_tiler.cu — K1: overlapped grid tiling + letterbox resize + normalise, uint8 BGR page ->
+// planar RGB fp16 tiles.
+//
+// Reference path replaced: split_image_into_grid (1_doclayout_bboxes.py:366-444) feeding
+// YOLODocumentLayoutDetector.detect_regions (1_doclayout_bboxes.py:191-210), i.e. the third-party
+// LetterBox -> cv2.resize(INTER_LINEAR) -> copyMakeBorder(114) -> BGR->RGB -> CHW -> /255 chain.
+//
+// Design (B200): HBM-bound streaming kernel, no tensor cores.  One persistent CTA per SM slot;
+// warp 8 is a producer that stages, per output row, the two source rows it needs with TMA bulk
+// copies (cp.async.bulk -> UBLKCP) into a 4-deep shared-memory ring guarded by full/empty
+// mbarriers; warps 0-7 consume: 3x LDS.32 per source row and pixel, PRMT + IDP.2A for the 11-bit
+// horizontal pass, integer vertical pass (bit-exact cv2 model, pg_math.h), cvt.rn.f16x2 and
+// streaming half2 stores into the three colour planes.  Source rows that no output row samples
+// (scale > 2) are never read.  Work items are bands of 16 output rows ordered
+// (page, grid, tile row, band, tile col) so that horizontally adjacent tiles are in flight together
+// and their 20 % overlap is served from L2.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+
+#include "pg_common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing (shared by all translation units)
+static thread_local char g_err[512] = "";
+void pg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* pg_last_error(void) { return g_err; }
+extern "C" int pg_version(void) { return 100; }
+extern "C" int pg_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  int dev = 0;
+  PG_CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  PG_CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return PG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan
+constexpr int TL_BAND = 16;             // output rows per work item
+constexpr uint32_t TL_PADMARK = 0xFFFFFFFFu;
+constexpr int TL_PAD_VALUE = 114;
+
+struct TileDev {
+  int32_t x0, y0, src_w, src_h;
+  int32_t new_w, new_h, pad_l, pad_t, out_w, out_h;
+  int32_t xtab_off, ytab_off;
+  int32_t row_bytes;  // bulk-copy size per source row (multiple of 16)
+  int32_t row_skew;   // byte offset of source pixel 0 inside the staged row
+  int64_t out_off;    // fp16 elements from the page's output base
+};
+
+struct PgTilePlan {
+  int32_t page_w = 0, page_h = 0, imgsz = 0;
+  std::vector<PgTileInfo> info;
+  std::vector<TileDev> tiles;
+  std::vector<uint2> xtab;  // per tile, out_w entries: {3*s0, a0 | a1<<16} or {0, PADMARK}
+  std::vector<int4> ytab;   // per tile, new_h entries: {s0, s1, b0, b1}
+  std::vector<int4> items;  // {tile, oy0, nrows, 0}
+  int64_t out_elems = 0;
+  int32_t max_row_bytes = 0;
+  int32_t max_out_w = 0;
+  // device mirrors (lazy)
+  int device = -1;
+  TileDev* d_tiles = nullptr;
+  uint2* d_xtab = nullptr;
+  int4* d_ytab = nullptr;
+  int4* d_items = nullptr;
+};
+
+static double py_round_half_even(double v) { return std::nearbyint(v); }
+
+extern "C" int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t* grid_rows,
+                                   const int32_t* grid_cols, int32_t n_grids, double overlap_percentage,
+                                   int32_t imgsz, int32_t stride, int32_t auto_pad, int32_t scaleup,
+                                   PgTilePlan** plan_out) {
+  PG_REQUIRE(plan_out != nullptr, "plan");
+  PG_REQUIRE(page_w > 0 && page_h > 0, "page size");
+  PG_REQUIRE(n_grids > 0 && grid_rows && grid_cols, "grids");
+  PG_REQUIRE(imgsz > 0 && stride > 0 && imgsz % 2 == 0, "imgsz/stride");
+  auto* plan = new PgTilePlan();
+  plan->page_w = page_w;
+  plan->page_h = page_h;
+  plan->imgsz = imgsz;
+  int64_t out_off = 0;
+  for (int g = 0; g < n_grids; ++g) {
+    const int rows = grid_rows[g], cols = grid_cols[g];
+    if (rows <= 0 || cols <= 0) {
+      delete plan;
+      pg_set_error("invalid argument: grid %d is %dx%d", g, rows, cols);
+      return PG_ERR_INVALID;
+    }
+    // 1_doclayout_bboxes.py:388-394 (Python doubles)
+    const double bw = (double)page_w / (double)cols;
+    const double bh = (double)page_h / (double)rows;
+    const double ox = bw * (overlap_percentage / 100.0);
+    const double oy = bh * (overlap_percentage / 100.0);
+    const size_t first_tile = plan->tiles.size();
+    for (int r = 0; r < rows; ++r) {
+      for (int c = 0; c < cols; ++c) {
+        double xs = c * bw;                       // :401-403
+        if (c > 0) xs -= ox;
+        double ys = r * bh;                       // :405-407
+        if (r > 0) ys -= oy;
+        double xe = (c + 1) * bw;                 // :409-411
+        if (c < cols - 1) xe += ox;
+        double ye = (r + 1) * bh;                 // :413-415
+        if (r < rows - 1) ye += oy;
+        xs = std::max(0.0, xs);                   // :418-421
+        ys = std::max(0.0, ys);
+        xe = std::min((double)page_w, xe);
+        ye = std::min((double)page_h, ye);
+        PgTileInfo ti;
+        std::memset(&ti, 0, sizeof(ti));
+        ti.x_start = xs; ti.y_start = ys; ti.x_end = xe; ti.y_end = ye;
+        ti.grid_rows = rows; ti.grid_cols = cols; ti.row = r + 1; ti.col = c + 1;
+        ti.x0 = (int32_t)xs; ti.y0 = (int32_t)ys; ti.x1 = (int32_t)xe; ti.y1 = (int32_t)ye;  // :424-427
+        const int sw = ti.x1 - ti.x0, sh = ti.y1 - ti.y0;
+        if (sw <= 0 || sh <= 0) {
+          delete plan;
+          pg_set_error("invalid argument: empty tile (grid %dx%d on %dx%d)", rows, cols, page_w, page_h);
+          return PG_ERR_INVALID;
+        }
+        // LetterBox geometry (ultralytics published behaviour)
+        double rr = std::min((double)imgsz / (double)sh, (double)imgsz / (double)sw);
+        if (!scaleup) rr = std::min(rr, 1.0);
+        ti.new_w = (int32_t)py_round_half_even((double)sw * rr);
+        ti.new_h = (int32_t)py_round_half_even((double)sh * rr);
+        if (ti.new_w < 1 || ti.new_h < 1 || ti.new_w > imgsz || ti.new_h > imgsz) {
+          delete plan;
+          pg_set_error("unsupported: tile %dx%d letterboxes to %dx%d", sw, sh, ti.new_w, ti.new_h);
+          return PG_ERR_UNSUPPORTED;
+        }
+        int dwi = imgsz - ti.new_w, dhi = imgsz - ti.new_h;
+        if (auto_pad) { dwi %= stride; dhi %= stride; }
+        const double dw = dwi / 2.0, dh = dhi / 2.0;
+        const int top = (int)py_round_half_even(dh - 0.1), bottom = (int)py_round_half_even(dh + 0.1);
+        const int left = (int)py_round_half_even(dw - 0.1), right = (int)py_round_half_even(dw + 0.1);
+        ti.pad_l = left; ti.pad_t = top;
+        ti.out_w = ti.new_w + left + right;
+        ti.out_h = ti.new_h + top + bottom;
+        if (ti.out_w % 2 != 0) {
+          delete plan;
+          pg_set_error("unsupported: odd output width %d", ti.out_w);
+          return PG_ERR_UNSUPPORTED;
+        }
+        ti.out_offset = out_off;
+        out_off += (int64_t)3 * ti.out_h * ti.out_w;
+
+        TileDev td;
+        td.x0 = ti.x0; td.y0 = ti.y0; td.src_w = sw; td.src_h = sh;
+        td.new_w = ti.new_w; td.new_h = ti.new_h; td.pad_l = ti.pad_l; td.pad_t = ti.pad_t;
+        td.out_w = ti.out_w; td.out_h = ti.out_h;
+        td.xtab_off = (int32_t)plan->xtab.size();
+        td.ytab_off = (int32_t)plan->ytab.size();
+        td.row_skew = (3 * ti.x0) & 15;
+        td.row_bytes = (td.row_skew + 3 * sw + 15) & ~15;
+        td.out_off = ti.out_offset;
+        for (int x = 0; x < ti.out_w; ++x) {
+          const int rx = x - ti.pad_l;
+          if (rx < 0 || rx >= ti.new_w) {
+            plan->xtab.push_back(make_uint2(0u, TL_PADMARK));
+          } else {
+            const PgCoef cf = pg_resize_coef(sw, ti.new_w, rx, true);
+            // when c1 == 0 the neighbour is multiplied by zero, so s1 never needs to be stored
+            plan->xtab.push_back(make_uint2((uint32_t)(3 * cf.s0), (uint32_t)cf.c0 | ((uint32_t)cf.c1 << 16)));
+          }
+        }
+        for (int y = 0; y < ti.new_h; ++y) {
+          const PgCoef cf = pg_resize_coef(sh, ti.new_h, y, false);
+          plan->ytab.push_back(make_int4(cf.s0, cf.s1, cf.c0, cf.c1));
+        }
+        plan->max_row_bytes = std::max(plan->max_row_bytes, td.row_bytes);
+        plan->max_out_w = std::max(plan->max_out_w, ti.out_w);
+        plan->info.push_back(ti);
+        plan->tiles.push_back(td);
+      }
+    }
+    // work items: (tile row, band, tile col)
+    for (int r = 0; r < rows; ++r) {
+      int max_h = 0;
+      for (int c = 0; c < cols; ++c) max_h = std::max(max_h, plan->tiles[first_tile + r * cols + c].out_h);
+      for (int b = 0; b * TL_BAND < max_h; ++b) {
+        for (int c = 0; c < cols; ++c) {
+          const int t = (int)first_tile + r * cols + c;
+          const int oy0 = b * TL_BAND;
+          if (oy0 >= plan->tiles[t].out_h) continue;
+          plan->items.push_back(make_int4(t, oy0, std::min(TL_BAND, plan->tiles[t].out_h - oy0), 0));
+        }
+      }
+    }
+  }
+  plan->out_elems = out_off;
+  *plan_out = plan;
+  return PG_OK;
+}
+
+static void plan_free_device(PgTilePlan* p) {
+  if (p->d_tiles) cudaFree(p->d_tiles);
+  if (p->d_xtab) cudaFree(p->d_xtab);
+  if (p->d_ytab) cudaFree(p->d_ytab);
+  if (p->d_items) cudaFree(p->d_items);
+  p->d_tiles = nullptr; p->d_xtab = nullptr; p->d_ytab = nullptr; p->d_items = nullptr;
+  p->device = -1;
+}
+
+extern "C" void pg_tile_plan_destroy(PgTilePlan* plan) {
+  if (!plan) return;
+  plan_free_device(plan);
+  delete plan;
+}
+extern "C" int32_t pg_tile_plan_num_tiles(const PgTilePlan* plan) { return plan ? (int32_t)plan->tiles.size() : 0; }
+extern "C" int pg_tile_plan_tile(const PgTilePlan* plan, int32_t tile, PgTileInfo* info) {
+  PG_REQUIRE(plan && info && tile >= 0 && tile < (int32_t)plan->info.size(), "tile index");
+  *info = plan->info[tile];
+  return PG_OK;
+}
+extern "C" int64_t pg_tile_plan_out_elems(const PgTilePlan* plan) { return plan ? plan->out_elems : 0; }
+extern "C" int64_t pg_tile_plan_algorithmic_bytes(const PgTilePlan* plan) {
+  return plan ? (int64_t)3 * plan->page_w * plan->page_h + 2 * plan->out_elems : 0;
+}
+
+static int plan_upload(PgTilePlan* p, cudaStream_t s) {
+  int dev = 0;
+  PG_CUDA_TRY(cudaGetDevice(&dev));
+  if (p->device == dev) return PG_OK;
+  plan_free_device(p);
+  PG_CUDA_TRY(cudaMalloc(&p->d_tiles, p->tiles.size() * sizeof(TileDev)));
+  PG_CUDA_TRY(cudaMalloc(&p->d_xtab, p->xtab.size() * sizeof(uint2)));
+  PG_CUDA_TRY(cudaMalloc(&p->d_ytab, p->ytab.size() * sizeof(int4)));
+  PG_CUDA_TRY(cudaMalloc(&p->d_items, p->items.size() * sizeof(int4)));
+  PG_CUDA_TRY(cudaMemcpyAsync(p->d_tiles, p->tiles.data(), p->tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice, s));
+  PG_CUDA_TRY(cudaMemcpyAsync(p->d_xtab, p->xtab.data(), p->xtab.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
+  PG_CUDA_TRY(cudaMemcpyAsync(p->d_ytab, p->ytab.data(), p->ytab.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
+  PG_CUDA_TRY(cudaMemcpyAsync(p->d_items, p->items.data(), p->items.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
+  PG_CUDA_TRY(cudaStreamSynchronize(s));  // host vectors may not be pinned; one-time cost
+  p->device = dev;
+  return PG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trap (launch error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 4000000000ull) __trap();  // 4 s
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// 8 source bytes starting at byte offset `off` of a staged row -> horizontal pass of one pixel.
+// lo = B0 G0 R0 B1, hi = G1 R1 . .   (BGR interleaved source, neighbour pixel 3 bytes on)
+__device__ __forceinline__ void hpass_smem(uint32_t row_addr, uint32_t off, uint32_t coef, uint32_t& hb,
+                                           uint32_t& hg, uint32_t& hr) {
+  const uint32_t a = row_addr + (off & ~3u);
+  const uint32_t w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8);
+  const uint32_t sh = (off & 3u) * 8u;
+  const uint32_t lo = __funnelshift_r(w0, w1, sh);
+  const uint32_t hi = __funnelshift_r(w1, w2, sh);
+  const uint32_t bg = __byte_perm(lo, hi, 0x4130);  // B0 B1 G0 G1
+  const uint32_t rr = __byte_perm(lo, hi, 0x0052);  // R0 R1 . .
+  hb = __dp2a_lo(coef, bg, 0u);                     // a0*B0 + a1*B1
+  hg = __dp2a_hi(coef, bg, 0u);
+  hr = __dp2a_lo(coef, rr, 0u);
+}
+
+__device__ __forceinline__ uint32_t pack_unit_half2(uint32_t va, uint32_t vb) {
+  // fp16(v/255): v*(1/255) in fp32 then one RN conversion matches fp16(fp32(v)/255) for all 256 v
+  const float k = 1.0f / 255.0f;
+  __half2 h = __floats2half2_rn((float)va * k, (float)vb * k);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 persistent pipeline kernel
+constexpr int TL_CW = 8;                     // consumer warps
+constexpr int TL_THREADS = 32 * (TL_CW + 1);  // + producer warp
+constexpr int TL_STAGES = 4;
+constexpr int TL_PAIR_STRIDE = TL_CW * 64;    // pixels covered by all consumer warps per iteration
+
+struct TilerArgs {
+  const uint8_t* pages;
+  __half* out;
+  const TileDev* tiles;
+  const uint2* xtab;
+  const int4* ytab;
+  const int4* items;
+  int64_t pitch, page_stride, out_page_stride;
+  int32_t items_per_page;
+  int64_t total_items;
+  int32_t row_stride;  // shared-memory bytes per staged row
+};
+
+template <int ITER>
+__global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const TilerArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[TL_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TL_STAGES];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TL_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], TL_CW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const uint32_t stage_bytes = 2u * (uint32_t)a.row_stride;
+  uint32_t stage = 0, phase = 0;
+
+  if (warp == TL_CW) {
+    // ===================== producer: one elected lane issues the bulk copies =====================
+    if (lane == 0) {
+      for (int64_t it = blockIdx.x; it < a.total_items; it += gridDim.x) {
+        const int64_t page = it / a.items_per_page;
+        const int4 item = a.items[it - page * a.items_per_page];
+        const TileDev& t = a.tiles[item.x];
+        const uint8_t* src = a.pages + page * a.page_stride + (int64_t)t.y0 * a.pitch + ((3 * t.x0) & ~15);
+        const uint32_t bytes = (uint32_t)t.row_bytes;
+        for (int oy = item.y; oy < item.y + item.z; ++oy) {
+          const int ry = oy - t.pad_t;
+          if (ry < 0 || ry >= t.new_h) continue;  // pad row: nothing to stage
+          const int4 yt = a.ytab[t.ytab_off + ry];
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], 2u * bytes);
+          uint8_t* dst = smem + stage * stage_bytes;
+          bulk_g2s(dst, src + (int64_t)yt.x * a.pitch, bytes, &full_bar[stage]);
+          bulk_g2s(dst + a.row_stride, src + (int64_t)yt.y * a.pitch, bytes, &full_bar[stage]);
+          if (++stage == TL_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers =====================
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t pad_pair = pack_unit_half2(TL_PAD_VALUE, TL_PAD_VALUE);
+  uint32_t xoff[ITER][2], coef[ITER][2];
+  int cached_tile = -1;
+
+  for (int64_t it = blockIdx.x; it < a.total_items; it += gridDim.x) {
+    const int64_t page = it / a.items_per_page;
+    const int4 item = a.items[it - page * a.items_per_page];
+    const TileDev& t = a.tiles[item.x];
+    const int out_w = t.out_w, out_h = t.out_h;
+    if (item.x != cached_tile) {
+      cached_tile = item.x;
+      const uint32_t skew = (uint32_t)t.row_skew;
+#pragma unroll
+      for (int i = 0; i < ITER; ++i) {
+        const int ox = i * TL_PAIR_STRIDE + warp * 64 + lane * 2;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint2 e = make_uint2(0u, TL_PADMARK);
+          if (ox + j < out_w) e = __ldg(&a.xtab[t.xtab_off + ox + j]);
+          xoff[i][j] = e.x + skew;
+          coef[i][j] = e.y;
+        }
+      }
+    }
+    __half* out_tile = a.out + page * a.out_page_stride + t.out_off;
+    const int64_t plane = (int64_t)out_h * out_w;
+
+    for (int oy = item.y; oy < item.y + item.z; ++oy) {
+      const int ry = oy - t.pad_t;
+      uint32_t* orow = reinterpret_cast<uint32_t*>(out_tile + (int64_t)oy * out_w);  // R plane row (half2 units)
+      if (ry < 0 || ry >= t.new_h) {
+#pragma unroll
+        for (int i = 0; i < ITER; ++i) {
+          const int ox = i * TL_PAIR_STRIDE + warp * 64 + lane * 2;
+          if (ox < out_w) {
+            __stcs(orow + (ox >> 1), pad_pair);
+            __stcs(orow + ((plane + ox) >> 1), pad_pair);
+            __stcs(orow + ((2 * plane + ox) >> 1), pad_pair);
+          }
+        }
+        continue;
+      }
+      const int4 yt = __ldg(&a.ytab[t.ytab_off + ry]);
+      const uint32_t b0 = (uint32_t)yt.z, b1 = (uint32_t)yt.w;
+      mbar_wait(&full_bar[stage], phase);
+      const uint32_t row0 = smem_base + stage * stage_bytes;
+      const uint32_t row1 = row0 + (uint32_t)a.row_stride;
+#pragma unroll
+      for (int i = 0; i < ITER; ++i) {
+        const int ox = i * TL_PAIR_STRIDE + warp * 64 + lane * 2;
+        if (ox < out_w) {
+          uint32_t vb[2], vg[2], vr[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (coef[i][j] == TL_PADMARK) {
+              vb[j] = vg[j] = vr[j] = TL_PAD_VALUE;
+            } else {
+              uint32_t tb, tg, tr, ub, ug, ur;
+              hpass_smem(row0, xoff[i][j], coef[i][j], tb, tg, tr);
+              hpass_smem(row1, xoff[i][j], coef[i][j], ub, ug, ur);
+              vb[j] = pg_vpass(tb, ub, b0, b1);
+              vg[j] = pg_vpass(tg, ug, b0, b1);
+              vr[j] = pg_vpass(tr, ur, b0, b1);
+            }
+          }
+          // BGR -> RGB planes
+          __stcs(orow + (ox >> 1), pack_unit_half2(vr[0], vr[1]));
+          __stcs(orow + ((plane + ox) >> 1), pack_unit_half2(vg[0], vg[1]));
+          __stcs(orow + ((2 * plane + ox) >> 1), pack_unit_half2(vb[0], vb[1]));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == TL_STAGES) { stage = 0; phase ^= 1u; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// validation twin: plain global loads, one thread per output pixel pair
+__global__ void __launch_bounds__(256) tile_letterbox_direct_kernel(const TilerArgs a, int32_t n_tiles, int32_t n_pages) {
+  const int tile = blockIdx.y % n_tiles, page = blockIdx.y / n_tiles;
+  if (page >= n_pages) return;
+  const TileDev t = a.tiles[tile];
+  const int pairs_w = t.out_w >> 1;
+  const int64_t npairs = (int64_t)pairs_w * t.out_h;
+  __half* out_tile = a.out + (int64_t)page * a.out_page_stride + t.out_off;
+  const int64_t plane = (int64_t)t.out_h * t.out_w;
+  const uint8_t* src = a.pages + (int64_t)page * a.page_stride + (int64_t)t.y0 * a.pitch + 3 * (int64_t)t.x0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * blockDim.x) {
+    const int oy = (int)(p / pairs_w), ox = (int)(p - (int64_t)oy * pairs_w) * 2;
+    const int ry = oy - t.pad_t;
+    uint32_t v[3][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint2 e = a.xtab[t.xtab_off + ox + j];
+      if (ry < 0 || ry >= t.new_h || e.y == TL_PADMARK) {
+        v[0][j] = v[1][j] = v[2][j] = TL_PAD_VALUE;
+      } else {
+        const int4 yt = a.ytab[t.ytab_off + ry];
+        const uint32_t a0 = e.y & 0xFFFFu, a1 = e.y >> 16;
+        const uint8_t* r0 = src + (int64_t)yt.x * a.pitch + e.x;
+        const uint8_t* r1 = src + (int64_t)yt.y * a.pitch + e.x;
+        const int dx = a1 ? 3 : 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const uint32_t h0 = pg_hpass(r0[c], r0[c + dx], a0, a1);
+          const uint32_t h1 = pg_hpass(r1[c], r1[c + dx], a0, a1);
+          v[c][j] = pg_vpass(h0, h1, (uint32_t)yt.z, (uint32_t)yt.w);
+        }
+      }
+    }
+    uint32_t* o = reinterpret_cast<uint32_t*>(out_tile + (int64_t)oy * t.out_w);
+    o[ox >> 1] = pack_unit_half2(v[2][0], v[2][1]);
+    o[(plane + ox) >> 1] = pack_unit_half2(v[1][0], v[1][1]);
+    o[(2 * plane + ox) >> 1] = pack_unit_half2(v[0][0], v[0][1]);
+  }
+}
+
+static int check_pages_layout(const PgTilePlan* plan, const uint8_t* pages, int32_t n_pages, int64_t pitch,
+                              int64_t page_stride, const void* out, int64_t out_page_stride) {
+  PG_REQUIRE(plan != nullptr, "plan");
+  PG_REQUIRE(pages != nullptr && out != nullptr, "null device pointer");
+  PG_REQUIRE(n_pages >= 0, "n_pages");
+  PG_REQUIRE(pitch >= (int64_t)3 * plan->page_w && pitch % 16 == 0, "pitch must be >= 3*W and a multiple of 16");
+  PG_REQUIRE(page_stride >= pitch * plan->page_h && page_stride % 16 == 0, "page_stride");
+  PG_REQUIRE(((uintptr_t)pages & 15) == 0, "pages must be 16-byte aligned");
+  PG_REQUIRE(out_page_stride >= plan->out_elems && out_page_stride % 2 == 0, "out_page_stride");
+  PG_REQUIRE(((uintptr_t)out & 3) == 0, "out must be 4-byte aligned");
+  return PG_OK;
+}
+
+static TilerArgs make_args(const PgTilePlan* plan, const uint8_t* pages, int32_t n_pages, int64_t pitch,
+                           int64_t page_stride, void* out, int64_t out_page_stride) {
+  TilerArgs a;
+  a.pages = pages;
+  a.out = reinterpret_cast<__half*>(out);
+  a.tiles = plan->d_tiles;
+  a.xtab = plan->d_xtab;
+  a.ytab = plan->d_ytab;
+  a.items = plan->d_items;
+  a.pitch = pitch;
+  a.page_stride = page_stride;
+  a.out_page_stride = out_page_stride;
+  a.items_per_page = (int32_t)plan->items.size();
+  a.total_items = (int64_t)plan->items.size() * n_pages;
+  a.row_stride = (plan->max_row_bytes + 16 + 127) & ~127;
+  return a;
+}
+
+template <int ITER>
+static int launch_pipeline(const TilerArgs& a, cudaStream_t s) {
+  const size_t smem = (size_t)TL_STAGES * 2 * a.row_stride;
+  int dev = 0, sms = 0, max_smem = 0;
+  PG_CUDA_TRY(cudaGetDevice(&dev));
+  PG_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  PG_CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (smem + 1024 > (size_t)max_smem) {
+    pg_set_error("unsupported: tile rows of %d bytes need %zu B of shared memory (max %d)", a.row_stride, smem, max_smem);
+    return PG_ERR_UNSUPPORTED;
+  }
+  PG_CUDA_TRY(cudaFuncSetAttribute(tile_letterbox_kernel<ITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  PG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_letterbox_kernel<ITER>, TL_THREADS, smem));
+  if (per_sm < 1) {
+    pg_set_error("unsupported: tiler kernel does not fit on an SM");
+    return PG_ERR_UNSUPPORTED;
+  }
+  int64_t grid = (int64_t)sms * per_sm;
+  if (grid > a.total_items) grid = a.total_items;
+  if (grid < 1) return PG_OK;
+  tile_letterbox_kernel<ITER><<<(unsigned)grid, TL_THREADS, smem, s>>>(a);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+extern "C" int pg_tile_letterbox(PgTilePlan* plan, const uint8_t* pages, int32_t n_pages, int64_t pitch,
+                                 int64_t page_stride, void* out_f16, int64_t out_page_stride, void* stream) {
+  int rc = check_pages_layout(plan, pages, n_pages, pitch, page_stride, out_f16, out_page_stride);
+  if (rc != PG_OK) return rc;
+  if (n_pages == 0) return PG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = plan_upload(plan, s);
+  if (rc != PG_OK) return rc;
+  const TilerArgs a = make_args(plan, pages, n_pages, pitch, page_stride, out_f16, out_page_stride);
+  const int iters = (plan->max_out_w + TL_PAIR_STRIDE - 1) / TL_PAIR_STRIDE;
+  if (iters <= 1) return launch_pipeline<1>(a, s);
+  if (iters <= 2) return launch_pipeline<2>(a, s);
+  if (iters <= 4) return launch_pipeline<4>(a, s);
+  pg_set_error("unsupported: output width %d > %d", plan->max_out_w, 4 * TL_PAIR_STRIDE);
+  return PG_ERR_UNSUPPORTED;
+}
+
+extern "C" int pg_tile_letterbox_direct(PgTilePlan* plan, const uint8_t* pages, int32_t n_pages, int64_t pitch,
+                                        int64_t page_stride, void* out_f16, int64_t out_page_stride, void* stream) {
+  int rc = check_pages_layout(plan, pages, n_pages, pitch, page_stride, out_f16, out_page_stride);
+  if (rc != PG_OK) return rc;
+  if (n_pages == 0) return PG_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = plan_upload(plan, s);
+  if (rc != PG_OK) return rc;
+  const TilerArgs a = make_args(plan, pages, n_pages, pitch, page_stride, out_f16, out_page_stride);
+  const int n_tiles = (int)plan->tiles.size();
+  const int64_t gy = (int64_t)n_tiles * n_pages;
+  PG_REQUIRE(gy <= 65535, "direct kernel: n_tiles*n_pages must be <= 65535");
+  dim3 grid(64, (unsigned)gy);
+  tile_letterbox_direct_kernel<<<grid, 256, 0, s>>>(a, n_tiles, n_pages);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic pages (bench input generator; device-resident, counter-based)
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+__global__ void synth_pages_kernel(uint8_t* pages, int32_t n_pages, int32_t w, int32_t h, int64_t pitch,
+                                   int64_t page_stride, uint64_t seed0, int64_t first_page) {
+  // one thread per 4 bytes of a row (pitch is a multiple of 16)
+  const int64_t words_per_row = pitch >> 2;
+  const int64_t total = (int64_t)n_pages * h * words_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / words_per_row;
+    const int wx = (int)(i - row * words_per_row);
+    const int page = (int)(row / h), y = (int)(row - (int64_t)page * h);
+    const uint32_t pseed = mix32((uint32_t)(seed0 + (uint64_t)(first_page + page)) * 0x9E3779B9u + 0x85EBCA6Bu);
+    uint32_t word = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int byte = wx * 4 + b;
+      const int x = byte / 3;
+      uint32_t v = 0;
+      if (x < w) {
+        const uint32_t hp = mix32(pseed ^ mix32((uint32_t)y * 0x01000193u + (uint32_t)x));
+        // text-line bands of 24 px with 9 px leading; ink probability higher inside a line
+        const bool in_line = (y % 33) < 24;
+        const bool ink = (hp & 0xFFu) < (in_line ? 70u : 4u);
+        const uint32_t hc = mix32(hp + (uint32_t)(byte - 3 * x) + 1u);
+        v = ink ? 20u + (hc & 31u) : 215u + (hc & 31u);
+      }
+      word |= v << (8 * b);
+    }
+    *reinterpret_cast<uint32_t*>(pages + (int64_t)page * page_stride + (int64_t)y * pitch + (int64_t)wx * 4) = word;
+  }
+}
+
+extern "C" int pg_synth_pages(uint8_t* pages, int32_t n_pages, int32_t page_w, int32_t page_h, int64_t pitch,
+                              int64_t page_stride, uint64_t seed0, int64_t first_page, void* stream) {
+  PG_REQUIRE(pages != nullptr && n_pages >= 0 && page_w > 0 && page_h > 0, "pages");
+  PG_REQUIRE(pitch >= (int64_t)3 * page_w && pitch % 16 == 0, "pitch");
+  PG_REQUIRE(page_stride >= pitch * page_h && page_stride % 16 == 0, "page_stride");
+  if (n_pages == 0) return PG_OK;
+  synth_pages_kernel<<<148 * 16, 256, 0, (cudaStream_t)stream>>>(pages, n_pages, page_w, page_h, pitch, page_stride,
+                                                                  seed0, first_page);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// test hooks (host evaluations of pg_math.h)
+extern "C" double pg_hostcheck_iou(const double* a, const double* b) {
+  return pg_iou(a[0], a[1], a[2], a[3], pg_box_area(a[0], a[1], a[2], a[3]), b[0], b[1], b[2], b[3],
+                pg_box_area(b[0], b[1], b[2], b[3]));
+}
+extern "C" int32_t pg_hostcheck_edge_touch(const double* box, const double* cell, int32_t w, int32_t h, double thr) {
+  return pg_edge_touch(box[0], box[1], box[2], box[3], cell[0], cell[1], cell[2], cell[3], (double)w, (double)h, thr) ? 1 : 0;
+}
+extern "C" double pg_hostcheck_density_weight(int32_t bin, int32_t left, int32_t right, int32_t center) {
+  return pg_density_weight(bin, left, right, center);
+}
+// one output row (BGR uint8, dst_w pixels) of the fixed-point resize from the two source rows it needs
+extern "C" int pg_hostcheck_resize_row(const uint8_t* row0, const uint8_t* row1, int32_t src_w, int32_t src_h,
+                                       int32_t dst_w, int32_t dst_h, int32_t dy, uint8_t* out_bgr) {
+  const PgCoef cy = pg_resize_coef(src_h, dst_h, dy, false);
+  for (int x = 0; x < dst_w; ++x) {
+    const PgCoef cx = pg_resize_coef(src_w, dst_w, x, true);
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t h0 = pg_hpass(row0[3 * cx.s0 + c], row0[3 * cx.s1 + c], cx.c0, cx.c1);
+      const uint32_t h1 = pg_hpass(row1[3 * cx.s0 + c], row1[3 * cx.s1 + c], cx.c0, cx.c1);
+      out_bgr[3 * x + c] = (uint8_t)pg_vpass(h0, h1, cy.c0, cy.c1);
+    }
+  }
+  return cy.s0 | (cy.s1 << 16);
+}

@@ -1,0 +1,305 @@
+"""Device-level wrappers: one function per C-ABI entry point, torch tensors in/out.
+
+PyTorch is only the allocator / stream provider here; every computation is a kernel of
+libpagegeom.so.  All tensors must live on the current CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PgTileInfo, check, lib, ptr, stream_ptr
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.PageGeomError("a CUDA device is required: the page-geometry path has no CPU fallback")
+
+
+def row_pitch(width: int) -> int:
+    """Row pitch (bytes) of a BGR uint8 page for the tiler: 3*W rounded up to 16 (bulk-copy alignment)."""
+    return (3 * int(width) + 15) // 16 * 16
+
+
+# --------------------------------------------------------------------------------------------
+# K1 tiler
+# --------------------------------------------------------------------------------------------
+class TilePlan:
+    """Tiling + letterbox plan for one page size (pg_tile_plan_*).
+
+    grids: sequence of (rows, cols); (1, 1) is the reference's full-page pass.
+    Tiles are enumerated grid-major then row-major, like 1_doclayout_bboxes.py:756,399-400.
+    """
+
+    def __init__(self, page_w: int, page_h: int, grids: Sequence[Tuple[int, int]] = ((2, 2),),
+                 overlap: float = 20.0, imgsz: int = 1024, stride: int = 32, auto: bool = True,
+                 scaleup: bool = True):
+        self.page_w, self.page_h = int(page_w), int(page_h)
+        self.grids = [(int(r), int(c)) for r, c in grids]
+        self.overlap, self.imgsz, self.stride, self.auto = float(overlap), int(imgsz), int(stride), bool(auto)
+        rows = (C.c_int32 * len(self.grids))(*[g[0] for g in self.grids])
+        cols = (C.c_int32 * len(self.grids))(*[g[1] for g in self.grids])
+        handle = C.c_void_p()
+        check(lib().pg_tile_plan_create(self.page_w, self.page_h, rows, cols, len(self.grids), self.overlap,
+                                        self.imgsz, self.stride, int(auto), int(scaleup), C.byref(handle)))
+        self._h = handle
+        self.tiles: List[dict] = []
+        for t in range(lib().pg_tile_plan_num_tiles(self._h)):
+            info = PgTileInfo()
+            check(lib().pg_tile_plan_tile(self._h, t, C.byref(info)))
+            self.tiles.append({name: getattr(info, name) for name, _ in PgTileInfo._fields_})
+        self.out_elems = int(lib().pg_tile_plan_out_elems(self._h))
+        self.algorithmic_bytes = int(lib().pg_tile_plan_algorithmic_bytes(self._h))
+        self.pitch = row_pitch(self.page_w)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().pg_tile_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # -- cell coordinates with the reference's int/float mixing (1_doclayout_bboxes.py:418-421)
+    def cell_coordinates(self, tile: int) -> dict:
+        t = self.tiles[tile]
+
+        def lo(v):
+            return 0 if v == 0 else v
+
+        def hi(v, bound):
+            return bound if v == bound else v
+
+        return {"x_start": lo(t["x_start"]), "y_start": lo(t["y_start"]),
+                "x_end": hi(t["x_end"], self.page_w), "y_end": hi(t["y_end"], self.page_h)}
+
+    def alloc_pages(self, n_pages: int) -> torch.Tensor:
+        _require_cuda()
+        return torch.empty((n_pages, self.page_h, self.pitch), dtype=torch.uint8, device="cuda")
+
+    def alloc_out(self, n_pages: int) -> torch.Tensor:
+        _require_cuda()
+        return torch.empty((n_pages, self.out_elems), dtype=torch.float16, device="cuda")
+
+    def run(self, pages: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None,
+            direct: bool = False) -> torch.Tensor:
+        """pages: cuda uint8 [P, H, pitch] (BGR interleaved rows, pitch % 16 == 0).
+        Returns fp16 [P, out_elems]; tile_view() slices a tile out of it."""
+        _require_cuda()
+        assert pages.is_cuda and pages.dtype == torch.uint8 and pages.dim() == 3 and pages.is_contiguous()
+        n_pages, h, pitch = pages.shape
+        assert h == self.page_h, (h, self.page_h)
+        if out is None:
+            out = self.alloc_out(n_pages)
+        assert out.is_cuda and out.dtype == torch.float16 and out.is_contiguous() and out.shape[0] == n_pages
+        fn = lib().pg_tile_letterbox_direct if direct else lib().pg_tile_letterbox
+        check(fn(self._h, ptr(pages), n_pages, pitch, h * pitch, ptr(out), out.stride(0), stream_ptr(stream)))
+        return out
+
+    def tile_view(self, out: torch.Tensor, page: int, tile: int) -> torch.Tensor:
+        t = self.tiles[tile]
+        n = 3 * t["out_h"] * t["out_w"]
+        return out[page, t["out_offset"]: t["out_offset"] + n].view(3, t["out_h"], t["out_w"])
+
+
+def upload_pages(images: Sequence[np.ndarray], plan: TilePlan, stream=None) -> torch.Tensor:
+    """Host BGR uint8 HxWx3 arrays -> pitched cuda tensor [P, H, pitch] through pinned memory."""
+    _require_cuda()
+    n = len(images)
+    host = torch.zeros((n, plan.page_h, plan.pitch), dtype=torch.uint8).pin_memory()
+    hv = host.numpy()
+    for i, img in enumerate(images):
+        assert img.shape == (plan.page_h, plan.page_w, 3) and img.dtype == np.uint8
+        hv[i, :, : 3 * plan.page_w] = img.reshape(plan.page_h, 3 * plan.page_w)
+    return host.to("cuda", non_blocking=True)
+
+
+def synth_pages(plan: TilePlan, n_pages: int, seed0: int, first_page: int = 0, out: Optional[torch.Tensor] = None,
+                stream=None) -> torch.Tensor:
+    _require_cuda()
+    if out is None:
+        out = plan.alloc_pages(n_pages)
+    check(lib().pg_synth_pages(ptr(out), n_pages, plan.page_w, plan.page_h, plan.pitch, plan.page_h * plan.pitch,
+                               seed0, first_page, stream_ptr(stream)))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# box stages
+# --------------------------------------------------------------------------------------------
+def _dev(a, dtype) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        t = a.to(device="cuda", dtype=dtype)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(a))).to(device="cuda", dtype=dtype)
+    return t.contiguous()
+
+
+def edge_filter(boxes, box_cell, cells, page_wh, page_off, threshold: float = 10, boxes_are_local: bool = True,
+                want_boxes_page: bool = True, stream=None):
+    """pg_edge_filter.  Returns (boxes_page [N,4] f64 or None, keep [N] u8, kept_idx [N] i32, n_kept [P] i32)."""
+    _require_cuda()
+    boxes = _dev(boxes, torch.float64).view(-1, 4)
+    box_cell = _dev(box_cell, torch.int32)
+    cells = _dev(cells, torch.float64).view(-1, 4)
+    page_wh = _dev(page_wh, torch.int32).view(-1, 2)
+    page_off = _dev(page_off, torch.int64)
+    n, p = boxes.shape[0], page_wh.shape[0]
+    assert page_off.numel() == p + 1 and box_cell.numel() == n
+    boxes_page = torch.empty_like(boxes) if want_boxes_page else None
+    keep = torch.empty(n, dtype=torch.uint8, device="cuda")
+    kept_idx = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
+    n_kept = torch.zeros(max(p, 1), dtype=torch.int32, device="cuda")
+    check(lib().pg_edge_filter(ptr(boxes), int(boxes_are_local), ptr(box_cell), ptr(cells), ptr(page_wh),
+                               ptr(page_off), p, float(threshold), ptr(boxes_page), ptr(keep), ptr(kept_idx),
+                               ptr(n_kept), stream_ptr(stream)))
+    return boxes_page, keep, kept_idx, n_kept[:p]
+
+
+@dataclass
+class NmsWorkspace:
+    n_boxes: int
+    n_pages: int
+    pairs_per_block: int = 64
+    buf: torch.Tensor = field(init=False)
+
+    def __post_init__(self):
+        nbytes = int(lib().pg_nms_workspace_bytes(self.n_boxes, self.n_pages, self.pairs_per_block))
+        self.buf = torch.empty(nbytes + 256, dtype=torch.uint8, device="cuda")
+        self.offset = (-self.buf.data_ptr()) % 256
+        self.nbytes = nbytes
+
+    @property
+    def ptr(self) -> int:
+        return self.buf.data_ptr() + self.offset
+
+    def stats(self) -> dict:
+        arr = (C.c_int64 * 4)()
+        check(lib().pg_nms_stats(self.ptr, arr))
+        return {"status": arr[0], "candidate_block_pairs": arr[1], "rounds": arr[2], "box_pairs_tested": arr[3]}
+
+
+def nms_merge(boxes, scores, classes, page_off, iou_threshold: float = 0.5, sel_idx=None, n_sel=None,
+              max_boxes_per_page: int = 0, workspace: Optional[NmsWorkspace] = None, stream=None,
+              kept_idx: Optional[torch.Tensor] = None, n_kept: Optional[torch.Tensor] = None):
+    """pg_nms_merge.  Returns (kept_idx [N] i32 global indices in pick order, n_kept [P] i32, workspace)."""
+    _require_cuda()
+    boxes = _dev(boxes, torch.float64).view(-1, 4)
+    scores = _dev(scores, torch.float64)
+    classes = _dev(classes, torch.float64)
+    page_off = _dev(page_off, torch.int64)
+    n, p = boxes.shape[0], page_off.numel() - 1
+    if sel_idx is not None:
+        sel_idx = _dev(sel_idx, torch.int32)
+        n_sel = _dev(n_sel, torch.int32)
+    if workspace is None or workspace.n_boxes < n or workspace.n_pages < p:
+        workspace = NmsWorkspace(n, p)
+    if kept_idx is None:
+        kept_idx = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
+    if n_kept is None:
+        n_kept = torch.zeros(max(p, 1), dtype=torch.int32, device="cuda")
+    check(lib().pg_nms_merge(ptr(boxes), ptr(scores), ptr(classes), ptr(sel_idx), ptr(page_off), ptr(n_sel), p, n,
+                             int(max_boxes_per_page), float(iou_threshold), ptr(kept_idx), ptr(n_kept),
+                             workspace.ptr, workspace.nbytes, stream_ptr(stream)))
+    return kept_idx, n_kept[:p], workspace
+
+
+def class_flags(classes, plain_text_id: float = 1.0, title_id: float = 0.0, stream=None) -> torch.Tensor:
+    _require_cuda()
+    classes = _dev(classes, torch.float64)
+    flags = torch.empty(classes.numel(), dtype=torch.uint8, device="cuda")
+    check(lib().pg_class_flags(ptr(classes), classes.numel(), float(plain_text_id), float(title_id), ptr(flags),
+                               stream_ptr(stream)))
+    return flags
+
+
+def width_median(boxes, flags, page_off, page_wh, min_margin_percent: float = 0.2, sel_idx=None, n_sel=None,
+                 width_hist: Optional[torch.Tensor] = None, stream=None):
+    """pg_width_median.  Returns (median [P] f64, n_bins [P] i32)."""
+    _require_cuda()
+    boxes = _dev(boxes, torch.float64).view(-1, 4)
+    flags = _dev(flags, torch.uint8)
+    page_off = _dev(page_off, torch.int64)
+    page_wh = _dev(page_wh, torch.int32).view(-1, 2)
+    n, p = boxes.shape[0], page_wh.shape[0]
+    if sel_idx is not None:
+        sel_idx = _dev(sel_idx, torch.int32)
+        n_sel = _dev(n_sel, torch.int32)
+    median = torch.zeros(max(p, 1), dtype=torch.float64, device="cuda")
+    n_bins = torch.zeros(max(p, 1), dtype=torch.int32, device="cuda")
+    ws_keys = torch.empty(max(n, 1), dtype=torch.float64, device="cuda")
+    ws_counts = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
+    check(lib().pg_width_median(ptr(boxes), ptr(flags), ptr(sel_idx), ptr(page_off), ptr(n_sel), p, ptr(page_wh),
+                                float(min_margin_percent), ptr(median), ptr(n_bins), ptr(ws_keys), ptr(ws_counts),
+                                ptr(width_hist), stream_ptr(stream)))
+    return median[:p], n_bins[:p]
+
+
+class GaussTable:
+    """Normalised scipy.signal.windows.gaussian(M, std=M/6) for every odd M <= max_window
+    (5_detect_column_centers.py:151-153), built on the host with numpy so np.exp rounding is
+    shared with the reference, uploaded once."""
+
+    def __init__(self, max_window: int = 1023):
+        _require_cuda()
+        self.max_window = int(max_window) | 1
+        offs, chunks, off = [], [], 0
+        for k in range((self.max_window - 1) // 2 + 1):
+            m = 2 * k + 1
+            sigma = m / 6.0
+            nn = np.arange(0, m) - (m - 1.0) / 2.0
+            w = np.exp(-(nn ** 2) / (2 * sigma * sigma))
+            w = w / w.sum()
+            offs.append(off)
+            chunks.append(w)
+            off += m
+        self.table = torch.from_numpy(np.concatenate(chunks)).to("cuda")
+        self.offsets = torch.tensor(offs, dtype=torch.int64, device="cuda")
+
+
+_GAUSS: Optional[GaussTable] = None
+
+
+def gauss_table() -> GaussTable:
+    global _GAUSS
+    if _GAUSS is None:
+        _GAUSS = GaussTable()
+    return _GAUSS
+
+
+def column_peaks(boxes, flags, scores, page_off, page_wh, median, min_confidence: float = 0.3, sel_idx=None,
+                 n_sel=None, max_cols: int = 64, max_bins: int = 0, col_hist: Optional[torch.Tensor] = None,
+                 stream=None):
+    """pg_column_peaks.  Returns (centers [P,max_cols] i32, widths [P,max_cols] f64, n_cols [P] i32)."""
+    _require_cuda()
+    boxes = _dev(boxes, torch.float64).view(-1, 4)
+    flags = _dev(flags, torch.uint8)
+    scores = _dev(scores, torch.float64)
+    page_off = _dev(page_off, torch.int64)
+    page_wh_t = _dev(page_wh, torch.int32).view(-1, 2)
+    median = _dev(median, torch.float64)
+    p = page_wh_t.shape[0]
+    if sel_idx is not None:
+        sel_idx = _dev(sel_idx, torch.int32)
+        n_sel = _dev(n_sel, torch.int32)
+    if max_bins <= 0:
+        max_bins = 1024
+        if p:
+            wmax = int(page_wh_t[:, 0].max().item())
+            max_bins = max(1024, wmax // max(1, wmax // 1000) + 2)
+    gt = gauss_table()
+    centers = torch.zeros((max(p, 1), max_cols), dtype=torch.int32, device="cuda")
+    widths = torch.zeros((max(p, 1), max_cols), dtype=torch.float64, device="cuda")
+    n_cols = torch.zeros(max(p, 1), dtype=torch.int32, device="cuda")
+    ws = torch.empty((max(p, 1), 2 * max_bins), dtype=torch.float64, device="cuda")
+    check(lib().pg_column_peaks(ptr(boxes), ptr(flags), ptr(scores), ptr(sel_idx), ptr(page_off), ptr(n_sel), p,
+                                ptr(page_wh_t), ptr(median), ptr(gt.table), ptr(gt.offsets), gt.max_window,
+                                float(min_confidence), max_cols, ptr(centers), ptr(widths), ptr(n_cols), ptr(ws),
+                                max_bins, ptr(col_hist), stream_ptr(stream)))
+    return centers[:p], widths[:p], n_cols[:p]

@@ -1,0 +1,179 @@
+"""Whole hot path for a shard of pages, chained on the device:
+
+    tile+letterbox (K1) -> translate+edge filter (K2) -> NMS merge (K3) -> class flags
+    -> plain_text width median (K4) -> column centres (K5)   [-> corpus histograms (K6)]
+
+All buffers are allocated once; a step is a fixed sequence of libpagegeom.so launches on one
+stream with no host synchronisation in between (each stage consumes the previous stage's
+kept_idx / n_kept directly).  Pages are independent, so multi-GPU runs shard pages across
+ranks with no collective; only the optional corpus histograms are all-reduced.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import PG_COL_HIST_BINS, PG_WIDTH_HIST_BINS, check, lib, ptr, stream_ptr
+
+KERNELS_PER_STEP = 11  # tiler, edge filter, 6 NMS kernels, class flags, width median, column peaks
+
+
+def shard_pages(n_pages_total: int, rank: int, world: int) -> range:
+    """Contiguous page shard of ``rank`` (pages are independent units)."""
+    per = (n_pages_total + world - 1) // world
+    lo = min(n_pages_total, rank * per)
+    return range(lo, min(n_pages_total, lo + per))
+
+
+class PagePipeline:
+    def __init__(self, plan: ops.TilePlan, n_pages: int, iou_threshold: float = 0.5, edge_threshold: float = 10,
+                 min_margin_percent: float = 0.2, min_confidence: float = 0.3, max_cols: int = 64,
+                 plain_text_id: float = 1.0, title_id: float = 0.0, corpus_stats: bool = False):
+        self.plan, self.n_pages = plan, int(n_pages)
+        self.iou_threshold, self.edge_threshold = float(iou_threshold), float(edge_threshold)
+        self.min_margin_percent, self.min_confidence = float(min_margin_percent), float(min_confidence)
+        self.max_cols, self.plain_text_id, self.title_id = int(max_cols), float(plain_text_id), float(title_id)
+        self.tiles_out = plan.alloc_out(self.n_pages)
+        self.n_boxes = 0
+        self.corpus_stats = corpus_stats
+        self.width_hist = self.col_hist = None
+        if corpus_stats:
+            self.hist = torch.zeros(PG_WIDTH_HIST_BINS + PG_COL_HIST_BINS, dtype=torch.int32, device="cuda")
+            self.width_hist = self.hist[:PG_WIDTH_HIST_BINS]
+            self.col_hist = self.hist[PG_WIDTH_HIST_BINS:]
+        self.gauss = ops.gauss_table()
+        w = plan.page_w
+        self.max_bins = max(1024, w // max(1, w // 1000) + 2)
+
+    # ---------------------------------------------------------------- detections
+    def set_detections(self, dets: Sequence[dict], stream=None, host_staging: Optional[dict] = None):
+        """dets: one dict per page as produced by synth.page_detections (or replayed stage-1
+        JSON): cells [C,4], box_cell [n], boxes_local [n,4], scores [n], classes [n]."""
+        assert len(dets) == self.n_pages
+        counts = [len(d["boxes_local"]) for d in dets]
+        off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        cell_base = np.concatenate([[0], np.cumsum([len(d["cells"]) for d in dets])])
+        host = {
+            "boxes_local": np.concatenate([d["boxes_local"].reshape(-1, 4) for d in dets]).astype(np.float64),
+            "box_cell": np.concatenate([d["box_cell"].astype(np.int64) + cell_base[i] for i, d in enumerate(dets)]).astype(np.int32),
+            "cells": np.concatenate([d["cells"] for d in dets]).astype(np.float64),
+            "scores": np.concatenate([d["scores"] for d in dets]).astype(np.float64),
+            "classes": np.concatenate([d["classes"] for d in dets]).astype(np.float64),
+            "page_off": off,
+            "page_wh": np.asarray([[d["width"], d["height"]] for d in dets], np.int32),
+        }
+        self._alloc_boxes(int(off[-1]), int(max(counts) if counts else 0))
+        self.upload_detections(host, stream)
+        return host
+
+    def _alloc_boxes(self, n: int, max_per_page: int):
+        if n == self.n_boxes and getattr(self, "max_per_page", -1) == max_per_page:
+            return
+        self.n_boxes, self.max_per_page = n, max_per_page
+        p, dev = self.n_pages, "cuda"
+        m = max(n, 1)
+        self.boxes_local = torch.empty((m, 4), dtype=torch.float64, device=dev)
+        self.boxes_page = torch.empty((m, 4), dtype=torch.float64, device=dev)
+        self.box_cell = torch.empty(m, dtype=torch.int32, device=dev)
+        self.scores = torch.empty(m, dtype=torch.float64, device=dev)
+        self.classes = torch.empty(m, dtype=torch.float64, device=dev)
+        self.flags = torch.empty(m, dtype=torch.uint8, device=dev)
+        self.page_off = torch.empty(p + 1, dtype=torch.int64, device=dev)
+        self.page_wh = torch.empty((p, 2), dtype=torch.int32, device=dev)
+        self.cells = None
+        self.kept1 = torch.empty(m, dtype=torch.int32, device=dev)
+        self.n_kept1 = torch.zeros(p, dtype=torch.int32, device=dev)
+        self.kept2 = torch.empty(m, dtype=torch.int32, device=dev)
+        self.n_kept2 = torch.zeros(p, dtype=torch.int32, device=dev)
+        self.median = torch.zeros(p, dtype=torch.float64, device=dev)
+        self.n_bins = torch.zeros(p, dtype=torch.int32, device=dev)
+        self.ws_keys = torch.empty(m, dtype=torch.float64, device=dev)
+        self.ws_counts = torch.empty(m, dtype=torch.int32, device=dev)
+        self.centers = torch.zeros((p, self.max_cols), dtype=torch.int32, device=dev)
+        self.col_widths = torch.zeros((p, self.max_cols), dtype=torch.float64, device=dev)
+        self.n_cols = torch.zeros(p, dtype=torch.int32, device=dev)
+        self.col_ws = torch.empty((p, 2 * self.max_bins), dtype=torch.float64, device=dev)
+        self.nms_ws = ops.NmsWorkspace(n, p)
+
+    def upload_detections(self, host: Dict[str, np.ndarray], stream=None, pinned: Optional[dict] = None) -> int:
+        """Host -> device copy of one step's detections.  Returns bytes copied."""
+        nbytes = 0
+        if self.cells is None or self.cells.shape[0] != host["cells"].shape[0]:
+            self.cells = torch.empty((host["cells"].shape[0], 4), dtype=torch.float64, device="cuda")
+        for name, dst in (("boxes_local", self.boxes_local), ("box_cell", self.box_cell), ("cells", self.cells),
+                          ("scores", self.scores), ("classes", self.classes), ("page_off", self.page_off),
+                          ("page_wh", self.page_wh)):
+            src = pinned[name] if pinned is not None else torch.from_numpy(host[name])
+            n = src.shape[0]
+            if n:
+                dst[:n].copy_(src.view(dst[:n].shape), non_blocking=True)
+            nbytes += src.numel() * src.element_size()
+        return nbytes
+
+    # ---------------------------------------------------------------- one step
+    def run(self, pages: torch.Tensor, stream=None, tiler_events=None) -> None:
+        """One pass of the hot path over the shard.  pages: cuda uint8 [P, H, pitch]."""
+        L, s, p = lib(), stream_ptr(stream), self.n_pages
+        plan = self.plan
+        if tiler_events is not None:
+            tiler_events[0].record(stream)
+        check(L.pg_tile_letterbox(plan._h, ptr(pages), p, pages.shape[2], pages.shape[1] * pages.shape[2],
+                                  ptr(self.tiles_out), self.tiles_out.stride(0), s))
+        if tiler_events is not None:
+            tiler_events[1].record(stream)
+        if self.n_boxes == 0:
+            return
+        check(L.pg_edge_filter(ptr(self.boxes_local), 1, ptr(self.box_cell), ptr(self.cells), ptr(self.page_wh),
+                               ptr(self.page_off), p, self.edge_threshold, ptr(self.boxes_page), None,
+                               ptr(self.kept1), ptr(self.n_kept1), s))
+        check(L.pg_nms_merge(ptr(self.boxes_page), ptr(self.scores), ptr(self.classes), ptr(self.kept1),
+                             ptr(self.page_off), ptr(self.n_kept1), p, self.n_boxes, self.max_per_page,
+                             self.iou_threshold, ptr(self.kept2), ptr(self.n_kept2), self.nms_ws.ptr,
+                             self.nms_ws.nbytes, s))
+        check(L.pg_class_flags(ptr(self.classes), self.n_boxes, self.plain_text_id, self.title_id, ptr(self.flags), s))
+        check(L.pg_width_median(ptr(self.boxes_page), ptr(self.flags), ptr(self.kept2), ptr(self.page_off),
+                                ptr(self.n_kept2), p, ptr(self.page_wh), self.min_margin_percent, ptr(self.median),
+                                ptr(self.n_bins), ptr(self.ws_keys), ptr(self.ws_counts), ptr(self.width_hist), s))
+        check(L.pg_column_peaks(ptr(self.boxes_page), ptr(self.flags), ptr(self.scores), ptr(self.kept2),
+                                ptr(self.page_off), ptr(self.n_kept2), p, ptr(self.page_wh), ptr(self.median),
+                                ptr(self.gauss.table), ptr(self.gauss.offsets), self.gauss.max_window,
+                                self.min_confidence, self.max_cols, ptr(self.centers), ptr(self.col_widths),
+                                ptr(self.n_cols), ptr(self.col_ws), self.max_bins, ptr(self.col_hist), s))
+
+    def allreduce_corpus_stats(self):
+        """K6: the one exchange step of the path — integer histograms summed over ranks
+        (NCCL over NVLink; order-independent, so 1/2/4/8-GPU results are bit-identical)."""
+        import torch.distributed as dist
+        if self.corpus_stats and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.hist, op=dist.ReduceOp.SUM)
+        return self.hist
+
+    # ---------------------------------------------------------------- results
+    def results_to_host(self, pinned: Optional[dict] = None) -> Dict[str, np.ndarray]:
+        """Device -> host read of the step's results (what the stage-3/4/5 JSON writers need)."""
+        out = {}
+        for name in ("kept2", "n_kept2", "median", "n_bins", "centers", "col_widths", "n_cols"):
+            t = getattr(self, name)
+            if pinned is not None:
+                pinned[name].copy_(t, non_blocking=True)
+                out[name] = pinned[name]
+            else:
+                out[name] = t.cpu()
+        return out
+
+    def result_bytes(self) -> int:
+        return sum(getattr(self, n).numel() * getattr(self, n).element_size()
+                   for n in ("kept2", "n_kept2", "median", "n_bins", "centers", "col_widths", "n_cols"))
+
+    def check_status(self) -> dict:
+        st = self.nms_ws.stats()
+        if st["status"] != 0:
+            raise RuntimeError(f"NMS merge reported an error on device: {st}")
+        if bool((self.n_cols < 0).any().item()):
+            raise RuntimeError("column kernel: a page exceeded the kernel limits")
+        if bool((self.n_cols > self.max_cols).any().item()):
+            raise RuntimeError("column kernel: more columns than max_cols")
+        return st

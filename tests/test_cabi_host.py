@@ -1,0 +1,146 @@
+"""CPU checks of libpagegeom.so: it loads, exports every symbol include/pagegeom.h declares,
+its host-only tile planner reproduces the reference geometry, and the inline arithmetic the
+kernels are compiled from (csrc/pg_math.h, evaluated on the host through the pg_hostcheck_*
+hooks) agrees bit-for-bit with the oracle.  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from multimodal_embeddings_b200 import _lib, build, ops, synth
+from oracle import boxes as ob
+from oracle import tiler as ot
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.lib()
+
+
+def test_header_symbols_exported(lib):
+    text = open(os.path.join(ROOT, "include", "pagegeom.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", text))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pg_version() >= 100
+
+
+def test_invalid_arguments_are_reported(lib):
+    handle = C.c_void_p()
+    rows = (C.c_int32 * 1)(2)
+    cols = (C.c_int32 * 1)(0)
+    rc = lib.pg_tile_plan_create(100, 100, rows, cols, 1, 20.0, 1024, 32, 1, 1, C.byref(handle))
+    assert rc == 1 and b"grid" in lib.pg_last_error()
+    assert lib.pg_edge_filter(None, 0, None, None, None, None, 3, 10.0, None, None, None, None, None) == 1
+    assert lib.pg_nms_merge(None, None, None, None, None, None, 0, 0, 0, 0.5, None, None, None, 0, None) == 0
+
+
+def test_plan_geometry_matches_reference_goldens(lib):
+    g = load_golden("stage1_geometry.json")
+    for case in g["split"]:
+        plan = ops.TilePlan(case["width"], case["height"], [(case["rows"], case["cols"])], case["overlap"])
+        assert len(plan.tiles) == len(case["cells"])
+        for t, ref in enumerate(case["cells"]):
+            cc = plan.cell_coordinates(t)
+            assert cc == ref["coordinates"]
+            for k, v in ref["coordinates"].items():
+                assert type(cc[k]) is type(v)
+            info = plan.tiles[t]
+            assert (info["row"], info["col"]) == (ref["row"], ref["col"])
+            assert [info["y1"] - info["y0"], info["x1"] - info["x0"]] == ref["shape"]
+
+
+def test_plan_letterbox_and_offsets_match_oracle(lib):
+    for (w, h) in [(8000, 6000), (7934, 5755), (3801, 5601), (2778, 4187), (640, 480)]:
+        for auto in (True, False):
+            plan = ops.TilePlan(w, h, [(1, 1), (2, 2), (3, 3), (4, 4)], 20.0, 1024, 32, auto)
+            assert len(plan.tiles) == 30
+            off = 0
+            for info in plan.tiles:
+                g = ot.letterbox_geometry(info["x1"] - info["x0"], info["y1"] - info["y0"], 1024, 32, auto)
+                for k in ("new_w", "new_h", "pad_l", "pad_t", "out_w", "out_h"):
+                    assert info[k] == g[k], (w, h, auto, k)
+                assert info["out_offset"] == off
+                off += 3 * info["out_w"] * info["out_h"]
+            assert plan.out_elems == off
+            assert plan.algorithmic_bytes == 3 * w * h + 2 * off
+    # BASELINE.md figures: cfg3 = 8000x6000, 4x4, stride-32 letterbox -> 220.3 MB per page
+    plan = ops.TilePlan(8000, 6000, [(4, 4)], 20.0)
+    assert abs(plan.algorithmic_bytes / 1e6 - 220.3) < 0.05
+    sq = ops.TilePlan(8000, 6000, [(4, 4)], 20.0, auto=False)
+    assert abs(sq.algorithmic_bytes / 1e6 - 244.7) < 0.05
+
+
+def test_hostcheck_iou_bit_exact(lib):
+    g = load_golden("stage3_nms.npz")
+    for p, ref in zip(g["iou_pairs"], g["iou_values"]):
+        a, b = np.ascontiguousarray(p[:4]), np.ascontiguousarray(p[4:])
+        assert lib.pg_hostcheck_iou(_lib.ptr(a), _lib.ptr(b)) == ref
+
+
+def test_hostcheck_edge_touch_matches_reference(lib):
+    n = 0
+    for case in load_golden("stage2_filter.json.gz"):
+        w, h, thr = case["width"], case["height"], case["threshold"]
+        for cc, boxes, kept in zip(case["cell_coordinates"], case["boxes_original"], case["kept"]):
+            cell = np.asarray(ob.cell_tuple(cc, w, h), np.float64)
+            ks = set(kept)
+            for i, b in enumerate(boxes[:150]):
+                bb = np.asarray(b, np.float64)
+                assert bool(lib.pg_hostcheck_edge_touch(_lib.ptr(bb), _lib.ptr(cell), w, h, float(thr))) == (i not in ks)
+                n += 1
+    assert n > 2000
+
+
+def test_hostcheck_density_weight(lib):
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        left = int(rng.integers(0, 900))
+        right = left + int(rng.integers(0, 300))
+        center = int(rng.integers(left - 5, right + 6))
+        b = int(rng.integers(left, right + 1))
+        ref = 1.0 - 0.5 * min(1.0, abs(b - center) / ((right - left) / 2 + 1e-6))
+        assert lib.pg_hostcheck_density_weight(b, left, right, center) == ref
+
+
+@pytest.mark.parametrize("src,dst", [((97, 131), (64, 48)), ((211, 280), (102, 77)), ((40, 50), (100, 80))])
+def test_hostcheck_resize_rows_equal_cv2(lib, src, dst):
+    cv2 = pytest.importorskip("cv2")
+    sh, sw = src
+    dw, dh = dst
+    img = np.random.default_rng(sh + dw).integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+    ref = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)
+    out = np.zeros((dw, 3), np.uint8)
+    _, _, _, _ = ot.resize_coeffs(sh, dh, False)
+    y0, y1, _, _ = ot.resize_coeffs(sh, dh, False)
+    for dy in range(dh):
+        r0, r1 = np.ascontiguousarray(img[y0[dy]]), np.ascontiguousarray(img[y1[dy]])
+        packed = lib.pg_hostcheck_resize_row(_lib.ptr(r0), _lib.ptr(r1), sw, sh, dw, dh, dy, _lib.ptr(out))
+        assert (packed & 0xFFFF, packed >> 16) == (int(y0[dy]), int(y1[dy]))
+        assert np.array_equal(out, ref[dy])
+
+
+def test_no_cpu_fallback_without_cuda(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_lib.PageGeomError):
+        ops.edge_filter(np.zeros((1, 4)), [0], np.zeros((1, 4)), [[10, 10]], [0, 1])
+    det = synth.page_detections(640, 480, 2, 2, 20.0, 50, 1)
+    assert det["boxes_local"].shape == (50, 4)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "multimodal_embeddings_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--pages-per-gpu", type=int, default=64)
     ap.add_argument("--e2e-pages", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling helper: skip the host-buffer leg")
     ap.add_argument("--corpus-stats", action="store_true", help="accumulate + all-reduce corpus histograms (cfg5)")
     ap.add_argument("--tiler-only", action="store_true", help="profiling helper: time the tiler alone")
     args = ap.parse_args()
@@ -287,9 +288,12 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    nms_stats = None
     for _, pipe, _, _, _ in pipes:
         if not args.tiler_only:
-            pipe.check_status()
+            st = pipe.check_status()
+            nms_stats = {"boxes_in": pipe.n_boxes, "boxes_after_edge_filter": int(pipe.n_kept1.sum().item()),
+                         "boxes_kept": int(pipe.n_kept2.sum().item()), **{k: int(v) for k, v in st.items()}}
     pages_total = ppg * world * args.steps
     value = pages_total / (ms * 1e-3)
 
@@ -322,12 +326,12 @@ def main():
                    "parallelism": f"page-sharded x{world}, no collective" + (" + hist all-reduce" if args.corpus_stats else ""),
                    "l2": f"inputs {sum(p[2].numel() for p in pipes) / 1e9:.1f} GB/step per GPU >> 126 MB L2 (no flush needed)",
                    "stages": "tiler only" if args.tiler_only else "tile+letterbox, translate+edge filter, NMS merge, width median, column peaks"},
-        "roofline": roofline, "clocks": clocks,
+        "roofline": roofline, "clocks": clocks, "merge_stats_last_group": nms_stats,
         "gpu_launches": (len(pipes) if args.tiler_only else KERNELS_PER_STEP * len(pipes)) * args.steps,
     }
 
     # ---- e2e: same metric through the host-buffer API, H2D of pages+detections and D2H of results timed
-    if rank == 0 or world > 1:
+    if not args.no_e2e and not args.tiler_only:
         plan, pipe0, pages0, host0, dets0 = pipes[0]
         n_e = min(args.e2e_pages, pipe0.n_pages)
         epipe = PagePipeline(plan, n_e)

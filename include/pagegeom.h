@@ -136,10 +136,10 @@ int pg_nms_stats(const void* workspace /*dev*/, int64_t stats[4]);
 int pg_class_flags(const double* classes /*dev [N]*/, int64_t n, double plain_text_id,
                    double title_id, uint8_t* flags /*dev [N]*/, void* stream);
 int pg_width_median(const double* boxes, const uint8_t* flags, const int32_t* sel_idx,
-                    const int64_t* page_off, const int32_t* n_sel, int32_t n_pages,
+                    const int64_t* page_off, const int32_t* n_sel, int32_t n_pages, int64_t n_boxes,
                     const int32_t* page_wh, double min_margin_percent,
                     double* median /*dev [P]*/, int32_t* n_bins /*dev [P]*/,
-                    double* ws_keys /*dev [N]*/, int32_t* ws_counts /*dev [N]*/,
+                    double* ws_keys /*dev [2N]: bin keys + gathered widths*/, int32_t* ws_counts /*dev [N]*/,
                     uint32_t* width_hist /*dev [PG_WIDTH_HIST_BINS] or NULL*/, void* stream);
 
 /* ------------------------------------------------------------------ K5 column centres
@@ -165,6 +165,9 @@ int pg_column_peaks(const double* boxes, const uint8_t* flags, const double* sco
 double pg_hostcheck_iou(const double* a, const double* b);
 int32_t pg_hostcheck_edge_touch(const double* box, const double* cell, int32_t w, int32_t h, double thr);
 double pg_hostcheck_density_weight(int32_t bin, int32_t left, int32_t right, int32_t center);
+/* number of (right-left, |bin-center|) pairs in [0,max_span]x[0,max_n] where the reciprocal+FMA
+ * form used by the density kernel differs from the true divide (must be 0) */
+int64_t pg_hostcheck_density_rcp_mismatches(int32_t max_span, int32_t max_n);
 int pg_hostcheck_resize_row(const uint8_t* row0, const uint8_t* row1, int32_t src_w, int32_t src_h,
                             int32_t dst_w, int32_t dst_h, int32_t dy, uint8_t* out_bgr);
 

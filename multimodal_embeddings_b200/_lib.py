@@ -56,12 +56,13 @@ SIGNATURES = {
     "pg_nms_merge": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I64, _I32, _F64, _P, _P, _P, C.c_size_t, _P]),
     "pg_nms_stats": (C.c_int, [_P, _P]),
     "pg_class_flags": (C.c_int, [_P, _I64, _F64, _F64, _P, _P]),
-    "pg_width_median": (C.c_int, [_P, _P, _P, _P, _P, _I32, _P, _F64, _P, _P, _P, _P, _P, _P]),
+    "pg_width_median": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I64, _P, _F64, _P, _P, _P, _P, _P, _P]),
     "pg_column_peaks": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I32, _F64, _I32,
                                   _P, _P, _P, _P, _I32, _P, _P]),
     "pg_hostcheck_iou": (_F64, [_P, _P]),
     "pg_hostcheck_edge_touch": (_I32, [_P, _P, _I32, _I32, _F64]),
     "pg_hostcheck_density_weight": (_F64, [_I32, _I32, _I32, _I32]),
+    "pg_hostcheck_density_rcp_mismatches": (_I64, [_I32, _I32]),
     "pg_hostcheck_resize_row": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
 }
 

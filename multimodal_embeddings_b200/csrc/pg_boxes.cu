@@ -15,13 +15,12 @@
 //              filter_grid_info 2_edge_box_filter.py:206-217 (kept order = input order)
 // One CTA per page; order-preserving compaction by block scan.
 // =============================================================================================
-__global__ void __launch_bounds__(256) edge_filter_kernel(const double* __restrict__ boxes, int local,
-                                                          const int32_t* __restrict__ box_cell,
-                                                          const double* __restrict__ cells,
-                                                          const int32_t* __restrict__ page_wh,
-                                                          const int64_t* __restrict__ page_off, double thr,
-                                                          double* __restrict__ boxes_out, uint8_t* __restrict__ keep,
-                                                          int32_t* __restrict__ kept_idx, int32_t* __restrict__ n_kept) {
+constexpr int EDGE_THREADS = 1024;
+__global__ void __launch_bounds__(EDGE_THREADS) edge_filter_kernel(
+    const double* __restrict__ boxes, int local, const int32_t* __restrict__ box_cell,
+    const double* __restrict__ cells, const int32_t* __restrict__ page_wh, const int64_t* __restrict__ page_off,
+    double thr, double* __restrict__ boxes_out, uint8_t* __restrict__ keep, int32_t* __restrict__ kept_idx,
+    int32_t* __restrict__ n_kept) {
   __shared__ int scan_smem[34];
   const int p = blockIdx.x;
   const int64_t b0 = page_off[p], b1 = page_off[p + 1];
@@ -62,9 +61,8 @@ extern "C" int pg_edge_filter(const double* boxes, int32_t boxes_are_local, cons
   PG_REQUIRE(n_pages >= 0, "n_pages");
   if (n_pages == 0) return PG_OK;
   PG_REQUIRE(boxes && box_cell && cells && page_wh && page_off && kept_idx && n_kept, "null device pointer");
-  edge_filter_kernel<<<n_pages, 256, 0, (cudaStream_t)stream>>>(boxes, boxes_are_local, box_cell, cells, page_wh,
-                                                                page_off, threshold, boxes_page_out, keep, kept_idx,
-                                                                n_kept);
+  edge_filter_kernel<<<n_pages, EDGE_THREADS, 0, (cudaStream_t)stream>>>(
+      boxes, boxes_are_local, box_cell, cells, page_wh, page_off, threshold, boxes_page_out, keep, kept_idx, n_kept);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
@@ -76,9 +74,9 @@ extern "C" int pg_edge_filter(const double* boxes, int32_t boxes_are_local, cons
 // Greedy NMS keeps box i iff no *kept* box j with higher priority (score desc, earlier pooled
 // position on ties, :112), same class and IoU > thr (:130) exists.  That fixed point is unique,
 // so it can be computed without replaying the sequential loop:
-//   A  bin      per page, counting-sort the boxes into a 64x64 grid of centre cells (x-major)
-//               so that runs of 32 consecutive boxes ("blocks") are spatially compact; write a
-//               blocked SoA copy and each block's bounding box;
+//   A  bin      per page, a stable two-pass block radix sort orders the boxes by
+//               (x strip, y cell) of their centres so that runs of 32 consecutive boxes
+//               ("blocks") are spatially compact; write a blocked AoS copy + block bounding boxes;
 //   B  count    per block I, count blocks J of the same page whose bounding boxes intersect
 //               (IoU > thr >= 0 needs a non-empty intersection, the reference's own early-out);
 //   C  scan     exclusive scan of the counts -> entry offsets (workspace overflow -> status);
@@ -89,25 +87,31 @@ extern "C" int pg_edge_filter(const double* boxes, int32_t boxes_are_local, cons
 //               undecided box becomes suppressed if a suppressor is kept, kept if none of its
 //               suppressors is still undecided.  Each round decides at least the best undecided
 //               box, typical depth is 3-6 rounds;
-//   F  emit     rank the kept boxes by priority (counting rank, shared-memory tiles) and write
-//               global indices in pick order.
+//   F  emit     sort the kept boxes by priority (normalised bitonic network in shared memory,
+//               global-memory network for > 8192 survivors) and write global indices in pick order.
 // =============================================================================================
-constexpr int NMS_GX = 64, NMS_GY = 64, NMS_CELLS = NMS_GX * NMS_GY;
+constexpr int NMS_GY = 128;     // y cells (7-bit digit)
+constexpr int NMS_GX_MAX = 64;  // x strips (6-bit digit), chosen per page from the mean box width
+
+struct __align__(16) SBox {  // one box in spatial order
+  double x0, y0, x1, y1;
+  double area, score, cls;
+  long long k;  // position in the pooled list (priority tie-break), -1 = padding lane
+};
 
 struct NmsWs {
   int64_t* stats;      // [8]: status, candidate pairs, rounds, box pairs tested
   int32_t* sorted_pos; // [N]   spatial order -> local position k
   int32_t* cellid;     // [N]
-  double* sx0; double* sy0; double* sx1; double* sy1; double* sarea; double* sscore; double* scls;  // [NB*32]
-  int32_t* skpos;      // [NB*32] local position, -1 = padding lane
+  SBox* sbox;          // [NB*32]
   double* bbox;        // [NB*4]
   int32_t* blk_page;   // [NB]
   int32_t* cand_cnt;   // [NB]
   int64_t* cand_off;   // [NB+1]
   uint32_t* st_kept;   // [2*NB]
   uint32_t* st_undec;  // [2*NB]
-  double* kscore;      // [N]
-  int32_t* kpos;       // [N]
+  double* kscore;      // [N]  (re-used as sortable u64 keys by emit)
+  int32_t* kpos;       // [N]  (scratch of the radix sort, then kept positions)
   int32_t* ent_j;      // [E]
   uint32_t* ent_mask;  // [E*32]
   int64_t nb_cap, ent_cap;
@@ -128,14 +132,7 @@ static size_t nms_layout(int64_t n, int32_t n_pages, int32_t pairs_per_block, ui
   w.stats = (int64_t*)take(8 * sizeof(int64_t));
   w.sorted_pos = (int32_t*)take((size_t)n * 4);
   w.cellid = (int32_t*)take((size_t)n * 4);
-  w.sx0 = (double*)take((size_t)nb * 32 * 8);
-  w.sy0 = (double*)take((size_t)nb * 32 * 8);
-  w.sx1 = (double*)take((size_t)nb * 32 * 8);
-  w.sy1 = (double*)take((size_t)nb * 32 * 8);
-  w.sarea = (double*)take((size_t)nb * 32 * 8);
-  w.sscore = (double*)take((size_t)nb * 32 * 8);
-  w.scls = (double*)take((size_t)nb * 32 * 8);
-  w.skpos = (int32_t*)take((size_t)nb * 32 * 4);
+  w.sbox = (SBox*)take((size_t)nb * 32 * sizeof(SBox));
   w.bbox = (double*)take((size_t)nb * 4 * 8);
   w.blk_page = (int32_t*)take((size_t)nb * 4);
   w.cand_cnt = (int32_t*)take((size_t)nb * 4);
@@ -183,6 +180,63 @@ __device__ __forceinline__ double warp_max_d(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One stable counting-sort pass of a 1024-thread CTA (32 warps, warp w owns a contiguous chunk
+// of the input so that (digit, warp, position) order == (digit, input order)).
+//   hist: shared int[32 * NDIG]; elem(i) -> element id of input slot i; digit(e) -> [0, NDIG)
+template <int NDIG, typename ElemOf, typename DigitOf>
+__device__ __forceinline__ void block_stable_pass(int m, int* hist, int* scan_smem, ElemOf elem, DigitOf digit,
+                                                  int32_t* dst) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 32 * NDIG; i += 1024) hist[i] = 0;
+  __syncthreads();
+  const int chunk = (((m + 31) >> 5) + 31) & ~31;
+  const int lo = min(m, warp * chunk), hi = min(m, lo + chunk);
+  for (int i = lo + lane; i < hi; i += 32) atomicAdd(&hist[warp * NDIG + digit(elem(i))], 1);
+  __syncthreads();
+  {
+    constexpr int PER = (32 * NDIG) / 1024;
+    int v[PER], sum = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int idx = tid * PER + q;  // (digit major, warp minor)
+      v[q] = hist[(idx & 31) * NDIG + (idx >> 5)];
+      sum += v[q];
+    }
+    int total;
+    int ex = pg_block_exscan(sum, scan_smem, &total);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int idx = tid * PER + q;
+      hist[(idx & 31) * NDIG + (idx >> 5)] = ex;
+      ex += v[q];
+    }
+  }
+  __syncthreads();
+  for (int c = lo; c < hi; c += 32) {
+    const int i = c + lane;
+    const bool act = i < hi;
+    const int e = act ? elem(i) : 0;
+    const int d = act ? digit(e) : -1 - lane;
+    const unsigned grp = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(grp) - 1;
+    const int rank = __popc(grp & ((1u << lane) - 1u));
+    int basepos = 0;
+    if (act && lane == leader) {
+      basepos = hist[warp * NDIG + d];
+      hist[warp * NDIG + d] = basepos + __popc(grp);
+    }
+    basepos = __shfl_sync(0xffffffffu, basepos, leader);
+    if (act) dst[basepos + rank] = e;
+    __syncwarp();
+  }
+  __syncthreads();
+}
 
 // ---- A: bin --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) nms_bin_kernel(const double* __restrict__ boxes,
@@ -191,90 +245,84 @@ __global__ void __launch_bounds__(1024) nms_bin_kernel(const double* __restrict_
                                                        const int32_t* __restrict__ sel_idx,
                                                        const int64_t* __restrict__ page_off,
                                                        const int32_t* __restrict__ n_sel, int n_pages, NmsWs ws) {
-  __shared__ int counts[NMS_CELLS];
-  __shared__ double red[4][32];
+  __shared__ int hist[32 * NMS_GY];
+  __shared__ double red[5][32];
   __shared__ int scan_smem[34];
   const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const PageSpan sp = page_span(page_off, n_sel, p);
   const int64_t blk_next = (p + 1 < n_pages) ? (page_off[p + 1] >> 5) + p + 1 : ws.nb_cap;
   for (int64_t b = sp.blk0 + sp.nb + tid; b < blk_next; b += blockDim.x) ws.blk_page[b] = -1;
 
-  // extent of the box centres
-  double mnx = DBL_MAX, mny = DBL_MAX, mxx = -DBL_MAX, mxy = -DBL_MAX;
+  // extent of the box centres and mean box width
+  double mnx = DBL_MAX, mny = DBL_MAX, mxx = -DBL_MAX, mxy = -DBL_MAX, sw = 0.0;
   for (int k = tid; k < sp.m; k += blockDim.x) {
     const int64_t gi = sel_idx ? (int64_t)sel_idx[sp.base + k] : sp.base + k;
-    const double cx = (boxes[4 * gi] + boxes[4 * gi + 2]) * 0.5, cy = (boxes[4 * gi + 1] + boxes[4 * gi + 3]) * 0.5;
+    const double2 a = *reinterpret_cast<const double2*>(boxes + 4 * gi);
+    const double2 b = *reinterpret_cast<const double2*>(boxes + 4 * gi + 2);
+    const double cx = (a.x + b.x) * 0.5, cy = (a.y + b.y) * 0.5;
     mnx = fmin(mnx, cx); mxx = fmax(mxx, cx); mny = fmin(mny, cy); mxy = fmax(mxy, cy);
+    sw += fabs(b.x - a.x);
   }
-  mnx = warp_min_d(mnx); mny = warp_min_d(mny); mxx = warp_max_d(mxx); mxy = warp_max_d(mxy);
-  if (lane == 0) { red[0][warp] = mnx; red[1][warp] = mny; red[2][warp] = mxx; red[3][warp] = mxy; }
-  for (int c = tid; c < NMS_CELLS; c += blockDim.x) counts[c] = 0;
+  mnx = warp_min_d(mnx); mny = warp_min_d(mny); mxx = warp_max_d(mxx); mxy = warp_max_d(mxy); sw = warp_sum_d(sw);
+  if (lane == 0) { red[0][warp] = mnx; red[1][warp] = mny; red[2][warp] = mxx; red[3][warp] = mxy; red[4][warp] = sw; }
   __syncthreads();
   if (warp == 0) {
-    double a = warp_min_d(red[0][lane]), b = warp_min_d(red[1][lane]);
-    double c = warp_max_d(red[2][lane]), d = warp_max_d(red[3][lane]);
-    if (lane == 0) { red[0][0] = a; red[1][0] = b; red[2][0] = c; red[3][0] = d; }
+    const double a = warp_min_d(red[0][lane]), b = warp_min_d(red[1][lane]);
+    const double c = warp_max_d(red[2][lane]), d = warp_max_d(red[3][lane]), e = warp_sum_d(red[4][lane]);
+    if (lane == 0) { red[0][0] = a; red[1][0] = b; red[2][0] = c; red[3][0] = d; red[4][0] = e; }
   }
   __syncthreads();
   mnx = red[0][0]; mny = red[1][0]; mxx = red[2][0]; mxy = red[3][0];
-  const double sx = (mxx > mnx) ? (double)NMS_GX / (mxx - mnx) : 0.0;
+  // one x strip per mean box width: the boxes of one text column share a strip (pure heuristic:
+  // any ordering gives the same result, a good one gives fewer candidate block pairs)
+  int gxn = 1;
+  if (sp.m > 0 && mxx > mnx) {
+    const double meanw = red[4][0] / (double)sp.m;
+    const double s = meanw > 0.0 ? (mxx - mnx) / meanw : 1.0;
+    gxn = s >= (double)NMS_GX_MAX ? NMS_GX_MAX : (s >= 1.0 ? (int)s + 1 : 1);
+    if (gxn > NMS_GX_MAX) gxn = NMS_GX_MAX;
+  }
+  const double sx = (mxx > mnx) ? (double)gxn / (mxx - mnx) : 0.0;
   const double sy = (mxy > mny) ? (double)NMS_GY / (mxy - mny) : 0.0;
 
-  // cell ids + histogram
   for (int k = tid; k < sp.m; k += blockDim.x) {
     const int64_t gi = sel_idx ? (int64_t)sel_idx[sp.base + k] : sp.base + k;
-    const double cx = (boxes[4 * gi] + boxes[4 * gi + 2]) * 0.5, cy = (boxes[4 * gi + 1] + boxes[4 * gi + 3]) * 0.5;
-    const double fx = (cx - mnx) * sx, fy = (cy - mny) * sy;
-    int gx = (fx >= 0.0) ? (fx < (double)(NMS_GX - 1) ? (int)fx : NMS_GX - 1) : 0;
-    int gy = (fy >= 0.0) ? (fy < (double)(NMS_GY - 1) ? (int)fy : NMS_GY - 1) : 0;
-    const int cell = gx * NMS_GY + gy;  // x-major: consecutive cells walk down a column
-    ws.cellid[sp.base + k] = cell;
-    atomicAdd(&counts[cell], 1);
+    const double2 a = *reinterpret_cast<const double2*>(boxes + 4 * gi);
+    const double2 b = *reinterpret_cast<const double2*>(boxes + 4 * gi + 2);
+    const double fx = ((a.x + b.x) * 0.5 - mnx) * sx, fy = ((a.y + b.y) * 0.5 - mny) * sy;
+    const int gx = (fx >= 0.0) ? (fx < (double)(gxn - 1) ? (int)fx : gxn - 1) : 0;
+    const int gy = (fy >= 0.0) ? (fy < (double)(NMS_GY - 1) ? (int)fy : NMS_GY - 1) : 0;
+    ws.cellid[sp.base + k] = gx * NMS_GY + gy;
   }
   __syncthreads();
-  {  // exclusive scan of the 4096 cell counts (4 per thread)
-    const int c0 = counts[4 * tid], c1 = counts[4 * tid + 1], c2 = counts[4 * tid + 2], c3 = counts[4 * tid + 3];
-    int total;
-    const int ex = pg_block_exscan(c0 + c1 + c2 + c3, scan_smem, &total);
-    counts[4 * tid] = ex; counts[4 * tid + 1] = ex + c0; counts[4 * tid + 2] = ex + c0 + c1;
-    counts[4 * tid + 3] = ex + c0 + c1 + c2;
-  }
-  __syncthreads();
-  // stable scatter by one warp (deterministic spatial order)
-  if (warp == 0) {
-    for (int c = 0; c < sp.m; c += 32) {
-      const int k = c + lane;
-      const bool act = k < sp.m;
-      const int cell = act ? ws.cellid[sp.base + k] : -1 - lane;
-      const unsigned grp = __match_any_sync(0xffffffffu, cell);
-      const int leader = __ffs(grp) - 1;
-      const int rank = __popc(grp & ((1u << lane) - 1u));
-      int basepos = 0;
-      if (act && lane == leader) { basepos = counts[cell]; counts[cell] = basepos + __popc(grp); }
-      basepos = __shfl_sync(0xffffffffu, basepos, leader);
-      if (act) ws.sorted_pos[sp.base + basepos + rank] = k;
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  // blocked SoA copy + block bounding boxes
+  // stable LSD radix sort by (x strip, y cell): pass 1 on y, pass 2 on x
+  const int32_t* cellid = ws.cellid + sp.base;
+  int32_t* tmp = ws.kpos + sp.base;
+  int32_t* sorted = ws.sorted_pos + sp.base;
+  block_stable_pass<NMS_GY>(sp.m, hist, scan_smem, [](int i) { return i; },
+                            [cellid](int e) { return cellid[e] & (NMS_GY - 1); }, tmp);
+  block_stable_pass<NMS_GX_MAX>(sp.m, hist, scan_smem, [tmp](int i) { return tmp[i]; },
+                                [cellid](int e) { return cellid[e] >> 7; }, sorted);
+
+  // blocked copy + block bounding boxes
   for (int b = warp; b < sp.nb; b += (blockDim.x >> 5)) {
     const int pos = b * 32 + lane;
     const bool valid = pos < sp.m;
-    const int64_t slot = (sp.blk0 + b) * 32 + lane;
-    double x0 = 0, y0 = 0, x1 = 0, y1 = 0, sc = 0, cl = 0;
-    int k = -1;
+    SBox sb;
+    sb.x0 = sb.y0 = sb.x1 = sb.y1 = sb.area = sb.score = sb.cls = 0.0;
+    sb.k = -1;
     if (valid) {
-      k = ws.sorted_pos[sp.base + pos];
+      const int k = sorted[pos];
       const int64_t gi = sel_idx ? (int64_t)sel_idx[sp.base + k] : sp.base + k;
-      x0 = boxes[4 * gi]; y0 = boxes[4 * gi + 1]; x1 = boxes[4 * gi + 2]; y1 = boxes[4 * gi + 3];
-      sc = scores[gi]; cl = classes[gi];
+      const double2 a = *reinterpret_cast<const double2*>(boxes + 4 * gi);
+      const double2 c = *reinterpret_cast<const double2*>(boxes + 4 * gi + 2);
+      sb.x0 = a.x; sb.y0 = a.y; sb.x1 = c.x; sb.y1 = c.y;
+      sb.area = pg_box_area(a.x, a.y, c.x, c.y);
+      sb.score = scores[gi]; sb.cls = classes[gi]; sb.k = k;
     }
-    ws.sx0[slot] = x0; ws.sy0[slot] = y0; ws.sx1[slot] = x1; ws.sy1[slot] = y1;
-    ws.sarea[slot] = pg_box_area(x0, y0, x1, y1);
-    ws.sscore[slot] = sc; ws.scls[slot] = cl; ws.skpos[slot] = k;
-    const double bx0 = warp_min_d(valid ? fmin(x0, x1) : DBL_MAX), by0 = warp_min_d(valid ? fmin(y0, y1) : DBL_MAX);
-    const double bx1 = warp_max_d(valid ? fmax(x0, x1) : -DBL_MAX), by1 = warp_max_d(valid ? fmax(y0, y1) : -DBL_MAX);
+    ws.sbox[(sp.blk0 + b) * 32 + lane] = sb;
+    const double bx0 = warp_min_d(valid ? fmin(sb.x0, sb.x1) : DBL_MAX), by0 = warp_min_d(valid ? fmin(sb.y0, sb.y1) : DBL_MAX);
+    const double bx1 = warp_max_d(valid ? fmax(sb.x0, sb.x1) : -DBL_MAX), by1 = warp_max_d(valid ? fmax(sb.y0, sb.y1) : -DBL_MAX);
     if (lane == 0) {
       double* bb = ws.bbox + 4 * (sp.blk0 + b);
       bb[0] = bx0; bb[1] = by0; bb[2] = bx1; bb[3] = by1;
@@ -292,8 +340,7 @@ template <bool FILL>
 __global__ void __launch_bounds__(256) nms_pairs_kernel(const int64_t* __restrict__ page_off,
                                                         const int32_t* __restrict__ n_sel, NmsWs ws, double thr,
                                                         int all_pairs) {
-  __shared__ double jbox[8][7][32];
-  __shared__ int jk[8][32];
+  __shared__ SBox jb[8][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t I = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   if (I >= ws.nb_cap) return;
@@ -308,14 +355,10 @@ __global__ void __launch_bounds__(256) nms_pairs_kernel(const int64_t* __restric
 #pragma unroll
   for (int q = 0; q < 4; ++q) bbI[q] = ws.bbox[4 * I + q];
 
-  // lane i <-> box i of block I
-  double ix0 = 0, iy0 = 0, ix1 = 0, iy1 = 0, iarea = 0, iscore = 0, icls = 0;
-  int ik = -1;
+  SBox bi;  // lane i <-> box i of block I
   int64_t e = 0;
   if (FILL) {
-    const int64_t slot = I * 32 + lane;
-    ix0 = ws.sx0[slot]; iy0 = ws.sy0[slot]; ix1 = ws.sx1[slot]; iy1 = ws.sy1[slot];
-    iarea = ws.sarea[slot]; iscore = ws.sscore[slot]; icls = ws.scls[slot]; ik = ws.skpos[slot];
+    bi = ws.sbox[I * 32 + lane];
     e = ws.cand_off[I];
   }
   int cnt = 0;
@@ -330,23 +373,18 @@ __global__ void __launch_bounds__(256) nms_pairs_kernel(const int64_t* __restric
         const int b = __ffs(hits) - 1;
         hits &= hits - 1;
         const int64_t Jb = sp.blk0 + j0 + b;
-        const int64_t js = Jb * 32 + lane;
         __syncwarp();
-        jbox[wib][0][lane] = ws.sx0[js]; jbox[wib][1][lane] = ws.sy0[js]; jbox[wib][2][lane] = ws.sx1[js];
-        jbox[wib][3][lane] = ws.sy1[js]; jbox[wib][4][lane] = ws.sarea[js]; jbox[wib][5][lane] = ws.sscore[js];
-        jbox[wib][6][lane] = ws.scls[js]; jk[wib][lane] = ws.skpos[js];
+        jb[wib][lane] = ws.sbox[Jb * 32 + lane];
         __syncwarp();
         uint32_t mask = 0;
-        if (ik >= 0) {
+        if (bi.k >= 0) {
 #pragma unroll 4
           for (int jj = 0; jj < 32; ++jj) {
-            const int kj = jk[wib][jj];
-            const double sj = jbox[wib][5][jj];
+            const SBox bj = jb[wib][jj];  // broadcast LDS.128 x4
             // j must outrank i: higher score, or equal score and earlier pooled position (:112)
-            const bool outranks = (sj > iscore) || (sj == iscore && kj < ik);
-            if (kj >= 0 && outranks && jbox[wib][6][jj] == icls) {
-              const double v = pg_iou(jbox[wib][0][jj], jbox[wib][1][jj], jbox[wib][2][jj], jbox[wib][3][jj],
-                                      jbox[wib][4][jj], ix0, iy0, ix1, iy1, iarea);
+            const bool outranks = (bj.score > bi.score) || (bj.score == bi.score && bj.k < bi.k);
+            if (bj.k >= 0 && outranks && bj.cls == bi.cls) {
+              const double v = pg_iou(bj.x0, bj.y0, bj.x1, bj.y1, bj.area, bi.x0, bi.y0, bi.x1, bi.y1, bi.area);
               if (v > thr) mask |= 1u << jj;
             }
           }
@@ -425,10 +463,10 @@ __global__ void __launch_bounds__(1024) nms_resolve_kernel(const int64_t* __rest
       bool sup = false, wait = false;
       const int64_t e0 = ws.cand_off[I], e1 = ws.cand_off[I + 1];
       for (int64_t e = e0; e < e1; ++e) {
-        const int jb = ws.ent_j[e];
-        if (jb < 0) continue;
+        const int jbk = ws.ent_j[e];
+        if (jbk < 0) continue;
         const uint32_t m = mine ? ws.ent_mask[e * 32 + lane] : 0u;
-        const uint32_t kj = kept[rc + sp.blk0 + jb], uj = undec[rc + sp.blk0 + jb];
+        const uint32_t kj = kept[rc + sp.blk0 + jbk], uj = undec[rc + sp.blk0 + jbk];
         if (m & kj) sup = true;
         else if (m & uj) wait = true;
       }
@@ -449,15 +487,15 @@ __global__ void __launch_bounds__(1024) nms_resolve_kernel(const int64_t* __rest
     const int b = b0 + tid;
     const uint32_t k = b < sp.nb ? kept[rc + sp.blk0 + b] : 0u;
     int total;
-    int ex = pg_block_exscan(__popc(k), scan_smem, &total);
+    const int ex = pg_block_exscan(__popc(k), scan_smem, &total);
     uint32_t bits = k;
     int64_t dst = sp.base + running + ex;
     while (bits) {
       const int l = __ffs(bits) - 1;
       bits &= bits - 1;
-      const int64_t slot = (sp.blk0 + b) * 32 + l;
-      ws.kscore[dst] = ws.sscore[slot];
-      ws.kpos[dst] = ws.skpos[slot];
+      const SBox* sb = ws.sbox + (sp.blk0 + b) * 32 + l;
+      ws.kscore[dst] = sb->score;
+      ws.kpos[dst] = (int32_t)sb->k;
       ++dst;
     }
     running += total;
@@ -469,37 +507,68 @@ __global__ void __launch_bounds__(1024) nms_resolve_kernel(const int64_t* __rest
 }
 
 // ---- F: emit -------------------------------------------------------------------------------
-constexpr int EMIT_TILE = 1024;
-__global__ void __launch_bounds__(EMIT_TILE) nms_emit_kernel(const int32_t* __restrict__ sel_idx,
-                                                             const int64_t* __restrict__ page_off, NmsWs ws,
-                                                             const int32_t* __restrict__ n_kept,
-                                                             int32_t* __restrict__ kept_idx) {
-  __shared__ double ts[EMIT_TILE];
-  __shared__ int tk[EMIT_TILE];
+constexpr int EMIT_SMEM_ELEMS = 8192;
+
+// ascending u64 key == descending score (positive and negative doubles, -0.0 < +0.0)
+__device__ __forceinline__ unsigned long long score_desc_key(double s) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(s);
+  b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);  // ascending-orderable
+  return ~b;
+}
+
+// Normalised bitonic network (every comparator ascending), so virtual +inf padding above K never moves.
+template <typename KeyT>
+__device__ __forceinline__ void bitonic_sort_pairs(KeyT* keys, int32_t* idx, int K, int n2) {
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int pr = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
+        if (pr < K) {
+          const KeyT a = keys[i], b = keys[pr];
+          const int32_t ia = idx[i], ib = idx[pr];
+          if (b < a || (b == a && ib < ia)) {
+            keys[i] = b; keys[pr] = a; idx[i] = ib; idx[pr] = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) nms_emit_kernel(const int32_t* __restrict__ sel_idx,
+                                                        const int64_t* __restrict__ page_off, NmsWs ws,
+                                                        const int32_t* __restrict__ n_kept,
+                                                        int32_t* __restrict__ kept_idx) {
+  extern __shared__ __align__(16) unsigned char emit_smem[];
   const int p = blockIdx.x, tid = threadIdx.x;
   const int K = n_kept[p];
   if (K <= 0) return;
   const int64_t base = page_off[p];
-  for (int i0 = blockIdx.y * EMIT_TILE; i0 < K; i0 += gridDim.y * EMIT_TILE) {
-    const int i = i0 + tid;
-    const bool act = i < K;
-    const double si = act ? ws.kscore[base + i] : 0.0;
-    const int ki = act ? ws.kpos[base + i] : 0;
-    int rank = 0;
-    for (int t0 = 0; t0 < K; t0 += EMIT_TILE) {
-      __syncthreads();
-      if (t0 + tid < K) { ts[tid] = ws.kscore[base + t0 + tid]; tk[tid] = ws.kpos[base + t0 + tid]; }
-      __syncthreads();
-      const int n = min(EMIT_TILE, K - t0);
-      if (act) {
-#pragma unroll 8
-        for (int j = 0; j < n; ++j) {
-          const double sj = ts[j];
-          rank += (sj > si || (sj == si && tk[j] < ki)) ? 1 : 0;
-        }
-      }
+  int n2 = 1;
+  while (n2 < K) n2 <<= 1;
+  if (n2 <= EMIT_SMEM_ELEMS) {
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(emit_smem);
+    int32_t* idx = reinterpret_cast<int32_t*>(emit_smem + (size_t)EMIT_SMEM_ELEMS * 8);
+    for (int i = tid; i < K; i += blockDim.x) { keys[i] = score_desc_key(ws.kscore[base + i]); idx[i] = ws.kpos[base + i]; }
+    __syncthreads();
+    bitonic_sort_pairs(keys, idx, K, n2);
+    for (int i = tid; i < K; i += blockDim.x) {
+      const int k = idx[i];
+      kept_idx[base + i] = sel_idx ? sel_idx[base + k] : (int32_t)(base + k);
     }
-    if (act) kept_idx[base + rank] = sel_idx ? sel_idx[base + ki] : (int32_t)(base + ki);
+  } else {
+    // large pages: the same network straight on the (L2-resident) workspace arrays
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws.kscore + base);
+    int32_t* idx = ws.kpos + base;
+    for (int i = tid; i < K; i += blockDim.x) keys[i] = score_desc_key(__longlong_as_double((long long)keys[i]));
+    __syncthreads();
+    bitonic_sort_pairs(keys, idx, K, n2);
+    for (int i = tid; i < K; i += blockDim.x) {
+      const int k = idx[i];
+      kept_idx[base + i] = sel_idx ? sel_idx[base + k] : (int32_t)(base + k);
+    }
   }
 }
 
@@ -508,6 +577,7 @@ extern "C" int pg_nms_merge(const double* boxes, const double* scores, const dou
                             int32_t n_pages, int64_t n_boxes, int32_t max_boxes_per_page, double iou_threshold,
                             int32_t* kept_idx, int32_t* n_kept, void* workspace, size_t workspace_bytes,
                             void* stream) {
+  (void)max_boxes_per_page;
   PG_REQUIRE(n_pages >= 0 && n_boxes >= 0, "sizes");
   if (n_pages == 0) return PG_OK;
   PG_REQUIRE(boxes && scores && classes && page_off && kept_idx && n_kept && workspace, "null device pointer");
@@ -525,6 +595,8 @@ extern "C" int pg_nms_merge(const double* boxes, const double* scores, const dou
   while (ppb > 1 && nms_layout(n_boxes, n_pages, (int32_t)ppb, nullptr, nullptr) > workspace_bytes) --ppb;
   nms_layout(n_boxes, n_pages, (int32_t)ppb, (uint8_t*)workspace, &ws);
   cudaStream_t s = (cudaStream_t)stream;
+  const int emit_smem = EMIT_SMEM_ELEMS * 12;
+  PG_CUDA_TRY(cudaFuncSetAttribute(nms_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem));
   PG_CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 8 * sizeof(int64_t), s));
   const int all_pairs = !(iou_threshold >= 0.0);  // thr < 0: disjoint boxes (IoU 0) suppress too
   nms_bin_kernel<<<n_pages, 1024, 0, s>>>(boxes, scores, classes, sel_idx, page_off, n_sel, n_pages, ws);
@@ -538,10 +610,7 @@ extern "C" int pg_nms_merge(const double* boxes, const double* scores, const dou
   PG_LAUNCH_CHECK();
   nms_resolve_kernel<<<n_pages, 1024, 0, s>>>(page_off, n_sel, ws, n_kept);
   PG_LAUNCH_CHECK();
-  const int64_t mb = max_boxes_per_page > 0 ? max_boxes_per_page : n_boxes;
-  int gy = (int)((mb + EMIT_TILE - 1) / EMIT_TILE);
-  gy = gy < 1 ? 1 : (gy > 64 ? 64 : gy);
-  nms_emit_kernel<<<dim3((unsigned)n_pages, (unsigned)gy), EMIT_TILE, 0, s>>>(sel_idx, page_off, ws, n_kept, kept_idx);
+  nms_emit_kernel<<<n_pages, 1024, emit_smem, s>>>(sel_idx, page_off, ws, n_kept, kept_idx);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
@@ -559,7 +628,8 @@ extern "C" int pg_nms_stats(const void* workspace, int64_t stats[4]) {
 //   reference: bin_widths 4_extract_median_widths.py:49-80 (sequential leader binning, joins the
 //   smallest-key bin within the margin), calculate_median_width :82-101 (np.median), width
 //   extraction :135-141.
-// One warp per page.  32 widths are matched against the sorted bin keys at once (binary search
+// One CTA per page.  All warps first gather the plain_text widths in order (independent loads);
+// warp 0 then bins them: 32 widths are matched against the sorted bin keys at once (binary search
 // on the reference's own fabs(w-key) <= margin predicate); only a width that founds a new bin
 // serialises, and lanes behind it re-check just that new key.
 // =============================================================================================
@@ -593,29 +663,31 @@ __device__ __forceinline__ int bins_find(const double* keys, int n, double w, do
   return -1;
 }
 
-__global__ void __launch_bounds__(32) width_median_kernel(const double* __restrict__ boxes,
-                                                          const uint8_t* __restrict__ flags,
-                                                          const int32_t* __restrict__ sel_idx,
-                                                          const int64_t* __restrict__ page_off,
-                                                          const int32_t* __restrict__ n_sel,
-                                                          const int32_t* __restrict__ page_wh, double margin_pct,
-                                                          double* __restrict__ median, int32_t* __restrict__ n_bins,
-                                                          double* ws_keys, int32_t* ws_counts, uint32_t* width_hist) {
-  const int p = blockIdx.x, lane = threadIdx.x;
+constexpr int MED_THREADS = 256;
+__global__ void __launch_bounds__(MED_THREADS) width_median_kernel(
+    const double* __restrict__ boxes, const uint8_t* __restrict__ flags, const int32_t* __restrict__ sel_idx,
+    const int64_t* __restrict__ page_off, const int32_t* __restrict__ n_sel, const int32_t* __restrict__ page_wh,
+    double margin_pct, double* __restrict__ median, int32_t* __restrict__ n_bins, double* ws_keys, int32_t* ws_counts,
+    int64_t n_total, uint32_t* width_hist) {
+  __shared__ int scan_smem[34];
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int64_t base = page_off[p];
   const int m = n_sel ? n_sel[p] : (int)(page_off[p + 1] - base);
   double* keys = ws_keys + base;
+  double* wlist = ws_keys + n_total + base;
   int* counts = ws_counts + base;
   const double margin = (double)page_wh[2 * p] * (margin_pct / 100.0);  // :64
-  int nb = 0;
-  for (int c = 0; c < m; c += 32) {
-    const int k = c + lane;
-    bool act = false;
+
+  // ---- gather the plain_text widths in pooled order (:135-141) ----
+  int nw = 0;
+  for (int c = 0; c < m; c += MED_THREADS) {
+    const int k = c + tid;
+    int act = 0;
     double w = 0.0;
     if (k < m) {
       const int64_t gi = sel_idx ? (int64_t)sel_idx[base + k] : base + k;
       if (flags[gi] & PG_FLAG_PLAIN_TEXT) {
-        act = true;
+        act = 1;
         w = boxes[4 * gi + 2] - boxes[4 * gi];  // :139
         if (width_hist) {
           const int hb = w >= 0.0 ? (w < (double)(PG_WIDTH_HIST_BINS - 1) ? (int)w : PG_WIDTH_HIST_BINS - 1) : 0;
@@ -623,8 +695,20 @@ __global__ void __launch_bounds__(32) width_median_kernel(const double* __restri
         }
       }
     }
+    int total;
+    const int ex = pg_block_exscan(act, scan_smem, &total);
+    if (act) wlist[nw + ex] = w;
+    nw += total;
+  }
+  __syncthreads();
+  if (tid >= 32) return;
+
+  // ---- sequential-equivalent leader binning, 32 widths at a time ----
+  int nb = 0;
+  for (int c = 0; c < nw; c += 32) {
+    const bool act = c + lane < nw;
+    const double w = act ? wlist[c + lane] : 0.0;
     unsigned pend = __ballot_sync(0xffffffffu, act);
-    if (!pend) continue;
     int mt = act ? bins_find(keys, nb, w, margin) : -1;
     while (pend) {
       const bool mine = (pend >> lane) & 1u;
@@ -665,7 +749,7 @@ __global__ void __launch_bounds__(32) width_median_kernel(const double* __restri
       }
     }
   }
-  // median over keys repeated by count; keys are already ascending
+  // ---- median over keys repeated by count; keys are already ascending ----
   int total = 0;
   for (int b = lane; b < nb; b += 32) total += counts[b];
 #pragma unroll
@@ -699,16 +783,16 @@ __global__ void __launch_bounds__(32) width_median_kernel(const double* __restri
 }
 
 extern "C" int pg_width_median(const double* boxes, const uint8_t* flags, const int32_t* sel_idx,
-                               const int64_t* page_off, const int32_t* n_sel, int32_t n_pages,
+                               const int64_t* page_off, const int32_t* n_sel, int32_t n_pages, int64_t n_boxes,
                                const int32_t* page_wh, double min_margin_percent, double* median,
                                int32_t* n_bins, double* ws_keys, int32_t* ws_counts, uint32_t* width_hist,
                                void* stream) {
-  PG_REQUIRE(n_pages >= 0, "n_pages");
+  PG_REQUIRE(n_pages >= 0 && n_boxes >= 0, "sizes");
   if (n_pages == 0) return PG_OK;
   PG_REQUIRE(boxes && flags && page_off && page_wh && median && n_bins && ws_keys && ws_counts, "null device pointer");
-  width_median_kernel<<<n_pages, 32, 0, (cudaStream_t)stream>>>(boxes, flags, sel_idx, page_off, n_sel, page_wh,
-                                                                 min_margin_percent, median, n_bins, ws_keys,
-                                                                 ws_counts, width_hist);
+  width_median_kernel<<<n_pages, MED_THREADS, 0, (cudaStream_t)stream>>>(
+      boxes, flags, sel_idx, page_off, n_sel, page_wh, min_margin_percent, median, n_bins, ws_keys, ws_counts, n_boxes,
+      width_hist);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
@@ -717,13 +801,111 @@ extern "C" int pg_width_median(const double* boxes, const uint8_t* flags, const 
 // K5 — column centres
 //   reference: find_column_centers 5_detect_column_centers.py:91-224 (+ scipy find_peaks step
 //   order: local maxima -> height -> distance -> prominence; np.convolve 'same').
-// One CTA per page, one thread per density bin.  Each bin accumulates its own contributions in
-// box order (the reference's `density[bin] += w` order), so the density map is bit-identical to
-// numpy's; the smoothing sum runs left to right.
+// Two kernels.  (a) density: each warp owns 32 consecutive bins of one page and walks the
+// page's accepted boxes in pooled order (block-scan compaction, then ballot over the boxes that
+// overlap the warp's bins), so every bin receives its `density[bin] += w` contributions in the
+// reference's order and the map is bit-identical to numpy's; the per-bin divide is the exact
+// reciprocal+FMA form of pg_math.h.  (b) peaks: one CTA per page — left-to-right smoothing sum,
+// maximum, plateau-aware local maxima, scipy's distance / prominence filters, valley walk.
 // =============================================================================================
+constexpr int DEN_THREADS = 256;  // 8 warps x 32 bins per CTA
 constexpr int COL_THREADS = 1024;
-constexpr int COL_BPT = 8;        // bins per thread -> up to 8192 bins
+constexpr int COL_BPT = 2;        // peaks kernel: bins per thread -> 2048 bins (>= the 2000-bin bound)
 constexpr int COL_MAX_PEAKS = 1024;
+
+struct ColGeom {
+  int res, nbins, win;
+  bool ok;       // page passes the process_page guards
+  bool in_range; // shape inside the kernel limits
+};
+
+__device__ __forceinline__ ColGeom col_geom(int W, int Hh, double med, int max_bins, int max_window) {
+  ColGeom g;
+  g.ok = (med > 0.0) && W > 0 && Hh > 0;  // 5_detect_column_centers.py:361-364, 381-383
+  g.res = max(1, W / 1000);                                 // :120
+  g.nbins = W / g.res + 1;                                  // :121
+  g.win = 5;
+  if (g.ok) {
+    const double wv = med / (4.0 * (double)g.res);         // :147
+    g.win = wv >= 5.0 ? (wv < 1.0e9 ? (int)wv : 1000000000) : 5;
+    if ((g.win & 1) == 0) g.win += 1;
+  }
+  g.in_range = g.nbins <= max_bins && g.nbins <= COL_THREADS * COL_BPT && g.win <= max_window && g.win <= g.nbins;
+  return g;
+}
+
+struct __align__(16) DenEntry {
+  int left, right, center, pad;
+  double half, inv_half;
+};
+
+__global__ void __launch_bounds__(DEN_THREADS) column_density_kernel(
+    const double* __restrict__ boxes, const uint8_t* __restrict__ flags, const double* __restrict__ scores,
+    const int32_t* __restrict__ sel_idx, const int64_t* __restrict__ page_off, const int32_t* __restrict__ n_sel,
+    const int32_t* __restrict__ page_wh, const double* __restrict__ median, int max_window, double min_conf,
+    double* ws_all, int max_bins) {
+  __shared__ DenEntry elist[DEN_THREADS];
+  __shared__ int scan_smem[34];
+  const int p = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = page_wh[2 * p], Hh = page_wh[2 * p + 1];
+  const double med = median[p];
+  const ColGeom g = col_geom(W, Hh, med, max_bins, max_window);
+  if (!g.ok || !g.in_range || (int)blockIdx.x * DEN_THREADS >= g.nbins) return;
+  const int64_t base = page_off[p];
+  const int m = n_sel ? n_sel[p] : (int)(page_off[p + 1] - base);
+  const int seg0 = ((int)blockIdx.x * (DEN_THREADS / 32) + warp) * 32;
+  const int bin = seg0 + lane;
+  const double lo_w = 0.33 * med, hi_w = 2.0 * med;  // :131
+  double d = 0.0;
+  for (int c0 = 0; c0 < m; c0 += DEN_THREADS) {
+    const int k = c0 + tid;
+    int acc = 0;
+    DenEntry ent;
+    ent.left = 1; ent.right = 0; ent.center = 0; ent.pad = 0; ent.half = 1.0; ent.inv_half = 1.0;
+    if (k < m) {
+      const int64_t gi = sel_idx ? (int64_t)sel_idx[base + k] : base + k;
+      if ((flags[gi] & (PG_FLAG_PLAIN_TEXT | PG_FLAG_TITLE)) && scores[gi] >= min_conf) {  // :110-112
+        const int x1 = (int)boxes[4 * gi], x2 = (int)boxes[4 * gi + 2];                    // :127 int() truncation
+        const int bw = x2 - x1;
+        if (lo_w <= (double)bw && (double)bw <= hi_w) {
+          ent.left = max(0, pg_floordiv(x1, g.res));                 // :133
+          ent.right = min(g.nbins - 1, pg_floordiv(x2, g.res));      // :134
+          ent.center = pg_floordiv(x1 + x2, 2 * g.res);              // :137
+          if (ent.left <= ent.right) {
+            acc = 1;
+            ent.half = pg_density_half(ent.left, ent.right);
+            ent.inv_half = 1.0 / ent.half;
+            // outside the exhaustively verified domain of the reciprocal form: flag for the true divide
+            const int far = max(abs(ent.left - ent.center), abs(ent.right - ent.center));
+            ent.pad = (ent.right - ent.left > PG_RCP_DOMAIN || far > PG_RCP_DOMAIN) ? 1 : 0;
+          }
+        }
+      }
+    }
+    int total;
+    const int ex = pg_block_exscan(acc, scan_smem, &total);
+    if (acc) elist[ex] = ent;
+    __syncthreads();
+    for (int e0 = 0; e0 < total; e0 += 32) {
+      const int e = e0 + lane;
+      int L = 1, R = -1;  // padding lanes overlap nothing (R < 0 <= seg0)
+      if (e < total) { L = elist[e].left; R = elist[e].right; }
+      unsigned bits = __ballot_sync(0xffffffffu, L <= seg0 + 31 && R >= seg0);
+      while (bits) {
+        const int l = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const DenEntry en = elist[e0 + l];  // broadcast
+        if (bin >= en.left && bin <= en.right) {  // :139-144, contributions added in box order
+          const double wgt = en.pad ? pg_density_weight(bin, en.left, en.right, en.center)
+                                    : pg_density_weight_rcp(bin, en.center, en.half, en.inv_half);
+          d = d + wgt;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (bin < g.nbins) ws_all[(int64_t)p * 2 * max_bins + bin] = d;
+}
 
 __device__ __forceinline__ double block_max_d(double v, double* red) {
   v = warp_max_d(v);
@@ -741,113 +923,52 @@ __device__ __forceinline__ double block_max_d(double v, double* red) {
 }
 
 __global__ void __launch_bounds__(COL_THREADS) column_peaks_kernel(
-    const double* __restrict__ boxes, const uint8_t* __restrict__ flags, const double* __restrict__ scores,
-    const int32_t* __restrict__ sel_idx, const int64_t* __restrict__ page_off, const int32_t* __restrict__ n_sel,
     const int32_t* __restrict__ page_wh, const double* __restrict__ median, const double* __restrict__ gauss_table,
-    const int64_t* __restrict__ gauss_off, int max_window, double min_conf, int max_cols,
-    int32_t* __restrict__ centers, double* __restrict__ widths, int32_t* __restrict__ n_cols, double* ws_all,
-    int max_bins, uint32_t* col_hist) {
-  __shared__ int4 elist[COL_THREADS];
+    const int64_t* __restrict__ gauss_off, int max_window, int max_cols, int32_t* __restrict__ centers,
+    double* __restrict__ widths, int32_t* __restrict__ n_cols, double* ws_all, int max_bins, uint32_t* col_hist) {
   __shared__ int scan_smem[34];
   __shared__ double red[33];
   __shared__ int pk_pos[COL_MAX_PEAKS];
   __shared__ double pk_h[COL_MAX_PEAKS];
   __shared__ unsigned char pk_keep[COL_MAX_PEAKS];
-  __shared__ int s_npk;
+  __shared__ double sm_s[COL_THREADS * COL_BPT];
 
   const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t base = page_off[p];
-  const int m = n_sel ? n_sel[p] : (int)(page_off[p + 1] - base);
   const int W = page_wh[2 * p], Hh = page_wh[2 * p + 1];
   const double med = median[p];
-  // process_page guards (5_detect_column_centers.py:361-364, 381-383)
-  if (!(med > 0.0) || W <= 0 || Hh <= 0) {
-    if (tid == 0) n_cols[p] = 0;
+  const ColGeom g = col_geom(W, Hh, med, max_bins, max_window);
+  if (!g.ok || !g.in_range) {
+    if (tid == 0) n_cols[p] = g.ok ? -1 : 0;
     return;
   }
-  const int res = max(1, W / 1000);                 // :120
-  const int nbins = W / res + 1;                    // :121
-  int win = max(5, (int)(med / (4.0 * (double)res)));  // :147
-  if ((win & 1) == 0) win += 1;
-  if (nbins > max_bins || nbins > COL_THREADS * COL_BPT || win > max_window || win > nbins) {
-    if (tid == 0) n_cols[p] = -1;
-    return;
-  }
-  double* dens = ws_all + (int64_t)p * 2 * max_bins;
-  double* sm = dens + max_bins;
-  const double lo_w = 0.33 * med, hi_w = 2.0 * med;  // :131
+  const int res = g.res, nbins = g.nbins;
+  const double* dens = ws_all + (int64_t)p * 2 * max_bins;
+  double* sm_out = ws_all + (int64_t)p * 2 * max_bins + max_bins;
 
-  // ---- density map -------------------------------------------------------------------------
-  double d[COL_BPT];
-#pragma unroll
-  for (int q = 0; q < COL_BPT; ++q) d[q] = 0.0;
-  const int wb0 = warp * 32, wstride = COL_THREADS;  // bins owned: tid + q*1024
-  for (int c0 = 0; c0 < m; c0 += COL_THREADS) {
-    const int k = c0 + tid;
-    int acc = 0;
-    int4 ent = make_int4(0, 0, 0, 0);
-    if (k < m) {
-      const int64_t gi = sel_idx ? (int64_t)sel_idx[base + k] : base + k;
-      if ((flags[gi] & (PG_FLAG_PLAIN_TEXT | PG_FLAG_TITLE)) && scores[gi] >= min_conf) {  // :110-112
-        const int x1 = (int)boxes[4 * gi], x2 = (int)boxes[4 * gi + 2];                    // :127 int() truncation
-        const int bw = x2 - x1;
-        if (lo_w <= (double)bw && (double)bw <= hi_w) {
-          const int left = max(0, pg_floordiv(x1, res));               // :133
-          const int right = min(nbins - 1, pg_floordiv(x2, res));      // :134
-          const int center = pg_floordiv(x1 + x2, 2 * res);            // :137
-          if (left <= right) { acc = 1; ent = make_int4(left, right, center, 0); }
-        }
-      }
-    }
-    int total;
-    const int ex = pg_block_exscan(acc, scan_smem, &total);
-    if (acc) elist[ex] = ent;
-    __syncthreads();
-    for (int e = 0; e < total; ++e) {
-      const int4 en = elist[e];
-#pragma unroll
-      for (int q = 0; q < COL_BPT; ++q) {
-        const int q0 = wb0 + q * wstride;           // first bin of this warp's q-th slab
-        if (q0 < nbins && en.x <= q0 + 31 && en.y >= q0) {   // warp-uniform reject
-          const int b = q0 + lane;
-          if (b >= en.x && b <= en.y) d[q] = d[q] + pg_density_weight(b, en.x, en.y, en.z);  // :140-144
-        }
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int q = 0; q < COL_BPT; ++q) {
-    const int b = tid + q * wstride;
-    if (b < nbins) dens[b] = d[q];
-  }
-  __syncthreads();
-
-  // ---- gaussian smoothing, np.convolve(density, g, 'same') ----------------------------------
-  const int hw = (win - 1) >> 1;
-  const double* g = gauss_table + gauss_off[hw];
+  // ---- gaussian smoothing, np.convolve(density, g, 'same'), left-to-right sum (:147-156) ----
+  const int hw = (g.win - 1) >> 1;
+  const double* gw = gauss_table + gauss_off[hw];
   double mx = -DBL_MAX;
 #pragma unroll
   for (int q = 0; q < COL_BPT; ++q) {
-    const int i = tid + q * wstride;
+    const int i = tid + q * COL_THREADS;
     if (i < nbins) {
       const int j0 = max(0, i - hw), j1 = min(nbins - 1, i + hw);
       double s = 0.0;
-      for (int j = j0; j <= j1; ++j) s = s + dens[j] * g[i + hw - j];
-      sm[i] = s;
+      for (int j = j0; j <= j1; ++j) s = s + dens[j] * gw[i + hw - j];
+      sm_s[i] = s;
+      sm_out[i] = s;
       mx = fmax(mx, s);
     }
   }
-  mx = block_max_d(mx, red);   // also orders the sm[] writes before the reads below
+  mx = block_max_d(mx, red);   // also orders the sm_s[] writes before the reads below
+  const double* sm = sm_s;
   const double hmin = mx * 0.2;                                   // :159
   const double pmin = mx * 0.05;                                  // :168
   const int dist = max(1, (int)(med / (1.5 * (double)res)));      // :163
 
-  // ---- local maxima (plateau midpoint) + height, ascending order ----------------------------
-  if (tid == 0) s_npk = 0;
-  __syncthreads();
+  // ---- local maxima (plateau midpoint) + height, ascending order ----
   int npk_run = 0;
-  bool overflow = false;
   for (int i0 = 0; i0 < nbins; i0 += COL_THREADS) {
     const int i = i0 + tid;
     int is_pk = 0, pos = 0;
@@ -867,17 +988,15 @@ __global__ void __launch_bounds__(COL_THREADS) column_peaks_kernel(
     }
     npk_run += total;
   }
-  if (npk_run > COL_MAX_PEAKS) overflow = true;
   __syncthreads();
-  if (overflow) {
+  if (npk_run > COL_MAX_PEAKS) {
     if (tid == 0) n_cols[p] = -1;
     return;
   }
   const int npk = npk_run;
 
-  // ---- distance selection (scipy _select_by_peak_distance), warp 0 --------------------------
+  // ---- distance selection (scipy _select_by_peak_distance), warp 0 ----
   if (warp == 0 && npk > 0) {
-    // visited flags live in bit 1 of pk_keep
     for (int it = 0; it < npk; ++it) {
       double bh = -DBL_MAX;
       int bi = -1;
@@ -906,7 +1025,7 @@ __global__ void __launch_bounds__(COL_THREADS) column_peaks_kernel(
   }
   __syncthreads();
 
-  // ---- prominence (wlen=None) + final ordered compaction ------------------------------------
+  // ---- prominence (wlen=None) + final ordered compaction ----
   int fin = 0, fpos = 0;
   if (tid < npk && pk_keep[tid]) {
     const int pkp = pk_pos[tid];
@@ -923,7 +1042,7 @@ __global__ void __launch_bounds__(COL_THREADS) column_peaks_kernel(
   if (fin) pk_pos[fex] = fpos;   // safe: every thread has read its own pk_pos[tid] above
   __syncthreads();
 
-  // ---- centres + valley-walk widths (:176-222) ----------------------------------------------
+  // ---- centres + valley-walk widths (:176-222) ----
   if (tid < nfin && tid < max_cols) {
     const int pk = pk_pos[tid];
     int left = pk;
@@ -970,9 +1089,14 @@ extern "C" int pg_column_peaks(const double* boxes, const uint8_t* flags, const 
                  widths && n_cols && ws,
              "null device pointer");
   PG_REQUIRE(max_cols > 0 && max_cols <= COL_MAX_PEAKS && max_bins > 0 && max_window > 0, "limits");
-  column_peaks_kernel<<<n_pages, COL_THREADS, 0, (cudaStream_t)stream>>>(
-      boxes, flags, scores, sel_idx, page_off, n_sel, page_wh, median, gauss_table, gauss_off, max_window,
-      min_confidence, max_cols, centers, widths, n_cols, ws, max_bins, col_hist);
+  PG_REQUIRE(n_pages <= 65535, "n_pages per launch must be <= 65535");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int gx = (min(max_bins, COL_THREADS * COL_BPT) + DEN_THREADS - 1) / DEN_THREADS;
+  column_density_kernel<<<dim3((unsigned)gx, (unsigned)n_pages), DEN_THREADS, 0, s>>>(
+      boxes, flags, scores, sel_idx, page_off, n_sel, page_wh, median, max_window, min_confidence, ws, max_bins);
+  PG_LAUNCH_CHECK();
+  column_peaks_kernel<<<n_pages, COL_THREADS, 0, s>>>(page_wh, median, gauss_table, gauss_off, max_window, max_cols,
+                                                     centers, widths, n_cols, ws, max_bins, col_hist);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

@@ -55,6 +55,21 @@ PG_HD double pg_density_weight(int32_t bin, int32_t left, int32_t right, int32_t
   return 1.0 - 0.5 * (dist < 1.0 ? dist : 1.0);
 }
 
+// Same value with the divide replaced by a reciprocal and one FMA correction (Markstein):
+//   y = RN(1/half) (one IEEE divide per box), q0 = n*y, r = fma(-q0, half, n), dist = fma(r, y, q0).
+// dist is the correctly rounded n/half; verified exhaustively (host test) for every integer
+// n, right-left in [0, PG_RCP_DOMAIN], which covers all density bins (< 2048).
+#define PG_RCP_DOMAIN 2100
+PG_HD double pg_density_half(int32_t left, int32_t right) { return (double)(right - left) / 2.0 + 1e-6; }
+PG_HD double pg_density_weight_rcp(int32_t bin, int32_t center, double half, double inv_half) {
+  const int32_t ad = bin - center;
+  const double n = (double)(ad < 0 ? -ad : ad);
+  const double q0 = n * inv_half;
+  const double rem = fma(-q0, half, n);
+  const double dist = fma(rem, inv_half, q0);
+  return 1.0 - 0.5 * (dist < 1.0 ? dist : 1.0);
+}
+
 // ---------------------------------------------------------------------------------------------
 // cv2.resize(uint8, INTER_LINEAR) fixed-point model (validated bit-exact against
 // cv2 4.13).  Coefficient for destination index d: s0/s1 = the two source indices, c0/c1 =

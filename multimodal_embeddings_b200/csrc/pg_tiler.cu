@@ -660,6 +660,16 @@ extern "C" int32_t pg_hostcheck_edge_touch(const double* box, const double* cell
 extern "C" double pg_hostcheck_density_weight(int32_t bin, int32_t left, int32_t right, int32_t center) {
   return pg_density_weight(bin, left, right, center);
 }
+extern "C" int64_t pg_hostcheck_density_rcp_mismatches(int32_t max_span, int32_t max_n) {
+  int64_t bad = 0;
+  for (int32_t span = 0; span <= max_span; ++span) {
+    const double half = pg_density_half(0, span);
+    const double inv = 1.0 / half;
+    for (int32_t n = 0; n <= max_n; ++n)
+      bad += pg_density_weight_rcp(n, 0, half, inv) != pg_density_weight(n, 0, span, 0) ? 1 : 0;
+  }
+  return bad;
+}
 // one output row (BGR uint8, dst_w pixels) of the fixed-point resize from the two source rows it needs
 extern "C" int pg_hostcheck_resize_row(const uint8_t* row0, const uint8_t* row1, int32_t src_w, int32_t src_h,
                                        int32_t dst_w, int32_t dst_h, int32_t dy, uint8_t* out_bgr) {

@@ -21,6 +21,10 @@ def _require_cuda():
         raise _lib.PageGeomError("a CUDA device is required: the page-geometry path has no CPU fallback")
 
 
+# density bins of 5_detect_column_centers.py:120-121: W // max(1, W // 1000) + 1 <= 2000 for every W
+MAX_DENSITY_BINS = 2048
+
+
 def row_pitch(width: int) -> int:
     """Row pitch (bytes) of a BGR uint8 page for the tiler: 3*W rounded up to 16 (bulk-copy alignment)."""
     return (3 * int(width) + 15) // 16 * 16
@@ -233,9 +237,9 @@ def width_median(boxes, flags, page_off, page_wh, min_margin_percent: float = 0.
         n_sel = _dev(n_sel, torch.int32)
     median = torch.zeros(max(p, 1), dtype=torch.float64, device="cuda")
     n_bins = torch.zeros(max(p, 1), dtype=torch.int32, device="cuda")
-    ws_keys = torch.empty(max(n, 1), dtype=torch.float64, device="cuda")
+    ws_keys = torch.empty(2 * max(n, 1), dtype=torch.float64, device="cuda")
     ws_counts = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
-    check(lib().pg_width_median(ptr(boxes), ptr(flags), ptr(sel_idx), ptr(page_off), ptr(n_sel), p, ptr(page_wh),
+    check(lib().pg_width_median(ptr(boxes), ptr(flags), ptr(sel_idx), ptr(page_off), ptr(n_sel), p, n, ptr(page_wh),
                                 float(min_margin_percent), ptr(median), ptr(n_bins), ptr(ws_keys), ptr(ws_counts),
                                 ptr(width_hist), stream_ptr(stream)))
     return median[:p], n_bins[:p]
@@ -275,7 +279,7 @@ def gauss_table() -> GaussTable:
 
 def column_peaks(boxes, flags, scores, page_off, page_wh, median, min_confidence: float = 0.3, sel_idx=None,
                  n_sel=None, max_cols: int = 64, max_bins: int = 0, col_hist: Optional[torch.Tensor] = None,
-                 stream=None):
+                 stream=None, return_ws: bool = False):
     """pg_column_peaks.  Returns (centers [P,max_cols] i32, widths [P,max_cols] f64, n_cols [P] i32)."""
     _require_cuda()
     boxes = _dev(boxes, torch.float64).view(-1, 4)
@@ -289,10 +293,7 @@ def column_peaks(boxes, flags, scores, page_off, page_wh, median, min_confidence
         sel_idx = _dev(sel_idx, torch.int32)
         n_sel = _dev(n_sel, torch.int32)
     if max_bins <= 0:
-        max_bins = 1024
-        if p:
-            wmax = int(page_wh_t[:, 0].max().item())
-            max_bins = max(1024, wmax // max(1, wmax // 1000) + 2)
+        max_bins = MAX_DENSITY_BINS
     gt = gauss_table()
     centers = torch.zeros((max(p, 1), max_cols), dtype=torch.int32, device="cuda")
     widths = torch.zeros((max(p, 1), max_cols), dtype=torch.float64, device="cuda")
@@ -302,4 +303,6 @@ def column_peaks(boxes, flags, scores, page_off, page_wh, median, min_confidence
                                 ptr(page_wh_t), ptr(median), ptr(gt.table), ptr(gt.offsets), gt.max_window,
                                 float(min_confidence), max_cols, ptr(centers), ptr(widths), ptr(n_cols), ptr(ws),
                                 max_bins, ptr(col_hist), stream_ptr(stream)))
+    if return_ws:  # [P, 2, max_bins]: density map and smoothed density (debug / tests)
+        return centers[:p], widths[:p], n_cols[:p], ws.view(-1, 2, max_bins)[:p]
     return centers[:p], widths[:p], n_cols[:p]

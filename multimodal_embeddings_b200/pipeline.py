@@ -18,7 +18,7 @@ import torch
 from . import ops
 from ._lib import PG_COL_HIST_BINS, PG_WIDTH_HIST_BINS, check, lib, ptr, stream_ptr
 
-KERNELS_PER_STEP = 11  # tiler, edge filter, 6 NMS kernels, class flags, width median, column peaks
+KERNELS_PER_STEP = 12  # tiler, edge filter, 6 NMS kernels, class flags, width median, column density + peaks
 
 
 def shard_pages(n_pages_total: int, rank: int, world: int) -> range:
@@ -45,8 +45,7 @@ class PagePipeline:
             self.width_hist = self.hist[:PG_WIDTH_HIST_BINS]
             self.col_hist = self.hist[PG_WIDTH_HIST_BINS:]
         self.gauss = ops.gauss_table()
-        w = plan.page_w
-        self.max_bins = max(1024, w // max(1, w // 1000) + 2)
+        self.max_bins = ops.MAX_DENSITY_BINS
 
     # ---------------------------------------------------------------- detections
     def set_detections(self, dets: Sequence[dict], stream=None, host_staging: Optional[dict] = None):
@@ -90,7 +89,7 @@ class PagePipeline:
         self.n_kept2 = torch.zeros(p, dtype=torch.int32, device=dev)
         self.median = torch.zeros(p, dtype=torch.float64, device=dev)
         self.n_bins = torch.zeros(p, dtype=torch.int32, device=dev)
-        self.ws_keys = torch.empty(m, dtype=torch.float64, device=dev)
+        self.ws_keys = torch.empty(2 * m, dtype=torch.float64, device=dev)
         self.ws_counts = torch.empty(m, dtype=torch.int32, device=dev)
         self.centers = torch.zeros((p, self.max_cols), dtype=torch.int32, device=dev)
         self.col_widths = torch.zeros((p, self.max_cols), dtype=torch.float64, device=dev)
@@ -135,7 +134,7 @@ class PagePipeline:
                              self.nms_ws.nbytes, s))
         check(L.pg_class_flags(ptr(self.classes), self.n_boxes, self.plain_text_id, self.title_id, ptr(self.flags), s))
         check(L.pg_width_median(ptr(self.boxes_page), ptr(self.flags), ptr(self.kept2), ptr(self.page_off),
-                                ptr(self.n_kept2), p, ptr(self.page_wh), self.min_margin_percent, ptr(self.median),
+                                ptr(self.n_kept2), p, self.n_boxes, ptr(self.page_wh), self.min_margin_percent, ptr(self.median),
                                 ptr(self.n_bins), ptr(self.ws_keys), ptr(self.ws_counts), ptr(self.width_hist), s))
         check(L.pg_column_peaks(ptr(self.boxes_page), ptr(self.flags), ptr(self.scores), ptr(self.kept2),
                                 ptr(self.page_off), ptr(self.n_kept2), p, ptr(self.page_wh), ptr(self.median),

@@ -184,10 +184,16 @@ def nms_keep_indices(boxes, scores, classes, iou_threshold=0.5) -> List[int]:
     n = len(boxes)
     if n == 0:
         return []
-    kept, n_kept, ws = ops.nms_merge(np.asarray(boxes, np.float64), np.asarray(scores, np.float64),
-                                     np.asarray(classes, np.float64), [0, n], iou_threshold, max_boxes_per_page=n)
+    args = (np.asarray(boxes, np.float64), np.asarray(scores, np.float64), np.asarray(classes, np.float64), [0, n],
+            iou_threshold)
+    kept, n_kept, ws = ops.nms_merge(*args, max_boxes_per_page=n)
     k = int(n_kept[0].item())
     st = ws.stats()
+    if st["status"] == 3:  # candidate list outgrew the default workspace: retry with the dense bound
+        dense = ops.NmsWorkspace(n, 1, pairs_per_block=(n + 31) // 32 + 1)
+        kept, n_kept, ws = ops.nms_merge(*args, max_boxes_per_page=n, workspace=dense)
+        k = int(n_kept[0].item())
+        st = ws.stats()
     if st["status"] != 0 or k < 0:
         raise RuntimeError(f"pg_nms_merge failed on device: {st}")
     return kept[:k].cpu().numpy().tolist()

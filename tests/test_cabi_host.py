@@ -110,6 +110,12 @@ def test_hostcheck_density_weight(lib):
         assert lib.pg_hostcheck_density_weight(b, left, right, center) == ref
 
 
+def test_hostcheck_density_reciprocal_form_is_exact_on_its_whole_domain(lib):
+    # the density kernel replaces n/half by y=1/half, q0=n*y, r=fma(-q0,half,n), fma(r,y,q0);
+    # exhaustive over every (right-left, |bin-center|) the kernel can meet (PG_RCP_DOMAIN = 2100)
+    assert lib.pg_hostcheck_density_rcp_mismatches(2100, 2100) == 0
+
+
 @pytest.mark.parametrize("src,dst", [((97, 131), (64, 48)), ((211, 280), (102, 77)), ((40, 50), (100, 80))])
 def test_hostcheck_resize_rows_equal_cv2(lib, src, dst):
     cv2 = pytest.importorskip("cv2")

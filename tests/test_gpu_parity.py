@@ -214,7 +214,9 @@ def test_nms_synthetic_batch_vs_oracle(thr):
         ss.append(d["scores"]); cs.append(d["classes"]); off.append(off[-1] + n)
     boxes, scores, classes = np.concatenate(bs), np.concatenate(ss), np.concatenate(cs)
     scores[100:140] = scores[100]  # exact score ties inside page 0
-    kept, n_kept, ws = ops.nms_merge(boxes, scores, classes, off, thr, max_boxes_per_page=10000)
+    # thr < 0 makes every same-class pair a suppressor: needs the dense candidate bound
+    ws = ops.NmsWorkspace(len(boxes), len(cfgs), pairs_per_block=320 if thr < 0 else 64)
+    kept, n_kept, ws = ops.nms_merge(boxes, scores, classes, off, thr, max_boxes_per_page=10000, workspace=ws)
     kept, n_kept = kept.cpu().numpy(), n_kept.cpu().numpy()
     st = ws.stats()
     assert st["status"] == 0 and st["rounds"] >= 1

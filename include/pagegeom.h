@@ -163,6 +163,8 @@ int pg_column_peaks(const double* boxes, const uint8_t* flags, const double* sco
  * Host evaluations of the same inline arithmetic the kernels are compiled from
  * (csrc/pg_math.h).  Used by the CPU test-suite only; not a compute path. */
 double pg_hostcheck_iou(const double* a, const double* b);
+/* the divide-free predicate the merge kernel uses for `iou > thr` (must equal pg_hostcheck_iou(a,b) > thr) */
+int32_t pg_hostcheck_iou_gt(const double* a, const double* b, double thr);
 int32_t pg_hostcheck_edge_touch(const double* box, const double* cell, int32_t w, int32_t h, double thr);
 double pg_hostcheck_density_weight(int32_t bin, int32_t left, int32_t right, int32_t center);
 /* number of (right-left, |bin-center|) pairs in [0,max_span]x[0,max_n] where the reciprocal+FMA

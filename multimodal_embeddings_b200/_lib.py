@@ -60,6 +60,7 @@ SIGNATURES = {
     "pg_column_peaks": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I32, _F64, _I32,
                                   _P, _P, _P, _P, _I32, _P, _P]),
     "pg_hostcheck_iou": (_F64, [_P, _P]),
+    "pg_hostcheck_iou_gt": (_I32, [_P, _P, _F64]),
     "pg_hostcheck_edge_touch": (_I32, [_P, _P, _I32, _I32, _F64]),
     "pg_hostcheck_density_weight": (_F64, [_I32, _I32, _I32, _I32]),
     "pg_hostcheck_density_rcp_mismatches": (_I64, [_I32, _I32]),

@@ -112,10 +112,13 @@ struct NmsWs {
   uint32_t* st_undec;  // [2*NB]
   double* kscore;      // [N]  (re-used as sortable u64 keys by emit)
   int32_t* kpos;       // [N]  (scratch of the radix sort, then kept positions)
-  int32_t* ent_j;      // [E]
+  int32_t* ent_j;      // [E]  candidate block J (page-relative), -1 once its masks are all zero
+  int32_t* ent_i;      // [E]  block I the entry belongs to (global block id)
   uint32_t* ent_mask;  // [E*32]
   int64_t nb_cap, ent_cap;
 };
+// stats[] slots
+enum { ST_STATUS = 0, ST_PAIRS = 1, ST_ROUNDS = 2, ST_TESTS = 3, ST_ENT_TOTAL = 4 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -142,6 +145,7 @@ static size_t nms_layout(int64_t n, int32_t n_pages, int32_t pairs_per_block, ui
   w.kscore = (double*)take((size_t)n * 8);
   w.kpos = (int32_t*)take((size_t)n * 4);
   w.ent_j = (int32_t*)take((size_t)ecap * 4);
+  w.ent_i = (int32_t*)take((size_t)ecap * 4);
   w.ent_mask = (uint32_t*)take((size_t)ecap * 32 * 4);
   w.nb_cap = nb;
   w.ent_cap = ecap;
@@ -335,96 +339,98 @@ __device__ __forceinline__ bool bbox_hit(const double* a, const double* b) {
   return !(b[2] < a[0] || a[2] < b[0] || b[3] < a[1] || a[3] < b[1]);
 }
 
-// ---- B: count / D: fill (same traversal) ---------------------------------------------------
-template <bool FILL>
-__global__ void __launch_bounds__(256) nms_pairs_kernel(const int64_t* __restrict__ page_off,
-                                                        const int32_t* __restrict__ n_sel, NmsWs ws, double thr,
-                                                        int all_pairs) {
-  __shared__ SBox jb[8][32];
+// ---- B: candidates -------------------------------------------------------------------------
+// One warp per block I: count the blocks J of the page whose bounding boxes intersect bbox(I),
+// reserve that many entries with one atomicAdd, then list them (entries of one I stay contiguous;
+// their global order depends on the atomics but nothing downstream depends on it).
+__global__ void __launch_bounds__(256) nms_cand_kernel(const int64_t* __restrict__ page_off,
+                                                       const int32_t* __restrict__ n_sel, NmsWs ws, int all_pairs) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t I = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
   if (I >= ws.nb_cap) return;
-  if (FILL && ws.stats[0] != PG_OK) return;
   const int p = ws.blk_page[I];
   if (p < 0) {
-    if (!FILL && lane == 0) ws.cand_cnt[I] = 0;
+    if (lane == 0) { ws.cand_cnt[I] = 0; ws.cand_off[I] = 0; }
     return;
   }
   const PageSpan sp = page_span(page_off, n_sel, p);
   double bbI[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) bbI[q] = ws.bbox[4 * I + q];
-
-  SBox bi;  // lane i <-> box i of block I
-  int64_t e = 0;
-  if (FILL) {
-    bi = ws.sbox[I * 32 + lane];
-    e = ws.cand_off[I];
-  }
   int cnt = 0;
   for (int j0 = 0; j0 < sp.nb; j0 += 32) {
-    const int64_t J = sp.blk0 + j0 + lane;
     bool hit = false;
-    if (j0 + lane < sp.nb) hit = all_pairs || bbox_hit(bbI, ws.bbox + 4 * J);
-    unsigned hits = __ballot_sync(0xffffffffu, hit);
-    cnt += __popc(hits);
-    if (FILL) {
-      while (hits) {
-        const int b = __ffs(hits) - 1;
-        hits &= hits - 1;
-        const int64_t Jb = sp.blk0 + j0 + b;
-        __syncwarp();
-        jb[wib][lane] = ws.sbox[Jb * 32 + lane];
-        __syncwarp();
-        uint32_t mask = 0;
-        if (bi.k >= 0) {
-#pragma unroll 4
-          for (int jj = 0; jj < 32; ++jj) {
-            const SBox bj = jb[wib][jj];  // broadcast LDS.128 x4
-            // j must outrank i: higher score, or equal score and earlier pooled position (:112)
-            const bool outranks = (bj.score > bi.score) || (bj.score == bi.score && bj.k < bi.k);
-            if (bj.k >= 0 && outranks && bj.cls == bi.cls) {
-              const double v = pg_iou(bj.x0, bj.y0, bj.x1, bj.y1, bj.area, bi.x0, bi.y0, bi.x1, bi.y1, bi.area);
-              if (v > thr) mask |= 1u << jj;
-            }
-          }
-        }
-        const bool any = __any_sync(0xffffffffu, mask != 0);
-        ws.ent_mask[e * 32 + lane] = mask;
-        if (lane == 0) ws.ent_j[e] = any ? (int32_t)(Jb - sp.blk0) : -1;
-        ++e;
-      }
-    }
+    if (j0 + lane < sp.nb) hit = all_pairs || bbox_hit(bbI, ws.bbox + 4 * (sp.blk0 + j0 + lane));
+    cnt += __popc(__ballot_sync(0xffffffffu, hit));
   }
-  if (!FILL) {
-    if (lane == 0) ws.cand_cnt[I] = cnt;
-  } else if (lane == 0 && cnt) {
-    atomicAdd((unsigned long long*)&ws.stats[3], (unsigned long long)cnt * 1024ull);
+  long long off = 0;
+  if (lane == 0) off = (long long)atomicAdd((unsigned long long*)&ws.stats[ST_ENT_TOTAL], (unsigned long long)cnt);
+  off = __shfl_sync(0xffffffffu, off, 0);
+  const bool fits = off + cnt <= ws.ent_cap;
+  if (lane == 0) {
+    ws.cand_off[I] = off;
+    ws.cand_cnt[I] = fits ? cnt : 0;
+    if (!fits) ws.stats[ST_STATUS] = PG_ERR_WORKSPACE;  // every writer stores the same value
+  }
+  if (!fits) return;
+  long long e = off;
+  for (int j0 = 0; j0 < sp.nb; j0 += 32) {
+    bool hit = false;
+    if (j0 + lane < sp.nb) hit = all_pairs || bbox_hit(bbI, ws.bbox + 4 * (sp.blk0 + j0 + lane));
+    const unsigned hits = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const long long slot = e + __popc(hits & ((1u << lane) - 1u));
+      ws.ent_j[slot] = (int32_t)(sp.blk0 + j0 + lane);
+      ws.ent_i[slot] = (int32_t)I;
+    }
+    e += __popc(hits);
   }
 }
 
-// ---- C: scan -------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) nms_scan_kernel(NmsWs ws) {
-  __shared__ int scan_smem[34];
-  __shared__ long long carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int64_t b0 = 0; b0 < ws.nb_cap; b0 += blockDim.x) {
-    const int64_t b = b0 + threadIdx.x;
-    const int v = b < ws.nb_cap ? ws.cand_cnt[b] : 0;
-    int total;
-    const int ex = pg_block_exscan(v, scan_smem, &total);
-    const long long carry = carry_s;
-    if (b < ws.nb_cap) ws.cand_off[b] = carry + ex;
-    __syncthreads();
-    if (threadIdx.x == 0) carry_s = carry + total;
-    __syncthreads();
+// ---- C: masks ------------------------------------------------------------------------------
+// Persistent grid over candidate entries (each entry = 32x32 box pairs, so the work is balanced
+// whatever the spread of candidates per block).  Lane i holds box i of block I, the 32 boxes of J
+// are broadcast from shared memory, and lane i accumulates the mask of boxes of J that outrank it,
+// share its class and overlap it by more than thr.
+constexpr int MASK_UNIT = 4;  // consecutive entries per work unit (mostly the same I)
+__global__ void __launch_bounds__(256) nms_mask_kernel(NmsWs ws, double thr) {
+  __shared__ SBox jb[8][32];
+  if (ws.stats[ST_STATUS] != PG_OK) return;
+  const long long total = ws.stats[ST_ENT_TOTAL];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * 8 + wib, nw = (long long)gridDim.x * 8;
+  int cached = -1;
+  SBox bi;
+  bi.k = -1;
+  for (long long u = gw; u * MASK_UNIT < total; u += nw) {
+    for (int q = 0; q < MASK_UNIT; ++q) {
+      const long long e = u * MASK_UNIT + q;
+      if (e >= total) break;
+      const int I = ws.ent_i[e], J = ws.ent_j[e];
+      if (I != cached) { bi = ws.sbox[(int64_t)I * 32 + lane]; cached = I; }
+      __syncwarp();
+      jb[wib][lane] = ws.sbox[(int64_t)J * 32 + lane];
+      __syncwarp();
+      uint32_t mask = 0;
+      const int ik = (int)bi.k;
+      if (ik >= 0) {
+#pragma unroll 4
+        for (int jj = 0; jj < 32; ++jj) {
+          const SBox bj = jb[wib][jj];  // broadcast LDS.128 x4
+          const int jk = (int)bj.k;
+          // j must outrank i: higher score, or equal score and earlier pooled position (:112)
+          const bool outranks = (bj.score > bi.score) || (bj.score == bi.score && jk < ik);
+          if (jk >= 0 && outranks && bj.cls == bi.cls &&
+              pg_iou_gt(bj.x0, bj.y0, bj.x1, bj.y1, bj.area, bi.x0, bi.y0, bi.x1, bi.y1, bi.area, thr))
+            mask |= 1u << jj;
+        }
+      }
+      const bool any = __any_sync(0xffffffffu, mask != 0);
+      ws.ent_mask[e * 32 + lane] = mask;
+      if (lane == 0 && !any) ws.ent_j[e] = -1;
+    }
   }
-  if (threadIdx.x == 0) {
-    ws.cand_off[ws.nb_cap] = carry_s;
-    ws.stats[1] = carry_s;
-    ws.stats[0] = (carry_s > ws.ent_cap) ? PG_ERR_WORKSPACE : PG_OK;
-  }
+  if (gw == 0 && lane == 0) ws.stats[ST_TESTS] = total * 1024;
 }
 
 // ---- E: resolve ----------------------------------------------------------------------------
@@ -461,12 +467,12 @@ __global__ void __launch_bounds__(1024) nms_resolve_kernel(const int64_t* __rest
       }
       const bool mine = (u >> lane) & 1u;
       bool sup = false, wait = false;
-      const int64_t e0 = ws.cand_off[I], e1 = ws.cand_off[I + 1];
+      const int64_t e0 = ws.cand_off[I], e1 = e0 + ws.cand_cnt[I];
       for (int64_t e = e0; e < e1; ++e) {
-        const int jbk = ws.ent_j[e];
+        const int jbk = ws.ent_j[e];  // global block id, -1 = no suppressor in that block
         if (jbk < 0) continue;
         const uint32_t m = mine ? ws.ent_mask[e * 32 + lane] : 0u;
-        const uint32_t kj = kept[rc + sp.blk0 + jbk], uj = undec[rc + sp.blk0 + jbk];
+        const uint32_t kj = kept[rc + jbk], uj = undec[rc + jbk];
         if (m & kj) sup = true;
         else if (m & uj) wait = true;
       }
@@ -601,12 +607,15 @@ extern "C" int pg_nms_merge(const double* boxes, const double* scores, const dou
   const int all_pairs = !(iou_threshold >= 0.0);  // thr < 0: disjoint boxes (IoU 0) suppress too
   nms_bin_kernel<<<n_pages, 1024, 0, s>>>(boxes, scores, classes, sel_idx, page_off, n_sel, n_pages, ws);
   PG_LAUNCH_CHECK();
-  const unsigned pair_grid = (unsigned)((ws.nb_cap + 7) / 8);
-  nms_pairs_kernel<false><<<pair_grid, 256, 0, s>>>(page_off, n_sel, ws, iou_threshold, all_pairs);
+  const unsigned cand_grid = (unsigned)((ws.nb_cap + 7) / 8);
+  nms_cand_kernel<<<cand_grid, 256, 0, s>>>(page_off, n_sel, ws, all_pairs);
   PG_LAUNCH_CHECK();
-  nms_scan_kernel<<<1, 1024, 0, s>>>(ws);
-  PG_LAUNCH_CHECK();
-  nms_pairs_kernel<true><<<pair_grid, 256, 0, s>>>(page_off, n_sel, ws, iou_threshold, all_pairs);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t mask_want = (ws.ent_cap + 8 * MASK_UNIT - 1) / (8 * MASK_UNIT);
+  const unsigned mask_grid = (unsigned)(mask_want < (int64_t)sms * 4 ? (mask_want < 1 ? 1 : mask_want) : (int64_t)sms * 4);
+  nms_mask_kernel<<<mask_grid, 256, 0, s>>>(ws, iou_threshold);
   PG_LAUNCH_CHECK();
   nms_resolve_kernel<<<n_pages, 1024, 0, s>>>(page_off, n_sel, ws, n_kept);
   PG_LAUNCH_CHECK();
@@ -619,7 +628,10 @@ extern "C" int pg_nms_stats(const void* workspace, int64_t stats[4]) {
   PG_REQUIRE(workspace && stats, "null pointer");
   int64_t h[8];
   PG_CUDA_TRY(cudaMemcpy(h, workspace, sizeof(h), cudaMemcpyDeviceToHost));
-  for (int i = 0; i < 4; ++i) stats[i] = h[i];
+  stats[0] = h[ST_STATUS];
+  stats[1] = h[ST_ENT_TOTAL];
+  stats[2] = h[ST_ROUNDS];
+  stats[3] = h[ST_TESTS];
   return PG_OK;
 }
 

@@ -30,6 +30,30 @@ PG_HD double pg_iou(double ax0, double ay0, double ax1, double ay1, double area_
 
 PG_HD double pg_box_area(double x0, double y0, double x1, double y1) { return (x1 - x0) * (y1 - y0); }
 
+// Exactly `pg_iou(a, b) > thr` (3_combine_grids.py:130), without the divide on the common path.
+// With p = fl(thr*uni) (relative error <= 2^-53): inter > fl(p*(1+2^-50)) puts the real quotient
+// above thr*(1+2^-51), i.e. beyond the midpoint to nextafter(thr), so fl(inter/uni) > thr;
+// inter < fl(p*(1-2^-50)) puts it below thr, so fl(inter/uni) <= thr.  Only inside that 2^-50-wide
+// band is the IEEE divide evaluated (thr > 0 and normal-range operands; every other case falls
+// back to the literal expression).
+PG_HD bool pg_iou_gt(double ax0, double ay0, double ax1, double ay1, double area_a,
+                     double bx0, double by0, double bx1, double by1, double area_b, double thr) {
+  const double xl = ax0 > bx0 ? ax0 : bx0;
+  const double yt = ay0 > by0 ? ay0 : by0;
+  const double xr = ax1 < bx1 ? ax1 : bx1;
+  const double yb = ay1 < by1 ? ay1 : by1;
+  if (xr < xl || yb < yt) return 0.0 > thr;
+  const double inter = (xr - xl) * (yb - yt);
+  const double uni = area_a + area_b - inter;
+  if (!(uni > 0.0)) return 0.0 > thr;
+  if (thr > 1e-300 && thr < 1e300 && uni > 1e-280 && uni < 1e280) {
+    const double p = thr * uni;
+    if (inter > p * (1.0 + 0x1p-50)) return true;
+    if (inter < p * (1.0 - 0x1p-50)) return false;
+  }
+  return inter / uni > thr;
+}
+
 // is_box_touching_internal_edge (2_edge_box_filter.py:44-90), test order right, bottom,
 // left, top.  Pure predicate: the order only matters for short-circuiting.
 PG_HD bool pg_edge_touch(double x_min, double y_min, double x_max, double y_max,

@@ -18,7 +18,7 @@ import torch
 from . import ops
 from ._lib import PG_COL_HIST_BINS, PG_WIDTH_HIST_BINS, check, lib, ptr, stream_ptr
 
-KERNELS_PER_STEP = 12  # tiler, edge filter, 6 NMS kernels, class flags, width median, column density + peaks
+KERNELS_PER_STEP = 11  # tiler, edge filter, 5 NMS kernels, class flags, width median, column density + peaks
 
 
 def shard_pages(n_pages_total: int, rank: int, world: int) -> range:

@@ -85,6 +85,39 @@ def test_hostcheck_iou_bit_exact(lib):
         assert lib.pg_hostcheck_iou(_lib.ptr(a), _lib.ptr(b)) == ref
 
 
+def test_hostcheck_iou_gt_equals_divide_then_compare(lib):
+    """The merge kernel decides `iou > thr` without a divide except in a 2^-50 band around thr;
+    it must agree with the reference expression everywhere, in particular AT the threshold."""
+    rng = np.random.default_rng(11)
+    cases = []
+    g = load_golden("stage3_nms.npz")
+    for p in g["iou_pairs"]:
+        for thr in (0.5, 0.3, 0.45, 0.0, -1.0, 0.7):
+            cases.append((p[:4].copy(), p[4:].copy(), thr))
+    # pairs whose IoU is exactly representable and equal to the threshold, then nudged by ulps
+    for thr, a, b in [(0.5, [0, 0, 2, 1], [0, 0, 1, 1]), (0.25, [0, 0, 4, 1], [0, 0, 1, 1]),
+                      (0.5, [10, 10, 30, 20], [10, 10, 20, 20]), (0.75, [0, 0, 4, 1], [0, 0, 3, 1]),
+                      (0.5, [100.5, 7.25, 300.5, 57.25], [100.5, 7.25, 200.5, 57.25])]:
+        for _ in range(400):
+            aa, bb = np.asarray(a, np.float64), np.asarray(b, np.float64)
+            for arr in (aa, bb):
+                for k in range(4):
+                    steps = int(rng.integers(-3, 4))
+                    for _s in range(abs(steps)):
+                        arr[k] = np.nextafter(arr[k], np.inf if steps > 0 else -np.inf)
+            cases.append((aa, bb, thr))
+            cases.append((aa * 3.0, bb * 3.0, thr))
+    n_true = n_band = 0
+    for a, b, thr in cases:
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        v = ob.iou(a.tolist(), b.tolist())
+        ref = v > thr
+        n_true += ref
+        n_band += (thr > 0 and abs(v - thr) <= 4e-16 * thr)
+        assert bool(lib.pg_hostcheck_iou_gt(_lib.ptr(a), _lib.ptr(b), float(thr))) == ref, (a, b, thr, v)
+    assert n_true > 100 and n_band > 50  # the band (true-divide path) is really exercised
+
+
 def test_hostcheck_edge_touch_matches_reference(lib):
     n = 0
     for case in load_golden("stage2_filter.json.gz"):

@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--e2e-pages", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling helper: skip the host-buffer leg")
+    ap.add_argument("--no-overlap", action="store_true", help="run the box stages after the tiler on one stream")
     ap.add_argument("--corpus-stats", action="store_true", help="accumulate + all-reduce corpus histograms (cfg5)")
     ap.add_argument("--tiler-only", action="store_true", help="profiling helper: time the tiler alone")
     args = ap.parse_args()
@@ -244,7 +245,7 @@ def main():
         for j, gi in enumerate(idxs):  # page content depends on the global page index only
             ops.synth_pages(plan, 1, synth.PAGE_SEED0, first_page=gi, out=pages[j:j + 1])
         dets = [synth.page_detections(w, h, rows, cols, 20.0, spec["boxes"], synth.PAGE_SEED0 + gi) for gi in idxs]
-        pipe = PagePipeline(plan, len(idxs), corpus_stats=args.corpus_stats)
+        pipe = PagePipeline(plan, len(idxs), corpus_stats=args.corpus_stats, overlap=not args.no_overlap)
         host = pipe.set_detections(dets)
         pipes.append((plan, pipe, pages, host, dets))
         alg_bytes_step += plan.algorithmic_bytes * len(idxs) + 48 * pipe.n_boxes
@@ -325,6 +326,7 @@ def main():
         "config": {"workload": spec["name"], "pages_per_gpu": ppg, "global_pages_per_step": ppg * world,
                    "parallelism": f"page-sharded x{world}, no collective" + (" + hist all-reduce" if args.corpus_stats else ""),
                    "l2": f"inputs {sum(p[2].numel() for p in pipes) / 1e9:.1f} GB/step per GPU >> 126 MB L2 (no flush needed)",
+                   "streams": "tiler (low priority) || box stages (high priority)" if not args.no_overlap else "single stream",
                    "stages": "tiler only" if args.tiler_only else "tile+letterbox, translate+edge filter, NMS merge, width median, column peaks"},
         "roofline": roofline, "clocks": clocks, "merge_stats_last_group": nms_stats,
         "gpu_launches": (len(pipes) if args.tiler_only else KERNELS_PER_STEP * len(pipes)) * args.steps,
@@ -334,7 +336,7 @@ def main():
     if not args.no_e2e and not args.tiler_only:
         plan, pipe0, pages0, host0, dets0 = pipes[0]
         n_e = min(args.e2e_pages, pipe0.n_pages)
-        epipe = PagePipeline(plan, n_e)
+        epipe = PagePipeline(plan, n_e, overlap=not args.no_overlap)
         ehost = epipe.set_detections(dets0[:n_e])
         pin_pages = torch.empty((n_e, plan.page_h, plan.pitch), dtype=torch.uint8).pin_memory()
         pin_pages.copy_(pages0[:n_e])

@@ -77,6 +77,7 @@ struct PgTilePlan {
   uint2* d_xtab = nullptr;
   int4* d_ytab = nullptr;
   int4* d_items = nullptr;
+  unsigned long long* d_counters = nullptr;  // work-item counter + retired-CTA counter (self-resetting)
 };
 
 static double py_round_half_even(double v) { return std::nearbyint(v); }
@@ -211,7 +212,8 @@ static void plan_free_device(PgTilePlan* p) {
   if (p->d_xtab) cudaFree(p->d_xtab);
   if (p->d_ytab) cudaFree(p->d_ytab);
   if (p->d_items) cudaFree(p->d_items);
-  p->d_tiles = nullptr; p->d_xtab = nullptr; p->d_ytab = nullptr; p->d_items = nullptr;
+  if (p->d_counters) cudaFree(p->d_counters);
+  p->d_tiles = nullptr; p->d_xtab = nullptr; p->d_ytab = nullptr; p->d_items = nullptr; p->d_counters = nullptr;
   p->device = -1;
 }
 
@@ -240,6 +242,8 @@ static int plan_upload(PgTilePlan* p, cudaStream_t s) {
   PG_CUDA_TRY(cudaMalloc(&p->d_xtab, p->xtab.size() * sizeof(uint2)));
   PG_CUDA_TRY(cudaMalloc(&p->d_ytab, p->ytab.size() * sizeof(int4)));
   PG_CUDA_TRY(cudaMalloc(&p->d_items, p->items.size() * sizeof(int4)));
+  PG_CUDA_TRY(cudaMalloc(&p->d_counters, 2 * sizeof(unsigned long long)));
+  PG_CUDA_TRY(cudaMemsetAsync(p->d_counters, 0, 2 * sizeof(unsigned long long), s));
   PG_CUDA_TRY(cudaMemcpyAsync(p->d_tiles, p->tiles.data(), p->tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice, s));
   PG_CUDA_TRY(cudaMemcpyAsync(p->d_xtab, p->xtab.data(), p->xtab.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
   PG_CUDA_TRY(cudaMemcpyAsync(p->d_ytab, p->ytab.data(), p->ytab.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
@@ -327,6 +331,7 @@ __device__ __forceinline__ uint32_t pack_unit_half2(uint32_t va, uint32_t vb) {
 constexpr int TL_CW = 8;                     // consumer warps
 constexpr int TL_THREADS = 32 * (TL_CW + 1);  // + producer warp
 constexpr int TL_STAGES = 4;
+constexpr int TL_ITEMS_PER_CTA = 8;           // bands of TL_BAND rows a CTA claims before retiring
 constexpr int TL_PAIR_STRIDE = TL_CW * 64;    // pixels covered by all consumer warps per iteration
 
 struct TilerArgs {
@@ -339,14 +344,52 @@ struct TilerArgs {
   int64_t pitch, page_stride, out_page_stride;
   int32_t items_per_page;
   int64_t total_items;
-  int32_t row_stride;  // shared-memory bytes per staged row
+  int32_t row_stride;     // shared-memory bytes per staged row
+  int32_t items_per_cta;  // work items a CTA may claim before it retires
+  unsigned long long* counters;  // [0] next item, [1] CTAs finished (self-resetting)
 };
+
+// Stage message, written by the producer before it arms the stage's full barrier:
+//   x = tile (-1: no more work), y = page, z = output row | TL_MSG_PADROW, w = b0 | b1 << 16
+constexpr int TL_MSG_PADROW = 1 << 30;
+
+// one output row for this thread's pixel pairs; XPAD: the tile has 114-valued columns
+template <int ITER, bool XPAD>
+__device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const uint32_t (&xoff)[ITER][2],
+                                          const uint32_t (&coef)[ITER][2], uint32_t b0, uint32_t b1,
+                                          uint32_t* orow, int64_t plane, int out_w, int px0) {
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int ox = i * TL_PAIR_STRIDE + px0;
+    if (ox < out_w) {
+      uint32_t vb[2], vg[2], vr[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (XPAD && coef[i][j] == TL_PADMARK) {
+          vb[j] = vg[j] = vr[j] = TL_PAD_VALUE;
+        } else {
+          uint32_t tb, tg, tr, ub, ug, ur;
+          hpass_smem(row0, xoff[i][j], coef[i][j], tb, tg, tr);
+          hpass_smem(row1, xoff[i][j], coef[i][j], ub, ug, ur);
+          vb[j] = pg_vpass(tb, ub, b0, b1);
+          vg[j] = pg_vpass(tg, ug, b0, b1);
+          vr[j] = pg_vpass(tr, ur, b0, b1);
+        }
+      }
+      // BGR -> RGB planes
+      __stcs(orow + (ox >> 1), pack_unit_half2(vr[0], vr[1]));
+      __stcs(orow + ((plane + ox) >> 1), pack_unit_half2(vg[0], vg[1]));
+      __stcs(orow + ((2 * plane + ox) >> 1), pack_unit_half2(vb[0], vb[1]));
+    }
+  }
+}
 
 template <int ITER>
 __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const TilerArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[TL_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TL_STAGES];
+  __shared__ __align__(16) int4 msg[TL_STAGES];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -362,25 +405,45 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
   uint32_t stage = 0, phase = 0;
 
   if (warp == TL_CW) {
-    // ===================== producer: one elected lane issues the bulk copies =====================
+    // ============ producer: one elected lane claims work items and issues the bulk copies ============
     if (lane == 0) {
-      for (int64_t it = blockIdx.x; it < a.total_items; it += gridDim.x) {
-        const int64_t page = it / a.items_per_page;
+      for (int n = 0; n < a.items_per_cta; ++n) {
+        const long long it = (long long)atomicAdd(&a.counters[0], 1ull);
+        if (it >= a.total_items) break;
+        const long long page = it / a.items_per_page;
         const int4 item = a.items[it - page * a.items_per_page];
         const TileDev& t = a.tiles[item.x];
+        const int pad_t = t.pad_t, new_h = t.new_h, ytab_off = t.ytab_off;
         const uint8_t* src = a.pages + page * a.page_stride + (int64_t)t.y0 * a.pitch + ((3 * t.x0) & ~15);
         const uint32_t bytes = (uint32_t)t.row_bytes;
         for (int oy = item.y; oy < item.y + item.z; ++oy) {
-          const int ry = oy - t.pad_t;
-          if (ry < 0 || ry >= t.new_h) continue;  // pad row: nothing to stage
-          const int4 yt = a.ytab[t.ytab_off + ry];
+          const int ry = oy - pad_t;
+          const bool pad_row = ry < 0 || ry >= new_h;
+          int4 yt = make_int4(0, 0, 0, 0);
+          if (!pad_row) yt = a.ytab[ytab_off + ry];
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_expect_tx(&full_bar[stage], 2u * bytes);
-          uint8_t* dst = smem + stage * stage_bytes;
-          bulk_g2s(dst, src + (int64_t)yt.x * a.pitch, bytes, &full_bar[stage]);
-          bulk_g2s(dst + a.row_stride, src + (int64_t)yt.y * a.pitch, bytes, &full_bar[stage]);
+          msg[stage] = make_int4(item.x, (int)page, oy | (pad_row ? TL_MSG_PADROW : 0), yt.z | (yt.w << 16));
+          if (pad_row) {
+            mbar_arrive(&full_bar[stage]);  // nothing to stage: the message alone completes the phase
+          } else {
+            mbar_expect_tx(&full_bar[stage], 2u * bytes);
+            uint8_t* dst = smem + stage * stage_bytes;
+            bulk_g2s(dst, src + (int64_t)yt.x * a.pitch, bytes, &full_bar[stage]);
+            bulk_g2s(dst + a.row_stride, src + (int64_t)yt.y * a.pitch, bytes, &full_bar[stage]);
+          }
           if (++stage == TL_STAGES) { stage = 0; phase ^= 1u; }
         }
+      }
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      msg[stage] = make_int4(-1, 0, 0, 0);
+      mbar_arrive(&full_bar[stage]);
+      // the last CTA to retire re-arms the counters for the next launch on this plan
+      __threadfence();
+      const unsigned long long prev = atomicAdd(&a.counters[1], 1ull);
+      if (prev == (unsigned long long)gridDim.x - 1ull) {
+        a.counters[0] = 0ull;
+        a.counters[1] = 0ull;
+        __threadfence();
       }
     }
     return;
@@ -389,80 +452,58 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
   // ===================== consumers =====================
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t pad_pair = pack_unit_half2(TL_PAD_VALUE, TL_PAD_VALUE);
+  const int px0 = warp * 64 + lane * 2;
   uint32_t xoff[ITER][2], coef[ITER][2];
-  int cached_tile = -1;
+  int cached_tile = -1, out_w = 0, xpad = 0;
+  int64_t plane = 0, out_off = 0;
 
-  for (int64_t it = blockIdx.x; it < a.total_items; it += gridDim.x) {
-    const int64_t page = it / a.items_per_page;
-    const int4 item = a.items[it - page * a.items_per_page];
-    const TileDev& t = a.tiles[item.x];
-    const int out_w = t.out_w, out_h = t.out_h;
-    if (item.x != cached_tile) {
-      cached_tile = item.x;
+  while (true) {
+    mbar_wait(&full_bar[stage], phase);
+    const int4 m = msg[stage];
+    if (m.x < 0) break;
+    if (m.x != cached_tile) {
+      cached_tile = m.x;
+      const TileDev& t = a.tiles[m.x];
+      out_w = t.out_w;
+      plane = (int64_t)t.out_h * out_w;
+      out_off = t.out_off;
+      xpad = (t.pad_l != 0) || (t.new_w != out_w);
       const uint32_t skew = (uint32_t)t.row_skew;
+      const int xtab_off = t.xtab_off;
 #pragma unroll
       for (int i = 0; i < ITER; ++i) {
-        const int ox = i * TL_PAIR_STRIDE + warp * 64 + lane * 2;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
+          const int ox = i * TL_PAIR_STRIDE + px0 + j;
           uint2 e = make_uint2(0u, TL_PADMARK);
-          if (ox + j < out_w) e = __ldg(&a.xtab[t.xtab_off + ox + j]);
+          if (ox < out_w) e = __ldg(&a.xtab[xtab_off + ox]);
           xoff[i][j] = e.x + skew;
           coef[i][j] = e.y;
         }
       }
     }
-    __half* out_tile = a.out + page * a.out_page_stride + t.out_off;
-    const int64_t plane = (int64_t)out_h * out_w;
-
-    for (int oy = item.y; oy < item.y + item.z; ++oy) {
-      const int ry = oy - t.pad_t;
-      uint32_t* orow = reinterpret_cast<uint32_t*>(out_tile + (int64_t)oy * out_w);  // R plane row (half2 units)
-      if (ry < 0 || ry >= t.new_h) {
-#pragma unroll
-        for (int i = 0; i < ITER; ++i) {
-          const int ox = i * TL_PAIR_STRIDE + warp * 64 + lane * 2;
-          if (ox < out_w) {
-            __stcs(orow + (ox >> 1), pad_pair);
-            __stcs(orow + ((plane + ox) >> 1), pad_pair);
-            __stcs(orow + ((2 * plane + ox) >> 1), pad_pair);
-          }
-        }
-        continue;
-      }
-      const int4 yt = __ldg(&a.ytab[t.ytab_off + ry]);
-      const uint32_t b0 = (uint32_t)yt.z, b1 = (uint32_t)yt.w;
-      mbar_wait(&full_bar[stage], phase);
-      const uint32_t row0 = smem_base + stage * stage_bytes;
-      const uint32_t row1 = row0 + (uint32_t)a.row_stride;
+    const int oy = m.z & ~TL_MSG_PADROW;
+    uint32_t* orow = reinterpret_cast<uint32_t*>(a.out + (int64_t)m.y * a.out_page_stride + out_off + (int64_t)oy * out_w);
+    if (m.z & TL_MSG_PADROW) {
 #pragma unroll
       for (int i = 0; i < ITER; ++i) {
-        const int ox = i * TL_PAIR_STRIDE + warp * 64 + lane * 2;
+        const int ox = i * TL_PAIR_STRIDE + px0;
         if (ox < out_w) {
-          uint32_t vb[2], vg[2], vr[2];
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            if (coef[i][j] == TL_PADMARK) {
-              vb[j] = vg[j] = vr[j] = TL_PAD_VALUE;
-            } else {
-              uint32_t tb, tg, tr, ub, ug, ur;
-              hpass_smem(row0, xoff[i][j], coef[i][j], tb, tg, tr);
-              hpass_smem(row1, xoff[i][j], coef[i][j], ub, ug, ur);
-              vb[j] = pg_vpass(tb, ub, b0, b1);
-              vg[j] = pg_vpass(tg, ug, b0, b1);
-              vr[j] = pg_vpass(tr, ur, b0, b1);
-            }
-          }
-          // BGR -> RGB planes
-          __stcs(orow + (ox >> 1), pack_unit_half2(vr[0], vr[1]));
-          __stcs(orow + ((plane + ox) >> 1), pack_unit_half2(vg[0], vg[1]));
-          __stcs(orow + ((2 * plane + ox) >> 1), pack_unit_half2(vb[0], vb[1]));
+          __stcs(orow + (ox >> 1), pad_pair);
+          __stcs(orow + ((plane + ox) >> 1), pad_pair);
+          __stcs(orow + ((2 * plane + ox) >> 1), pad_pair);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[stage]);
-      if (++stage == TL_STAGES) { stage = 0; phase ^= 1u; }
+    } else {
+      const uint32_t b0 = (uint32_t)m.w & 0xFFFFu, b1 = (uint32_t)m.w >> 16;
+      const uint32_t row0 = smem_base + stage * stage_bytes;
+      const uint32_t row1 = row0 + (uint32_t)a.row_stride;
+      if (xpad) tiler_row<ITER, true>(row0, row1, xoff, coef, b0, b1, orow, plane, out_w, px0);
+      else tiler_row<ITER, false>(row0, row1, xoff, coef, b0, b1, orow, plane, out_w, px0);
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    if (++stage == TL_STAGES) { stage = 0; phase ^= 1u; }
   }
 }
 
@@ -535,11 +576,13 @@ static TilerArgs make_args(const PgTilePlan* plan, const uint8_t* pages, int32_t
   a.items_per_page = (int32_t)plan->items.size();
   a.total_items = (int64_t)plan->items.size() * n_pages;
   a.row_stride = (plan->max_row_bytes + 16 + 127) & ~127;
+  a.items_per_cta = 1;
+  a.counters = plan->d_counters;
   return a;
 }
 
 template <int ITER>
-static int launch_pipeline(const TilerArgs& a, cudaStream_t s) {
+static int launch_pipeline(TilerArgs a, cudaStream_t s) {
   const size_t smem = (size_t)TL_STAGES * 2 * a.row_stride;
   int dev = 0, sms = 0, max_smem = 0;
   PG_CUDA_TRY(cudaGetDevice(&dev));
@@ -556,9 +599,19 @@ static int launch_pipeline(const TilerArgs& a, cudaStream_t s) {
     pg_set_error("unsupported: tiler kernel does not fit on an SM");
     return PG_ERR_UNSUPPORTED;
   }
-  int64_t grid = (int64_t)sms * per_sm;
-  if (grid > a.total_items) grid = a.total_items;
+  // Bounded-lifetime CTAs: each claims up to items_per_cta bands of 16 rows from the shared counter
+  // and retires, so kernels queued on a higher-priority stream (the box stages) can take over SM
+  // slots while the tiler is still streaming.  Small launches get 1 item per CTA to fill the chip.
+  const int64_t slots = (int64_t)sms * per_sm;
+  int64_t ipc = a.total_items / (slots * 4);
+  ipc = ipc < 1 ? 1 : (ipc > TL_ITEMS_PER_CTA ? TL_ITEMS_PER_CTA : ipc);
+  a.items_per_cta = (int32_t)ipc;
+  const int64_t grid = (a.total_items + ipc - 1) / ipc;
   if (grid < 1) return PG_OK;
+  if (grid > 0x7fffffffll) {
+    pg_set_error("unsupported: %lld work items in one launch", (long long)a.total_items);
+    return PG_ERR_UNSUPPORTED;
+  }
   tile_letterbox_kernel<ITER><<<(unsigned)grid, TL_THREADS, smem, s>>>(a);
   PG_LAUNCH_CHECK();
   return PG_OK;

@@ -31,8 +31,18 @@ def shard_pages(n_pages_total: int, rank: int, world: int) -> range:
 class PagePipeline:
     def __init__(self, plan: ops.TilePlan, n_pages: int, iou_threshold: float = 0.5, edge_threshold: float = 10,
                  min_margin_percent: float = 0.2, min_confidence: float = 0.3, max_cols: int = 64,
-                 plain_text_id: float = 1.0, title_id: float = 0.0, corpus_stats: bool = False):
+                 plain_text_id: float = 1.0, title_id: float = 0.0, corpus_stats: bool = False,
+                 overlap: bool = True):
         self.plan, self.n_pages = plan, int(n_pages)
+        # The tiler streams pixels (HBM-bound), the box stages are short latency-bound kernels on a few
+        # SMs: run them side by side.  The tiler's CTAs retire after a few work items, so the box
+        # kernels, queued on a higher-priority stream, pick up SM slots as they free.
+        self.overlap = bool(overlap)
+        if self.overlap:
+            lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+            self.s_tiler = torch.cuda.Stream(priority=lo)
+            self.s_box = torch.cuda.Stream(priority=hi)
+            self._ev = [torch.cuda.Event() for _ in range(3)]
         self.iou_threshold, self.edge_threshold = float(iou_threshold), float(edge_threshold)
         self.min_margin_percent, self.min_confidence = float(min_margin_percent), float(min_confidence)
         self.max_cols, self.plain_text_id, self.title_id = int(max_cols), float(plain_text_id), float(title_id)
@@ -115,16 +125,34 @@ class PagePipeline:
     # ---------------------------------------------------------------- one step
     def run(self, pages: torch.Tensor, stream=None, tiler_events=None) -> None:
         """One pass of the hot path over the shard.  pages: cuda uint8 [P, H, pitch]."""
-        L, s, p = lib(), stream_ptr(stream), self.n_pages
-        plan = self.plan
+        main = stream if stream is not None else torch.cuda.current_stream()
+        if self.overlap and self.n_boxes:
+            start, box_done, tiler_done = self._ev
+            start.record(main)
+            self.s_box.wait_event(start)
+            self.s_tiler.wait_event(start)
+            self._run_boxes(self.s_box)       # queued first: its kernels outrank the tiler's CTAs
+            box_done.record(self.s_box)
+            self._run_tiler(pages, self.s_tiler, tiler_events)
+            tiler_done.record(self.s_tiler)
+            main.wait_event(box_done)
+            main.wait_event(tiler_done)
+        else:
+            self._run_tiler(pages, main, tiler_events)
+            if self.n_boxes:
+                self._run_boxes(main)
+
+    def _run_tiler(self, pages, stream, tiler_events=None) -> None:
+        L, s, p, plan = lib(), stream.cuda_stream, self.n_pages, self.plan
         if tiler_events is not None:
             tiler_events[0].record(stream)
         check(L.pg_tile_letterbox(plan._h, ptr(pages), p, pages.shape[2], pages.shape[1] * pages.shape[2],
                                   ptr(self.tiles_out), self.tiles_out.stride(0), s))
         if tiler_events is not None:
             tiler_events[1].record(stream)
-        if self.n_boxes == 0:
-            return
+
+    def _run_boxes(self, stream) -> None:
+        L, s, p = lib(), stream.cuda_stream, self.n_pages
         check(L.pg_edge_filter(ptr(self.boxes_local), 1, ptr(self.box_cell), ptr(self.cells), ptr(self.page_wh),
                                ptr(self.page_off), p, self.edge_threshold, ptr(self.boxes_page), None,
                                ptr(self.kept1), ptr(self.n_kept1), s))

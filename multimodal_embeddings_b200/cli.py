@@ -1,0 +1,575 @@
+"""Drop-in command lines for the numbered scripts of calhounpaul/multimodal_embeddings
+(stages 1-5 of run.sh:60-70), same argv and same on-disk JSON schemas, with the geometry done by
+libpagegeom.so.  Every stage batches all pages it finds into single kernel launches.
+
+    1_doclayout_bboxes.py      -> main_stage1   (tiler + pluggable detector; 1:682-785)
+    2_edge_box_filter.py       -> main_stage2   (2:670-766)
+    3_combine_grids.py         -> main_stage3   (3:403-458)
+    4_extract_median_widths.py -> main_stage4   (4:227-292)
+    5_detect_column_centers.py -> main_stage5   (5:541-588)
+
+Not reproduced (out of scope): the DocLayout-YOLO network itself —
+stage 1 hands the letterboxed fp16 tiles to a detector object (synthetic or replayed
+detections ship here) — and the JPEG visualisations (--viz_alpha is accepted and ignored).
+Extra flags, all optional: --no_image_check lets stages 2-5 run on JSON trees whose page images
+are absent (page size then comes from the JSON), --detections/--replay_folder/--boxes_per_page
+choose stage 1's detection source.
+"""
+from __future__ import annotations
+
+import argparse
+import glob
+import json
+import logging
+import os
+import re
+import sys
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+FMT = "%(asctime)s - %(name)s - %(levelname)s - %(message)s"
+IMAGE_EXTENSIONS = (".jpg", ".jpeg", ".png", ".bmp", ".tiff", ".tif", ".webp")
+
+
+def _logger(name: str) -> logging.Logger:
+    lg = logging.getLogger(name)  # same logger names as the reference (1:43, 2:26, 3:28, 4:31, 5:56)
+    if not lg.handlers:
+        h = logging.StreamHandler()
+        h.setFormatter(logging.Formatter(FMT))
+        lg.addHandler(h)
+        lg.setLevel(logging.INFO)
+    return lg
+
+
+def _dump(obj, path):
+    with open(path, "w") as f:
+        json.dump(obj, f, indent=2)
+
+
+def _image_size(path) -> Optional[Tuple[int, int]]:
+    try:
+        from PIL import Image
+        with Image.open(path) as im:  # header only
+            return im.width, im.height
+    except Exception:
+        return None
+
+
+# =============================================================================================
+# stage 1
+# =============================================================================================
+class SyntheticDetector:
+    """Stands in for DocLayout-YOLO (weights unavailable offline): deterministic per-tile detections
+    from multimodal_embeddings_b200.synth, keyed by page name."""
+
+    def __init__(self, boxes_per_page: int = 2000, seed: int = 0xB200):
+        self.boxes_per_page, self.seed = boxes_per_page, seed
+
+    def detect_page(self, base: str, width: int, height: int, rows: int, cols: int, overlap: float, tiles):
+        from . import synth
+        n = max(1, self.boxes_per_page * rows * cols // max(1, rows * cols))
+        seed = (self.seed + sum(ord(c) * (i + 1) for i, c in enumerate(base)) + 97 * rows + cols) & 0x7FFFFFFF
+        d = synth.page_detections(width, height, rows, cols, overlap, n, seed)
+        out = []
+        for ci in range(rows * cols):
+            m = d["box_cell"] == ci
+            out.append({"boxes": d["boxes_local"][m].tolist(), "classes": d["classes"][m].tolist(),
+                        "scores": d["scores"][m].tolist(), "class_names": synth.class_names_of(d["classes"][m])})
+        return out
+
+
+class ReplayDetector:
+    """Replays detections from a folder of stage-1 JSONs (``<folder>/json/<base>.json`` and
+    ``<folder>/json/<base>_grid_RxC.json``), e.g. a previous run of the reference."""
+
+    def __init__(self, folder: str):
+        self.folder = folder
+
+    def detect_page(self, base, width, height, rows, cols, overlap, tiles):
+        name = f"{base}.json" if (rows, cols) == (1, 1) else f"{base}_grid_{rows}x{cols}.json"
+        with open(os.path.join(self.folder, "json", name)) as f:
+            d = json.load(f)
+        if "cells" in d:
+            return [{k: c["regions"][k] for k in ("boxes", "classes", "scores", "class_names")} for c in d["cells"]]
+        return [{k: d[k] for k in ("boxes", "classes", "scores", "class_names")}]
+
+
+def get_image_paths(input_folder):
+    """1_doclayout_bboxes.py:345-364."""
+    paths = []
+    for root, _, files in os.walk(input_folder):
+        for file in files:
+            if os.path.splitext(file)[1].lower() in IMAGE_EXTENSIONS:
+                paths.append(os.path.join(root, file))
+    return sorted(paths)
+
+
+def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
+    from . import ops
+    from .reference_api import parse_grid_configs, translate_coordinates_to_original
+    logger = _logger("DocLayoutAnalyzer")
+    p = argparse.ArgumentParser(description="Document Layout Analysis")
+    p.add_argument("--input_folder", required=True)
+    p.add_argument("--output_folder", required=True)
+    p.add_argument("--conf_threshold", type=float, default=0.1)
+    p.add_argument("--iou_threshold", type=float, default=0.45)
+    p.add_argument("--device", choices=["cpu", "cuda"])
+    p.add_argument("--model_path")
+    p.add_argument("--skip_errors", action="store_true")
+    p.add_argument("--rows", type=int, default=2)
+    p.add_argument("--cols", type=int, default=2)
+    p.add_argument("--grids", type=str, default="2x2,3x3,4x4")
+    p.add_argument("--overlap", type=float, default=20.0)
+    p.add_argument("--disable_grid", action="store_true")
+    p.add_argument("--detections", choices=["synthetic", "replay"], default="synthetic")
+    p.add_argument("--replay_folder")
+    p.add_argument("--boxes_per_page", type=int, default=2000)
+    p.add_argument("--imgsz", type=int, default=1024)
+    args = p.parse_args(argv)
+    if args.device == "cpu":
+        logger.error("--device cpu: this implementation has no CPU path (libpagegeom.so is CUDA only)")
+        return 2
+    json_folder = os.path.join(args.output_folder, "json")
+    os.makedirs(json_folder, exist_ok=True)
+    os.makedirs(os.path.join(args.output_folder, "visualizations"), exist_ok=True)
+    grid_configs: List[Tuple[int, int]] = []
+    if not args.disable_grid:  # 1:712-725
+        if args.grids:
+            grid_configs = parse_grid_configs(args.grids) or [(args.rows, args.cols)]
+        else:
+            grid_configs = [(args.rows, args.cols)]
+    image_paths = get_image_paths(args.input_folder)
+    if not image_paths:
+        logger.error(f"No images found in {args.input_folder}")
+        return 0
+    detector = ReplayDetector(args.replay_folder) if args.detections == "replay" else SyntheticDetector(args.boxes_per_page)
+    processed = errors = 0
+    import cv2
+    for image_path in image_paths:
+        try:
+            page = cv2.imread(image_path)  # host decode (out of scope)
+            if page is None:
+                raise RuntimeError(f"Failed to load image: {image_path}")
+            h, w = page.shape[:2]
+            base, ext = os.path.splitext(os.path.basename(image_path))
+            grids = [(1, 1)] + grid_configs
+            plan = ops.TilePlan(w, h, grids, args.overlap, args.imgsz)
+            tiles = plan.run(ops.upload_pages([page], plan))  # every tile of every grid in ONE launch
+            params = {"conf_threshold": args.conf_threshold, "iou_threshold": args.iou_threshold}
+            t0 = 0
+            for rows, cols in grids:
+                n_t = rows * cols
+                views = [plan.tile_view(tiles, 0, t0 + k) for k in range(n_t)]
+                dets = detector.detect_page(base, w, h, rows, cols, args.overlap, views)
+                if (rows, cols) == (1, 1) and t0 == 0:  # full-page pass, 1:446-482 / schema 1:227-235
+                    d = dets[0]
+                    _dump({"image_path": image_path, "image_size": {"width": w, "height": h}, "parameters": params,
+                           "boxes": d["boxes"], "classes": d["classes"], "scores": d["scores"],
+                           "class_names": d["class_names"]}, os.path.join(json_folder, f"{base}.json"))
+                else:  # 1:513-654
+                    grid_folder = os.path.join(args.output_folder, f"grid_{rows}x{cols}")
+                    for sub in ("images", "json", "visualizations", "visualizations_original_coords"):
+                        os.makedirs(os.path.join(grid_folder, sub), exist_ok=True)
+                    info = {"original_image_path": image_path,
+                            "grid_config": {"rows": rows, "cols": cols, "overlap_percentage": args.overlap}, "cells": []}
+                    for k, d in enumerate(dets):
+                        ti = plan.tiles[t0 + k]
+                        cc = plan.cell_coordinates(t0 + k)
+                        cell_name = f"{base}_row{ti['row']}_col{ti['col']}{ext}"
+                        cell_path = os.path.join(grid_folder, "images", cell_name)
+                        cell_json = os.path.join(grid_folder, "json", cell_name.replace(ext, ".json"))
+                        orig = translate_coordinates_to_original(d["boxes"], cc)
+                        cell_regions = {"image_path": cell_path,
+                                        "image_size": {"width": ti["x1"] - ti["x0"], "height": ti["y1"] - ti["y0"]},
+                                        "parameters": params, "boxes": d["boxes"], "classes": d["classes"],
+                                        "scores": d["scores"], "class_names": d["class_names"],
+                                        "cell_coordinates": cc, "original_image_path": image_path,
+                                        "boxes_original": orig,
+                                        "grid_info": {"rows": rows, "cols": cols, "row": ti["row"], "col": ti["col"]}}
+                        _dump(cell_regions, cell_json)
+                        info["cells"].append({"cell_path": cell_path, "cell_json_path": cell_json, "cell_coordinates": cc,
+                                              "row": ti["row"], "col": ti["col"],
+                                              "regions": {"boxes": d["boxes"], "boxes_original": orig,
+                                                          "classes": d["classes"], "scores": d["scores"],
+                                                          "class_names": d["class_names"]}})
+                    if info["cells"]:
+                        _dump(info, os.path.join(json_folder, f"{base}_grid_{rows}x{cols}.json"))
+                t0 += n_t
+            processed += 1
+        except Exception as e:  # 1:778-783
+            errors += 1
+            logger.error(f"Error processing {os.path.basename(image_path)}: {str(e)}")
+            if not args.skip_errors:
+                logger.error("Stopping due to error. Use --skip_errors to continue despite errors.")
+                break
+    logger.info(f"Processing complete. Successfully processed {processed} images with {errors} errors. "
+                f"Results saved to {args.output_folder}")
+    return 0
+
+
+# =============================================================================================
+# stage 2
+# =============================================================================================
+def _grid_page_size(grid_info, no_image_check: bool):
+    path = grid_info.get("image_path") if ("image_path" in grid_info and os.path.exists(grid_info["image_path"])) \
+        else grid_info.get("original_image_path")
+    if path and os.path.exists(path):
+        return _image_size(path)
+    if no_image_check and grid_info.get("cells"):
+        w = max(c["cell_coordinates"]["x_end"] for c in grid_info["cells"])
+        h = max(c["cell_coordinates"]["y_end"] for c in grid_info["cells"])
+        return int(w), int(h)
+    return None
+
+
+def main_stage2(argv: Optional[Sequence[str]] = None) -> int:
+    from . import reference_api as api
+    logger = _logger("EdgeBoxFilter")
+    p = argparse.ArgumentParser(description="Filter bounding boxes that touch internal grid edges")
+    p.add_argument("--input_folder", required=True)
+    p.add_argument("--output_folder", required=True)
+    p.add_argument("--edge_threshold", type=int, default=10)
+    p.add_argument("--viz_alpha", type=float, default=0.3)
+    p.add_argument("--skip_errors", action="store_true")
+    p.add_argument("--process_grids", action="store_true")
+    p.add_argument("--no_image_check", action="store_true")
+    args = p.parse_args(argv)
+    out_json = os.path.join(args.output_folder, "json")
+    os.makedirs(out_json, exist_ok=True)
+    os.makedirs(os.path.join(args.output_folder, "visualizations"), exist_ok=True)
+
+    def run_folder(in_folder, out_folder):
+        paths = sorted(os.path.join(r, f) for r, _, fs in os.walk(in_folder) for f in fs if f.endswith(".json"))
+        ok = err = 0
+        for path in paths:
+            try:
+                with open(path) as f:
+                    regions = json.load(f)
+                target = os.path.join(out_folder, os.path.basename(path))
+                if "cells" in regions and ("grid_config" in regions or "grid_info" in regions):  # 2:374
+                    size = _grid_page_size(regions, args.no_image_check)
+                    filtered = api.filter_grid_info(regions, args.edge_threshold, image_size=size) if size else None
+                    _dump(filtered if filtered else regions, target)  # 2:485-487 / 2:567-573
+                    ok += 1
+                    continue
+                image_path = regions.get("image_path")
+                if not args.no_image_check and not (image_path and os.path.exists(image_path)):  # 2:381-412
+                    alt = regions.get("original_image_path")
+                    if not (alt and os.path.exists(alt)):
+                        logger.error(f"Image path not found: {image_path}")
+                        err += 1
+                        continue
+                _dump(api.filter_edge_boxes(regions, args.edge_threshold), target)
+                ok += 1
+            except Exception as e:
+                err += 1
+                logger.error(f"Error processing {os.path.basename(path)}: {str(e)}")
+                if not args.skip_errors:
+                    logger.error("Stopping due to error. Use --skip_errors to continue despite errors.")
+                    break
+        return ok, err
+
+    json_folder = os.path.join(args.input_folder, "json")
+    if os.path.exists(json_folder):
+        ok, err = run_folder(json_folder, out_json)
+        logger.info(f"Main JSON processing complete. Successfully processed {ok} JSON files with {err} errors")
+    else:
+        logger.warning(f"Main JSON folder not found: {json_folder}")
+    if args.process_grids:  # 2:579-649
+        for item in sorted(os.listdir(args.input_folder)):
+            src = os.path.join(args.input_folder, item, "json")
+            if item.startswith("grid_") and os.path.isdir(src):
+                dst = os.path.join(args.output_folder, item, "json")
+                os.makedirs(dst, exist_ok=True)
+                os.makedirs(os.path.join(args.output_folder, item, "visualizations"), exist_ok=True)
+                run_folder(src, dst)
+    logger.info(f"All processing complete. Results saved to {args.output_folder}")
+    return 0
+
+
+# =============================================================================================
+# stage 3
+# =============================================================================================
+def find_grid_jsons(input_folder) -> Dict[str, List[str]]:
+    """3_combine_grids.py:140-198.  Same grouping rules; globs are sorted here (the reference's
+    order is whatever the filesystem returns) with the standard JSON still first (:175)."""
+    groups: Dict[str, List[str]] = {}
+    json_folder = os.path.join(input_folder, "json")
+    if os.path.exists(json_folder):
+        for g in sorted(glob.glob(os.path.join(json_folder, "*_grid_*.json"))):
+            groups.setdefault(os.path.basename(g).split("_grid_")[0], []).append(g)
+        for j in sorted(glob.glob(os.path.join(json_folder, "*.json"))):
+            if "_grid_" not in j and "_combined" not in j:
+                groups.setdefault(os.path.splitext(os.path.basename(j))[0], []).insert(0, j)
+    for sub in sorted(os.listdir(input_folder)):
+        sj = os.path.join(input_folder, sub, "json")
+        if sub.startswith("grid_") and os.path.isdir(os.path.join(input_folder, sub)) and os.path.exists(sj):
+            for g in sorted(glob.glob(os.path.join(sj, "*.json"))):
+                fn = os.path.basename(g)
+                base = fn.split("_row")[0] if ("_row" in fn and "_col" in fn) else os.path.splitext(fn)[0]
+                groups.setdefault(base, []).append(g)
+    return groups
+
+
+def pool_documents(json_paths, logger):
+    """Concatenation of combine_boxes_for_image (3_combine_grids.py:222-270)."""
+    boxes, scores, classes, names = [], [], [], []
+    image_path = image_size = None
+    for path in json_paths:
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            if "cells" in d:
+                if not image_path and "original_image_path" in d:
+                    image_path = d["original_image_path"]
+                for cell in d["cells"]:
+                    if "regions" in cell and "boxes_original" in cell["regions"]:
+                        r = cell["regions"]
+                        boxes.extend(r["boxes_original"]); scores.extend(r["scores"])
+                        classes.extend(r["classes"]); names.extend(r["class_names"])
+            elif "boxes" in d:
+                if not image_path and "image_path" in d:
+                    image_path = d["image_path"]
+                if not image_size and "image_size" in d:
+                    image_size = d["image_size"]
+                boxes.extend(d["boxes_original"] if "boxes_original" in d else d["boxes"])
+                scores.extend(d["scores"]); classes.extend(d["classes"]); names.extend(d["class_names"])
+        except Exception as e:
+            logger.error(f"Error reading {path}: {str(e)}")
+    return boxes, scores, classes, names, image_path, image_size
+
+
+def main_stage3(argv: Optional[Sequence[str]] = None) -> int:
+    from . import ops
+    logger = _logger("GridBoxCombiner")
+    p = argparse.ArgumentParser(description="Combine bounding boxes from different grid patterns")
+    p.add_argument("--input_folder", required=True)
+    p.add_argument("--output_folder", required=True)
+    p.add_argument("--iou_threshold", type=float, default=0.5)
+    p.add_argument("--viz_alpha", type=float, default=0.3)
+    args = p.parse_args(argv)
+    out_json = os.path.join(args.output_folder, "json")
+    os.makedirs(out_json, exist_ok=True)
+    os.makedirs(os.path.join(args.output_folder, "visualizations"), exist_ok=True)
+    groups = find_grid_jsons(args.input_folder)
+    if not groups:
+        logger.error(f"No JSON files found in {args.input_folder}")
+        return 0
+    pooled = []
+    for base, paths in groups.items():
+        b, s, c, n, image_path, image_size = pool_documents(paths, logger)
+        if not b:
+            logger.warning(f"No boxes found for {base}")
+            continue
+        pooled.append((base, paths, b, s, c, n, image_path, image_size))
+    if pooled:  # one batched merge for every page
+        off = np.cumsum([0] + [len(x[2]) for x in pooled])
+        boxes = np.concatenate([np.asarray(x[2], np.float64).reshape(-1, 4) for x in pooled])
+        scores = np.concatenate([np.asarray(x[3], np.float64) for x in pooled])
+        classes = np.concatenate([np.asarray(x[4], np.float64) for x in pooled])
+        ws = ops.NmsWorkspace(len(boxes), len(pooled), 64 if args.iou_threshold >= 0 else int(max(np.diff(off)) // 32 + 2))
+        kept, n_kept, ws = ops.nms_merge(boxes, scores, classes, off, args.iou_threshold, workspace=ws,
+                                         max_boxes_per_page=int(max(np.diff(off))))
+        kept, n_kept = kept.cpu().numpy(), n_kept.cpu().numpy()
+        st = ws.stats()
+        if st["status"] != 0:
+            dense = ops.NmsWorkspace(len(boxes), len(pooled), int(max(np.diff(off)) // 32 + 2))
+            kept, n_kept, ws = ops.nms_merge(boxes, scores, classes, off, args.iou_threshold, workspace=dense)
+            kept, n_kept = kept.cpu().numpy(), n_kept.cpu().numpy()
+            if ws.stats()["status"] != 0:
+                raise RuntimeError(f"pg_nms_merge failed: {ws.stats()}")
+        for i, (base, paths, b, s, c, n, image_path, image_size) in enumerate(pooled):
+            idx = (kept[off[i]: off[i] + n_kept[i]] - off[i]).tolist()
+            _dump({"image_path": image_path, "image_size": image_size,  # key order of 3:282-291
+                   "parameters": {"iou_threshold": args.iou_threshold},
+                   "boxes": [b[j] for j in idx], "classes": [c[j] for j in idx], "scores": [s[j] for j in idx],
+                   "class_names": [n[j] for j in idx], "source_jsons": paths},
+                  os.path.join(out_json, f"{base}_combined.json"))
+    logger.info(f"Processing complete. Combined results saved to {args.output_folder}")
+    return 0
+
+
+# =============================================================================================
+# stage 4
+# =============================================================================================
+def main_stage4(argv: Optional[Sequence[str]] = None) -> int:
+    from . import ops
+    from .reference_api import _flags_from_names
+    logger = _logger("MedianWidthExtractor")
+    p = argparse.ArgumentParser(description="Extract median width of plain_text boxes")
+    p.add_argument("--input_folder", required=True)
+    p.add_argument("--output_folder", required=True)
+    p.add_argument("--min_margin_percent", type=float, default=0.2)
+    p.add_argument("--no_image_check", action="store_true")
+    args = p.parse_args(argv)
+    out_json = os.path.join(args.output_folder, "json")
+    os.makedirs(out_json, exist_ok=True)
+    os.makedirs(os.path.join(args.output_folder, "visualizations"), exist_ok=True)
+    json_folder = args.input_folder  # 4:245-247
+    if not os.path.isdir(json_folder):
+        json_folder = os.path.join(args.input_folder, "json")
+    if not os.path.exists(json_folder):
+        logger.error(f"JSON folder not found: {json_folder}")
+        return 0
+    files = sorted(glob.glob(os.path.join(json_folder, "*.json")))
+    if not files:
+        logger.error(f"No JSON files found in {json_folder}")
+        return 0
+    pages = []
+    for path in files:
+        try:  # 4:103-151
+            with open(path) as f:
+                d = json.load(f)
+            size = d.get("image_size", {}) or {}
+            names, boxes = d.get("class_names", []), d.get("boxes", [])
+            n = min(len(names), len(boxes))
+            pages.append((path, d.get("image_path", ""), size.get("width", 0), size.get("height", 0), boxes[:n], names[:n]))
+        except Exception as e:
+            logger.error(f"Error processing {path}: {str(e)}")
+    live = [pg for pg in pages if len(pg[4])]
+    med = {}
+    if live:
+        off = np.cumsum([0] + [len(pg[4]) for pg in live])
+        boxes = np.concatenate([np.asarray(pg[4], np.float64).reshape(-1, 4) for pg in live])
+        flags = np.concatenate([_flags_from_names(pg[5]) for pg in live])
+        m, nb = ops.width_median(boxes, flags, off, [[pg[2], pg[3]] for pg in live], args.min_margin_percent)
+        m, nb = m.cpu().numpy(), nb.cpu().numpy()
+        med = {pg[0]: (np.float64(m[i]) if nb[i] else 0) for i, pg in enumerate(live)}
+    for path, image_path, w, h, _, _ in pages:
+        median_width = med.get(path, 0)
+        if image_path and (args.no_image_check or os.path.exists(image_path)):  # 4:272
+            base = os.path.splitext(os.path.basename(path))[0]
+            _dump({"image_path": image_path, "median_width": median_width, "page_width": w, "page_height": h,
+                   "width_ratio": median_width / w if w > 0 else 0},
+                  os.path.join(out_json, f"{base}_median_width.json"))
+    logger.info(f"Processing complete. Individual results saved to {out_json}")
+    return 0
+
+
+# =============================================================================================
+# stage 5
+# =============================================================================================
+def find_matching_median_json(layout_json_path, median_json_folder):
+    """5_detect_column_centers.py:480-539 (same fallback ladder)."""
+    base = os.path.splitext(os.path.basename(layout_json_path))[0]
+    exact = os.path.join(median_json_folder, f"{base}_median_width.json")
+    if os.path.exists(exact):
+        return exact
+    listing = sorted(os.listdir(median_json_folder)) if os.path.isdir(median_json_folder) else []
+    if "_grid_" in base:
+        prefix = base.split("_grid_")[0]
+        cand = os.path.join(median_json_folder, f"{prefix}_median_width.json")
+        if os.path.exists(cand):
+            return cand
+        for fn in listing:
+            if fn.endswith("_median_width.json") and fn.startswith(f"{prefix}_"):
+                return os.path.join(median_json_folder, fn)
+    for part in base.split("_"):
+        if part.lower().startswith("page") or (len(part) >= 4 and part.isdigit()):
+            for fn in listing:
+                if part in fn and fn.endswith("_median_width.json"):
+                    return os.path.join(median_json_folder, fn)
+    mt = re.search(r"(page[_-]?\d+)", base, re.IGNORECASE)
+    if mt:
+        for fn in listing:
+            if mt.group(1) in fn and fn.endswith("_median_width.json"):
+                return os.path.join(median_json_folder, fn)
+    med_files = [f for f in listing if f.endswith("_median_width.json")]
+    if len(med_files) == 1:
+        return os.path.join(median_json_folder, med_files[0])
+    return None
+
+
+def main_stage5(argv: Optional[Sequence[str]] = None) -> int:
+    from . import ops
+    from .reference_api import _flags_from_names
+    logger = _logger("ColumnCenterDetector")
+    p = argparse.ArgumentParser(description="Detect column centers in document pages")
+    p.add_argument("--input_folder", required=True)
+    p.add_argument("--median_folder", required=True)
+    p.add_argument("--output_folder", required=True)
+    p.add_argument("--min_confidence", type=float, default=0.3)
+    p.add_argument("--verbose", action="store_true")
+    p.add_argument("--no_image_check", action="store_true")
+    args = p.parse_args(argv)
+    os.makedirs(args.output_folder, exist_ok=True)
+    files = sorted(glob.glob(os.path.join(args.input_folder, "*.json")))
+    if not files:
+        logger.error(f"No JSON files found in {args.input_folder}")
+        return 0
+    jobs, failures = [], 0
+    for path in files:
+        mpath = find_matching_median_json(path, args.median_folder)
+        if not mpath:
+            logger.warning(f"No matching median width JSON found for {os.path.basename(path)}")
+            failures += 1
+            continue
+        try:  # 5:337-400
+            with open(path) as f:
+                layout = json.load(f)
+            with open(mpath) as f:
+                median_width = json.load(f).get("median_width", 0)
+            if median_width <= 0:
+                logger.error(f"Invalid median width: {median_width}")
+                failures += 1
+                continue
+            image_path = layout.get("image_path", "")
+            size = layout.get("image_size", {})
+            if isinstance(size, dict):
+                w, h = size.get("width", 0), size.get("height", 0)
+            elif isinstance(size, list) and len(size) >= 2:
+                w, h = size[0], size[1]
+            else:
+                w = h = 0
+            if not image_path or not (args.no_image_check or os.path.exists(image_path)) or w <= 0 or h <= 0:
+                logger.error(f"Invalid image information: {image_path}, {w}x{h}")
+                failures += 1
+                continue
+            boxes, names = layout.get("boxes", []), layout.get("class_names", [])
+            scores = layout.get("scores", [1.0] * len(boxes))
+            n = min(len(boxes), len(names), len(scores))  # zip() semantics of 5:110
+            jobs.append((path, image_path, w, h, median_width, boxes[:n], names[:n], scores[:n]))
+        except Exception as e:
+            logger.error(f"Error processing {os.path.basename(path)}: {str(e)}")
+            failures += 1
+    ok = 0
+    live = [j for j in jobs if len(j[5])]
+    results = {}
+    if live:
+        off = np.cumsum([0] + [len(j[5]) for j in live])
+        boxes = np.concatenate([np.asarray(j[5], np.float64).reshape(-1, 4) for j in live])
+        flags = np.concatenate([_flags_from_names(j[6]) for j in live])
+        scores = np.concatenate([np.asarray(j[7], np.float64) for j in live])
+        centers, widths, n_cols = ops.column_peaks(boxes, flags, scores, off, [[j[2], j[3]] for j in live],
+                                                   [float(j[4]) for j in live], args.min_confidence, max_cols=256)
+        centers, widths, n_cols = centers.cpu().numpy(), widths.cpu().numpy(), n_cols.cpu().numpy()
+        for i, j in enumerate(live):
+            if n_cols[i] < 0 or n_cols[i] > 256:
+                logger.error(f"Error processing {os.path.basename(j[0])}: page outside kernel limits")
+                continue
+            results[j[0]] = ([float(x) for x in centers[i, : n_cols[i]]], [float(x) for x in widths[i, : n_cols[i]]])
+    for path, image_path, w, h, median_width, *_ in jobs:
+        cc, cw = results.get(path, ([], []))
+        if not cc:
+            logger.warning(f"No column centers found for {os.path.basename(path)}")
+            failures += 1
+            continue
+        out_json = os.path.join(args.output_folder, "json")
+        os.makedirs(out_json, exist_ok=True)
+        os.makedirs(os.path.join(args.output_folder, "visualizations"), exist_ok=True)
+        base = os.path.splitext(os.path.basename(path))[0]
+        _dump({"image_path": image_path, "page_width": w, "page_height": h, "median_width": median_width,
+               "column_centers": cc, "column_widths": cw, "num_columns": len(cc)},  # 5:426-434
+              os.path.join(out_json, f"{base}_columns.json"))
+        ok += 1
+    logger.info(f"Processing complete. Successfully processed {ok} pages, {failures} failures.")
+    return 0
+
+
+MAINS = {"1": main_stage1, "2": main_stage2, "3": main_stage3, "4": main_stage4, "5": main_stage5}
+
+if __name__ == "__main__":
+    if len(sys.argv) < 2 or sys.argv[1] not in MAINS:
+        sys.exit("usage: python -m multimodal_embeddings_b200.cli {1,2,3,4,5} [stage args]")
+    sys.exit(MAINS[sys.argv[1]](sys.argv[2:]))

@@ -28,6 +28,28 @@ def shard_pages(n_pages_total: int, rank: int, world: int) -> range:
     return range(lo, min(n_pages_total, lo + per))
 
 
+def allreduce_histograms(hist: torch.Tensor) -> torch.Tensor:
+    """K6 — the only exchange step of the path: corpus-level integer histograms (plain_text widths,
+    column centres) summed over ranks in place.  NCCL over NVLink on GPUs (gloo in the CPU tests);
+    integer sums are order-independent, so 1/2/4/8-rank results are bit-identical."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    return hist
+
+
+def corpus_median_width(width_hist: torch.Tensor) -> float:
+    """Median of the all-reduced 1-px plain_text width histogram (lower-middle / upper-middle mean)."""
+    h = width_hist.to(torch.int64).cpu().numpy()
+    total = int(h.sum())
+    if total == 0:
+        return 0.0
+    c = np.cumsum(h)
+    lo = int(np.searchsorted(c, (total - 1) // 2 + 1))
+    hi = int(np.searchsorted(c, total // 2 + 1))
+    return (lo + hi) / 2.0
+
+
 class PagePipeline:
     def __init__(self, plan: ops.TilePlan, n_pages: int, iou_threshold: float = 0.5, edge_threshold: float = 10,
                  min_margin_percent: float = 0.2, min_confidence: float = 0.3, max_cols: int = 64,
@@ -173,9 +195,8 @@ class PagePipeline:
     def allreduce_corpus_stats(self):
         """K6: the one exchange step of the path — integer histograms summed over ranks
         (NCCL over NVLink; order-independent, so 1/2/4/8-GPU results are bit-identical)."""
-        import torch.distributed as dist
-        if self.corpus_stats and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.hist, op=dist.ReduceOp.SUM)
+        if self.corpus_stats:
+            allreduce_histograms(self.hist)
         return self.hist
 
     # ---------------------------------------------------------------- results

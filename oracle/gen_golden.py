@@ -250,6 +250,24 @@ def gen_stage45_synth(r3, r4, r5):
     return out
 
 
+def gen_cli_tree(mods):
+    """Run the reference's own main()s for stages 2-5 on a synthetic stage-1 tree (tests/cli_tree.py)
+    and record every JSON they write, with the tree root normalised."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cli_tree
+    with tempfile.TemporaryDirectory() as root:
+        cli_tree.build_stage1_tree(root)
+        argv = cli_tree.stage_argv(root)
+        old = sys.argv
+        try:
+            for stage, mod in zip((2, 3, 4, 5), mods):
+                sys.argv = [f"stage{stage}"] + argv[stage]
+                mod.main()
+        finally:
+            sys.argv = old
+        return cli_tree.collect_outputs(root)
+
+
 def main():
     global _R1
     os.makedirs(OUT, exist_ok=True)
@@ -274,6 +292,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "stage3_nms.npz"), **gen_stage3(r3))
     with open(os.path.join(OUT, "stage45_synth.json"), "w") as f:
         json.dump(gen_stage45_synth(r3, r4, r5), f, indent=1)
+    with gzip.open(os.path.join(OUT, "cli_tree.json.gz"), "wt") as f:
+        json.dump(gen_cli_tree((r2, r3, r4, r5)), f)
     print("golden fixtures written to", OUT)
 
 

@@ -1,0 +1,63 @@
+"""CPU checks of the CLI host logic (file discovery, pooling order, median-file matching, argv)."""
+import json
+import os
+
+import pytest
+
+from multimodal_embeddings_b200 import cli
+from oracle import boxes as ob
+import cli_tree
+
+
+def test_discovery_and_pooling_order(tmp_path):
+    # NB: like the reference (3:168-170) the "_grid_" / "_combined" tests look at the FULL path
+    # string, so this test must not run under a directory whose name contains them.
+    root = str(tmp_path)
+    s1 = cli_tree.build_stage1_tree(root)
+    groups = cli.find_grid_jsons(s1)
+    assert sorted(groups) == sorted(p[0] for p in cli_tree.PAGES)
+    for base, paths in groups.items():
+        assert [os.path.basename(p) for p in paths] == [f"{base}.json", f"{base}_grid_2x2.json"]  # standard first (3:175)
+        docs = [json.load(open(p)) for p in paths]
+        mine = cli.pool_documents(paths, cli._logger("GridBoxCombiner"))
+        ref = ob.pool_boxes(docs)
+        assert list(mine) == list(ref)
+        assert mine[5] == docs[0]["image_size"]
+    # '_combined' files are never re-pooled (3:170)
+    open(os.path.join(s1, "json", "x_combined.json"), "w").write("{}")
+    assert "x_combined" not in cli.find_grid_jsons(s1)
+
+
+def test_find_matching_median_json_ladder(tmp_path):
+    med = tmp_path / "med"
+    med.mkdir()
+    for n in ("a_page_0001_combined_median_width.json", "b_page_0002_median_width.json"):
+        (med / n).write_text("{}")
+    f = cli.find_matching_median_json
+    assert f("/x/a_page_0001_combined.json", str(med)).endswith("a_page_0001_combined_median_width.json")
+    assert f("/x/b_page_0002_grid_2x2.json", str(med)).endswith("b_page_0002_median_width.json")
+    assert f("/x/zzz_0002_other.json", str(med)).endswith("b_page_0002_median_width.json")  # digit-part fallback
+    assert f("/x/nomatch.json", str(med)) is None
+    (med / "a_page_0001_combined_median_width.json").unlink()
+    assert f("/x/nomatch.json", str(med)).endswith("b_page_0002_median_width.json")  # single file fallback
+
+
+def test_stage_argv_surfaces_match_reference():
+    # every flag of the reference CLIs is accepted (run.sh:60-70)
+    for main, argv in (
+        (cli.main_stage3, ["--input_folder", "/nonexistent_in", "--output_folder", "{out}", "--iou_threshold", "0.4",
+                           "--viz_alpha", "0.5"]),
+        (cli.main_stage4, ["--input_folder", "/nonexistent_in", "--output_folder", "{out}", "--min_margin_percent", "0.3"]),
+        (cli.main_stage5, ["--input_folder", "/nonexistent_in", "--median_folder", "/nonexistent_m", "--output_folder",
+                           "{out}", "--min_confidence", "0.25", "--verbose"]),
+    ):
+        import tempfile
+        with tempfile.TemporaryDirectory() as out:
+            try:
+                rc = main([a.replace("{out}", out) for a in argv])
+            except FileNotFoundError:
+                rc = 0  # stage 3 lists the (missing) input folder like the reference does
+            assert rc == 0
+    with pytest.raises(SystemExit):
+        cli.main_stage2(["--input_folder", "x"])  # --output_folder is required
+    assert cli.get_image_paths("/nonexistent") == []

@@ -1,0 +1,70 @@
+"""Drop-in check at the CLI level: this repo's numbered stage mains run on the same synthetic
+stage-1 tree the reference's own main()s were run on (oracle/gen_golden.py -> cli_tree.json.gz);
+every JSON file they write must be identical — same files, same key order, same numbers."""
+import json
+
+import pytest
+
+from conftest import load_golden
+from multimodal_embeddings_b200 import cli
+import cli_tree
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cli_stages_2_to_5_match_reference_outputs(tmp_path):
+    golden = load_golden("cli_tree.json.gz")
+    root = str(tmp_path)
+    cli_tree.build_stage1_tree(root)
+    argv = cli_tree.stage_argv(root)
+    for stage, main in ((2, cli.main_stage2), (3, cli.main_stage3), (4, cli.main_stage4), (5, cli.main_stage5)):
+        assert main(argv[stage]) == 0
+    got = cli_tree.collect_outputs(root)
+    assert sorted(got) == sorted(golden)
+    for name in golden:
+        assert json.loads(got[name]) == json.loads(golden[name]), name
+        assert got[name] == golden[name], f"{name}: key order / number formatting differs"
+
+
+def test_cli_stage1_writes_reference_schema(tmp_path):
+    import numpy as np
+    from PIL import Image
+    from multimodal_embeddings_b200 import synth
+    from oracle import tiler as ot
+    src = tmp_path / "in"
+    src.mkdir()
+    w, h = 1500, 1100
+    Image.fromarray(synth.page_pixels(w, h, 9)[..., ::-1].copy()).save(src / "scan A.png")
+    out = tmp_path / "out"
+    assert cli.main_stage1(["--input_folder", str(src), "--output_folder", str(out), "--grids", "2x2,3x3",
+                            "--boxes_per_page", "300", "--imgsz", "512"]) == 0
+    std = json.load(open(out / "json" / "scan A.json"))
+    assert list(std) == ["image_path", "image_size", "parameters", "boxes", "classes", "scores", "class_names"]
+    assert std["image_size"] == {"width": w, "height": h}
+    for rows, cols in ((2, 2), (3, 3)):
+        gi = json.load(open(out / "json" / f"scan A_grid_{rows}x{cols}.json"))
+        assert list(gi) == ["original_image_path", "grid_config", "cells"]
+        assert gi["grid_config"] == {"rows": rows, "cols": cols, "overlap_percentage": 20.0}
+        ref_cells = ot.grid_cells(w, h, rows, cols, 20.0)
+        assert len(gi["cells"]) == rows * cols
+        for cell, ref in zip(gi["cells"], ref_cells):
+            assert list(cell) == ["cell_path", "cell_json_path", "cell_coordinates", "row", "col", "regions"]
+            assert cell["cell_coordinates"] == ref["coordinates"] and (cell["row"], cell["col"]) == (ref["row"], ref["col"])
+            assert list(cell["regions"]) == ["boxes", "boxes_original", "classes", "scores", "class_names"]
+            assert cell["regions"]["boxes_original"] == ot.translate_boxes(cell["regions"]["boxes"], ref["coordinates"])
+            per_cell = json.load(open(cell["cell_json_path"]))
+            assert per_cell["grid_info"] == {"rows": rows, "cols": cols, "row": ref["row"], "col": ref["col"]}
+            assert per_cell["boxes_original"] == cell["regions"]["boxes_original"]
+    # the whole chain runs on what stage 1 wrote
+    for stage, main, argv in (
+            (2, cli.main_stage2, ["--input_folder", str(out), "--output_folder", str(tmp_path / "s2")]),
+            (3, cli.main_stage3, ["--input_folder", str(tmp_path / "s2"), "--output_folder", str(tmp_path / "s3")]),
+            (4, cli.main_stage4, ["--input_folder", str(tmp_path / "s3" / "json"), "--output_folder", str(tmp_path / "s4")]),
+            (5, cli.main_stage5, ["--input_folder", str(tmp_path / "s3" / "json"), "--median_folder",
+                                  str(tmp_path / "s4" / "json"), "--output_folder", str(tmp_path / "s5")])):
+        assert main(argv) == 0
+    comb = json.load(open(tmp_path / "s3" / "json" / "scan A_combined.json"))
+    assert list(comb) == ["image_path", "image_size", "parameters", "boxes", "classes", "scores", "class_names",
+                          "source_jsons"]
+    assert comb["scores"] == sorted(comb["scores"], reverse=True) and len(comb["boxes"]) > 10
+    assert (tmp_path / "s4" / "json" / "scan A_combined_median_width.json").exists()

@@ -43,6 +43,7 @@ extern "C" {
 
 #define PG_WIDTH_HIST_BINS 16384 /* corpus width histogram: 1-px bins            */
 #define PG_COL_HIST_BINS 1001    /* corpus column histogram: per-mille of page W */
+#define PG_COL_SPAN_BYTES 32     /* pg_column_peaks scratch: bytes per input box      */
 
 const char* pg_last_error(void);
 int pg_version(void);
@@ -156,7 +157,9 @@ int pg_column_peaks(const double* boxes, const uint8_t* flags, const double* sco
                     int32_t max_window, double min_confidence, int32_t max_cols,
                     int32_t* centers /*dev [P,max_cols]*/, double* widths /*dev [P,max_cols]*/,
                     int32_t* n_cols /*dev [P]; <0 = unsupported shape*/,
-                    double* ws /*dev [P, 2*max_bins]*/, int32_t max_bins,
+                    double* ws /*dev [P, 2*max_bins]: density, smoothed density*/, int32_t max_bins,
+                    void* ws_spans /*dev, PG_COL_SPAN_BYTES * N, 16-byte aligned*/,
+                    int32_t* ws_span_counts /*dev [P]*/,
                     uint32_t* col_hist /*dev [PG_COL_HIST_BINS] or NULL*/, void* stream);
 
 /* ------------------------------------------------------------------ test hooks

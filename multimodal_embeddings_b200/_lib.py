@@ -16,6 +16,7 @@ PG_FLAG_PLAIN_TEXT = 1
 PG_FLAG_TITLE = 2
 PG_WIDTH_HIST_BINS = 16384
 PG_COL_HIST_BINS = 1001
+PG_COL_SPAN_BYTES = 32
 
 
 class PgTileInfo(C.Structure):
@@ -58,7 +59,7 @@ SIGNATURES = {
     "pg_class_flags": (C.c_int, [_P, _I64, _F64, _F64, _P, _P]),
     "pg_width_median": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I64, _P, _F64, _P, _P, _P, _P, _P, _P]),
     "pg_column_peaks": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I32, _F64, _I32,
-                                  _P, _P, _P, _P, _I32, _P, _P]),
+                                  _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
     "pg_hostcheck_iou": (_F64, [_P, _P]),
     "pg_hostcheck_iou_gt": (_I32, [_P, _P, _F64]),
     "pg_hostcheck_edge_touch": (_I32, [_P, _P, _I32, _I32, _F64]),

@@ -411,18 +411,28 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(NmsWs ws, double thr) {
       __syncwarp();
       jb[wib][lane] = ws.sbox[(int64_t)J * 32 + lane];
       __syncwarp();
-      uint32_t mask = 0;
+      // phase 1 (cheap, branch-free, every jj): boxes of J that outrank i (:112), share its class (:130)
+      // and are not disjoint from it (:65) — the only ones whose IoU can exceed thr >= 0
+      uint32_t cand = 0;
       const int ik = (int)bi.k;
-      if (ik >= 0) {
-#pragma unroll 4
-        for (int jj = 0; jj < 32; ++jj) {
-          const SBox bj = jb[wib][jj];  // broadcast LDS.128 x4
-          const int jk = (int)bj.k;
-          // j must outrank i: higher score, or equal score and earlier pooled position (:112)
-          const bool outranks = (bj.score > bi.score) || (bj.score == bi.score && jk < ik);
-          if (jk >= 0 && outranks && bj.cls == bi.cls &&
-              pg_iou_gt(bj.x0, bj.y0, bj.x1, bj.y1, bj.area, bi.x0, bi.y0, bi.x1, bi.y1, bi.area, thr))
-            mask |= 1u << jj;
+      const bool need_disjoint_too = !(thr >= 0.0);  // thr < 0: IoU 0 already suppresses
+#pragma unroll 8
+      for (int jj = 0; jj < 32; ++jj) {
+        const SBox bj = jb[wib][jj];  // broadcast LDS.128 x4
+        const int jk = (int)bj.k;
+        const bool outranks = (bj.score > bi.score) || (bj.score == bi.score && jk < ik);
+        const bool apart = bj.x1 < bi.x0 || bi.x1 < bj.x0 || bj.y1 < bi.y0 || bi.y1 < bj.y0;
+        const bool c = (jk >= 0) & (ik >= 0) & outranks & (bj.cls == bi.cls) & (!apart | need_disjoint_too);
+        cand |= (c ? 1u : 0u) << jj;
+      }
+      // phase 2 (exact predicate, only on the set bits; lanes walk their own bit lists)
+      uint32_t mask = 0;
+      while (__any_sync(0xffffffffu, cand != 0)) {
+        if (cand) {
+          const int jj = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const SBox bj = jb[wib][jj];
+          if (pg_iou_gt(bj.x0, bj.y0, bj.x1, bj.y1, bj.area, bi.x0, bi.y0, bi.x1, bi.y1, bi.area, thr)) mask |= 1u << jj;
         }
       }
       const bool any = __any_sync(0xffffffffu, mask != 0);
@@ -851,29 +861,30 @@ struct __align__(16) DenEntry {
   double half, inv_half;
 };
 
-__global__ void __launch_bounds__(DEN_THREADS) column_density_kernel(
+// (a1) prep: one CTA per page turns the page's boxes into the ordered list of accepted bin spans
+__global__ void __launch_bounds__(DEN_THREADS) column_prep_kernel(
     const double* __restrict__ boxes, const uint8_t* __restrict__ flags, const double* __restrict__ scores,
     const int32_t* __restrict__ sel_idx, const int64_t* __restrict__ page_off, const int32_t* __restrict__ n_sel,
     const int32_t* __restrict__ page_wh, const double* __restrict__ median, int max_window, double min_conf,
-    double* ws_all, int max_bins) {
-  __shared__ DenEntry elist[DEN_THREADS];
+    int max_bins, DenEntry* __restrict__ list, int32_t* __restrict__ list_n) {
   __shared__ int scan_smem[34];
-  const int p = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p = blockIdx.x, tid = threadIdx.x;
   const int W = page_wh[2 * p], Hh = page_wh[2 * p + 1];
   const double med = median[p];
   const ColGeom g = col_geom(W, Hh, med, max_bins, max_window);
-  if (!g.ok || !g.in_range || (int)blockIdx.x * DEN_THREADS >= g.nbins) return;
+  if (!g.ok || !g.in_range) {
+    if (tid == 0) list_n[p] = 0;
+    return;
+  }
   const int64_t base = page_off[p];
   const int m = n_sel ? n_sel[p] : (int)(page_off[p + 1] - base);
-  const int seg0 = ((int)blockIdx.x * (DEN_THREADS / 32) + warp) * 32;
-  const int bin = seg0 + lane;
   const double lo_w = 0.33 * med, hi_w = 2.0 * med;  // :131
-  double d = 0.0;
+  int running = 0;
   for (int c0 = 0; c0 < m; c0 += DEN_THREADS) {
     const int k = c0 + tid;
     int acc = 0;
     DenEntry ent;
-    ent.left = 1; ent.right = 0; ent.center = 0; ent.pad = 0; ent.half = 1.0; ent.inv_half = 1.0;
+    ent.left = 1; ent.right = -1; ent.center = 0; ent.pad = 0; ent.half = 1.0; ent.inv_half = 1.0;
     if (k < m) {
       const int64_t gi = sel_idx ? (int64_t)sel_idx[base + k] : base + k;
       if ((flags[gi] & (PG_FLAG_PLAIN_TEXT | PG_FLAG_TITLE)) && scores[gi] >= min_conf) {  // :110-112
@@ -896,28 +907,51 @@ __global__ void __launch_bounds__(DEN_THREADS) column_density_kernel(
     }
     int total;
     const int ex = pg_block_exscan(acc, scan_smem, &total);
-    if (acc) elist[ex] = ent;
-    __syncthreads();
-    for (int e0 = 0; e0 < total; e0 += 32) {
-      const int e = e0 + lane;
-      int L = 1, R = -1;  // padding lanes overlap nothing (R < 0 <= seg0)
-      if (e < total) { L = elist[e].left; R = elist[e].right; }
-      unsigned bits = __ballot_sync(0xffffffffu, L <= seg0 + 31 && R >= seg0);
-      while (bits) {
-        const int l = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const DenEntry en = elist[e0 + l];  // broadcast
-        if (bin >= en.left && bin <= en.right) {  // :139-144, contributions added in box order
-          const double wgt = en.pad ? pg_density_weight(bin, en.left, en.right, en.center)
-                                    : pg_density_weight_rcp(bin, en.center, en.half, en.inv_half);
-          d = d + wgt;
-        }
+    if (acc) list[base + running + ex] = ent;
+    running += total;
+  }
+  if (tid == 0) list_n[p] = running;
+}
+
+// (a2) density: each warp owns 32 bins and streams the page's span list in order
+__global__ void __launch_bounds__(DEN_THREADS) column_density_kernel(
+    const int64_t* __restrict__ page_off, const int32_t* __restrict__ page_wh, const double* __restrict__ median,
+    int max_window, const DenEntry* __restrict__ list, const int32_t* __restrict__ list_n, double* ws_all,
+    int max_bins) {
+  __shared__ DenEntry stage[DEN_THREADS / 32][32];
+  const int p = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const ColGeom g = col_geom(page_wh[2 * p], page_wh[2 * p + 1], median[p], max_bins, max_window);
+  if (!g.ok || !g.in_range || (int)blockIdx.x * DEN_THREADS >= g.nbins) return;
+  const DenEntry* lst = list + page_off[p];
+  const int n = list_n[p];
+  const int seg0 = ((int)blockIdx.x * (DEN_THREADS / 32) + warp) * 32;
+  const int bin = seg0 + lane;
+  double d = 0.0;
+  for (int e0 = 0; e0 < n; e0 += 32) {
+    const int e = e0 + lane;
+    int L = 1, R = -1;  // padding lanes overlap nothing (R < 0 <= seg0)
+    __syncwarp();
+    if (e < n) {
+      const DenEntry mine = lst[e];
+      stage[warp][lane] = mine;
+      L = mine.left; R = mine.right;
+    }
+    __syncwarp();
+    unsigned bits = __ballot_sync(0xffffffffu, L <= seg0 + 31 && R >= seg0);
+    while (bits) {
+      const int l = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const DenEntry en = stage[warp][l];  // broadcast
+      if (bin >= en.left && bin <= en.right) {  // :139-144, contributions added in box order
+        const double wgt = en.pad ? pg_density_weight(bin, en.left, en.right, en.center)
+                                  : pg_density_weight_rcp(bin, en.center, en.half, en.inv_half);
+        d = d + wgt;
       }
     }
-    __syncthreads();
   }
   if (bin < g.nbins) ws_all[(int64_t)p * 2 * max_bins + bin] = d;
 }
+
 
 __device__ __forceinline__ double block_max_d(double v, double* red) {
   v = warp_max_d(v);
@@ -1094,18 +1128,25 @@ extern "C" int pg_column_peaks(const double* boxes, const uint8_t* flags, const 
                                int32_t n_pages, const int32_t* page_wh, const double* median,
                                const double* gauss_table, const int64_t* gauss_off, int32_t max_window,
                                double min_confidence, int32_t max_cols, int32_t* centers, double* widths,
-                               int32_t* n_cols, double* ws, int32_t max_bins, uint32_t* col_hist, void* stream) {
+                               int32_t* n_cols, double* ws, int32_t max_bins, void* ws_spans,
+                               int32_t* ws_span_counts, uint32_t* col_hist, void* stream) {
   PG_REQUIRE(n_pages >= 0, "n_pages");
   if (n_pages == 0) return PG_OK;
   PG_REQUIRE(boxes && flags && scores && page_off && page_wh && median && gauss_table && gauss_off && centers &&
-                 widths && n_cols && ws,
+                 widths && n_cols && ws && ws_spans && ws_span_counts,
              "null device pointer");
   PG_REQUIRE(max_cols > 0 && max_cols <= COL_MAX_PEAKS && max_bins > 0 && max_window > 0, "limits");
   PG_REQUIRE(n_pages <= 65535, "n_pages per launch must be <= 65535");
+  PG_REQUIRE(((uintptr_t)ws_spans & 15) == 0, "ws_spans must be 16-byte aligned");
+  static_assert(sizeof(DenEntry) == PG_COL_SPAN_BYTES, "PG_COL_SPAN_BYTES must match DenEntry");
   cudaStream_t s = (cudaStream_t)stream;
+  DenEntry* spans = reinterpret_cast<DenEntry*>(ws_spans);
+  column_prep_kernel<<<n_pages, DEN_THREADS, 0, s>>>(boxes, flags, scores, sel_idx, page_off, n_sel, page_wh, median,
+                                                    max_window, min_confidence, max_bins, spans, ws_span_counts);
+  PG_LAUNCH_CHECK();
   const int gx = (min(max_bins, COL_THREADS * COL_BPT) + DEN_THREADS - 1) / DEN_THREADS;
   column_density_kernel<<<dim3((unsigned)gx, (unsigned)n_pages), DEN_THREADS, 0, s>>>(
-      boxes, flags, scores, sel_idx, page_off, n_sel, page_wh, median, max_window, min_confidence, ws, max_bins);
+      page_off, page_wh, median, max_window, spans, ws_span_counts, ws, max_bins);
   PG_LAUNCH_CHECK();
   column_peaks_kernel<<<n_pages, COL_THREADS, 0, s>>>(page_wh, median, gauss_table, gauss_off, max_window, max_cols,
                                                      centers, widths, n_cols, ws, max_bins, col_hist);

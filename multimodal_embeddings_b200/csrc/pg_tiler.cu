@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -330,8 +331,10 @@ __device__ __forceinline__ uint32_t pack_unit_half2(uint32_t va, uint32_t vb) {
 // K1 persistent pipeline kernel
 constexpr int TL_CW = 8;                     // consumer warps
 constexpr int TL_THREADS = 32 * (TL_CW + 1);  // + producer warp
-constexpr int TL_STAGES = 4;
-constexpr int TL_ITEMS_PER_CTA = 8;           // bands of TL_BAND rows a CTA claims before retiring
+// Measured on B200 (cfg3, 64 pages): ring depth 3 -> 4 CTAs/SM, 2.22 ms (0.97 of HBM peak) vs depth 4 ->
+// 3 CTAs/SM, 2.26 ms; claiming <= 4 bands per CTA beats 8/16/64 (2.26 / 2.28 / 2.39 ms at depth 4).
+constexpr int TL_STAGES_DEFAULT = 3;         // shared-memory ring depth (template parameter TL_STAGES)
+constexpr int TL_ITEMS_PER_CTA = 4;           // bands of TL_BAND rows a CTA claims before retiring
 constexpr int TL_PAIR_STRIDE = TL_CW * 64;    // pixels covered by all consumer warps per iteration
 
 struct TilerArgs {
@@ -384,7 +387,7 @@ __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const ui
   }
 }
 
-template <int ITER>
+template <int ITER, int TL_STAGES>
 __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const TilerArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[TL_STAGES];
@@ -581,7 +584,7 @@ static TilerArgs make_args(const PgTilePlan* plan, const uint8_t* pages, int32_t
   return a;
 }
 
-template <int ITER>
+template <int ITER, int TL_STAGES>
 static int launch_pipeline(TilerArgs a, cudaStream_t s) {
   const size_t smem = (size_t)TL_STAGES * 2 * a.row_stride;
   int dev = 0, sms = 0, max_smem = 0;
@@ -592,9 +595,10 @@ static int launch_pipeline(TilerArgs a, cudaStream_t s) {
     pg_set_error("unsupported: tile rows of %d bytes need %zu B of shared memory (max %d)", a.row_stride, smem, max_smem);
     return PG_ERR_UNSUPPORTED;
   }
-  PG_CUDA_TRY(cudaFuncSetAttribute(tile_letterbox_kernel<ITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kernel = tile_letterbox_kernel<ITER, TL_STAGES>;
+  PG_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  PG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_letterbox_kernel<ITER>, TL_THREADS, smem));
+  PG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TL_THREADS, smem));
   if (per_sm < 1) {
     pg_set_error("unsupported: tiler kernel does not fit on an SM");
     return PG_ERR_UNSUPPORTED;
@@ -604,7 +608,9 @@ static int launch_pipeline(TilerArgs a, cudaStream_t s) {
   // slots while the tiler is still streaming.  Small launches get 1 item per CTA to fill the chip.
   const int64_t slots = (int64_t)sms * per_sm;
   int64_t ipc = a.total_items / (slots * 4);
-  ipc = ipc < 1 ? 1 : (ipc > TL_ITEMS_PER_CTA ? TL_ITEMS_PER_CTA : ipc);
+  int64_t ipc_max = TL_ITEMS_PER_CTA;
+  if (const char* e = getenv("PG_TILER_IPC")) ipc_max = atoi(e) > 0 ? atoi(e) : ipc_max;  // tuning knob
+  ipc = ipc < 1 ? 1 : (ipc > ipc_max ? ipc_max : ipc);
   a.items_per_cta = (int32_t)ipc;
   const int64_t grid = (a.total_items + ipc - 1) / ipc;
   if (grid < 1) return PG_OK;
@@ -612,7 +618,7 @@ static int launch_pipeline(TilerArgs a, cudaStream_t s) {
     pg_set_error("unsupported: %lld work items in one launch", (long long)a.total_items);
     return PG_ERR_UNSUPPORTED;
   }
-  tile_letterbox_kernel<ITER><<<(unsigned)grid, TL_THREADS, smem, s>>>(a);
+  kernel<<<(unsigned)grid, TL_THREADS, smem, s>>>(a);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
@@ -627,9 +633,17 @@ extern "C" int pg_tile_letterbox(PgTilePlan* plan, const uint8_t* pages, int32_t
   if (rc != PG_OK) return rc;
   const TilerArgs a = make_args(plan, pages, n_pages, pitch, page_stride, out_f16, out_page_stride);
   const int iters = (plan->max_out_w + TL_PAIR_STRIDE - 1) / TL_PAIR_STRIDE;
-  if (iters <= 1) return launch_pipeline<1>(a, s);
-  if (iters <= 2) return launch_pipeline<2>(a, s);
-  if (iters <= 4) return launch_pipeline<4>(a, s);
+  int stages = TL_STAGES_DEFAULT;
+  if (const char* e = getenv("PG_TILER_STAGES")) stages = atoi(e);  // tuning knob: 3 (4 CTAs/SM) or 4 (3 CTAs/SM)
+  if (stages == 3) {
+    if (iters <= 1) return launch_pipeline<1, 3>(a, s);
+    if (iters <= 2) return launch_pipeline<2, 3>(a, s);
+    if (iters <= 4) return launch_pipeline<4, 3>(a, s);
+  } else {
+    if (iters <= 1) return launch_pipeline<1, 4>(a, s);
+    if (iters <= 2) return launch_pipeline<2, 4>(a, s);
+    if (iters <= 4) return launch_pipeline<4, 4>(a, s);
+  }
   pg_set_error("unsupported: output width %d > %d", plan->max_out_w, 4 * TL_PAIR_STRIDE);
   return PG_ERR_UNSUPPORTED;
 }

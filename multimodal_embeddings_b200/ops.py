@@ -299,10 +299,12 @@ def column_peaks(boxes, flags, scores, page_off, page_wh, median, min_confidence
     widths = torch.zeros((max(p, 1), max_cols), dtype=torch.float64, device="cuda")
     n_cols = torch.zeros(max(p, 1), dtype=torch.int32, device="cuda")
     ws = torch.empty((max(p, 1), 2 * max_bins), dtype=torch.float64, device="cuda")
+    ws_spans = torch.empty(max(boxes.shape[0], 1) * _lib.PG_COL_SPAN_BYTES, dtype=torch.uint8, device="cuda")
+    ws_span_counts = torch.zeros(max(p, 1), dtype=torch.int32, device="cuda")
     check(lib().pg_column_peaks(ptr(boxes), ptr(flags), ptr(scores), ptr(sel_idx), ptr(page_off), ptr(n_sel), p,
                                 ptr(page_wh_t), ptr(median), ptr(gt.table), ptr(gt.offsets), gt.max_window,
                                 float(min_confidence), max_cols, ptr(centers), ptr(widths), ptr(n_cols), ptr(ws),
-                                max_bins, ptr(col_hist), stream_ptr(stream)))
+                                max_bins, ptr(ws_spans), ptr(ws_span_counts), ptr(col_hist), stream_ptr(stream)))
     if return_ws:  # [P, 2, max_bins]: density map and smoothed density (debug / tests)
         return centers[:p], widths[:p], n_cols[:p], ws.view(-1, 2, max_bins)[:p]
     return centers[:p], widths[:p], n_cols[:p]

@@ -10,15 +10,16 @@ ranks with no collective; only the optional corpus histograms are all-reduced.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 import torch
 
 from . import ops
-from ._lib import PG_COL_HIST_BINS, PG_WIDTH_HIST_BINS, check, lib, ptr, stream_ptr
+from ._lib import PG_COL_HIST_BINS, PG_COL_SPAN_BYTES, PG_WIDTH_HIST_BINS, check, lib, ptr, stream_ptr
 
-KERNELS_PER_STEP = 11  # tiler, edge filter, 5 NMS kernels, class flags, width median, column density + peaks
+KERNELS_PER_STEP = 12  # tiler, edge filter, 5 NMS kernels, class flags, width median, column prep + density + peaks
 
 
 def shard_pages(n_pages_total: int, rank: int, world: int) -> range:
@@ -127,6 +128,8 @@ class PagePipeline:
         self.col_widths = torch.zeros((p, self.max_cols), dtype=torch.float64, device=dev)
         self.n_cols = torch.zeros(p, dtype=torch.int32, device=dev)
         self.col_ws = torch.empty((p, 2 * self.max_bins), dtype=torch.float64, device=dev)
+        self.col_spans = torch.empty(m * PG_COL_SPAN_BYTES, dtype=torch.uint8, device=dev)
+        self.col_span_n = torch.zeros(p, dtype=torch.int32, device=dev)
         self.nms_ws = ops.NmsWorkspace(n, p)
 
     def upload_detections(self, host: Dict[str, np.ndarray], stream=None, pinned: Optional[dict] = None) -> int:
@@ -153,10 +156,16 @@ class PagePipeline:
             start.record(main)
             self.s_box.wait_event(start)
             self.s_tiler.wait_event(start)
-            self._run_boxes(self.s_box)       # queued first: its kernels outrank the tiler's CTAs
-            box_done.record(self.s_box)
-            self._run_tiler(pages, self.s_tiler, tiler_events)
-            tiler_done.record(self.s_tiler)
+            if os.environ.get("PG_TILER_FIRST") == "1":  # tuning knob
+                self._run_tiler(pages, self.s_tiler, tiler_events)
+                tiler_done.record(self.s_tiler)
+                self._run_boxes(self.s_box)
+                box_done.record(self.s_box)
+            else:
+                self._run_boxes(self.s_box)       # queued first: its kernels outrank the tiler's CTAs
+                box_done.record(self.s_box)
+                self._run_tiler(pages, self.s_tiler, tiler_events)
+                tiler_done.record(self.s_tiler)
             main.wait_event(box_done)
             main.wait_event(tiler_done)
         else:
@@ -190,7 +199,8 @@ class PagePipeline:
                                 ptr(self.page_off), ptr(self.n_kept2), p, ptr(self.page_wh), ptr(self.median),
                                 ptr(self.gauss.table), ptr(self.gauss.offsets), self.gauss.max_window,
                                 self.min_confidence, self.max_cols, ptr(self.centers), ptr(self.col_widths),
-                                ptr(self.n_cols), ptr(self.col_ws), self.max_bins, ptr(self.col_hist), s))
+                                ptr(self.n_cols), ptr(self.col_ws), self.max_bins, ptr(self.col_spans), ptr(self.col_span_n),
+                                ptr(self.col_hist), s))
 
     def allreduce_corpus_stats(self):
         """K6: the one exchange step of the path — integer histograms summed over ranks

@@ -317,7 +317,23 @@ def main():
     roofline = {"bound": "hbm", "kernel": "tile_letterbox_kernel", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": tiler_bytes, "kernel_ms_per_launch": tiler_ms / max(1, len(pipes)),
-                "kernel_share_of_step": tiler_ms / (ms / args.steps)}
+                "kernel_share_of_step": tiler_ms / (ms / args.steps),
+                "timed": "inside the timed region" + ("" if args.no_overlap or args.tiler_only
+                                                      else ", while the box-stage kernels share the SMs on the other stream")}
+    if not args.tiler_only and not args.no_overlap:
+        # the same kernel with the GPU to itself (separate short loop after the timed region; burst peak applies)
+        ia, ib = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_iso = 5
+        torch.cuda.synchronize()
+        ia.record(stream)
+        for _ in range(n_iso):
+            for plan, pipe, pages, _, _ in pipes:
+                plan.run(pages, out=pipe.tiles_out)
+        ib.record(stream)
+        torch.cuda.synchronize()
+        iso_ms = ia.elapsed_time(ib) / n_iso
+        roofline["isolated"] = {"achieved": tiler_bytes / (iso_ms * 1e-3) / 1e9, "frac": tiler_bytes / (iso_ms * 1e-3) / 1e9 / peak,
+                                "kernel_ms_per_launch": iso_ms / max(1, len(pipes)), "launches": n_iso * len(pipes)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

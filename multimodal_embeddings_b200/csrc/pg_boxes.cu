@@ -105,6 +105,8 @@ struct NmsWs {
   int32_t* cellid;     // [N]
   SBox* sbox;          // [NB*32]
   double* bbox;        // [NB*4]
+  float4* bboxf;       // [NB]    the same, rounded outwards to fp32 (conservative prefilter only)
+  float4* subbox;      // [NB*4]  outward-rounded fp32 bounds of each run of 8 boxes inside a block
   int32_t* blk_page;   // [NB]
   int32_t* cand_cnt;   // [NB]
   int64_t* cand_off;   // [NB+1]
@@ -137,6 +139,8 @@ static size_t nms_layout(int64_t n, int32_t n_pages, int32_t pairs_per_block, ui
   w.cellid = (int32_t*)take((size_t)n * 4);
   w.sbox = (SBox*)take((size_t)nb * 32 * sizeof(SBox));
   w.bbox = (double*)take((size_t)nb * 4 * 8);
+  w.bboxf = (float4*)take((size_t)nb * sizeof(float4));
+  w.subbox = (float4*)take((size_t)nb * 4 * sizeof(float4));
   w.blk_page = (int32_t*)take((size_t)nb * 4);
   w.cand_cnt = (int32_t*)take((size_t)nb * 4);
   w.cand_off = (int64_t*)take((size_t)(nb + 1) * 8);
@@ -330,8 +334,19 @@ __global__ void __launch_bounds__(1024) nms_bin_kernel(const double* __restrict_
     if (lane == 0) {
       double* bb = ws.bbox + 4 * (sp.blk0 + b);
       bb[0] = bx0; bb[1] = by0; bb[2] = bx1; bb[3] = by1;
+      ws.bboxf[sp.blk0 + b] = make_float4(__double2float_rd(bx0), __double2float_rd(by0), __double2float_ru(bx1),
+                                          __double2float_ru(by1));
       ws.blk_page[sp.blk0 + b] = p;
     }
+    // bounds of each run of 8 boxes, rounded outwards: lets the mask kernel skip 8 pair tests at a time
+    float gx0 = valid ? __double2float_rd(fmin(sb.x0, sb.x1)) : FLT_MAX, gy0 = valid ? __double2float_rd(fmin(sb.y0, sb.y1)) : FLT_MAX;
+    float gx1 = valid ? __double2float_ru(fmax(sb.x0, sb.x1)) : -FLT_MAX, gy1 = valid ? __double2float_ru(fmax(sb.y0, sb.y1)) : -FLT_MAX;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      gx0 = fminf(gx0, __shfl_xor_sync(0xffffffffu, gx0, o)); gy0 = fminf(gy0, __shfl_xor_sync(0xffffffffu, gy0, o));
+      gx1 = fmaxf(gx1, __shfl_xor_sync(0xffffffffu, gx1, o)); gy1 = fmaxf(gy1, __shfl_xor_sync(0xffffffffu, gy1, o));
+    }
+    if ((lane & 7) == 0) ws.subbox[(sp.blk0 + b) * 4 + (lane >> 3)] = make_float4(gx0, gy0, gx1, gy1);
   }
 }
 
@@ -389,50 +404,96 @@ __global__ void __launch_bounds__(256) nms_cand_kernel(const int64_t* __restrict
 
 // ---- C: masks ------------------------------------------------------------------------------
 // Persistent grid over candidate entries (each entry = 32x32 box pairs, so the work is balanced
-// whatever the spread of candidates per block).  Lane i holds box i of block I, the 32 boxes of J
-// are broadcast from shared memory, and lane i accumulates the mask of boxes of J that outrank it,
-// share its class and overlap it by more than thr.
+// whatever the spread of candidates per block).  Lane i holds box i of block I; the boxes of J sit in
+// shared memory twice: as 32-byte prefilter records (outward-rounded fp32 bounds, score, position,
+// class hash — broadcast reads, 2x LDS.128 per box) and in full.  Phase 1 marks, per lane, the boxes
+// of J that outrank box i (:112), may share its class (:130) and are not provably disjoint from it
+// (:65); runs of 8 boxes of J whose bounds miss block I are skipped warp-wide.  Phase 2 evaluates the
+// exact predicate (exact class compare, pg_iou_gt) on the marked pairs only.  The kernel is bound by
+// shared-memory bandwidth, hence the compact records.
 constexpr int MASK_UNIT = 4;  // consecutive entries per work unit (mostly the same I)
+struct __align__(16) SLite {
+  float x0, y0, x1, y1;  // box rounded outwards: disjoint here => disjoint in fp64
+  double score;
+  int k;                 // pooled position, -1 = padding lane
+  uint32_t ch;           // class hash: equal classes => equal hashes
+};
+__device__ __forceinline__ SLite slite_of(const SBox& b) {
+  SLite s;
+  s.x0 = __double2float_rd(fmin(b.x0, b.x1)); s.y0 = __double2float_rd(fmin(b.y0, b.y1));
+  s.x1 = __double2float_ru(fmax(b.x0, b.x1)); s.y1 = __double2float_ru(fmax(b.y0, b.y1));
+  s.score = b.score;
+  s.k = (int)b.k;
+  const double c = (b.cls == 0.0) ? 0.0 : b.cls;  // -0.0 == +0.0 must hash alike
+  const unsigned long long u = (unsigned long long)__double_as_longlong(c);
+  s.ch = (uint32_t)(u >> 32) ^ (uint32_t)u;
+  return s;
+}
+
 __global__ void __launch_bounds__(256) nms_mask_kernel(NmsWs ws, double thr) {
   __shared__ SBox jb[8][32];
+  __shared__ SLite jl[8][32];
   if (ws.stats[ST_STATUS] != PG_OK) return;
   const long long total = ws.stats[ST_ENT_TOTAL];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long gw = (long long)blockIdx.x * 8 + wib, nw = (long long)gridDim.x * 8;
+  const bool all_pairs = !(thr >= 0.0);  // thr < 0: IoU 0 already suppresses, nothing can be skipped
   int cached = -1;
   SBox bi;
   bi.k = -1;
+  SLite li = slite_of(bi);
+  float4 bbI = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long u = gw; u * MASK_UNIT < total; u += nw) {
     for (int q = 0; q < MASK_UNIT; ++q) {
       const long long e = u * MASK_UNIT + q;
       if (e >= total) break;
       const int I = ws.ent_i[e], J = ws.ent_j[e];
-      if (I != cached) { bi = ws.sbox[(int64_t)I * 32 + lane]; cached = I; }
-      __syncwarp();
-      jb[wib][lane] = ws.sbox[(int64_t)J * 32 + lane];
-      __syncwarp();
-      // phase 1 (cheap, branch-free, every jj): boxes of J that outrank i (:112), share its class (:130)
-      // and are not disjoint from it (:65) — the only ones whose IoU can exceed thr >= 0
-      uint32_t cand = 0;
-      const int ik = (int)bi.k;
-      const bool need_disjoint_too = !(thr >= 0.0);  // thr < 0: IoU 0 already suppresses
-#pragma unroll 8
-      for (int jj = 0; jj < 32; ++jj) {
-        const SBox bj = jb[wib][jj];  // broadcast LDS.128 x4
-        const int jk = (int)bj.k;
-        const bool outranks = (bj.score > bi.score) || (bj.score == bi.score && jk < ik);
-        const bool apart = bj.x1 < bi.x0 || bi.x1 < bj.x0 || bj.y1 < bi.y0 || bi.y1 < bj.y0;
-        const bool c = (jk >= 0) & (ik >= 0) & outranks & (bj.cls == bi.cls) & (!apart | need_disjoint_too);
-        cand |= (c ? 1u : 0u) << jj;
+      if (I != cached) {
+        bi = ws.sbox[(int64_t)I * 32 + lane];
+        li = slite_of(bi);
+        bbI = ws.bboxf[I];
+        cached = I;
       }
-      // phase 2 (exact predicate, only on the set bits; lanes walk their own bit lists)
+      __syncwarp();
+      {
+        const SBox bj = ws.sbox[(int64_t)J * 32 + lane];
+        jb[wib][lane] = bj;
+        jl[wib][lane] = slite_of(bj);
+      }
+      // which runs of 8 boxes of J can touch block I at all (warp-uniform)
+      bool ghit = false;
+      if (lane < 4) {
+        const float4 sb = ws.subbox[(int64_t)J * 4 + lane];
+        ghit = all_pairs || !(sb.z < bbI.x || bbI.z < sb.x || sb.w < bbI.y || bbI.w < sb.y);
+      }
+      const unsigned groups = __ballot_sync(0xffffffffu, ghit) & 0xFu;
+      __syncwarp();
+      // phase 1
+      uint32_t cand = 0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (groups & (1u << g)) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int jj = g * 8 + t;
+            const SLite lj = jl[wib][jj];  // broadcast LDS.128 x2
+            const bool outranks = (lj.score > li.score) || (lj.score == li.score && lj.k < li.k);
+            const bool apart = lj.x1 < li.x0 || li.x1 < lj.x0 || lj.y1 < li.y0 || li.y1 < lj.y0;
+            const bool c = (lj.k >= 0) & (li.k >= 0) & outranks & (lj.ch == li.ch) & (!apart | all_pairs);
+            cand |= (c ? 1u : 0u) << jj;
+          }
+        }
+      }
+      // phase 2 (exact, only on the marked pairs; lanes walk their own bit lists)
       uint32_t mask = 0;
       while (__any_sync(0xffffffffu, cand != 0)) {
         if (cand) {
           const int jj = __ffs(cand) - 1;
           cand &= cand - 1;
           const SBox bj = jb[wib][jj];
-          if (pg_iou_gt(bj.x0, bj.y0, bj.x1, bj.y1, bj.area, bi.x0, bi.y0, bi.x1, bi.y1, bi.area, thr)) mask |= 1u << jj;
+          if (bj.cls == bi.cls &&
+              pg_iou_gt(bj.x0, bj.y0, bj.x1, bj.y1, bj.area, bi.x0, bi.y0, bi.x1, bi.y1, bi.area, thr))
+            mask |= 1u << jj;
         }
       }
       const bool any = __any_sync(0xffffffffu, mask != 0);
@@ -624,7 +685,10 @@ extern "C" int pg_nms_merge(const double* boxes, const double* scores, const dou
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t mask_want = (ws.ent_cap + 8 * MASK_UNIT - 1) / (8 * MASK_UNIT);
-  const unsigned mask_grid = (unsigned)(mask_want < (int64_t)sms * 4 ? (mask_want < 1 ? 1 : mask_want) : (int64_t)sms * 4);
+  int mask_per_sm = 3;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mask_per_sm, nms_mask_kernel, 256, 0);
+  const int64_t mask_slots = (int64_t)sms * (mask_per_sm > 0 ? mask_per_sm : 1);
+  const unsigned mask_grid = (unsigned)(mask_want < mask_slots ? (mask_want < 1 ? 1 : mask_want) : mask_slots);
   nms_mask_kernel<<<mask_grid, 256, 0, s>>>(ws, iou_threshold);
   PG_LAUNCH_CHECK();
   nms_resolve_kernel<<<n_pages, 1024, 0, s>>>(page_off, n_sel, ws, n_kept);
@@ -927,26 +991,56 @@ __global__ void __launch_bounds__(DEN_THREADS) column_density_kernel(
   const int seg0 = ((int)blockIdx.x * (DEN_THREADS / 32) + warp) * 32;
   const int bin = seg0 + lane;
   double d = 0.0;
+  DenEntry nxt;
+  nxt.left = 1; nxt.right = -1; nxt.center = 0; nxt.pad = 0; nxt.half = 1.0; nxt.inv_half = 1.0;
+  if (lane < n) nxt = lst[lane];
   for (int e0 = 0; e0 < n; e0 += 32) {
     const int e = e0 + lane;
+    const DenEntry mine = nxt;
+    if (e + 32 < n) nxt = lst[e + 32];  // prefetch the next 32 spans under this chunk's arithmetic
     int L = 1, R = -1;  // padding lanes overlap nothing (R < 0 <= seg0)
     __syncwarp();
     if (e < n) {
-      const DenEntry mine = lst[e];
       stage[warp][lane] = mine;
       L = mine.left; R = mine.right;
     }
     __syncwarp();
     unsigned bits = __ballot_sync(0xffffffffu, L <= seg0 + 31 && R >= seg0);
+    // Four spans at a time: their weights are independent (ILP hides the fp64 latency), the adds stay
+    // in box order (:139-144).  A bin outside a span adds +0.0, which leaves any d >= 0 bit-identical.
     while (bits) {
-      const int l = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const DenEntry en = stage[warp][l];  // broadcast
-      if (bin >= en.left && bin <= en.right) {  // :139-144, contributions added in box order
-        const double wgt = en.pad ? pg_density_weight(bin, en.left, en.right, en.center)
-                                  : pg_density_weight_rcp(bin, en.center, en.half, en.inv_half);
-        d = d + wgt;
+      DenEntry en[4];
+      bool ok[4];
+      int slow = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ok[q] = bits != 0;
+        const int l = ok[q] ? __ffs(bits) - 1 : 0;
+        bits &= bits - 1;              // 0 stays 0
+        en[q] = stage[warp][l];        // broadcast
+        slow |= en[q].pad;
       }
+      double w4[4];
+      if (!slow) {  // warp-uniform; straight-line code so the four chains interleave
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool in = ok[q] && bin >= en[q].left && bin <= en[q].right;
+          const double wgt = pg_density_weight_rcp(bin, en[q].center, en[q].half, en[q].inv_half);
+          w4[q] = in ? wgt : 0.0;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool in = ok[q] && bin >= en[q].left && bin <= en[q].right;
+          w4[q] = 0.0;
+          if (in) w4[q] = en[q].pad ? pg_density_weight(bin, en[q].left, en[q].right, en[q].center)
+                                    : pg_density_weight_rcp(bin, en[q].center, en[q].half, en[q].inv_half);
+        }
+      }
+      d = d + w4[0];
+      d = d + w4[1];
+      d = d + w4[2];
+      d = d + w4[3];
     }
   }
   if (bin < g.nbins) ws_all[(int64_t)p * 2 * max_bins + bin] = d;

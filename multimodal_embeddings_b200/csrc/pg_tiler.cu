@@ -360,7 +360,7 @@ constexpr int TL_MSG_PADROW = 1 << 30;
 template <int ITER, bool XPAD>
 __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const uint32_t (&xoff)[ITER][2],
                                           const uint32_t (&coef)[ITER][2], uint32_t b0, uint32_t b1,
-                                          uint32_t* orow, int64_t plane, int out_w, int px0) {
+                                          uint32_t* pr, uint32_t* pg, uint32_t* pb, int out_w, int px0) {
 #pragma unroll
   for (int i = 0; i < ITER; ++i) {
     const int ox = i * TL_PAIR_STRIDE + px0;
@@ -380,9 +380,10 @@ __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const ui
         }
       }
       // BGR -> RGB planes
-      __stcs(orow + (ox >> 1), pack_unit_half2(vr[0], vr[1]));
-      __stcs(orow + ((plane + ox) >> 1), pack_unit_half2(vg[0], vg[1]));
-      __stcs(orow + ((2 * plane + ox) >> 1), pack_unit_half2(vb[0], vb[1]));
+      // pr/pg/pb already point at this thread's first pixel pair of the row in each plane
+      __stcs(pr + i * (TL_PAIR_STRIDE / 2), pack_unit_half2(vr[0], vr[1]));
+      __stcs(pg + i * (TL_PAIR_STRIDE / 2), pack_unit_half2(vg[0], vg[1]));
+      __stcs(pb + i * (TL_PAIR_STRIDE / 2), pack_unit_half2(vb[0], vb[1]));
     }
   }
 }
@@ -457,8 +458,9 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
   const uint32_t pad_pair = pack_unit_half2(TL_PAD_VALUE, TL_PAD_VALUE);
   const int px0 = warp * 64 + lane * 2;
   uint32_t xoff[ITER][2], coef[ITER][2];
-  int cached_tile = -1, out_w = 0, xpad = 0;
-  int64_t plane = 0, out_off = 0;
+  int cached_tile = -1, cached_page = -1, out_w = 0, xpad = 0;
+  int64_t plane_w = 0, out_off = 0;   // plane size in half2 units
+  uint32_t* tile_ptr = nullptr;       // this thread's first pixel pair of row 0, R plane
 
   while (true) {
     mbar_wait(&full_bar[stage], phase);
@@ -468,8 +470,9 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
       cached_tile = m.x;
       const TileDev& t = a.tiles[m.x];
       out_w = t.out_w;
-      plane = (int64_t)t.out_h * out_w;
+      plane_w = ((int64_t)t.out_h * out_w) >> 1;
       out_off = t.out_off;
+      cached_page = -1;
       xpad = (t.pad_l != 0) || (t.new_w != out_w);
       const uint32_t skew = (uint32_t)t.row_skew;
       const int xtab_off = t.xtab_off;
@@ -485,24 +488,29 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
         }
       }
     }
+    if (m.y != cached_page) {
+      cached_page = m.y;
+      tile_ptr = reinterpret_cast<uint32_t*>(a.out + (int64_t)m.y * a.out_page_stride + out_off) + (px0 >> 1);
+    }
     const int oy = m.z & ~TL_MSG_PADROW;
-    uint32_t* orow = reinterpret_cast<uint32_t*>(a.out + (int64_t)m.y * a.out_page_stride + out_off + (int64_t)oy * out_w);
+    uint32_t* pr = tile_ptr + (int64_t)oy * (out_w >> 1);
+    uint32_t* pg = pr + plane_w;
+    uint32_t* pb = pg + plane_w;
     if (m.z & TL_MSG_PADROW) {
 #pragma unroll
       for (int i = 0; i < ITER; ++i) {
-        const int ox = i * TL_PAIR_STRIDE + px0;
-        if (ox < out_w) {
-          __stcs(orow + (ox >> 1), pad_pair);
-          __stcs(orow + ((plane + ox) >> 1), pad_pair);
-          __stcs(orow + ((2 * plane + ox) >> 1), pad_pair);
+        if (i * TL_PAIR_STRIDE + px0 < out_w) {
+          __stcs(pr + i * (TL_PAIR_STRIDE / 2), pad_pair);
+          __stcs(pg + i * (TL_PAIR_STRIDE / 2), pad_pair);
+          __stcs(pb + i * (TL_PAIR_STRIDE / 2), pad_pair);
         }
       }
     } else {
       const uint32_t b0 = (uint32_t)m.w & 0xFFFFu, b1 = (uint32_t)m.w >> 16;
       const uint32_t row0 = smem_base + stage * stage_bytes;
       const uint32_t row1 = row0 + (uint32_t)a.row_stride;
-      if (xpad) tiler_row<ITER, true>(row0, row1, xoff, coef, b0, b1, orow, plane, out_w, px0);
-      else tiler_row<ITER, false>(row0, row1, xoff, coef, b0, b1, orow, plane, out_w, px0);
+      if (xpad) tiler_row<ITER, true>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, out_w, px0);
+      else tiler_row<ITER, false>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, out_w, px0);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[stage]);

@@ -315,6 +315,43 @@ def test_width_median_edge_cases():
         assert (float(m), nb) == (float(ref_m), ref_nb), (trial, pct)
 
 
+def test_median_and_columns_random_page_shapes_one_batch():
+    """40 pages of very different widths (density resolution 1..9, 500..2000 bins, windows 5..101) and box
+    counts, all in ONE launch of K4 and K5, against the oracle (scipy find_peaks, np.convolve)."""
+    rng = np.random.default_rng(2024)
+    pages = []
+    for t in range(40):
+        w = int(rng.choice([517, 999, 1000, 1001, 1999, 2000, 2778, 3631, 4029, 6100, 7934, 9001]))
+        h = int(rng.integers(400, 6000))
+        n = int(rng.choice([0, 1, 7, 60, 400, 1500, 3000]))
+        d = synth.page_detections(w, h, 2, 2, 20.0, n, 7000 + t)
+        b = d["boxes_local"] + d["cells"][d["box_cell"]][:, [0, 1, 0, 1]] if n else np.zeros((0, 4))
+        keep = nms_pick_order_c(b, d["scores"], d["classes"], 0.5) if n else np.zeros(0, np.int64)
+        pages.append((w, h, b[keep], d["scores"][keep], d["classes"][keep]))
+    boxes = np.concatenate([p[2] for p in pages])
+    scores = np.concatenate([p[3] for p in pages])
+    classes = np.concatenate([p[4] for p in pages])
+    off = np.cumsum([0] + [len(p[2]) for p in pages])
+    wh = [[p[0], p[1]] for p in pages]
+    flags = ops.class_flags(classes)
+    for pct, conf in ((0.2, 0.3), (1.5, 0.6)):
+        med, nb = ops.width_median(boxes, flags, off, wh, pct)
+        centers, widths, n_cols = ops.column_peaks(boxes, flags, scores, off, wh, med, conf, max_cols=128)
+        med, nb, centers, widths, n_cols = (t.cpu().numpy() for t in (med, nb, centers, widths, n_cols))
+        n_with_cols = 0
+        for i, (w, h, b, s, c) in enumerate(pages):
+            names = synth.class_names_of(c)
+            ref_m, ref_nb = ob.median_width(b.tolist(), names, w, pct)
+            assert (med[i], nb[i]) == (float(ref_m), ref_nb), (i, w, len(b))
+            rc, rw = ob.column_centers(b.tolist(), names, s.tolist(), w, h, ref_m, conf) if ref_m > 0 else ([], [])
+            k = n_cols[i]
+            assert k >= 0
+            assert [float(x) for x in centers[i, :k]] == [float(x) for x in rc], (i, w, len(b))
+            assert [float(x) for x in widths[i, :k]] == [float(x) for x in rw], (i, w, len(b))
+            n_with_cols += k > 0
+        assert n_with_cols >= 15
+
+
 def test_columns_guards():
     assert api.find_column_centers([], [], [], 1000, 1000, 100.0) == ([], [])
     assert api.find_column_centers([[0, 0, 100, 10]], ["figure"], [0.9], 1000, 1000, 100.0) == ([], [])

@@ -126,6 +126,17 @@ int pg_nms_merge(const double* boxes /*dev [N,4]*/, const double* scores /*dev [
                  int32_t n_pages, int64_t n_boxes, int32_t max_boxes_per_page, double iou_threshold,
                  int32_t* kept_idx /*dev [N]*/, int32_t* n_kept /*dev [P]*/,
                  void* workspace /*dev*/, size_t workspace_bytes, void* stream);
+/* Same machinery with mode bits.  PG_NMS_CLASS_AGNOSTIC | PG_NMS_FP32 reproduces
+ * torchvision.ops.nms as the reference calls it per tile (1_doclayout_bboxes.py:217-225): boxes and
+ * scores are float32 values (passed here widened to double), areas / intersection / IoU are evaluated
+ * in float32, ties keep the earlier box, classes are ignored (may be NULL). */
+#define PG_NMS_CLASS_AGNOSTIC 1
+#define PG_NMS_FP32 2
+int pg_nms_merge_ex(const double* boxes, const double* scores, const double* classes,
+                    const int32_t* sel_idx, const int64_t* page_off, const int32_t* n_sel,
+                    int32_t n_pages, int64_t n_boxes, int32_t max_boxes_per_page, double iou_threshold,
+                    int32_t mode, int32_t* kept_idx, int32_t* n_kept, void* workspace,
+                    size_t workspace_bytes, void* stream);
 /* After the stream has been synchronised: status word + counters the merge left in
  * its workspace. stats[0]=status (PG_OK/PG_ERR_*), [1]=candidate block pairs,
  * [2]=resolve rounds (max over pages), [3]=box pairs tested. */
@@ -162,12 +173,22 @@ int pg_column_peaks(const double* boxes, const uint8_t* flags, const double* sco
                     int32_t* ws_span_counts /*dev [P]*/,
                     uint32_t* col_hist /*dev [PG_COL_HIST_BINS] or NULL*/, void* stream);
 
+/* Per-box column assignment.  The reference stops at centres/widths (SURVEY.md 8a note); this is the
+ * documented derived function: col_of_box[i] = index of the centre nearest to (x0+x1)/2 of box i
+ * (first minimum on ties), -1 for boxes outside the selection or pages with no column. */
+int pg_assign_columns(const double* boxes /*dev [N,4]*/, const int32_t* sel_idx, const int64_t* page_off,
+                      const int32_t* n_sel, int32_t n_pages, int64_t n_boxes,
+                      const int32_t* centers /*dev [P,max_cols]*/, const int32_t* n_cols /*dev [P]*/,
+                      int32_t max_cols, int32_t* col_of_box /*dev [N]*/, void* stream);
+
 /* ------------------------------------------------------------------ test hooks
  * Host evaluations of the same inline arithmetic the kernels are compiled from
  * (csrc/pg_math.h).  Used by the CPU test-suite only; not a compute path. */
 double pg_hostcheck_iou(const double* a, const double* b);
 /* the divide-free predicate the merge kernel uses for `iou > thr` (must equal pg_hostcheck_iou(a,b) > thr) */
 int32_t pg_hostcheck_iou_gt(const double* a, const double* b, double thr);
+/* the float32 predicate of the per-tile NMS mode (a suppresses b?) */
+int32_t pg_hostcheck_iou_gt_f32(const float* a, const float* b, double thr);
 int32_t pg_hostcheck_edge_touch(const double* box, const double* cell, int32_t w, int32_t h, double thr);
 double pg_hostcheck_density_weight(int32_t bin, int32_t left, int32_t right, int32_t center);
 /* number of (right-left, |bin-center|) pairs in [0,max_span]x[0,max_n] where the reciprocal+FMA

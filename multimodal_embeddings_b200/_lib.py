@@ -17,6 +17,8 @@ PG_FLAG_TITLE = 2
 PG_WIDTH_HIST_BINS = 16384
 PG_COL_HIST_BINS = 1001
 PG_COL_SPAN_BYTES = 32
+PG_NMS_CLASS_AGNOSTIC = 1
+PG_NMS_FP32 = 2
 
 
 class PgTileInfo(C.Structure):
@@ -55,13 +57,16 @@ SIGNATURES = {
     "pg_edge_filter": (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _F64, _P, _P, _P, _P, _P]),
     "pg_nms_workspace_bytes": (C.c_size_t, [_I64, _I32, _I32]),
     "pg_nms_merge": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I64, _I32, _F64, _P, _P, _P, C.c_size_t, _P]),
+    "pg_nms_merge_ex": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I64, _I32, _F64, _I32, _P, _P, _P, C.c_size_t, _P]),
     "pg_nms_stats": (C.c_int, [_P, _P]),
     "pg_class_flags": (C.c_int, [_P, _I64, _F64, _F64, _P, _P]),
     "pg_width_median": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I64, _P, _F64, _P, _P, _P, _P, _P, _P]),
     "pg_column_peaks": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I32, _F64, _I32,
                                   _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
+    "pg_assign_columns": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _P, _P, _I32, _P, _P]),
     "pg_hostcheck_iou": (_F64, [_P, _P]),
     "pg_hostcheck_iou_gt": (_I32, [_P, _P, _F64]),
+    "pg_hostcheck_iou_gt_f32": (_I32, [_P, _P, _F64]),
     "pg_hostcheck_edge_touch": (_I32, [_P, _P, _I32, _I32, _F64]),
     "pg_hostcheck_density_weight": (_F64, [_I32, _I32, _I32, _I32]),
     "pg_hostcheck_density_rcp_mismatches": (_I64, [_I32, _I32]),

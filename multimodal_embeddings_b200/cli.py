@@ -107,7 +107,7 @@ def get_image_paths(input_folder):
 
 def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
     from . import ops
-    from .reference_api import parse_grid_configs, translate_coordinates_to_original
+    from .reference_api import nms_per_tile, parse_grid_configs, translate_coordinates_to_original
     logger = _logger("DocLayoutAnalyzer")
     p = argparse.ArgumentParser(description="Document Layout Analysis")
     p.add_argument("--input_folder", required=True)
@@ -162,6 +162,10 @@ def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
                 n_t = rows * cols
                 views = [plan.tile_view(tiles, 0, t0 + k) for k in range(n_t)]
                 dets = detector.detect_page(base, w, h, rows, cols, args.overlap, views)
+                # per-tile class-agnostic NMS of detect_regions (1:217-225), all tiles of the grid in one launch
+                keeps = nms_per_tile([d["boxes"] for d in dets], [d["scores"] for d in dets], args.iou_threshold)
+                dets = [{k: [d[k][i] for i in keep.tolist()] for k in ("boxes", "classes", "scores", "class_names")}
+                        for d, keep in zip(dets, keeps)]
                 if (rows, cols) == (1, 1) and t0 == 0:  # full-page pass, 1:446-482 / schema 1:227-235
                     d = dets[0]
                     _dump({"image_path": image_path, "image_size": {"width": w, "height": h}, "parameters": params,

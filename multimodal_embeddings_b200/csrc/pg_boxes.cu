@@ -118,6 +118,7 @@ struct NmsWs {
   int32_t* ent_i;      // [E]  block I the entry belongs to (global block id)
   uint32_t* ent_mask;  // [E*32]
   int64_t nb_cap, ent_cap;
+  int32_t mode;        // PG_NMS_* bits
 };
 // stats[] slots
 enum { ST_STATUS = 0, ST_PAIRS = 1, ST_ROUNDS = 2, ST_TESTS = 3, ST_ENT_TOTAL = 4 };
@@ -325,8 +326,9 @@ __global__ void __launch_bounds__(1024) nms_bin_kernel(const double* __restrict_
       const double2 a = *reinterpret_cast<const double2*>(boxes + 4 * gi);
       const double2 c = *reinterpret_cast<const double2*>(boxes + 4 * gi + 2);
       sb.x0 = a.x; sb.y0 = a.y; sb.x1 = c.x; sb.y1 = c.y;
-      sb.area = pg_box_area(a.x, a.y, c.x, c.y);
-      sb.score = scores[gi]; sb.cls = classes[gi]; sb.k = k;
+      sb.area = (ws.mode & PG_NMS_FP32) ? (double)pg_box_area_f32((float)a.x, (float)a.y, (float)c.x, (float)c.y)
+                                        : pg_box_area(a.x, a.y, c.x, c.y);
+      sb.score = scores[gi]; sb.cls = classes ? classes[gi] : 0.0; sb.k = k;
     }
     ws.sbox[(sp.blk0 + b) * 32 + lane] = sb;
     const double bx0 = warp_min_d(valid ? fmin(sb.x0, sb.x1) : DBL_MAX), by0 = warp_min_d(valid ? fmin(sb.y0, sb.y1) : DBL_MAX);
@@ -438,6 +440,7 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(NmsWs ws, double thr) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long gw = (long long)blockIdx.x * 8 + wib, nw = (long long)gridDim.x * 8;
   const bool all_pairs = !(thr >= 0.0);  // thr < 0: IoU 0 already suppresses, nothing can be skipped
+  const bool agnostic = (ws.mode & PG_NMS_CLASS_AGNOSTIC) != 0, f32 = (ws.mode & PG_NMS_FP32) != 0;
   int cached = -1;
   SBox bi;
   bi.k = -1;
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(NmsWs ws, double thr) {
             const SLite lj = jl[wib][jj];  // broadcast LDS.128 x2
             const bool outranks = (lj.score > li.score) || (lj.score == li.score && lj.k < li.k);
             const bool apart = lj.x1 < li.x0 || li.x1 < lj.x0 || lj.y1 < li.y0 || li.y1 < lj.y0;
-            const bool c = (lj.k >= 0) & (li.k >= 0) & outranks & (lj.ch == li.ch) & (!apart | all_pairs);
+            const bool c = (lj.k >= 0) & (li.k >= 0) & outranks & ((lj.ch == li.ch) | agnostic) & (!apart | all_pairs);
             cand |= (c ? 1u : 0u) << jj;
           }
         }
@@ -491,9 +494,12 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(NmsWs ws, double thr) {
           const int jj = __ffs(cand) - 1;
           cand &= cand - 1;
           const SBox bj = jb[wib][jj];
-          if (bj.cls == bi.cls &&
-              pg_iou_gt(bj.x0, bj.y0, bj.x1, bj.y1, bj.area, bi.x0, bi.y0, bi.x1, bi.y1, bi.area, thr))
-            mask |= 1u << jj;
+          if (agnostic || bj.cls == bi.cls) {
+            const bool hit = f32 ? pg_iou_gt_f32((float)bj.x0, (float)bj.y0, (float)bj.x1, (float)bj.y1, (float)bj.area,
+                                                 (float)bi.x0, (float)bi.y0, (float)bi.x1, (float)bi.y1, (float)bi.area, thr)
+                                 : pg_iou_gt(bj.x0, bj.y0, bj.x1, bj.y1, bj.area, bi.x0, bi.y0, bi.x1, bi.y1, bi.area, thr);
+            if (hit) mask |= 1u << jj;
+          }
         }
       }
       const bool any = __any_sync(0xffffffffu, mask != 0);
@@ -654,10 +660,21 @@ extern "C" int pg_nms_merge(const double* boxes, const double* scores, const dou
                             int32_t n_pages, int64_t n_boxes, int32_t max_boxes_per_page, double iou_threshold,
                             int32_t* kept_idx, int32_t* n_kept, void* workspace, size_t workspace_bytes,
                             void* stream) {
+  return pg_nms_merge_ex(boxes, scores, classes, sel_idx, page_off, n_sel, n_pages, n_boxes, max_boxes_per_page,
+                         iou_threshold, 0, kept_idx, n_kept, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pg_nms_merge_ex(const double* boxes, const double* scores, const double* classes,
+                               const int32_t* sel_idx, const int64_t* page_off, const int32_t* n_sel,
+                               int32_t n_pages, int64_t n_boxes, int32_t max_boxes_per_page, double iou_threshold,
+                               int32_t mode, int32_t* kept_idx, int32_t* n_kept, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   (void)max_boxes_per_page;
   PG_REQUIRE(n_pages >= 0 && n_boxes >= 0, "sizes");
+  PG_REQUIRE((mode & ~(PG_NMS_CLASS_AGNOSTIC | PG_NMS_FP32)) == 0, "mode");
   if (n_pages == 0) return PG_OK;
-  PG_REQUIRE(boxes && scores && classes && page_off && kept_idx && n_kept && workspace, "null device pointer");
+  PG_REQUIRE(boxes && scores && (classes || (mode & PG_NMS_CLASS_AGNOSTIC)) && page_off && kept_idx && n_kept && workspace,
+             "null device pointer");
   PG_REQUIRE(n_boxes < (1ll << 31), "n_boxes must fit int32");
   PG_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
   // recover pairs_per_block from the size the caller allocated
@@ -671,6 +688,7 @@ extern "C" int pg_nms_merge(const double* boxes, const double* scores, const dou
   int64_t ppb = 1 + (int64_t)((workspace_bytes - fixed) / (per_pair_block + 512));
   while (ppb > 1 && nms_layout(n_boxes, n_pages, (int32_t)ppb, nullptr, nullptr) > workspace_bytes) --ppb;
   nms_layout(n_boxes, n_pages, (int32_t)ppb, (uint8_t*)workspace, &ws);
+  ws.mode = mode;
   cudaStream_t s = (cudaStream_t)stream;
   const int emit_smem = EMIT_SMEM_ELEMS * 12;
   PG_CUDA_TRY(cudaFuncSetAttribute(nms_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem));
@@ -1244,6 +1262,52 @@ extern "C" int pg_column_peaks(const double* boxes, const uint8_t* flags, const 
   PG_LAUNCH_CHECK();
   column_peaks_kernel<<<n_pages, COL_THREADS, 0, s>>>(page_wh, median, gauss_table, gauss_off, max_window, max_cols,
                                                      centers, widths, n_cols, ws, max_bins, col_hist);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+// =============================================================================================
+// K5b — per-box column assignment (derived; the reference stops at centres/widths, SURVEY §8a note)
+//   column(box) = index of the column centre nearest to the box's x-centre (x0+x1)/2, first minimum
+//   on ties; -1 for boxes that were not selected or pages without columns.  One thread per box.
+// =============================================================================================
+__global__ void __launch_bounds__(256) assign_columns_kernel(const double* __restrict__ boxes,
+                                                             const int32_t* __restrict__ sel_idx,
+                                                             const int64_t* __restrict__ page_off,
+                                                             const int32_t* __restrict__ n_sel,
+                                                             const int32_t* __restrict__ centers,
+                                                             const int32_t* __restrict__ n_cols, int max_cols,
+                                                             int32_t* __restrict__ col_of_box) {
+  const int p = blockIdx.y;
+  const int64_t base = page_off[p];
+  const int m = n_sel ? n_sel[p] : (int)(page_off[p + 1] - base);
+  int nc = n_cols[p];
+  nc = nc < 0 ? 0 : (nc > max_cols ? max_cols : nc);
+  const int32_t* cc = centers + (int64_t)p * max_cols;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) {
+    const int64_t gi = sel_idx ? (int64_t)sel_idx[base + k] : base + k;
+    const double cx = (boxes[4 * gi] + boxes[4 * gi + 2]) / 2.0;
+    int best = -1;
+    double bd = 0.0;
+    for (int c = 0; c < nc; ++c) {
+      const double dd = fabs(cx - (double)cc[c]);
+      if (best < 0 || dd < bd) { best = c; bd = dd; }
+    }
+    col_of_box[gi] = best;
+  }
+}
+
+extern "C" int pg_assign_columns(const double* boxes, const int32_t* sel_idx, const int64_t* page_off,
+                                 const int32_t* n_sel, int32_t n_pages, int64_t n_boxes, const int32_t* centers,
+                                 const int32_t* n_cols, int32_t max_cols, int32_t* col_of_box, void* stream) {
+  PG_REQUIRE(n_pages >= 0 && n_boxes >= 0 && max_cols > 0, "sizes");
+  if (n_pages == 0 || n_boxes == 0) return PG_OK;
+  PG_REQUIRE(boxes && page_off && centers && n_cols && col_of_box, "null device pointer");
+  PG_REQUIRE(n_pages <= 65535, "n_pages per launch must be <= 65535");
+  cudaStream_t s = (cudaStream_t)stream;
+  PG_CUDA_TRY(cudaMemsetAsync(col_of_box, 0xFF, (size_t)n_boxes * sizeof(int32_t), s));  // -1 everywhere
+  assign_columns_kernel<<<dim3(8, (unsigned)n_pages), 256, 0, s>>>(boxes, sel_idx, page_off, n_sel, centers, n_cols,
+                                                                  max_cols, col_of_box);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

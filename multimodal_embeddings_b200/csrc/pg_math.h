@@ -54,6 +54,24 @@ PG_HD bool pg_iou_gt(double ax0, double ay0, double ax1, double ay1, double area
   return inter / uni > thr;
 }
 
+// torchvision.ops.nms's test (called at 1_doclayout_bboxes.py:219-223 on float32 boxes): everything in
+// float32 — w = max(0, xx2-xx1), h likewise, inter = w*h, ovr = inter / (area_i + area_j - inter) —
+// then `ovr > iou_threshold` with the threshold a double.  0/0 gives NaN, which compares false.
+PG_HD float pg_box_area_f32(float x0, float y0, float x1, float y1) { return (x1 - x0) * (y1 - y0); }
+PG_HD bool pg_iou_gt_f32(float ix0, float iy0, float ix1, float iy1, float area_i,
+                         float jx0, float jy0, float jx1, float jy1, float area_j, double thr) {
+  const float xx1 = ix0 > jx0 ? ix0 : jx0;
+  const float yy1 = iy0 > jy0 ? iy0 : jy0;
+  const float xx2 = ix1 < jx1 ? ix1 : jx1;
+  const float yy2 = iy1 < jy1 ? iy1 : jy1;
+  const float dw = xx2 - xx1, dh = yy2 - yy1;
+  const float w = dw > 0.f ? dw : 0.f;
+  const float h = dh > 0.f ? dh : 0.f;
+  const float inter = w * h;
+  const float ovr = inter / (area_i + area_j - inter);
+  return (double)ovr > thr;
+}
+
 // is_box_touching_internal_edge (2_edge_box_filter.py:44-90), test order right, bottom,
 // left, top.  Pure predicate: the order only matters for short-circuiting.
 PG_HD bool pg_edge_touch(double x_min, double y_min, double x_max, double y_max,

@@ -733,6 +733,10 @@ extern "C" int32_t pg_hostcheck_iou_gt(const double* a, const double* b, double 
   return pg_iou_gt(a[0], a[1], a[2], a[3], pg_box_area(a[0], a[1], a[2], a[3]), b[0], b[1], b[2], b[3],
                    pg_box_area(b[0], b[1], b[2], b[3]), thr) ? 1 : 0;
 }
+extern "C" int32_t pg_hostcheck_iou_gt_f32(const float* a, const float* b, double thr) {
+  return pg_iou_gt_f32(a[0], a[1], a[2], a[3], pg_box_area_f32(a[0], a[1], a[2], a[3]), b[0], b[1], b[2], b[3],
+                       pg_box_area_f32(b[0], b[1], b[2], b[3]), thr) ? 1 : 0;
+}
 extern "C" int32_t pg_hostcheck_edge_touch(const double* box, const double* cell, int32_t w, int32_t h, double thr) {
   return pg_edge_touch(box[0], box[1], box[2], box[3], cell[0], cell[1], cell[2], cell[3], (double)w, (double)h, thr) ? 1 : 0;
 }

@@ -191,12 +191,13 @@ class NmsWorkspace:
 
 def nms_merge(boxes, scores, classes, page_off, iou_threshold: float = 0.5, sel_idx=None, n_sel=None,
               max_boxes_per_page: int = 0, workspace: Optional[NmsWorkspace] = None, stream=None,
-              kept_idx: Optional[torch.Tensor] = None, n_kept: Optional[torch.Tensor] = None):
-    """pg_nms_merge.  Returns (kept_idx [N] i32 global indices in pick order, n_kept [P] i32, workspace)."""
+              kept_idx: Optional[torch.Tensor] = None, n_kept: Optional[torch.Tensor] = None, mode: int = 0):
+    """pg_nms_merge_ex.  Returns (kept_idx [N] i32 global indices in pick order, n_kept [P] i32, workspace).
+    mode: 0 = stage-3 semantics (class-aware, fp64); PG_NMS_CLASS_AGNOSTIC | PG_NMS_FP32 = torchvision.ops.nms."""
     _require_cuda()
     boxes = _dev(boxes, torch.float64).view(-1, 4)
     scores = _dev(scores, torch.float64)
-    classes = _dev(classes, torch.float64)
+    classes = _dev(classes, torch.float64) if classes is not None else None
     page_off = _dev(page_off, torch.int64)
     n, p = boxes.shape[0], page_off.numel() - 1
     if sel_idx is not None:
@@ -208,9 +209,9 @@ def nms_merge(boxes, scores, classes, page_off, iou_threshold: float = 0.5, sel_
         kept_idx = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
     if n_kept is None:
         n_kept = torch.zeros(max(p, 1), dtype=torch.int32, device="cuda")
-    check(lib().pg_nms_merge(ptr(boxes), ptr(scores), ptr(classes), ptr(sel_idx), ptr(page_off), ptr(n_sel), p, n,
-                             int(max_boxes_per_page), float(iou_threshold), ptr(kept_idx), ptr(n_kept),
-                             workspace.ptr, workspace.nbytes, stream_ptr(stream)))
+    check(lib().pg_nms_merge_ex(ptr(boxes), ptr(scores), ptr(classes), ptr(sel_idx), ptr(page_off), ptr(n_sel), p, n,
+                                int(max_boxes_per_page), float(iou_threshold), int(mode), ptr(kept_idx), ptr(n_kept),
+                                workspace.ptr, workspace.nbytes, stream_ptr(stream)))
     return kept_idx, n_kept[:p], workspace
 
 
@@ -308,3 +309,21 @@ def column_peaks(boxes, flags, scores, page_off, page_wh, median, min_confidence
     if return_ws:  # [P, 2, max_bins]: density map and smoothed density (debug / tests)
         return centers[:p], widths[:p], n_cols[:p], ws.view(-1, 2, max_bins)[:p]
     return centers[:p], widths[:p], n_cols[:p]
+
+
+def assign_columns(boxes, page_off, centers, n_cols, sel_idx=None, n_sel=None, stream=None) -> torch.Tensor:
+    """pg_assign_columns.  Returns col_of_box [N] i32: nearest column centre per selected box, -1 otherwise."""
+    _require_cuda()
+    boxes = _dev(boxes, torch.float64).view(-1, 4)
+    page_off = _dev(page_off, torch.int64)
+    centers = _dev(centers, torch.int32)
+    n_cols = _dev(n_cols, torch.int32)
+    n, p = boxes.shape[0], page_off.numel() - 1
+    if sel_idx is not None:
+        sel_idx = _dev(sel_idx, torch.int32)
+        n_sel = _dev(n_sel, torch.int32)
+    out = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
+    check(lib().pg_assign_columns(ptr(boxes), ptr(sel_idx), ptr(page_off), ptr(n_sel), p, n, ptr(centers), ptr(n_cols),
+                                  centers.shape[1] if centers.dim() == 2 else max(1, centers.numel() // max(p, 1)),
+                                  ptr(out), stream_ptr(stream)))
+    return out[:n]

@@ -71,6 +71,46 @@ def split_image_into_grid(image, rows, cols, overlap_percentage, imgsz=1024, str
     return cells
 
 
+def nms(boxes, scores, iou_threshold: float):
+    """Drop-in for ``torchvision.ops.nms(boxes, scores, iou_threshold)`` as called per tile at
+    1_doclayout_bboxes.py:219-223: float32 boxes [N,4] / scores [N] (tensor or array) -> int64 tensor of the
+    kept indices in decreasing score order.  Class-agnostic greedy NMS evaluated in float32 like
+    torchvision's kernel (pg_nms_merge_ex, PG_NMS_CLASS_AGNOSTIC | PG_NMS_FP32)."""
+    return nms_per_tile([boxes], [scores], iou_threshold)[0]
+
+
+def nms_per_tile(boxes_list, scores_list, iou_threshold: float):
+    """The per-tile NMS of 1_doclayout_bboxes.py:217-225 for many tiles in ONE launch."""
+    from ._lib import PG_NMS_CLASS_AGNOSTIC, PG_NMS_FP32
+
+    def f32(x, shape):
+        if isinstance(x, torch.Tensor):
+            x = x.detach().cpu().numpy()
+        return np.asarray(x, np.float32).reshape(shape)
+
+    bs = [f32(b, (-1, 4)) for b in boxes_list]
+    ss = [f32(s, (-1,)) for s in scores_list]
+    counts = [len(s) for s in ss]
+    n = sum(counts)
+    if n == 0:
+        return [torch.zeros(0, dtype=torch.int64) for _ in bs]
+    off = np.concatenate([[0], np.cumsum(counts)])
+    kept, n_kept, ws = ops.nms_merge(np.concatenate(bs).astype(np.float64), np.concatenate(ss).astype(np.float64), None,
+                                     off, iou_threshold, max_boxes_per_page=max(counts),
+                                     mode=PG_NMS_CLASS_AGNOSTIC | PG_NMS_FP32)
+    st = ws.stats()
+    if st["status"] == 3:  # dense bound
+        dense = ops.NmsWorkspace(n, len(bs), pairs_per_block=max(counts) // 32 + 2)
+        kept, n_kept, ws = ops.nms_merge(np.concatenate(bs).astype(np.float64), np.concatenate(ss).astype(np.float64),
+                                         None, off, iou_threshold, workspace=dense,
+                                         mode=PG_NMS_CLASS_AGNOSTIC | PG_NMS_FP32)
+        st = ws.stats()
+    if st["status"] != 0:
+        raise RuntimeError(f"pg_nms_merge_ex failed on device: {st}")
+    kept, n_kept = kept.cpu().numpy(), n_kept.cpu().numpy()
+    return [torch.from_numpy((kept[off[i]: off[i] + n_kept[i]] - off[i]).astype(np.int64)) for i in range(len(bs))]
+
+
 def translate_coordinates_to_original(boxes, cell_coordinates):
     """1_doclayout_bboxes.py:484-511 on the GPU (pg_edge_filter's translation stage with the
     filter disabled by an infinite page)."""

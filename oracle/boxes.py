@@ -328,3 +328,59 @@ def valley_widths(sm, peaks, res, hmin, median_w):
             w = 2.0 * median_w
         out.append(w)
     return out
+
+
+# ----------------------------------------------------------------------------
+# stage 1 — per-tile class-agnostic NMS (torchvision.ops.nms at 1_doclayout_bboxes.py:217-225)
+# ----------------------------------------------------------------------------
+def nms_torchvision_f32(boxes, scores, iou_threshold):
+    """Restatement of torchvision's CPU nms kernel (third-party, present in the image; pinned by goldens
+    generated with torchvision 0.26): stable descending score order, everything in float32 —
+    w = max(0, xx2-xx1), inter = w*h, ovr = inter / (area_i + area_j - inter) — suppress when
+    ovr > threshold (threshold a double).  Returns kept indices in decreasing score order."""
+    b = np.asarray(boxes, np.float32).reshape(-1, 4)
+    s = np.asarray(scores, np.float32).reshape(-1)
+    n = len(s)
+    areas = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    order = np.argsort(-s.astype(np.float64), kind="stable")
+    dead = np.zeros(n, bool)
+    keep = []
+    zero = np.float32(0)
+    for a in range(n):
+        i = order[a]
+        if dead[i]:
+            continue
+        keep.append(int(i))
+        rest = order[a + 1:]
+        rest = rest[~dead[rest]]
+        if len(rest) == 0:
+            continue
+        xx1 = np.maximum(b[i, 0], b[rest, 0])
+        yy1 = np.maximum(b[i, 1], b[rest, 1])
+        xx2 = np.minimum(b[i, 2], b[rest, 2])
+        yy2 = np.minimum(b[i, 3], b[rest, 3])
+        w = np.maximum(zero, xx2 - xx1)
+        h = np.maximum(zero, yy2 - yy1)
+        inter = w * h
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ovr = inter / (areas[i] + areas[rest] - inter)
+        dead[rest[ovr.astype(np.float64) > iou_threshold]] = True
+    return keep
+
+
+# ----------------------------------------------------------------------------
+# derived: per-box column assignment (no reference analogue, SURVEY.md §8a note)
+# ----------------------------------------------------------------------------
+def assign_columns(boxes, centers):
+    """Index of the column centre nearest to each box's x-centre (x0+x1)/2, first minimum on ties;
+    -1 when there are no centres.  Specification of pg_assign_columns."""
+    out = []
+    for b in boxes:
+        cx = (b[0] + b[2]) / 2.0
+        best, bd = -1, 0.0
+        for c, cc in enumerate(centers):
+            dd = abs(cx - float(cc))
+            if best < 0 or dd < bd:
+                best, bd = c, dd
+        out.append(best)
+    return out

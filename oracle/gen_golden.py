@@ -250,6 +250,30 @@ def gen_stage45_synth(r3, r4, r5):
     return out
 
 
+def gen_tile_nms():
+    """torchvision.ops.nms exactly as 1_doclayout_bboxes.py:219-223 calls it (float32 tensors, CPU),
+    on per-tile synthetic detections at the reference's default 0.45 and two other thresholds."""
+    import torch
+    import torchvision
+    out, names = {}, []
+    specs = [("t045", 2800, 2100, 1200, 61, 0.45), ("t030", 1024, 1024, 700, 62, 0.3), ("t070", 2000, 1500, 900, 63, 0.7),
+             ("ties", 1500, 1500, 400, 64, 0.45), ("dense", 800, 800, 1500, 65, 0.45)]
+    for name, w, h, n, seed, thr in specs:
+        d = synth.page_detections(w, h, 1, 1, 20.0, n, seed, dups=3)
+        b = d["boxes_local"].astype(np.float32)
+        s = d["scores"].astype(np.float32)
+        if name == "ties":
+            s = np.round(s, 1).astype(np.float32)
+            b[30:40] = b[20:30]
+        keep = torchvision.ops.nms(boxes=torch.tensor(b), scores=torch.tensor(s), iou_threshold=thr).numpy()
+        out[name + "_boxes"], out[name + "_scores"] = b, s
+        out[name + "_thr"], out[name + "_keep"] = np.array([thr]), keep.astype(np.int64)
+        names.append(name)
+    out["cases"] = np.array(names)
+    out["torchvision_version"] = np.array([torchvision.__version__])
+    return out
+
+
 def gen_cli_tree(mods):
     """Run the reference's own main()s for stages 2-5 on a synthetic stage-1 tree (tests/cli_tree.py)
     and record every JSON they write, with the tree root normalised."""
@@ -292,6 +316,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "stage3_nms.npz"), **gen_stage3(r3))
     with open(os.path.join(OUT, "stage45_synth.json"), "w") as f:
         json.dump(gen_stage45_synth(r3, r4, r5), f, indent=1)
+    np.savez_compressed(os.path.join(OUT, "stage1_tile_nms.npz"), **gen_tile_nms())
     with gzip.open(os.path.join(OUT, "cli_tree.json.gz"), "wt") as f:
         json.dump(gen_cli_tree((r2, r3, r4, r5)), f)
     print("golden fixtures written to", OUT)

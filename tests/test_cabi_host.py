@@ -118,6 +118,29 @@ def test_hostcheck_iou_gt_equals_divide_then_compare(lib):
     assert n_true > 100 and n_band > 50  # the band (true-divide path) is really exercised
 
 
+def test_hostcheck_iou_gt_f32_matches_float32_restatement(lib):
+    rng = np.random.default_rng(5)
+    n_true = 0
+    for _ in range(3000):
+        xy = rng.uniform(0, 300, 4).astype(np.float32)
+        wh = rng.uniform(0, 150, 4).astype(np.float32)
+        a = np.array([xy[0], xy[1], xy[0] + wh[0], xy[1] + wh[1]], np.float32)
+        b = np.array([xy[2], xy[3], xy[2] + wh[2], xy[3] + wh[3]], np.float32)
+        if rng.random() < 0.3:
+            b = (a + rng.normal(0, 3, 4)).astype(np.float32)
+        thr = float(rng.choice([0.45, 0.3, 0.7, 0.0]))
+        area = lambda q: (q[2] - q[0]) * (q[3] - q[1])  # noqa: E731  float32 arithmetic
+        w = max(np.float32(0), min(a[2], b[2]) - max(a[0], b[0]))
+        h = max(np.float32(0), min(a[3], b[3]) - max(a[1], b[1]))
+        inter = np.float32(w * h)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ovr = inter / np.float32(np.float32(area(a) + area(b)) - inter)
+        ref = bool(np.float64(ovr) > thr)
+        n_true += ref
+        assert bool(lib.pg_hostcheck_iou_gt_f32(_lib.ptr(a), _lib.ptr(b), thr)) == ref
+    assert n_true > 200
+
+
 def test_hostcheck_edge_touch_matches_reference(lib):
     n = 0
     for case in load_golden("stage2_filter.json.gz"):

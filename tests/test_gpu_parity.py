@@ -256,6 +256,30 @@ def test_nms_adversarial_identical_boxes_and_workspace_overflow():
     assert small.stats()["status"] == 3 and int(n_kept2[0].item()) == -1  # reported, never silently wrong
 
 
+def test_per_tile_nms_matches_torchvision():
+    """the per-tile class-agnostic float32 NMS of 1_doclayout_bboxes.py:217-225."""
+    g = load_golden("stage1_tile_nms.npz")
+    boxes_list = [g[f"{n}_boxes"] for n in g["cases"]]
+    scores_list = [g[f"{n}_scores"] for n in g["cases"]]
+    for name, b, s in zip(g["cases"], boxes_list, scores_list):   # one tile per call, torchvision's signature
+        keep = api.nms(torch.tensor(b), torch.tensor(s), float(g[f"{name}_thr"][0]))
+        assert keep.dtype == torch.int64 and keep.tolist() == g[f"{name}_keep"].tolist(), name
+    # many tiles in one launch (same threshold), against the float32 restatement and live torchvision
+    import torchvision
+    rng = np.random.default_rng(8)
+    tiles_b, tiles_s = [], []
+    for t in range(16):
+        n = int(rng.choice([0, 1, 50, 700, 2500]))
+        d = synth.page_detections(2800, 2100, 1, 1, 20.0, n, 900 + t, dups=3)
+        tiles_b.append(d["boxes_local"].astype(np.float32))
+        tiles_s.append(d["scores"].astype(np.float32))
+    keeps = api.nms_per_tile(tiles_b, tiles_s, 0.45)
+    for b, s, k in zip(tiles_b, tiles_s, keeps):
+        ref = torchvision.ops.nms(torch.tensor(b).reshape(-1, 4), torch.tensor(s), 0.45).tolist() if len(s) else []
+        assert k.tolist() == ref
+        assert k.tolist() == ob.nms_torchvision_f32(b, s, 0.45)
+
+
 # ============================================================================== K4 / K5
 def test_width_median_and_columns_on_reference_outputs(f1_pages, f4):
     boxes = np.concatenate([np.asarray(p["boxes"], np.float64) for p in f1_pages])
@@ -350,6 +374,32 @@ def test_median_and_columns_random_page_shapes_one_batch():
             assert [float(x) for x in widths[i, :k]] == [float(x) for x in rw], (i, w, len(b))
             n_with_cols += k > 0
         assert n_with_cols >= 15
+
+
+def test_column_assignment_matches_specification(f1_pages, f4):
+    boxes = np.concatenate([np.asarray(p["boxes"], np.float64) for p in f1_pages])
+    off = np.cumsum([0] + [len(p["boxes"]) for p in f1_pages])
+    max_cols = 16
+    centers = np.zeros((len(f1_pages), max_cols), np.int32)
+    n_cols = np.zeros(len(f1_pages), np.int32)
+    for i, g in enumerate(f4):
+        n_cols[i] = len(g["column_centers"])
+        centers[i, : n_cols[i]] = np.asarray(g["column_centers"], np.int32)
+    n_cols[3] = 0  # a page without columns -> -1 everywhere
+    # select every second box of each page, the rest must stay -1
+    sel = np.concatenate([np.arange(off[i], off[i + 1], 2) for i in range(len(f1_pages))]).astype(np.int32)
+    n_sel = np.asarray([len(range(off[i], off[i + 1], 2)) for i in range(len(f1_pages))], np.int32)
+    sel_buf = np.zeros(len(boxes), np.int32)
+    for i in range(len(f1_pages)):
+        chunk = np.arange(off[i], off[i + 1], 2)
+        sel_buf[off[i]: off[i] + len(chunk)] = chunk
+    got = ops.assign_columns(boxes, off, centers, n_cols, sel_idx=sel_buf, n_sel=n_sel).cpu().numpy()
+    expect = np.full(len(boxes), -1, np.int64)
+    for i, p in enumerate(f1_pages):
+        idx = np.arange(off[i], off[i + 1], 2)
+        expect[idx] = ob.assign_columns(boxes[idx].tolist(), centers[i, : n_cols[i]].tolist())
+    assert np.array_equal(got, expect)
+    assert (got >= 0).sum() > 1500 and (got[off[3]: off[4]] == -1).all()
 
 
 def test_columns_guards():

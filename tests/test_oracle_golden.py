@@ -127,6 +127,31 @@ def test_nms_idempotent_on_reference_outputs(f1_pages):
         assert nms_pick_order_c(p["boxes"], p["scores"], p["classes"], 0.5).tolist() == list(range(n))
 
 
+def test_tile_nms_restatement_matches_torchvision_goldens():
+    """Per-tile class-agnostic NMS (1_doclayout_bboxes.py:217-225): the float32 restatement against
+    outputs of torchvision.ops.nms itself (goldens), and live when torchvision is importable."""
+    g = load_golden("stage1_tile_nms.npz")
+    assert len(g["cases"]) == 5
+    for name in g["cases"]:
+        b, s, thr = g[f"{name}_boxes"], g[f"{name}_scores"], float(g[f"{name}_thr"][0])
+        assert ob.nms_torchvision_f32(b, s, thr) == g[f"{name}_keep"].tolist(), name
+        assert 0 < len(g[f"{name}_keep"]) < len(s)
+    try:
+        import torch
+        import torchvision
+    except Exception:
+        return
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        n = int(rng.integers(1, 300))
+        xy = rng.uniform(0, 500, (n, 2)).astype(np.float32)
+        wh = rng.uniform(1, 200, (n, 2)).astype(np.float32)
+        b = np.concatenate([xy, xy + wh], 1)
+        s = rng.uniform(0, 1, n).astype(np.float32)
+        ref = torchvision.ops.nms(torch.tensor(b), torch.tensor(s), 0.45).numpy().tolist()
+        assert ob.nms_torchvision_f32(b, s, 0.45) == ref
+
+
 # ---------------------------------------------------------------- stages 4-5
 def test_stage45_on_reference_outputs(f1_pages, f4):
     for p, g in zip(f1_pages, f4):

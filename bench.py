@@ -238,8 +238,8 @@ def main():
         groups.setdefault(sizes[(first_page + i) % len(sizes)], []).append(first_page + i)
     stream = torch.cuda.current_stream()
     pipes = []
-    alg_bytes_step = 0
-    for (w, h), idxs in groups.items():
+    if len(groups) == 1:
+        (w, h), idxs = next(iter(groups.items()))
         plan = ops.TilePlan(w, h, [(rows, cols)], 20.0)
         pages = plan.alloc_pages(len(idxs))
         for j, gi in enumerate(idxs):  # page content depends on the global page index only
@@ -248,13 +248,36 @@ def main():
         pipe = PagePipeline(plan, len(idxs), corpus_stats=args.corpus_stats, overlap=not args.no_overlap)
         host = pipe.set_detections(dets)
         pipes.append((plan, pipe, pages, host, dets))
-        alg_bytes_step += plan.algorithmic_bytes * len(idxs) + 48 * pipe.n_boxes
+    else:  # mixed page sizes: ONE heterogeneous tiler batch + ONE box pipeline for the whole shard
+        page_sizes = [sizes[(first_page + i) % len(sizes)] for i in range(ppg)]
+        batch = ops.TileBatch(page_sizes, [(rows, cols)], 20.0)
+        pages = batch.alloc_pages()
+        for j, (w, h) in enumerate(page_sizes):
+            ops.synth_pages(batch.plan_of(j), 1, synth.PAGE_SEED0, first_page=first_page + j, out=pages[j].unsqueeze(0))
+        batch.bind(pages)
+        dets = [synth.page_detections(w, h, rows, cols, 20.0, spec["boxes"], synth.PAGE_SEED0 + first_page + j)
+                for j, (w, h) in enumerate(page_sizes)]
+        pipe = PagePipeline(batch, ppg, corpus_stats=args.corpus_stats, overlap=not args.no_overlap)
+        host = pipe.set_detections(dets)
+        pipes.append((batch, pipe, pages, host, dets))
     torch.cuda.synchronize()
+
+    def is_batch(t):
+        return isinstance(t, ops.TileBatch)
+
+    def tiler_alone(t, pipe, pages):
+        return t.run() if is_batch(t) else t.run(pages, out=pipe.tiles_out)
+
+    def tiler_alg_bytes(t, pipe):
+        return t.algorithmic_bytes if is_batch(t) else t.algorithmic_bytes * pipe.n_pages
+
+    def input_bytes(pages):
+        return sum(p.numel() for p in pages) if isinstance(pages, list) else pages.numel()
 
     def step(ev=None):
         for k, (plan, pipe, pages, _, _) in enumerate(pipes):
             if args.tiler_only:
-                plan.run(pages, out=pipe.tiles_out)
+                tiler_alone(plan, pipe, pages)
             else:
                 pipe.run(pages, tiler_events=ev[k] if ev is not None else None)
         if args.corpus_stats:
@@ -304,7 +327,7 @@ def main():
         tiler_ms = ms / args.steps
     else:
         tiler_ms = sum(a.elapsed_time(b) for evs in tiler_ev for (a, b) in evs) / args.steps
-    tiler_bytes = sum(plan.algorithmic_bytes * pipe.n_pages for plan, pipe, _, _, _ in pipes)
+    tiler_bytes = sum(tiler_alg_bytes(plan, pipe) for plan, pipe, _, _, _ in pipes)
     achieved = tiler_bytes / (tiler_ms * 1e-3) / 1e9
     traffic = None
     try:
@@ -328,7 +351,7 @@ def main():
         ia.record(stream)
         for _ in range(n_iso):
             for plan, pipe, pages, _, _ in pipes:
-                plan.run(pages, out=pipe.tiles_out)
+                tiler_alone(plan, pipe, pages)
         ib.record(stream)
         torch.cuda.synchronize()
         iso_ms = ia.elapsed_time(ib) / n_iso
@@ -341,7 +364,7 @@ def main():
         "dtype": "u8 pixels -> f16 tiles (11-bit fixed point), f64 boxes", "data": "synthetic",
         "config": {"workload": spec["name"], "pages_per_gpu": ppg, "global_pages_per_step": ppg * world,
                    "parallelism": f"page-sharded x{world}, no collective" + (" + hist all-reduce" if args.corpus_stats else ""),
-                   "l2": f"inputs {sum(p[2].numel() for p in pipes) / 1e9:.1f} GB/step per GPU >> 126 MB L2 (no flush needed)",
+                   "l2": f"inputs {sum(input_bytes(p[2]) for p in pipes) / 1e9:.1f} GB/step per GPU >> 126 MB L2 (no flush needed)",
                    "streams": "tiler (low priority) || box stages (high priority)" if not args.no_overlap else "single stream",
                    "stages": "tiler only" if args.tiler_only else "tile+letterbox, translate+edge filter, NMS merge, width median, column peaks"},
         "roofline": roofline, "clocks": clocks, "merge_stats_last_group": nms_stats,
@@ -352,17 +375,31 @@ def main():
     if not args.no_e2e and not args.tiler_only:
         plan, pipe0, pages0, host0, dets0 = pipes[0]
         n_e = min(args.e2e_pages, pipe0.n_pages)
-        epipe = PagePipeline(plan, n_e, overlap=not args.no_overlap)
+        if is_batch(plan):
+            etiler = ops.TileBatch(plan.sizes[:n_e], [(rows, cols)], 20.0)
+            dev_list = etiler.alloc_pages()
+            etiler.bind(dev_list)
+            pin_list = [torch.empty(p.shape, dtype=torch.uint8).pin_memory() for p in dev_list]
+            for dst, src in zip(pin_list, pages0[:n_e]):
+                dst.copy_(src)
+            dev_pages, page_bytes = None, sum(p.numel() for p in pin_list)
+        else:
+            etiler = plan
+            pin_pages = torch.empty((n_e, plan.page_h, plan.pitch), dtype=torch.uint8).pin_memory()
+            pin_pages.copy_(pages0[:n_e])
+            dev_pages, page_bytes = plan.alloc_pages(n_e), pin_pages.numel()
+        epipe = PagePipeline(etiler, n_e, overlap=not args.no_overlap)
         ehost = epipe.set_detections(dets0[:n_e])
-        pin_pages = torch.empty((n_e, plan.page_h, plan.pitch), dtype=torch.uint8).pin_memory()
-        pin_pages.copy_(pages0[:n_e])
         pin_in = {k: torch.from_numpy(v).pin_memory() for k, v in ehost.items()}
         pin_out = {n: torch.empty_like(getattr(epipe, n), device="cpu").pin_memory()
                    for n in ("kept2", "n_kept2", "median", "n_bins", "centers", "col_widths", "n_cols")}
-        dev_pages = plan.alloc_pages(n_e)
 
         def e2e_step():
-            dev_pages.copy_(pin_pages, non_blocking=True)
+            if dev_pages is None:
+                for dst, src in zip(dev_list, pin_list):
+                    dst.copy_(src, non_blocking=True)
+            else:
+                dev_pages.copy_(pin_pages, non_blocking=True)
             nb = epipe.upload_detections(ehost, pinned=pin_in)
             epipe.run(dev_pages)
             epipe.results_to_host(pinned=pin_out)
@@ -388,7 +425,7 @@ def main():
             e_ms = float(t.item())
         epipe.check_status()
         line["e2e"] = {"value": n_e * world * e2e_steps / (e_ms * 1e-3), "unit": UNIT,
-                       "h2d_bytes_per_step": int(pin_pages.numel() + box_bytes), "d2h_bytes_per_step": epipe.result_bytes(),
+                       "h2d_bytes_per_step": int(page_bytes + box_bytes), "d2h_bytes_per_step": epipe.result_bytes(),
                        "pages_per_step": n_e * world, "steps": e2e_steps,
                        "note": "pinned host pages+detections -> H2D -> 11 kernels -> D2H kept indices/medians/columns; "
                                "fp16 tiles stay in HBM for the detector"}

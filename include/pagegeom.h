@@ -95,6 +95,20 @@ int pg_tile_letterbox(PgTilePlan* plan, const uint8_t* pages, int32_t n_pages, i
 int pg_tile_letterbox_direct(PgTilePlan* plan, const uint8_t* pages, int32_t n_pages, int64_t pitch,
                              int64_t page_stride, void* out_f16, int64_t out_page_stride, void* stream);
 
+/* Heterogeneous batches: pages of different sizes (one plan per distinct size) tiled by ONE launch —
+ * what a real corpus looks like (the reference's 19 scans have 19 sizes).  page_plan[i] names the plan
+ * of page i; bind() records each page's device pointer, pitch and output buffer (pg_tile_plan_out_elems
+ * of its plan); the plans may be destroyed after create().  Same kernel, same arithmetic. */
+typedef struct PgTileBatch PgTileBatch;
+int pg_tile_batch_create(const PgTilePlan* const* plans, int32_t n_plans, const int32_t* page_plan,
+                         int32_t n_pages, PgTileBatch** batch);
+void pg_tile_batch_destroy(PgTileBatch* batch);
+int64_t pg_tile_batch_algorithmic_bytes(const PgTileBatch* batch);
+int pg_tile_batch_bind(PgTileBatch* batch, const uint8_t* const* page_ptrs /*host array of dev ptrs*/,
+                       const int64_t* pitches /*host [P]*/, void* const* out_ptrs /*host array of dev ptrs*/,
+                       void* stream);
+int pg_tile_letterbox_batch(PgTileBatch* batch, void* stream);
+
 /* Synthetic newspaper-like pages generated on the device (counter-based hash of
  * (seed0 + first_page + p, y, x)); used by bench.py so inputs are HBM-resident. */
 int pg_synth_pages(uint8_t* pages, int32_t n_pages, int32_t page_w, int32_t page_h, int64_t pitch,

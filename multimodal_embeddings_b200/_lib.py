@@ -53,6 +53,11 @@ SIGNATURES = {
     "pg_tile_plan_algorithmic_bytes": (_I64, [_P]),
     "pg_tile_letterbox": (C.c_int, [_P, _P, _I32, _I64, _I64, _P, _I64, _P]),
     "pg_tile_letterbox_direct": (C.c_int, [_P, _P, _I32, _I64, _I64, _P, _I64, _P]),
+    "pg_tile_batch_create": (C.c_int, [_P, _I32, _P, _I32, _P]),
+    "pg_tile_batch_destroy": (None, [_P]),
+    "pg_tile_batch_algorithmic_bytes": (_I64, [_P]),
+    "pg_tile_batch_bind": (C.c_int, [_P, _P, _P, _P, _P]),
+    "pg_tile_letterbox_batch": (C.c_int, [_P, _P]),
     "pg_synth_pages": (C.c_int, [_P, _I32, _I32, _I32, _I64, _I64, C.c_uint64, _I64, _P]),
     "pg_edge_filter": (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _F64, _P, _P, _P, _P, _P]),
     "pg_nms_workspace_bytes": (C.c_size_t, [_I64, _I32, _I32]),

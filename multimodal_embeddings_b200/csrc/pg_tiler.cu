@@ -337,7 +337,19 @@ constexpr int TL_STAGES_DEFAULT = 3;         // shared-memory ring depth (templa
 constexpr int TL_ITEMS_PER_CTA = 4;           // bands of TL_BAND rows a CTA claims before retiring
 constexpr int TL_PAIR_STRIDE = TL_CW * 64;    // pixels covered by all consumer warps per iteration
 
+// one page of a heterogeneous batch (pages of different sizes in one launch)
+struct PageDesc {
+  const uint8_t* src;  // page pixels
+  __half* out;         // this page's tile buffer
+  int64_t pitch;
+  long long item_off;  // first global work item of this page
+  int32_t item_base;   // where this page's plan starts in the concatenated item table
+  int32_t tile_base;   // ... and in the concatenated tile table
+};
+
 struct TilerArgs {
+  const PageDesc* page_desc;  // non-null: heterogeneous batch (pages/out/pitch/strides below unused)
+  int32_t n_pages;
   const uint8_t* pages;
   __half* out;
   const TileDev* tiles;
@@ -414,11 +426,31 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
       for (int n = 0; n < a.items_per_cta; ++n) {
         const long long it = (long long)atomicAdd(&a.counters[0], 1ull);
         if (it >= a.total_items) break;
-        const long long page = it / a.items_per_page;
-        const int4 item = a.items[it - page * a.items_per_page];
+        long long page;
+        int4 item;
+        int64_t pitch;
+        const uint8_t* page_src;
+        if (a.page_desc) {  // heterogeneous batch: find the page that owns work item `it`
+          int lo = 0, hi = a.n_pages - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (a.page_desc[mid].item_off <= it) lo = mid; else hi = mid - 1;
+          }
+          page = lo;
+          const PageDesc& pd = a.page_desc[lo];
+          item = a.items[pd.item_base + (int)(it - pd.item_off)];
+          item.x += pd.tile_base;
+          pitch = pd.pitch;
+          page_src = pd.src;
+        } else {
+          page = it / a.items_per_page;
+          item = a.items[it - page * a.items_per_page];
+          pitch = a.pitch;
+          page_src = a.pages + page * a.page_stride;
+        }
         const TileDev& t = a.tiles[item.x];
         const int pad_t = t.pad_t, new_h = t.new_h, ytab_off = t.ytab_off;
-        const uint8_t* src = a.pages + page * a.page_stride + (int64_t)t.y0 * a.pitch + ((3 * t.x0) & ~15);
+        const uint8_t* src = page_src + (int64_t)t.y0 * pitch + ((3 * t.x0) & ~15);
         const uint32_t bytes = (uint32_t)t.row_bytes;
         for (int oy = item.y; oy < item.y + item.z; ++oy) {
           const int ry = oy - pad_t;
@@ -432,8 +464,8 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
           } else {
             mbar_expect_tx(&full_bar[stage], 2u * bytes);
             uint8_t* dst = smem + stage * stage_bytes;
-            bulk_g2s(dst, src + (int64_t)yt.x * a.pitch, bytes, &full_bar[stage]);
-            bulk_g2s(dst + a.row_stride, src + (int64_t)yt.y * a.pitch, bytes, &full_bar[stage]);
+            bulk_g2s(dst, src + (int64_t)yt.x * pitch, bytes, &full_bar[stage]);
+            bulk_g2s(dst + a.row_stride, src + (int64_t)yt.y * pitch, bytes, &full_bar[stage]);
           }
           if (++stage == TL_STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -490,7 +522,8 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
     }
     if (m.y != cached_page) {
       cached_page = m.y;
-      tile_ptr = reinterpret_cast<uint32_t*>(a.out + (int64_t)m.y * a.out_page_stride + out_off) + (px0 >> 1);
+      __half* page_out = a.page_desc ? a.page_desc[m.y].out : a.out + (int64_t)m.y * a.out_page_stride;
+      tile_ptr = reinterpret_cast<uint32_t*>(page_out + out_off) + (px0 >> 1);
     }
     const int oy = m.z & ~TL_MSG_PADROW;
     uint32_t* pr = tile_ptr + (int64_t)oy * (out_w >> 1);
@@ -575,6 +608,8 @@ static int check_pages_layout(const PgTilePlan* plan, const uint8_t* pages, int3
 static TilerArgs make_args(const PgTilePlan* plan, const uint8_t* pages, int32_t n_pages, int64_t pitch,
                            int64_t page_stride, void* out, int64_t out_page_stride) {
   TilerArgs a;
+  a.page_desc = nullptr;
+  a.n_pages = n_pages;
   a.pages = pages;
   a.out = reinterpret_cast<__half*>(out);
   a.tiles = plan->d_tiles;
@@ -631,6 +666,8 @@ static int launch_pipeline(TilerArgs a, cudaStream_t s) {
   return PG_OK;
 }
 
+static int dispatch_pipeline(const TilerArgs& a, int max_out_w, cudaStream_t s);
+
 extern "C" int pg_tile_letterbox(PgTilePlan* plan, const uint8_t* pages, int32_t n_pages, int64_t pitch,
                                  int64_t page_stride, void* out_f16, int64_t out_page_stride, void* stream) {
   int rc = check_pages_layout(plan, pages, n_pages, pitch, page_stride, out_f16, out_page_stride);
@@ -640,7 +677,11 @@ extern "C" int pg_tile_letterbox(PgTilePlan* plan, const uint8_t* pages, int32_t
   rc = plan_upload(plan, s);
   if (rc != PG_OK) return rc;
   const TilerArgs a = make_args(plan, pages, n_pages, pitch, page_stride, out_f16, out_page_stride);
-  const int iters = (plan->max_out_w + TL_PAIR_STRIDE - 1) / TL_PAIR_STRIDE;
+  return dispatch_pipeline(a, plan->max_out_w, s);
+}
+
+static int dispatch_pipeline(const TilerArgs& a, int max_out_w, cudaStream_t s) {
+  const int iters = (max_out_w + TL_PAIR_STRIDE - 1) / TL_PAIR_STRIDE;
   int stages = TL_STAGES_DEFAULT;
   if (const char* e = getenv("PG_TILER_STAGES")) stages = atoi(e);  // tuning knob: 3 (4 CTAs/SM) or 4 (3 CTAs/SM)
   if (stages == 3) {
@@ -652,7 +693,7 @@ extern "C" int pg_tile_letterbox(PgTilePlan* plan, const uint8_t* pages, int32_t
     if (iters <= 2) return launch_pipeline<2, 4>(a, s);
     if (iters <= 4) return launch_pipeline<4, 4>(a, s);
   }
-  pg_set_error("unsupported: output width %d > %d", plan->max_out_w, 4 * TL_PAIR_STRIDE);
+  pg_set_error("unsupported: output width %d > %d", max_out_w, 4 * TL_PAIR_STRIDE);
   return PG_ERR_UNSUPPORTED;
 }
 
@@ -672,6 +713,161 @@ extern "C" int pg_tile_letterbox_direct(PgTilePlan* plan, const uint8_t* pages, 
   tile_letterbox_direct_kernel<<<grid, 256, 0, s>>>(a, n_tiles, n_pages);
   PG_LAUNCH_CHECK();
   return PG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// heterogeneous batches: pages of different sizes (one plan per size) tiled by ONE launch.
+// The batch concatenates the plans' tables; the kernel maps a global work item to its page by a
+// binary search over per-page item offsets (done by the producer lane, once per 16-row band).
+struct PgTileBatch {
+  std::vector<int32_t> page_plan;
+  std::vector<int32_t> plan_w, plan_h, plan_tile_base, plan_item_base, plan_item_count;
+  std::vector<int64_t> plan_out_elems;
+  std::vector<TileDev> tiles;
+  std::vector<uint2> xtab;
+  std::vector<int4> ytab;
+  std::vector<int4> items;
+  std::vector<PageDesc> desc;
+  int64_t total_items = 0, alg_bytes = 0;
+  int32_t max_row_bytes = 0, max_out_w = 0;
+  int device = -1;
+  bool bound = false;
+  TileDev* d_tiles = nullptr;
+  uint2* d_xtab = nullptr;
+  int4* d_ytab = nullptr;
+  int4* d_items = nullptr;
+  PageDesc* d_desc = nullptr;
+  unsigned long long* d_counters = nullptr;
+};
+
+static void batch_free_device(PgTileBatch* b) {
+  cudaFree(b->d_tiles); cudaFree(b->d_xtab); cudaFree(b->d_ytab); cudaFree(b->d_items); cudaFree(b->d_desc);
+  cudaFree(b->d_counters);
+  b->d_tiles = nullptr; b->d_xtab = nullptr; b->d_ytab = nullptr; b->d_items = nullptr; b->d_desc = nullptr;
+  b->d_counters = nullptr;
+  b->device = -1;
+  b->bound = false;
+}
+
+extern "C" int pg_tile_batch_create(const PgTilePlan* const* plans, int32_t n_plans, const int32_t* page_plan,
+                                    int32_t n_pages, PgTileBatch** out) {
+  PG_REQUIRE(plans && page_plan && out && n_plans > 0 && n_pages > 0, "batch arguments");
+  auto* b = new PgTileBatch();
+  for (int k = 0; k < n_plans; ++k) {
+    const PgTilePlan* p = plans[k];
+    if (!p) {
+      delete b;
+      pg_set_error("invalid argument: plan %d is null", k);
+      return PG_ERR_INVALID;
+    }
+    const int32_t xb = (int32_t)b->xtab.size(), yb = (int32_t)b->ytab.size();
+    b->plan_tile_base.push_back((int32_t)b->tiles.size());
+    b->plan_item_base.push_back((int32_t)b->items.size());
+    b->plan_item_count.push_back((int32_t)p->items.size());
+    b->plan_w.push_back(p->page_w);
+    b->plan_h.push_back(p->page_h);
+    b->plan_out_elems.push_back(p->out_elems);
+    for (TileDev t : p->tiles) {
+      t.xtab_off += xb;
+      t.ytab_off += yb;
+      b->tiles.push_back(t);
+    }
+    b->xtab.insert(b->xtab.end(), p->xtab.begin(), p->xtab.end());
+    b->ytab.insert(b->ytab.end(), p->ytab.begin(), p->ytab.end());
+    b->items.insert(b->items.end(), p->items.begin(), p->items.end());
+    b->max_row_bytes = std::max(b->max_row_bytes, p->max_row_bytes);
+    b->max_out_w = std::max(b->max_out_w, p->max_out_w);
+  }
+  b->page_plan.assign(page_plan, page_plan + n_pages);
+  long long off = 0;
+  for (int i = 0; i < n_pages; ++i) {
+    const int k = page_plan[i];
+    if (k < 0 || k >= n_plans) {
+      delete b;
+      pg_set_error("invalid argument: page %d refers to plan %d", i, k);
+      return PG_ERR_INVALID;
+    }
+    PageDesc d;
+    d.src = nullptr; d.out = nullptr; d.pitch = 0;
+    d.item_off = off;
+    d.item_base = b->plan_item_base[k];
+    d.tile_base = b->plan_tile_base[k];
+    b->desc.push_back(d);
+    off += b->plan_item_count[k];
+    b->alg_bytes += (int64_t)3 * b->plan_w[k] * b->plan_h[k] + 2 * b->plan_out_elems[k];
+  }
+  b->total_items = off;
+  *out = b;
+  return PG_OK;
+}
+
+extern "C" void pg_tile_batch_destroy(PgTileBatch* b) {
+  if (!b) return;
+  batch_free_device(b);
+  delete b;
+}
+extern "C" int64_t pg_tile_batch_algorithmic_bytes(const PgTileBatch* b) { return b ? b->alg_bytes : 0; }
+
+extern "C" int pg_tile_batch_bind(PgTileBatch* b, const uint8_t* const* page_ptrs, const int64_t* pitches,
+                                  void* const* out_ptrs, void* stream) {
+  PG_REQUIRE(b && page_ptrs && pitches && out_ptrs, "batch bind arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  int dev = 0;
+  PG_CUDA_TRY(cudaGetDevice(&dev));
+  const size_t n = b->desc.size();
+  for (size_t i = 0; i < n; ++i) {
+    const int k = b->page_plan[i];
+    PG_REQUIRE(page_ptrs[i] && out_ptrs[i], "null page / output pointer");
+    PG_REQUIRE(((uintptr_t)page_ptrs[i] & 15) == 0 && pitches[i] % 16 == 0 && pitches[i] >= (int64_t)3 * b->plan_w[k],
+               "each page must be 16-byte aligned with pitch >= 3*W and a multiple of 16");
+    PG_REQUIRE(((uintptr_t)out_ptrs[i] & 3) == 0, "outputs must be 4-byte aligned");
+    b->desc[i].src = page_ptrs[i];
+    b->desc[i].out = reinterpret_cast<__half*>(out_ptrs[i]);
+    b->desc[i].pitch = pitches[i];
+  }
+  if (b->device != dev) {
+    batch_free_device(b);
+    PG_CUDA_TRY(cudaMalloc(&b->d_tiles, b->tiles.size() * sizeof(TileDev)));
+    PG_CUDA_TRY(cudaMalloc(&b->d_xtab, b->xtab.size() * sizeof(uint2)));
+    PG_CUDA_TRY(cudaMalloc(&b->d_ytab, b->ytab.size() * sizeof(int4)));
+    PG_CUDA_TRY(cudaMalloc(&b->d_items, b->items.size() * sizeof(int4)));
+    PG_CUDA_TRY(cudaMalloc(&b->d_desc, n * sizeof(PageDesc)));
+    PG_CUDA_TRY(cudaMalloc(&b->d_counters, 2 * sizeof(unsigned long long)));
+    PG_CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, 2 * sizeof(unsigned long long), s));
+    PG_CUDA_TRY(cudaMemcpyAsync(b->d_tiles, b->tiles.data(), b->tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice, s));
+    PG_CUDA_TRY(cudaMemcpyAsync(b->d_xtab, b->xtab.data(), b->xtab.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
+    PG_CUDA_TRY(cudaMemcpyAsync(b->d_ytab, b->ytab.data(), b->ytab.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
+    PG_CUDA_TRY(cudaMemcpyAsync(b->d_items, b->items.data(), b->items.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
+    b->device = dev;
+  }
+  PG_CUDA_TRY(cudaMemcpyAsync(b->d_desc, b->desc.data(), n * sizeof(PageDesc), cudaMemcpyHostToDevice, s));
+  PG_CUDA_TRY(cudaStreamSynchronize(s));  // host vectors are pageable; binding is a one-off per buffer set
+  b->bound = true;
+  return PG_OK;
+}
+
+extern "C" int pg_tile_letterbox_batch(PgTileBatch* b, void* stream) {
+  PG_REQUIRE(b != nullptr, "batch");
+  if (!b->bound) {
+    pg_set_error("invalid argument: pg_tile_batch_bind must be called before pg_tile_letterbox_batch");
+    return PG_ERR_INVALID;
+  }
+  TilerArgs a;
+  a.page_desc = b->d_desc;
+  a.n_pages = (int32_t)b->desc.size();
+  a.pages = nullptr;
+  a.out = nullptr;
+  a.tiles = b->d_tiles;
+  a.xtab = b->d_xtab;
+  a.ytab = b->d_ytab;
+  a.items = b->d_items;
+  a.pitch = a.page_stride = a.out_page_stride = 0;
+  a.items_per_page = 1;
+  a.total_items = b->total_items;
+  a.row_stride = (b->max_row_bytes + 16 + 127) & ~127;
+  a.items_per_cta = 1;
+  a.counters = b->d_counters;
+  return dispatch_pipeline(a, b->max_out_w, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -112,6 +112,72 @@ class TilePlan:
         return out[page, t["out_offset"]: t["out_offset"] + n].view(3, t["out_h"], t["out_w"])
 
 
+class TileBatch:
+    """Pages of different sizes tiled by one launch (pg_tile_batch_*).
+
+    sizes: [(W, H)] per page; one TilePlan is built per distinct size.  ``pages[i]`` is a cuda uint8
+    tensor [H_i, pitch_i]; outputs are allocated here as one fp16 tensor per page."""
+
+    def __init__(self, sizes: Sequence[Tuple[int, int]], grids: Sequence[Tuple[int, int]] = ((2, 2),),
+                 overlap: float = 20.0, imgsz: int = 1024, stride: int = 32, auto: bool = True):
+        _require_cuda()
+        self.sizes = [(int(w), int(h)) for w, h in sizes]
+        self.plans: List[TilePlan] = []
+        index = {}
+        self.page_plan = []
+        for s in self.sizes:
+            if s not in index:
+                index[s] = len(self.plans)
+                self.plans.append(TilePlan(s[0], s[1], grids, overlap, imgsz, stride, auto))
+            self.page_plan.append(index[s])
+        n = len(self.sizes)
+        plan_arr = (C.c_void_p * len(self.plans))(*[p._h for p in self.plans])
+        pp = (C.c_int32 * n)(*self.page_plan)
+        handle = C.c_void_p()
+        check(lib().pg_tile_batch_create(plan_arr, len(self.plans), pp, n, C.byref(handle)))
+        self._h = handle
+        self.algorithmic_bytes = int(lib().pg_tile_batch_algorithmic_bytes(self._h))
+        self.pages: List[torch.Tensor] = []
+        self.outs: List[torch.Tensor] = []
+
+    def plan_of(self, page: int) -> TilePlan:
+        return self.plans[self.page_plan[page]]
+
+    def alloc_pages(self) -> List[torch.Tensor]:
+        return [torch.empty((h, row_pitch(w)), dtype=torch.uint8, device="cuda") for (w, h) in self.sizes]
+
+    def bind(self, pages: Sequence[torch.Tensor], stream=None) -> List[torch.Tensor]:
+        n = len(self.sizes)
+        assert len(pages) == n
+        for t, (w, h) in zip(pages, self.sizes):
+            assert t.is_cuda and t.dtype == torch.uint8 and t.dim() == 2 and t.shape[0] == h and t.is_contiguous()
+        self.pages = list(pages)
+        self.outs = [torch.empty(self.plan_of(i).out_elems, dtype=torch.float16, device="cuda") for i in range(n)]
+        src = (C.c_void_p * n)(*[t.data_ptr() for t in self.pages])
+        pit = (C.c_int64 * n)(*[t.shape[1] for t in self.pages])
+        dst = (C.c_void_p * n)(*[t.data_ptr() for t in self.outs])
+        check(lib().pg_tile_batch_bind(self._h, src, pit, dst, stream_ptr(stream)))
+        return self.outs
+
+    def run(self, stream=None) -> List[torch.Tensor]:
+        check(lib().pg_tile_letterbox_batch(self._h, stream_ptr(stream)))
+        return self.outs
+
+    def tile_view(self, page: int, tile: int) -> torch.Tensor:
+        t = self.plan_of(page).tiles[tile]
+        n = 3 * t["out_h"] * t["out_w"]
+        return self.outs[page][t["out_offset"]: t["out_offset"] + n].view(3, t["out_h"], t["out_w"])
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().pg_tile_batch_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
 def upload_pages(images: Sequence[np.ndarray], plan: TilePlan, stream=None) -> torch.Tensor:
     """Host BGR uint8 HxWx3 arrays -> pitched cuda tensor [P, H, pitch] through pinned memory."""
     _require_cuda()

@@ -69,7 +69,10 @@ class PagePipeline:
         self.iou_threshold, self.edge_threshold = float(iou_threshold), float(edge_threshold)
         self.min_margin_percent, self.min_confidence = float(min_margin_percent), float(min_confidence)
         self.max_cols, self.plain_text_id, self.title_id = int(max_cols), float(plain_text_id), float(title_id)
-        self.tiles_out = plan.alloc_out(self.n_pages)
+        # `plan` is a TilePlan (n_pages pages of one size, contiguous) or a TileBatch (pages of mixed sizes,
+        # already bound to their buffers): the box stages do not care, page sizes travel in page_wh
+        self.batch = plan if isinstance(plan, ops.TileBatch) else None
+        self.tiles_out = None if self.batch is not None else plan.alloc_out(self.n_pages)
         self.n_boxes = 0
         self.corpus_stats = corpus_stats
         self.width_hist = self.col_hist = None
@@ -177,8 +180,11 @@ class PagePipeline:
         L, s, p, plan = lib(), stream.cuda_stream, self.n_pages, self.plan
         if tiler_events is not None:
             tiler_events[0].record(stream)
-        check(L.pg_tile_letterbox(plan._h, ptr(pages), p, pages.shape[2], pages.shape[1] * pages.shape[2],
-                                  ptr(self.tiles_out), self.tiles_out.stride(0), s))
+        if self.batch is not None:
+            check(L.pg_tile_letterbox_batch(self.batch._h, s))
+        else:
+            check(L.pg_tile_letterbox(plan._h, ptr(pages), p, pages.shape[2], pages.shape[1] * pages.shape[2],
+                                      ptr(self.tiles_out), self.tiles_out.stride(0), s))
         if tiler_events is not None:
             tiler_events[1].record(stream)
 

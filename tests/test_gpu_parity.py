@@ -102,6 +102,32 @@ def test_tiler_full_size_page_cross_check():
     assert torch.equal(again[0], pages[1])
 
 
+def test_tiler_heterogeneous_batch_one_launch():
+    """Pages of different sizes (incl. a repeated size and an upscaled one) tiled by ONE launch."""
+    sizes = [(1203, 907), (640, 480), (997, 1501), (1203, 907), (333, 217), (2000, 1400)]
+    imgs = [synth.page_pixels(w, h, seed=100 + i) for i, (w, h) in enumerate(sizes)]
+    batch = ops.TileBatch(sizes, [(1, 1), (2, 2)], 20.0, imgsz=256)
+    assert len(batch.plans) == 5
+    pages = batch.alloc_pages()
+    for t, img, (w, h) in zip(pages, imgs, sizes):
+        host = np.zeros((h, t.shape[1]), np.uint8)
+        host[:, : 3 * w] = img.reshape(h, 3 * w)
+        t.copy_(torch.from_numpy(host))
+    batch.bind(pages)
+    batch.run()
+    batch.run()  # the work counter re-arms itself between launches
+    torch.cuda.synchronize()
+    for p, img in enumerate(imgs):
+        t = 0
+        for rows, cols in [(1, 1), (2, 2)]:
+            for cell in ot.split_array_into_grid(img, rows, cols, 20.0):
+                ref = ot.u8_to_f16_unit(ot.letterbox_tile_cv2(cell["image"], 256))
+                assert np.array_equal(batch.tile_view(p, t).cpu().numpy(), ref), (p, t)
+                t += 1
+    alg = sum(3 * w * h for w, h in sizes) + 2 * sum(batch.plan_of(i).out_elems for i in range(len(sizes)))
+    assert batch.algorithmic_bytes == alg
+
+
 def test_split_image_into_grid_mirror():
     page = synth.page_pixels(900, 700, seed=5)
     cells = api.split_image_into_grid(page, 2, 2, 20.0, imgsz=256)

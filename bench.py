@@ -427,7 +427,7 @@ def main():
         line["e2e"] = {"value": n_e * world * e2e_steps / (e_ms * 1e-3), "unit": UNIT,
                        "h2d_bytes_per_step": int(page_bytes + box_bytes), "d2h_bytes_per_step": epipe.result_bytes(),
                        "pages_per_step": n_e * world, "steps": e2e_steps,
-                       "note": "pinned host pages+detections -> H2D -> 11 kernels -> D2H kept indices/medians/columns; "
+                       "note": "pinned host pages+detections -> H2D -> 12 kernels -> D2H kept indices/medians/columns; "
                                "fp16 tiles stay in HBM for the detector"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only)

@@ -4,9 +4,16 @@
 
 sm_100a only; -fmad=false so the fp64 box arithmetic is never contracted into FMAs;
 -lineinfo so ncu's source page maps back to the .cu files.
+
+Staleness is decided by a content hash of the sources (stored next to the library), not by
+mtimes — a snapshot copied to another machine keeps the prebuilt library.  Concurrent callers
+(one process per GPU under torchrun) are serialised by a file lock and the library is replaced
+atomically.
 """
 from __future__ import annotations
 
+import fcntl
+import hashlib
 import os
 import subprocess
 import sys
@@ -14,6 +21,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpagegeom.so")
+STAMP = LIB + ".srchash"
 SOURCES = ["pg_tiler.cu", "pg_boxes.cu"]
 HEADERS = ["pg_common.cuh", "pg_math.h", os.path.join("..", "..", "include", "pagegeom.h")]
 NVCC_FLAGS = [
@@ -22,26 +30,45 @@ NVCC_FLAGS = [
 ]
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB):
+def source_hash() -> str:
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
+def _stale(want: str) -> bool:
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != want
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+    want = source_hash()
+    if not force and not _stale(want):
         return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libpagegeom.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale(want):  # another rank built it while we waited
+                return LIB
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            tmp = f"{LIB}.tmp.{os.getpid()}"
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+                ["-o", tmp] + [os.path.join(CSRC, f) for f in SOURCES]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                sys.stderr.write(res.stdout + res.stderr)
+                raise RuntimeError("nvcc failed building libpagegeom.so")
+            if verbose:
+                sys.stderr.write(res.stderr)
+            os.replace(tmp, LIB)
+            with open(STAMP, "w") as f:
+                f.write(want + "\n")
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

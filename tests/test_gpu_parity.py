@@ -102,6 +102,52 @@ def test_tiler_full_size_page_cross_check():
     assert torch.equal(again[0], pages[1])
 
 
+def test_tiler_random_shapes_and_imgsz_sweep():
+    """Random page shapes / grids / overlaps / letterbox sizes: every instantiation of the pipeline kernel
+    (1, 2 and 4 pixel-pair iterations, imgsz 320..2048) against the direct kernel everywhere and against
+    cv2 on two tiles per case."""
+    rng = np.random.default_rng(77)
+    cases = [(3000, 2200, 1, 1, 0.0, 2048, True), (2100, 1500, 2, 1, 35.0, 1280, False), (801, 613, 1, 3, 20.0, 320, True)]
+    for _ in range(9):
+        w, h = int(rng.integers(200, 2600)), int(rng.integers(200, 2600))
+        rows, cols = int(rng.integers(1, 5)), int(rng.integers(1, 5))
+        ov = float(rng.choice([0.0, 10.0, 20.0, 45.0]))
+        imgsz = int(rng.choice([320, 640, 1024, 1280]))
+        cases.append((w, h, rows, cols, ov, imgsz, bool(rng.integers(0, 2))))
+    for (w, h, rows, cols, ov, imgsz, auto) in cases:
+        page = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        try:
+            plan = ops.TilePlan(w, h, [(rows, cols)], ov, imgsz, 32, auto)
+        except Exception as e:  # tiny tiles may letterbox to a zero-sized image: must be reported, not crash
+            assert "unsupported" in str(e) or "empty tile" in str(e), e
+            continue
+        pages = ops.upload_pages([page], plan)
+        out = plan.run(pages)
+        out_d = plan.run(pages, direct=True)
+        torch.cuda.synchronize()
+        assert torch.equal(out, out_d), (w, h, rows, cols, ov, imgsz, auto)
+        cells = ot.split_array_into_grid(page, rows, cols, ov)
+        for t in {0, len(cells) - 1}:
+            ref = ot.u8_to_f16_unit(ot.letterbox_tile_cv2(cells[t]["image"], imgsz, 32, auto))
+            assert np.array_equal(plan.tile_view(out, 0, t).cpu().numpy(), ref), (w, h, rows, cols, ov, imgsz, auto, t)
+
+
+def test_tiler_very_wide_tile_uses_shallower_ring():
+    """A 1x1 grid on a 14000 px wide page needs 42 KB per staged row: 3 stages do not fit in shared memory,
+    the launcher falls back to a 2-deep ring; beyond that it must report PG_ERR_UNSUPPORTED."""
+    w, h = 14000, 300
+    page = np.random.default_rng(5).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    plan = ops.TilePlan(w, h, [(1, 1)], 20.0, 1024, 32, True)
+    out = plan.run(ops.upload_pages([page], plan))
+    torch.cuda.synchronize()
+    ref = ot.u8_to_f16_unit(ot.letterbox_tile_cv2(page, 1024, 32, True))
+    assert np.array_equal(plan.tile_view(out, 0, 0).cpu().numpy(), ref)
+    from multimodal_embeddings_b200._lib import PageGeomError
+    huge = ops.TilePlan(40000, 64, [(1, 1)], 20.0, 1024, 32, True)
+    with pytest.raises(PageGeomError, match="unsupported"):
+        huge.run(huge.alloc_pages(1))
+
+
 def test_tiler_heterogeneous_batch_one_launch():
     """Pages of different sizes (incl. a repeated size and an upscaled one) tiled by ONE launch."""
     sizes = [(1203, 907), (640, 480), (997, 1501), (1203, 907), (333, 217), (2000, 1400)]

@@ -31,6 +31,10 @@ def workload_spec(name: str):
     if name == "cfg3":
         return {"name": "cfg3: synthetic 8000x6000 px scans, 4x4 grid @20% overlap, 10k detections/page",
                 "sizes": [(8000, 6000)], "grid": (4, 4), "boxes": 10000}
+    if name == "cfg5":
+        return {"name": "cfg5: 102400-page synthetic corpus (64 distinct 8000x6000 pages per GPU batch, repeated), 4x4 grid, "
+                        "10k detections/page, corpus width/column histograms accumulated on device and all-reduced once",
+                "sizes": [(8000, 6000)], "grid": (4, 4), "boxes": 10000, "total_pages": 102400}
     if name == "cfg2":
         from multimodal_embeddings_b200.synth import FIXTURE_PAGE_SIZES
         return {"name": "cfg2: the 19 newspaper_images page sizes, 2x2 grid @20% overlap, 2k detections/page",
@@ -193,7 +197,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5"])
+    ap.add_argument("--total-pages", type=int, default=0, help="cfg5: corpus size (default 102400)")
     ap.add_argument("--pages-per-gpu", type=int, default=64)
     ap.add_argument("--e2e-pages", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -231,6 +236,15 @@ def main():
     rows, cols = spec["grid"]
     ppg = args.pages_per_gpu
     first_page = rank * ppg
+    cfg5 = args.workload == "cfg5"
+    if cfg5:
+        # the corpus is streamed in 64-page batches per GPU; every rank holds the same 64 distinct pages (the
+        # global page index is taken modulo 64), so the all-reduced corpus statistics are identical for any N
+        total_pages = args.total_pages or spec["total_pages"]
+        assert total_pages % (ppg * world) == 0, "total pages must be a multiple of pages_per_gpu * n_gpus"
+        args.steps = total_pages // (ppg * world)
+        args.corpus_stats = True
+        first_page = 0
     # group pages by size (cfg3: one size; cfg2: 19 sizes round-robin) -> one plan/pipeline per size
     sizes = spec["sizes"]
     groups = {}
@@ -280,7 +294,7 @@ def main():
                 tiler_alone(plan, pipe, pages)
             else:
                 pipe.run(pages, tiler_events=ev[k] if ev is not None else None)
-        if args.corpus_stats:
+        if args.corpus_stats and not cfg5:  # per-step exchange (cfg5 reduces once, at the end of the corpus)
             for _, pipe, _, _, _ in pipes:
                 pipe.allreduce_corpus_stats()
 
@@ -297,14 +311,33 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    if cfg5:
+        for _, pipe, _, _, _ in pipes:
+            pipe.hist.zero_()  # drop what the warm-up steps accumulated
+        torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0.record(stream)
     for s_i in range(args.steps):
         step(None if args.tiler_only else tiler_ev[s_i])
+    if cfg5:  # the one exchange step of the path: integer histograms summed over ranks (NCCL over NVLink)
+        for _, pipe, _, _, _ in pipes:
+            pipe.allreduce_corpus_stats()
     e1.record(stream)
     torch.cuda.synchronize()
     clocks = sampler.stop()
+    corpus = None
+    if cfg5:
+        import hashlib
+        from multimodal_embeddings_b200._lib import PG_WIDTH_HIST_BINS
+        from multimodal_embeddings_b200.pipeline import corpus_median_width
+        hist = pipes[0][1].hist
+        hh = hist.cpu().numpy()
+        col = hh[PG_WIDTH_HIST_BINS:]
+        corpus = {"pages": ppg * world * args.steps, "plain_text_boxes": int(hh[:PG_WIDTH_HIST_BINS].sum()),
+                  "median_plain_text_width_px": corpus_median_width(hist[:PG_WIDTH_HIST_BINS]),
+                  "columns_found": int(col.sum()), "modal_column_centre_permille": int(col.argmax()),
+                  "hist_sha256": hashlib.sha256(hh.tobytes()).hexdigest()[:16]}
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
@@ -367,7 +400,7 @@ def main():
                    "l2": f"inputs {sum(input_bytes(p[2]) for p in pipes) / 1e9:.1f} GB/step per GPU >> 126 MB L2 (no flush needed)",
                    "streams": "tiler (low priority) || box stages (high priority)" if not args.no_overlap else "single stream",
                    "stages": "tiler only" if args.tiler_only else "tile+letterbox, translate+edge filter, NMS merge, width median, column peaks"},
-        "roofline": roofline, "clocks": clocks, "merge_stats_last_group": nms_stats,
+        "roofline": roofline, "clocks": clocks, "merge_stats_last_group": nms_stats, "corpus": corpus,
         "gpu_launches": (len(pipes) if args.tiler_only else KERNELS_PER_STEP * len(pipes)) * args.steps,
     }
 

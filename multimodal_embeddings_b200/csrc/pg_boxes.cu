@@ -793,11 +793,13 @@ __global__ void __launch_bounds__(MED_THREADS) width_median_kernel(
       if (flags[gi] & PG_FLAG_PLAIN_TEXT) {
         act = 1;
         w = boxes[4 * gi + 2] - boxes[4 * gi];  // :139
-        if (width_hist) {
-          const int hb = w >= 0.0 ? (w < (double)(PG_WIDTH_HIST_BINS - 1) ? (int)w : PG_WIDTH_HIST_BINS - 1) : 0;
-          atomicAdd(&width_hist[hb], 1u);
-        }
       }
+    }
+    if (width_hist) {  // corpus histogram (K6): one atomic per distinct bin per warp (widths cluster heavily)
+      const int hb = act ? (w >= 0.0 ? (w < (double)(PG_WIDTH_HIST_BINS - 1) ? (int)w : PG_WIDTH_HIST_BINS - 1) : 0)
+                         : -1 - lane;
+      const unsigned grp = __match_any_sync(0xffffffffu, hb);
+      if (act && lane == __ffs(grp) - 1) atomicAdd(&width_hist[hb], (unsigned)__popc(grp));
     }
     int total;
     const int ex = pg_block_exscan(act, scan_smem, &total);

@@ -330,6 +330,23 @@ __device__ __forceinline__ uint32_t pack_unit_half2(uint32_t va, uint32_t vb) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Second half of pg_vpass for one pixel pair of one channel, 16 bits to a lane.  a[j] = b0*(h0>>4) +
+// (2 << 16) and b[j] = b1*(h1>>4) are the row products of pixel j; the sum of their high halves is
+// 4v+r (< 1024), so v = sum >> 2 lands in byte 1 of each lane after a multiply by 64.  The two bytes
+// are then read as fp16 SUBNORMALS (0x00vv = v * 2^-24, exact) and scaled by 2^24/255 split in two
+// fp16 constants: fma(x, 64608, x*1185) equals fp16(fp32(v) * (1/255)) for all 256 v (checked
+// exhaustively on the host: tests/test_cabi_host.py::test_half2_unit_scale_exhaustive).  The FMA pipe
+// is idle in this kernel while the ALU pipe is its second limiter, hence the trade.
+__device__ __forceinline__ uint32_t vpass_pair_half2(const uint32_t (&a)[2], const uint32_t (&b)[2]) {
+  const uint32_t s = __byte_perm(a[0], a[1], 0x7632) + __byte_perm(b[0], b[1], 0x7632);
+  const uint32_t v = __byte_perm(s * 64u, 0u, 0x4341);
+  const __half2 x = *reinterpret_cast<const __half2*>(&v);
+  const __half2 c_hi = __halves2half2(__ushort_as_half(0x7be3), __ushort_as_half(0x7be3));  // 64608
+  const __half2 c_lo = __halves2half2(__ushort_as_half(0x64a1), __ushort_as_half(0x64a1));  // 1185
+  const __half2 r = __hfma2(x, c_hi, __hmul2(x, c_lo));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
 // ------------------------------------------------------------------------------------------
 // K1 persistent pipeline kernel
 constexpr int TL_CW = 8;                     // consumer warps
@@ -380,25 +397,28 @@ __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const ui
   for (int i = 0; i < ITER; ++i) {
     const int ox = i * TL_PAIR_STRIDE + px0;
     if (ox < out_w) {
-      uint32_t vb[2], vg[2], vr[2];
+      // pg_vpass split in two: the 32-bit products of each source row (rounding +2 folded into the
+      // row-0 product's addend), then both pixels of the pair finished 16 bits to a lane.
+      uint32_t ab[2], ag[2], ar[2], bb[2], bg[2], br[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         if (XPAD && coef[i][j] == TL_PADMARK) {
-          vb[j] = vg[j] = vr[j] = TL_PAD_VALUE;
+          ab[j] = ag[j] = ar[j] = (4u * TL_PAD_VALUE + 2u) << 16;
+          bb[j] = bg[j] = br[j] = 0u;
         } else {
           uint32_t tb, tg, tr, ub, ug, ur;
           hpass_smem(row0, xoff[i][j], coef[i][j], tb, tg, tr);
           hpass_smem(row1, xoff[i][j], coef[i][j], ub, ug, ur);
-          vb[j] = pg_vpass(tb, ub, b0, b1);
-          vg[j] = pg_vpass(tg, ug, b0, b1);
-          vr[j] = pg_vpass(tr, ur, b0, b1);
+          ab[j] = b0 * (tb >> 4) + 0x20000u;  bb[j] = b1 * (ub >> 4);
+          ag[j] = b0 * (tg >> 4) + 0x20000u;  bg[j] = b1 * (ug >> 4);
+          ar[j] = b0 * (tr >> 4) + 0x20000u;  br[j] = b1 * (ur >> 4);
         }
       }
       // BGR -> RGB planes
       // pr/pg/pb already point at this thread's first pixel pair of the row in each plane
-      __stcs(pr + i * (TL_PAIR_STRIDE / 2), pack_unit_half2(vr[0], vr[1]));
-      __stcs(pg + i * (TL_PAIR_STRIDE / 2), pack_unit_half2(vg[0], vg[1]));
-      __stcs(pb + i * (TL_PAIR_STRIDE / 2), pack_unit_half2(vb[0], vb[1]));
+      __stcs(pr + i * (TL_PAIR_STRIDE / 2), vpass_pair_half2(ar, br));
+      __stcs(pg + i * (TL_PAIR_STRIDE / 2), vpass_pair_half2(ag, bg));
+      __stcs(pb + i * (TL_PAIR_STRIDE / 2), vpass_pair_half2(ab, bb));
     }
   }
 }

@@ -189,6 +189,30 @@ def test_hostcheck_resize_rows_equal_cv2(lib, src, dst):
         assert np.array_equal(out, ref[dy])
 
 
+def test_half2_unit_scale_exhaustive():
+    """The tiler's epilogue (pg_tiler.cu vpass_pair_half2) reads the byte v as the fp16 subnormal
+    v*2^-24 and computes fma(x, 64608, rn16(x*1185)).  Every product and sum below is exact in
+    fp64, so one np.float16 conversion models each fp16 rounding; the result must be
+    fp16(fp32(v)/255) — what LetterBox + `.half() / 255` produce — for all 256 byte values."""
+    c_hi = float(np.uint16(0x7BE3).view(np.float16))
+    c_lo = float(np.uint16(0x64A1).view(np.float16))
+    assert (c_hi, c_lo) == (64608.0, 1185.0)
+    v = np.arange(256)
+    want = (v.astype(np.float32) / np.float32(255.0)).astype(np.float16)
+    x = v.astype(np.uint16).view(np.float16).astype(np.float64)
+    e = (x * c_lo).astype(np.float16).astype(np.float64)
+    got = (x * c_hi + e).astype(np.float16)
+    assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
+    # and the integer half: ((a>>16)+(b>>16)+2)>>2 == byte 1 of 64*((a+(2<<16))>>16 + (b>>16))
+    rng = np.random.default_rng(7)
+    b0 = rng.integers(0, 2049, 200000)
+    h0, h1 = rng.integers(0, 255 * 2048 + 1, (2, 200000))
+    a, b = b0 * (h0 >> 4), (2048 - b0) * (h1 >> 4)
+    ref = ((a >> 16) + (b >> 16) + 2) >> 2
+    new = ((((a + 0x20000) >> 16) + (b >> 16)) * 64 >> 8) & 0xFF
+    assert np.array_equal(ref, new) and (((a + 0x20000) >> 16) + (b >> 16)).max() < 1024 and (a + 0x20000).max() < 2 ** 32
+
+
 def test_no_cpu_fallback_without_cuda(lib):
     import torch
     if torch.cuda.is_available():

@@ -448,6 +448,31 @@ def test_median_and_columns_random_page_shapes_one_batch():
         assert n_with_cols >= 15
 
 
+def test_corpus_histograms_match_numpy(f1_pages, f4):
+    """K6 inputs: the integer histograms K4/K5 accumulate on request (1-px plain_text widths, per-mille
+    column centres) equal numpy's on the reference's 19 pages; accumulating twice doubles them exactly."""
+    from multimodal_embeddings_b200._lib import PG_COL_HIST_BINS, PG_WIDTH_HIST_BINS
+    boxes = np.concatenate([np.asarray(p["boxes"], np.float64) for p in f1_pages])
+    scores = np.concatenate([np.asarray(p["scores"], np.float64) for p in f1_pages])
+    names = sum([p["class_names"] for p in f1_pages], [])
+    flags = api._flags_from_names(names)
+    off = np.cumsum([0] + [len(p["boxes"]) for p in f1_pages])
+    wh = [[p["image_size"]["width"], p["image_size"]["height"]] for p in f1_pages]
+    wh_hist = torch.zeros(PG_WIDTH_HIST_BINS, dtype=torch.int32, device="cuda")
+    col_hist = torch.zeros(PG_COL_HIST_BINS, dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        med, _ = ops.width_median(boxes, flags, off, wh, 0.2, width_hist=wh_hist)
+        ops.column_peaks(boxes, flags, scores, off, wh, med, 0.3, col_hist=col_hist)
+    widths = (boxes[:, 2] - boxes[:, 0])[np.asarray(names) == "plain_text"]
+    ref_w = np.bincount(np.clip(widths.astype(np.int64), 0, PG_WIDTH_HIST_BINS - 1), minlength=PG_WIDTH_HIST_BINS)
+    assert np.array_equal(wh_hist.cpu().numpy(), 2 * ref_w)
+    ref_c = np.zeros(PG_COL_HIST_BINS, np.int64)
+    for p, g in zip(f1_pages, f4):
+        for c in g["column_centers"]:
+            ref_c[min(PG_COL_HIST_BINS - 1, int(c) * 1000 // p["image_size"]["width"])] += 1
+    assert np.array_equal(col_hist.cpu().numpy(), 2 * ref_c) and ref_c.sum() == sum(len(g["column_centers"]) for g in f4)
+
+
 def test_column_assignment_matches_specification(f1_pages, f4):
     boxes = np.concatenate([np.asarray(p["boxes"], np.float64) for p in f1_pages])
     off = np.cumsum([0] + [len(p["boxes"]) for p in f1_pages])

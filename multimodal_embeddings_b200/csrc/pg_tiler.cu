@@ -309,11 +309,15 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 
 // 8 source bytes starting at byte offset `off` of a staged row -> horizontal pass of one pixel.
 // lo = B0 G0 R0 B1, hi = G1 R1 . .   (BGR interleaved source, neighbour pixel 3 bytes on)
+// `off` arrives packed (pack_xoff): word-aligned byte offset in the high half, bit shift in the low
+// five bits — one LEA.HI forms the address and the wrapping funnel shift takes the register as is.
+// A staged row is < 64 KB (two rows x two stages must fit 227 KB), so the offset fits 16 bits.
+__device__ __forceinline__ uint32_t pack_xoff(uint32_t off) { return ((off & ~3u) << 16) | ((off & 3u) * 8u); }
 __device__ __forceinline__ void hpass_smem(uint32_t row_addr, uint32_t off, uint32_t coef, uint32_t& hb,
                                            uint32_t& hg, uint32_t& hr) {
-  const uint32_t a = row_addr + (off & ~3u);
+  const uint32_t a = row_addr + (off >> 16);
   const uint32_t w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8);
-  const uint32_t sh = (off & 3u) * 8u;
+  const uint32_t sh = off;  // shf.r.wrap uses the low 5 bits only
   const uint32_t lo = __funnelshift_r(w0, w1, sh);
   const uint32_t hi = __funnelshift_r(w1, w2, sh);
   const uint32_t bg = __byte_perm(lo, hi, 0x4130);  // B0 B1 G0 G1
@@ -538,7 +542,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
           const int ox = i * TL_PAIR_STRIDE + px0 + j;
           uint2 e = make_uint2(0u, TL_PADMARK);
           if (ox < out_w) e = __ldg(&a.xtab[xtab_off + ox]);
-          xoff[i][j] = e.x + skew;
+          xoff[i][j] = pack_xoff(e.x + skew);
           coef[i][j] = e.y;
         }
       }

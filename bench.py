@@ -294,9 +294,9 @@ def main():
                 tiler_alone(plan, pipe, pages)
             else:
                 pipe.run(pages, tiler_events=ev[k] if ev is not None else None)
-        if args.corpus_stats and not cfg5:  # per-step exchange (cfg5 reduces once, at the end of the corpus)
+        if args.corpus_stats and not cfg5:  # running exchange every step (cfg5 reduces once, at the end of the corpus)
             for _, pipe, _, _, _ in pipes:
-                pipe.allreduce_corpus_stats()
+                pipe.exchange_corpus_stats_async()
 
     for _ in range(args.warmup):
         step()
@@ -323,6 +323,9 @@ def main():
     if cfg5:  # the one exchange step of the path: integer histograms summed over ranks (NCCL over NVLink)
         for _, pipe, _, _, _ in pipes:
             pipe.allreduce_corpus_stats()
+    elif args.corpus_stats:
+        for _, pipe, _, _, _ in pipes:
+            pipe.finish_exchange(stream)
     e1.record(stream)
     torch.cuda.synchronize()
     clocks = sampler.stop()

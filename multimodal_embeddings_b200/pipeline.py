@@ -210,10 +210,48 @@ class PagePipeline:
 
     def allreduce_corpus_stats(self):
         """K6: the one exchange step of the path — integer histograms summed over ranks
-        (NCCL over NVLink; order-independent, so 1/2/4/8-GPU results are bit-identical)."""
+        (NCCL over NVLink; order-independent, so 1/2/4/8-GPU results are bit-identical).
+        In place, so call it ONCE, when the shard is finished."""
         if self.corpus_stats:
             allreduce_histograms(self.hist)
         return self.hist
+
+    def exchange_corpus_stats_async(self):
+        """Running form of K6, callable after every step: a snapshot of the rank's running histograms is
+        summed over ranks on NCCL's own stream, ordered after this step's box kernels only, so the exchange
+        runs under the next steps' tiler instead of serialising the ranks.  `self.hist` stays rank-local;
+        the corpus-wide totals so far are `self.hist_global` once `finish_exchange()` has been called."""
+        if not self.corpus_stats:
+            return
+        import torch.distributed as dist
+        if not hasattr(self, "_xchg_buf"):
+            self._xchg_buf = [torch.zeros_like(self.hist) for _ in range(2)]
+            self._xchg_work, self._xchg_i = [None, None], 0
+        k = self._xchg_i & 1
+        self._xchg_i += 1
+        side = self.s_box if self.overlap else torch.cuda.current_stream()
+        with torch.cuda.stream(side):
+            if self._xchg_work[k] is not None:
+                self._xchg_work[k].wait()  # stream-level: the buffer's previous exchange (two steps ago)
+                self._xchg_work[k] = None
+            self._xchg_buf[k].copy_(self.hist)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                self._xchg_work[k] = dist.all_reduce(self._xchg_buf[k], op=dist.ReduceOp.SUM, async_op=True)
+        self.hist_global = self._xchg_buf[k]
+
+    def finish_exchange(self, stream=None):
+        """Make `stream` (default: current) wait for every outstanding running exchange."""
+        if not hasattr(self, "_xchg_buf"):
+            return getattr(self, "hist", None)
+        s = stream if stream is not None else torch.cuda.current_stream()
+        with torch.cuda.stream(s):
+            for k, w in enumerate(self._xchg_work):
+                if w is not None:
+                    w.wait()
+                    self._xchg_work[k] = None
+            if self.overlap:
+                s.wait_stream(self.s_box)
+        return self.hist_global
 
     # ---------------------------------------------------------------- results
     def results_to_host(self, pinned: Optional[dict] = None) -> Dict[str, np.ndarray]:

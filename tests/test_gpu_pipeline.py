@@ -1,0 +1,72 @@
+"""Whole hot path chained on the device (PagePipeline, the object bench.py times) against the oracle,
+in both launch orders (two streams / one stream), plus the corpus histograms and their running exchange."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from multimodal_embeddings_b200 import ops, synth  # noqa: E402
+from multimodal_embeddings_b200._lib import PG_COL_HIST_BINS, PG_WIDTH_HIST_BINS  # noqa: E402
+from multimodal_embeddings_b200.pipeline import PagePipeline, corpus_median_width  # noqa: E402
+from oracle import boxes as ob  # noqa: E402
+from oracle import tiler as ot  # noqa: E402
+from oracle.nms_fast import nms_pick_order_c  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+W, H, ROWS, COLS, NB, IMGSZ = 1800, 1300, 3, 2, 700, 512
+
+
+@pytest.fixture(scope="module")
+def workload():
+    plan = ops.TilePlan(W, H, [(ROWS, COLS)], 20.0, imgsz=IMGSZ)
+    imgs = [synth.page_pixels(W, H, seed=s) for s in (11, 12, 13)]
+    dets = [synth.page_detections(W, H, ROWS, COLS, 20.0, NB, synth.PAGE_SEED0 + s) for s in (11, 12, 13)]
+    return plan, imgs, dets, ops.upload_pages(imgs, plan)
+
+
+def oracle_page(d):
+    bp = d["boxes_local"] + d["cells"][d["box_cell"]][:, [0, 1, 0, 1]]
+    keep = np.asarray([j for j in range(len(bp)) if not ob.touches_internal_edge(bp[j], d["cells"][d["box_cell"][j]], W, H, 10)])
+    final = keep[nms_pick_order_c(bp[keep], d["scores"][keep], d["classes"][keep], 0.5)]
+    names = synth.class_names_of(d["classes"][final])
+    med, nb = ob.median_width(bp[final].tolist(), names, W, 0.2)
+    cc, cw = ob.column_centers(bp[final].tolist(), names, d["scores"][final].tolist(), W, H, med, 0.3)
+    widths = (bp[final][:, 2] - bp[final][:, 0])[np.asarray(names) == "plain_text"]
+    return final, float(med), nb, [float(x) for x in cc], [float(x) for x in cw], widths
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+def test_pipeline_matches_oracle_and_accumulates_corpus_histograms(workload, overlap):
+    plan, imgs, dets, pages = workload
+    pipe = PagePipeline(plan, len(imgs), corpus_stats=True, overlap=overlap)
+    pipe.set_detections(dets)
+    for _ in range(2):  # the second pass re-uses every buffer and the self-resetting work counters
+        pipe.run(pages)
+        pipe.exchange_corpus_stats_async()
+    total = pipe.finish_exchange()
+    torch.cuda.synchronize()
+    pipe.check_status()
+    res = pipe.results_to_host()
+    ref_w = np.zeros(PG_WIDTH_HIST_BINS, np.int64)
+    ref_c = np.zeros(PG_COL_HIST_BINS, np.int64)
+    for p, (img, d) in enumerate(zip(imgs, dets)):
+        for t, cell in enumerate(ot.split_array_into_grid(img, ROWS, COLS, 20.0)):
+            want = ot.u8_to_f16_unit(ot.letterbox_tile_cv2(cell["image"], IMGSZ))
+            assert np.array_equal(plan.tile_view(pipe.tiles_out, p, t).cpu().numpy(), want), (p, t)
+        final, med, nb, cc, cw, widths = oracle_page(d)
+        k = int(res["n_kept2"][p])
+        assert k == len(final) and np.array_equal(res["kept2"][p * NB: p * NB + k].numpy() - p * NB, final)
+        assert float(res["median"][p]) == med and int(res["n_bins"][p]) == nb
+        nc = int(res["n_cols"][p])
+        assert [float(x) for x in res["centers"][p, :nc]] == cc
+        assert [float(x) for x in res["col_widths"][p, :nc]] == cw
+        ref_w += np.bincount(np.clip(widths.astype(np.int64), 0, PG_WIDTH_HIST_BINS - 1), minlength=PG_WIDTH_HIST_BINS)
+        for c in cc:
+            ref_c[min(PG_COL_HIST_BINS - 1, int(c) * 1000 // W)] += 1
+    hist = pipe.hist.cpu().numpy()
+    assert np.array_equal(hist[:PG_WIDTH_HIST_BINS], 2 * ref_w) and np.array_equal(hist[PG_WIDTH_HIST_BINS:], 2 * ref_c)
+    assert np.array_equal(total.cpu().numpy(), hist)  # one rank: the running exchange is the local total
+    if ref_w.sum():
+        srt = np.sort(np.repeat(np.arange(PG_WIDTH_HIST_BINS), 2 * ref_w))
+        assert corpus_median_width(pipe.width_hist) == (srt[(len(srt) - 1) // 2] + srt[len(srt) // 2]) / 2.0

@@ -195,9 +195,37 @@ int pg_assign_columns(const double* boxes /*dev [N,4]*/, const int32_t* sel_idx,
                       const int32_t* centers /*dev [P,max_cols]*/, const int32_t* n_cols /*dev [P]*/,
                       int32_t max_cols, int32_t* col_of_box /*dev [N]*/, void* stream);
 
+/* ------------------------------------------------------------------ J1-J4 stage-3 record writer
+ * Replaces `json.dump(result, f, indent=2)` (3_combine_grids.py:441-443) of the dict built by
+ * combine_boxes_for_image (3:282-291): the documents of n_pages pages are laid out on the device, byte for
+ * byte as CPython prints them (floats as float.__repr__: shortest round-trip digits, csrc/pg_fmt.h), from the
+ * merge's own outputs — kept_idx/n_kept as everywhere (kept_idx NULL: every box of the page).
+ *
+ * The caller supplies the page-invariant text, already JSON-encoded, in one device blob `text`:
+ *   head  text[head_off[p] .. head_off[p+1])  from "{" up to and including  "boxes": [
+ *   tail  text[tail_off[p] .. tail_off[p+1])  from the newline before  "source_jsons"  up to the final "}"
+ *   name  text[name_off[i] .. name_off[i+1])  class-name string literal i (with its quotes); name_id[box] = i
+ * Documents are packed back to back into `out`: page p is out[out_off[p] .. out_off[p+1]).  out_off (device,
+ * n_pages+1) is always written; if out_off[n_pages] > out_capacity nothing is written to `out` and the
+ * caller retries with a larger buffer.  Workspace: pg_json_workspace_bytes(n_boxes, n_pages), 256-aligned. */
+#define PG_JSON_SLOT_BYTES 32
+int64_t pg_json_workspace_bytes(int64_t n_boxes, int32_t n_pages);
+int pg_json_combined(const double* boxes /*dev [N,4]*/, const double* classes /*dev [N]*/,
+                     const double* scores /*dev [N]*/, const int32_t* name_id /*dev [N]*/,
+                     const int32_t* kept_idx, const int64_t* page_off, const int32_t* n_kept,
+                     int32_t n_pages, int64_t n_boxes, int32_t max_boxes_per_page,
+                     const uint8_t* text /*dev*/, const int64_t* head_off /*dev [P+1]*/,
+                     const int64_t* tail_off /*dev [P+1]*/, const int64_t* name_off /*dev [n_names+1]*/,
+                     uint8_t* out /*dev*/, int64_t out_capacity, int64_t* out_off /*dev [P+1]*/,
+                     void* ws, int64_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ test hooks
  * Host evaluations of the same inline arithmetic the kernels are compiled from
- * (csrc/pg_math.h).  Used by the CPU test-suite only; not a compute path. */
+ * (csrc/pg_math.h, csrc/pg_fmt.h).  Used by the CPU test-suite only; not a compute path. */
+/* float.__repr__ of x into buf (>= 24 bytes, no terminator); returns the length */
+int32_t pg_hostcheck_format_double(double x, char* buf);
+/* the same for n values, value i at buf + 24*i with length len[i]; returns the total length */
+int64_t pg_hostcheck_format_doubles(const double* x, int64_t n, char* buf, int32_t* len);
 double pg_hostcheck_iou(const double* a, const double* b);
 /* the divide-free predicate the merge kernel uses for `iou > thr` (must equal pg_hostcheck_iou(a,b) > thr) */
 int32_t pg_hostcheck_iou_gt(const double* a, const double* b, double thr);

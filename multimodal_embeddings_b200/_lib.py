@@ -69,6 +69,11 @@ SIGNATURES = {
     "pg_column_peaks": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I32, _F64, _I32,
                                   _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
     "pg_assign_columns": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _P, _P, _I32, _P, _P]),
+    "pg_json_workspace_bytes": (_I64, [_I64, _I32]),
+    "pg_json_combined": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P,
+                                   _P, _I64, _P]),
+    "pg_hostcheck_format_double": (_I32, [_F64, _P]),
+    "pg_hostcheck_format_doubles": (_I64, [_P, _I64, _P, _P]),
     "pg_hostcheck_iou": (_F64, [_P, _P]),
     "pg_hostcheck_iou_gt": (_I32, [_P, _P, _F64]),
     "pg_hostcheck_iou_gt_f32": (_I32, [_P, _P, _F64]),

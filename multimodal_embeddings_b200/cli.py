@@ -383,6 +383,21 @@ def main_stage3(argv: Optional[Sequence[str]] = None) -> int:
             kept, n_kept = kept.cpu().numpy(), n_kept.cpu().numpy()
             if ws.stats()["status"] != 0:
                 raise RuntimeError(f"pg_nms_merge failed: {ws.stats()}")
+        # Records: laid out on the device (pg_json_combined), byte-identical to json.dump(indent=2).  Inputs that
+        # are not what stage 1/2 write (integer literals among the numbers) keep Python's own encoder, which
+        # would print them without ".0".
+        all_float = all(type(v) is float for x in pooled for row in x[2] for v in row) and \
+            all(type(v) is float for x in pooled for v in x[3]) and all(type(v) is float for x in pooled for v in x[4])
+        if all_float and os.environ.get("PG_PYTHON_JSON") != "1":
+            table = {}
+            name_id = np.asarray([table.setdefault(nm, len(table)) for x in pooled for nm in x[5]], np.int32)
+            ht = [ops.combined_head_tail(x[6], x[7], args.iou_threshold, x[1]) for x in pooled]
+            docs = ops.json_combined(boxes, classes, scores, name_id, off, [h for h, _ in ht], [t for _, t in ht],
+                                     [json.dumps(nm).encode("ascii") for nm in table], kept_idx=kept, n_kept=n_kept)
+            for x, doc in zip(pooled, docs):
+                with open(os.path.join(out_json, f"{x[0]}_combined.json"), "wb") as f:
+                    f.write(doc)
+            pooled = []
         for i, (base, paths, b, s, c, n, image_path, image_size) in enumerate(pooled):
             idx = (kept[off[i]: off[i] + n_kept[i]] - off[i]).tolist()
             _dump({"image_path": image_path, "image_size": image_size,  # key order of 3:282-291

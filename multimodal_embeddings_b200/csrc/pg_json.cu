@@ -1,0 +1,276 @@
+// pg_json.cu — device-side writer of the stage-3 records.
+//
+// The reference ends stage 3 with `json.dump(result, f, indent=2)` (3_combine_grids.py:441-443) of the
+// dict built at 3:282-291: image_path, image_size, parameters, boxes [[x1,y1,x2,y2]...], classes,
+// scores, class_names, source_jsons.  At tens of thousands of pages per second that Python call is the
+// wall-clock bottleneck of the drop-in CLI, so the documents are laid out here, byte for byte as CPython
+// prints them, straight from the merge's kept_idx / n_kept:
+//
+//   J1 json_format_kernel   one thread per kept box: six float reprs (pg_fmt.h) into 32-byte slots and
+//                           the byte length of the box's entry in each of the four arrays
+//   J2 json_scan_kernel     one CTA per page: exclusive scans of those lengths -> offsets, section sizes,
+//                           document size
+//   J3 json_offsets_kernel  exclusive scan of the document sizes -> out_off (documents densely packed)
+//   J4 json_emit_kernel     head / separators / tail copied cooperatively, one thread per kept box
+//                           writes its four entries
+//
+// The host supplies the page-invariant text (everything before the first array, everything after the
+// last, and the class-name string literals) already JSON-encoded; the numbers never visit the host.
+#include <cuda_runtime.h>
+
+#include "pg_common.cuh"
+#include "pg_fmt.h"
+
+constexpr int JSON_SLOT = PG_JSON_SLOT_BYTES;  // byte 0: length, bytes 1..24: characters
+constexpr int JSON_FMT_THREADS = 128;
+constexpr int JSON_SCAN_THREADS = 1024;
+
+struct JsonWs {
+  uint8_t* slots;     // [N][6][JSON_SLOT]: x1 y1 x2 y2 class score
+  uint32_t* len[4];   // [N] entry length, then (after J2) entry offset inside its section
+  int64_t* sec;       // [P][4] section byte totals (entries only)
+  int64_t* doc_len;   // [P]
+};
+
+__host__ __device__ inline int64_t json_align(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+JsonWs json_layout(void* ws, int64_t n, int32_t p, int64_t* total) {
+  uint8_t* b = static_cast<uint8_t*>(ws);
+  int64_t o = 0;
+  JsonWs w;
+  w.slots = b + o; o += json_align(n * 6 * JSON_SLOT);
+  for (int q = 0; q < 4; ++q) { w.len[q] = reinterpret_cast<uint32_t*>(b + o); o += json_align(n * 4); }
+  w.sec = reinterpret_cast<int64_t*>(b + o); o += json_align((int64_t)p * 4 * 8);
+  w.doc_len = reinterpret_cast<int64_t*>(b + o); o += json_align((int64_t)p * 8);
+  if (total) *total = o;
+  return w;
+}
+
+// the fixed text of json.dump(indent=2) around the four arrays (arrays sit at nesting depth 1)
+#define J_SEP_CLASSES "  \"classes\": ["
+#define J_SEP_SCORES "  \"scores\": ["
+#define J_SEP_NAMES "  \"class_names\": ["
+__constant__ char kSepText[3][24] = {J_SEP_CLASSES, J_SEP_SCORES, J_SEP_NAMES};
+__constant__ int kSepLen[3] = {sizeof(J_SEP_CLASSES) - 1, sizeof(J_SEP_SCORES) - 1, sizeof(J_SEP_NAMES) - 1};
+// a non-empty array closes with "\n  ]," (5 bytes + newline of the next key), an empty one with "],"
+__device__ __forceinline__ int close_len(int n) { return n > 0 ? 6 : 3; }  // "\n  ],\n" / "],\n"
+
+__device__ __forceinline__ int page_count(const int32_t* n_kept, const int64_t* page_off, int p) {
+  return n_kept ? n_kept[p] : (int)(page_off[p + 1] - page_off[p]);
+}
+
+__global__ void __launch_bounds__(JSON_FMT_THREADS) json_format_kernel(
+    const double* __restrict__ boxes, const double* __restrict__ classes, const double* __restrict__ scores,
+    const int32_t* __restrict__ name_id, const int32_t* __restrict__ kept_idx, const int64_t* __restrict__ page_off,
+    const int32_t* __restrict__ n_kept, const int64_t* __restrict__ name_off, JsonWs w) {
+  const int p = blockIdx.y;
+  const int n = page_count(n_kept, page_off, p);
+  const int k = blockIdx.x * JSON_FMT_THREADS + threadIdx.x;
+  if (k >= n) return;
+  const int64_t pos = page_off[p] + k;
+  const int64_t gi = kept_idx ? (int64_t)kept_idx[pos] : pos;
+  const double v[6] = {boxes[4 * gi], boxes[4 * gi + 1], boxes[4 * gi + 2], boxes[4 * gi + 3], classes[gi], scores[gi]};
+  const uint32_t comma = k < n - 1 ? 1u : 0u;
+  uint32_t lens[6];
+#pragma unroll 1
+  for (int q = 0; q < 6; ++q) {
+    __align__(16) char s[JSON_SLOT];
+    const int l = pg_format_double_repr(v[q], s + 1);
+    s[0] = (char)l;
+    lens[q] = (uint32_t)l;
+    uint4* dst = reinterpret_cast<uint4*>(w.slots + (pos * 6 + q) * JSON_SLOT);
+    dst[0] = reinterpret_cast<const uint4*>(s)[0];
+    dst[1] = reinterpret_cast<const uint4*>(s)[1];
+  }
+  // "\n    [" + 4 x ("\n      " + number) + 3 commas + "\n    ]" [+ ","]
+  w.len[0][pos] = 6u + 4u * 7u + 3u + 6u + lens[0] + lens[1] + lens[2] + lens[3] + comma;
+  w.len[1][pos] = 5u + lens[4] + comma;  // "\n    " + number [+ ","]
+  w.len[2][pos] = 5u + lens[5] + comma;
+  const int id = name_id[gi];
+  w.len[3][pos] = 5u + (uint32_t)(name_off[id + 1] - name_off[id]) + comma;
+}
+
+__global__ void __launch_bounds__(JSON_SCAN_THREADS) json_scan_kernel(
+    const int64_t* __restrict__ page_off, const int32_t* __restrict__ n_kept, const int64_t* __restrict__ head_off,
+    const int64_t* __restrict__ tail_off, JsonWs w) {
+  __shared__ int sm[33];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const int n = page_count(n_kept, page_off, p);
+  const int64_t base = page_off[p];
+  int64_t doc = (head_off[p + 1] - head_off[p]) + (tail_off[p + 1] - tail_off[p]);
+  for (int q = 0; q < 4; ++q) {
+    int64_t carry = 0;
+    for (int c = 0; c < n; c += JSON_SCAN_THREADS) {
+      const int k = c + tid;
+      const int v = k < n ? (int)w.len[q][base + k] : 0;
+      int total;
+      const int ex = pg_block_exscan(v, sm, &total);
+      if (k < n) w.len[q][base + k] = (uint32_t)(carry + ex);  // a section stays below 4 GB
+      carry += total;
+    }
+    if (tid == 0) w.sec[p * 4 + q] = carry;
+    doc += carry + close_len(n) + (q < 3 ? kSepLen[q] : -1);  // the tail brings its own leading newline
+  }
+  if (tid == 0) w.doc_len[p] = doc;
+}
+
+__global__ void __launch_bounds__(1024) json_offsets_kernel(int32_t n_pages, const int64_t* __restrict__ doc_len,
+                                                            int64_t* __restrict__ out_off) {
+  __shared__ int64_t sm[33];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int64_t carry = 0;
+  for (int c = 0; c < n_pages; c += 1024) {
+    const int p = c + tid;
+    const int64_t v = p < n_pages ? doc_len[p] : 0;
+    int64_t inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const int64_t ws_ = sm[lane];
+      int64_t winc = ws_;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      sm[lane] = winc - ws_;
+      if (lane == 31) sm[32] = winc;
+    }
+    __syncthreads();
+    if (p < n_pages) out_off[p] = carry + sm[warp] + inc - v;
+    carry += sm[32];
+    __syncthreads();
+  }
+  if (tid == 0) out_off[n_pages] = carry;
+}
+
+__device__ __forceinline__ void copy_bytes(uint8_t* dst, const uint8_t* src, int64_t n, int tid, int nthreads) {
+  for (int64_t i = tid; i < n; i += nthreads) dst[i] = src[i];
+}
+__device__ __forceinline__ uint8_t* put_indent(uint8_t* o, int spaces) {
+  *o++ = '\n';
+  for (int i = 0; i < spaces; ++i) *o++ = ' ';
+  return o;
+}
+__device__ __forceinline__ uint8_t* put_slot(uint8_t* o, const uint8_t* slot) {
+  const int l = slot[0];
+  for (int i = 0; i < l; ++i) o[i] = slot[1 + i];
+  return o + l;
+}
+
+__global__ void __launch_bounds__(JSON_FMT_THREADS) json_emit_kernel(
+    const int32_t* __restrict__ name_id, const int32_t* __restrict__ kept_idx, const int64_t* __restrict__ page_off,
+    const int32_t* __restrict__ n_kept, const uint8_t* __restrict__ text, const int64_t* __restrict__ head_off,
+    const int64_t* __restrict__ tail_off, const int64_t* __restrict__ name_off, JsonWs w, uint8_t* __restrict__ out,
+    int64_t out_capacity, const int64_t* __restrict__ out_off, int32_t n_pages) {
+  if (out_off[n_pages] > out_capacity) return;  // reported through out_off[n_pages]; nothing is written
+  const int p = blockIdx.y, tid = threadIdx.x;
+  const int n = page_count(n_kept, page_off, p);
+  const int64_t head_len = head_off[p + 1] - head_off[p], tail_len = tail_off[p + 1] - tail_off[p];
+  // section starts inside the document
+  int64_t sec_at[4], at = head_len;
+  for (int q = 0; q < 4; ++q) {
+    sec_at[q] = at;
+    at += w.sec[p * 4 + q] + close_len(n) + (q < 3 ? kSepLen[q] : -1);
+  }
+  uint8_t* doc = out + out_off[p];
+  if (blockIdx.x == 0) {  // the page-invariant text
+    copy_bytes(doc, text + head_off[p], head_len, tid, JSON_FMT_THREADS);
+    for (int q = tid; q < 4; q += JSON_FMT_THREADS) {
+      uint8_t* o = doc + sec_at[q] + w.sec[p * 4 + q];
+      if (n > 0) { *o++ = '\n'; *o++ = ' '; *o++ = ' '; }
+      *o++ = ']';
+      *o++ = ',';
+      if (q < 3) {
+        *o++ = '\n';
+        for (int i = 0; i < kSepLen[q]; ++i) *o++ = (uint8_t)kSepText[q][i];
+      }
+    }
+    copy_bytes(doc + at, text + tail_off[p], tail_len, tid, JSON_FMT_THREADS);
+  }
+  const int k = blockIdx.x * JSON_FMT_THREADS + tid;
+  if (k >= n) return;
+  const int64_t pos = page_off[p] + k;
+  const int64_t gi = kept_idx ? (int64_t)kept_idx[pos] : pos;
+  const uint8_t* slot = w.slots + pos * 6 * JSON_SLOT;
+  const bool comma = k < n - 1;
+  {  // boxes
+    uint8_t* o = put_indent(doc + sec_at[0] + w.len[0][pos], 4);
+    *o++ = '[';
+    for (int c = 0; c < 4; ++c) {
+      o = put_indent(o, 6);
+      o = put_slot(o, slot + c * JSON_SLOT);
+      if (c < 3) *o++ = ',';
+    }
+    o = put_indent(o, 4);
+    *o++ = ']';
+    if (comma) *o++ = ',';
+  }
+  for (int q = 1; q < 3; ++q) {  // classes, scores
+    uint8_t* o = put_indent(doc + sec_at[q] + w.len[q][pos], 4);
+    o = put_slot(o, slot + (3 + q) * JSON_SLOT);
+    if (comma) *o++ = ',';
+  }
+  {  // class names (already JSON string literals)
+    uint8_t* o = put_indent(doc + sec_at[3] + w.len[3][pos], 4);
+    const int id = name_id[gi];
+    const int64_t a = name_off[id], l = name_off[id + 1] - a;
+    for (int64_t i = 0; i < l; ++i) o[i] = text[a + i];
+    o += l;
+    if (comma) *o++ = ',';
+  }
+}
+
+extern "C" int64_t pg_json_workspace_bytes(int64_t n_boxes, int32_t n_pages) {
+  int64_t total = 0;
+  json_layout(nullptr, n_boxes < 1 ? 1 : n_boxes, n_pages < 1 ? 1 : n_pages, &total);
+  return total;
+}
+
+extern "C" int pg_json_combined(const double* boxes, const double* classes, const double* scores,
+                                const int32_t* name_id, const int32_t* kept_idx, const int64_t* page_off,
+                                const int32_t* n_kept, int32_t n_pages, int64_t n_boxes, int32_t max_boxes_per_page,
+                                const uint8_t* text, const int64_t* head_off, const int64_t* tail_off,
+                                const int64_t* name_off, uint8_t* out, int64_t out_capacity, int64_t* out_off,
+                                void* ws, int64_t ws_bytes, void* stream) {
+  PG_REQUIRE(n_pages >= 0 && n_boxes >= 0 && max_boxes_per_page >= 0 && out_capacity >= 0, "sizes");
+  if (n_pages == 0) return PG_OK;
+  PG_REQUIRE(boxes && classes && scores && name_id && page_off && text && head_off && tail_off && name_off && out &&
+                 out_off && ws, "null device pointer");
+  if (ws_bytes < pg_json_workspace_bytes(n_boxes, n_pages)) {
+    pg_set_error("workspace: pg_json_combined needs %lld bytes, got %lld",
+                 (long long)pg_json_workspace_bytes(n_boxes, n_pages), (long long)ws_bytes);
+    return PG_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const JsonWs w = json_layout(ws, n_boxes < 1 ? 1 : n_boxes, n_pages, nullptr);
+  const unsigned chunks = (unsigned)((max_boxes_per_page + JSON_FMT_THREADS - 1) / JSON_FMT_THREADS);
+  const dim3 grid(chunks < 1 ? 1 : chunks, (unsigned)n_pages);
+  if (max_boxes_per_page > 0) {
+    json_format_kernel<<<grid, JSON_FMT_THREADS, 0, s>>>(boxes, classes, scores, name_id, kept_idx, page_off, n_kept,
+                                                         name_off, w);
+    PG_LAUNCH_CHECK();
+  }
+  json_scan_kernel<<<n_pages, JSON_SCAN_THREADS, 0, s>>>(page_off, n_kept, head_off, tail_off, w);
+  PG_LAUNCH_CHECK();
+  json_offsets_kernel<<<1, 1024, 0, s>>>(n_pages, w.doc_len, out_off);
+  PG_LAUNCH_CHECK();
+  json_emit_kernel<<<grid, JSON_FMT_THREADS, 0, s>>>(name_id, kept_idx, page_off, n_kept, text, head_off, tail_off,
+                                                     name_off, w, out, out_capacity, out_off, n_pages);
+  PG_LAUNCH_CHECK();
+  return PG_OK;
+}
+
+extern "C" int32_t pg_hostcheck_format_double(double x, char* buf) { return pg_format_double_repr(x, buf); }
+
+extern "C" int64_t pg_hostcheck_format_doubles(const double* x, int64_t n, char* buf /*n * 24*/, int32_t* len) {
+  int64_t total = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    len[i] = pg_format_double_repr(x[i], buf + i * PG_FMT_MAX_DOUBLE);
+    total += len[i];
+  }
+  return total;
+}

@@ -393,3 +393,65 @@ def assign_columns(boxes, page_off, centers, n_cols, sel_idx=None, n_sel=None, s
                                   centers.shape[1] if centers.dim() == 2 else max(1, centers.numel() // max(p, 1)),
                                   ptr(out), stream_ptr(stream)))
     return out[:n]
+
+
+# --------------------------------------------------------------------------------------------
+# J1-J4 stage-3 record writer
+# --------------------------------------------------------------------------------------------
+def combined_head_tail(image_path, image_size, iou_threshold: float, source_jsons) -> Tuple[bytes, bytes]:
+    """The page-invariant text of a `<base>_combined.json` (3_combine_grids.py:282-291) exactly as
+    json.dump(indent=2) prints it: everything before the first array, and everything after the last."""
+    import json
+    first = json.dumps({"image_path": image_path, "image_size": image_size,
+                        "parameters": {"iou_threshold": iou_threshold}}, indent=2)
+    head = first[:-2] + ',\n  "boxes": ['
+    tail = json.dumps({"source_jsons": source_jsons}, indent=2)[1:]
+    return head.encode("ascii"), tail.encode("ascii")
+
+
+def json_combined(boxes, classes, scores, name_id, page_off, heads: Sequence[bytes], tails: Sequence[bytes],
+                  names: Sequence[bytes], kept_idx=None, n_kept=None, max_boxes_per_page: Optional[int] = None,
+                  stream=None) -> List[bytes]:
+    """pg_json_combined.  Returns one bytes object per page: the text json.dump(result, f, indent=2) writes
+    for the kept boxes of that page.  heads/tails: per-page text (combined_head_tail); names: JSON string
+    literals (with quotes) indexed by name_id[box]."""
+    _require_cuda()
+    boxes = _dev(boxes, torch.float64).view(-1, 4)
+    classes = _dev(classes, torch.float64)
+    scores = _dev(scores, torch.float64)
+    name_id = _dev(name_id, torch.int32)
+    page_off_h = page_off.cpu().numpy() if isinstance(page_off, torch.Tensor) else np.asarray(page_off, np.int64)
+    page_off = _dev(page_off, torch.int64)
+    n, p = boxes.shape[0], page_off.numel() - 1
+    assert len(heads) == p and len(tails) == p
+    if kept_idx is not None:
+        kept_idx = _dev(kept_idx, torch.int32)
+        n_kept = _dev(n_kept, torch.int32)
+    if max_boxes_per_page is None:
+        max_boxes_per_page = int(np.diff(page_off_h).max()) if p else 0
+    pieces = list(heads) + list(tails) + list(names)
+    lens = np.fromiter((len(x) for x in pieces), np.int64, len(pieces))
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    text = torch.frombuffer(bytearray(b"".join(pieces) + b"\0"), dtype=torch.uint8).cuda()
+    head_off = torch.from_numpy(offs[:p + 1].copy()).cuda()
+    tail_off = torch.from_numpy(offs[p:2 * p + 1].copy()).cuda()
+    name_off = torch.from_numpy(offs[2 * p:].copy()).cuda()
+    ws_bytes = int(lib().pg_json_workspace_bytes(n, p))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    out_off = torch.zeros(p + 1, dtype=torch.int64, device="cuda")
+    longest = int(max((len(x) for x in names), default=2))
+    capacity = int(lens[:2 * p].sum()) + 80 * p + n * (6 * 20 + 70 + longest)  # typical; retried when short
+    while True:
+        out = torch.empty(max(capacity, 1), dtype=torch.uint8, device="cuda")
+        check(lib().pg_json_combined(ptr(boxes), ptr(classes), ptr(scores), ptr(name_id), ptr(kept_idx), ptr(page_off),
+                                     ptr(n_kept), p, n, int(max_boxes_per_page), ptr(text), ptr(head_off), ptr(tail_off),
+                                     ptr(name_off), ptr(out), capacity, ptr(out_off), ptr(ws), ws_bytes,
+                                     stream_ptr(stream)))
+        if stream is not None:
+            stream.synchronize()
+        off = out_off.cpu().numpy()
+        if int(off[-1]) <= capacity:
+            break
+        capacity = int(off[-1])
+    host = out[:int(off[-1])].cpu().numpy().tobytes()
+    return [host[off[i]:off[i + 1]] for i in range(p)]

@@ -213,6 +213,53 @@ def test_half2_unit_scale_exhaustive():
     assert np.array_equal(ref, new) and (((a + 0x20000) >> 16) + (b >> 16)).max() < 1024 and (a + 0x20000).max() < 2 ** 32
 
 
+def _format_doubles(lib, x):
+    x = np.ascontiguousarray(x, np.float64)
+    buf, ln = np.zeros(len(x) * 24, np.uint8), np.zeros(len(x), np.int32)
+    total = lib.pg_hostcheck_format_doubles(_lib.ptr(x), len(x), _lib.ptr(buf), _lib.ptr(ln))
+    assert total == int(ln.sum()) and ln.max() <= 24
+    raw = buf.tobytes()
+    return [raw[24 * i: 24 * i + ln[i]].decode("ascii") for i in range(len(x))]
+
+
+def test_format_double_equals_python_repr(lib):
+    """csrc/pg_fmt.h (Ryu shortest digits + CPython's repr layout) against float.__repr__ / json.dumps —
+    the number formatting of every record the reference writes (json.dump, e.g. 3_combine_grids.py:441-443)."""
+    import json
+    special = [0.0, -0.0, 1.0, -1.0, 0.1, 0.5, 1e16, 1e15, 9999999999999998.0, 123456789012345680.0, 1e-4, 1e-5,
+               9.999e-5, 1.5e-5, 5e-324, 2.2250738585072014e-308, 2.225073858507201e-308, 1.7976931348623157e308,
+               float("inf"), float("-inf"), float("nan"), 1e22, 1e23, 9007199254740993.0, 0.3, 2 / 3, 100.0, 1e21,
+               4.35, 0.285, 1.005, 2.675, 1234567890123456.7, 12345678901234567.0, 0.001, 0.00012345]
+    assert _format_doubles(lib, special) == [json.dumps(v) for v in special]
+    rng = np.random.default_rng(1)
+    sets = {
+        "bit patterns": rng.integers(0, 2 ** 63, 400_000, dtype=np.int64).view(np.float64),
+        "negative bit patterns": -rng.integers(0, 2 ** 63, 100_000, dtype=np.int64).view(np.float64),
+        "float32 pixel coordinates": rng.uniform(0, 8000, 300_000).astype(np.float32).astype(np.float64),
+        "float32 scores": rng.uniform(0, 1, 200_000).astype(np.float32).astype(np.float64),
+        "two-decimal coordinates": np.round(rng.uniform(0, 8000, 200_000), 2),
+        "integers": rng.integers(-10 ** 17, 10 ** 17, 100_000).astype(np.float64),
+        "powers of ten": np.array([float(f"{m}e{e}") for m in (1, 2, 5, 9, 1.5, 9.5) for e in range(-323, 308)]),
+        "powers of two": np.array([2.0 ** e for e in range(-1074, 1024)]),
+        "neighbours of powers of two": np.nextafter(np.array([2.0 ** e for e in range(-1000, 1000)]), 0),
+    }
+    for name, x in sets.items():
+        x = x[np.isfinite(x)]
+        got = _format_doubles(lib, x)
+        bad = [(v, s) for v, s in zip(x.tolist(), got) if s != repr(v)]
+        assert not bad, (name, len(bad), bad[:3])
+
+
+def test_combined_head_tail_brackets_a_json_dump_document():
+    import json
+    for size, srcs in (({"width": 10, "height": 20}, ["a.json", "b_grid_2x2.json"]), (None, [])):
+        head, tail = ops.combined_head_tail('/x/pa"ge é.png', size, 0.5, srcs)
+        doc = {"image_path": '/x/pa"ge é.png', "image_size": size, "parameters": {"iou_threshold": 0.5},
+               "boxes": [], "classes": [], "scores": [], "class_names": [], "source_jsons": srcs}
+        empty = head + b'],\n  "classes": [],\n  "scores": [],\n  "class_names": [],' + tail
+        assert empty.decode("ascii") == json.dumps(doc, indent=2)
+
+
 def test_no_cpu_fallback_without_cuda(lib):
     import torch
     if torch.cuda.is_available():

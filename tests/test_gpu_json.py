@@ -1,0 +1,116 @@
+"""the device-side writer of the stage-3 records must produce, byte for byte, what the
+reference's `json.dump(result, f, indent=2)` (3_combine_grids.py:441-443) writes for the same kept boxes."""
+import json
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from multimodal_embeddings_b200 import ops  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["title", "plain_text", "abandon", "figure", "figure_caption", "table", 'quo"te\\back', "café ☃", "tab\there"]
+
+
+def reference_text(image_path, image_size, thr, boxes, classes, scores, names, sources):
+    doc = {"image_path": image_path, "image_size": image_size, "parameters": {"iou_threshold": thr},
+           "boxes": boxes, "classes": classes, "scores": scores, "class_names": names, "source_jsons": sources}
+    return json.dumps(doc, indent=2).encode("ascii")
+
+
+def make_pages(rng, counts):
+    pages = []
+    for i, n in enumerate(counts):
+        kind = i % 4
+        if kind == 0:    # what stage 1 really writes: float32 tensors through .tolist()
+            b = rng.uniform(0, 8000, (n, 4)).astype(np.float32).astype(np.float64)
+            s = rng.uniform(0.05, 1, n).astype(np.float32).astype(np.float64)
+        elif kind == 1:  # arbitrary doubles, both signs, integral values, tiny and huge magnitudes
+            b = rng.uniform(-1e4, 1e4, (n, 4))
+            b[rng.random((n, 4)) < 0.1] = 0.0
+            b[rng.random((n, 4)) < 0.05] = -0.0
+            b[::3] = np.round(b[::3])
+            b[1::7] *= 1e-7
+            b[2::11] *= 1e15
+            s = rng.random(n)
+        elif kind == 2:  # short decimals
+            b = np.round(rng.uniform(0, 5000, (n, 4)), 2)
+            s = np.round(rng.random(n), 3)
+        else:            # raw bit patterns (finite)
+            b = rng.integers(0, 0x7FE0000000000000, (n, 4), dtype=np.int64).view(np.float64)
+            b[::2] *= -1.0
+            s = rng.integers(0, 0x7FE0000000000000, n, dtype=np.int64).view(np.float64)
+        c = rng.integers(0, len(NAMES), n).astype(np.float64)
+        pages.append((b, c, s))
+    return pages
+
+
+@pytest.mark.parametrize("with_kept", [False, True])
+def test_documents_equal_json_dump(with_kept):
+    rng = np.random.default_rng(5 + with_kept)
+    counts = [0, 1, 2, 257, 1500, 31, 0, 640]
+    pages = make_pages(rng, counts)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    boxes = np.concatenate([p[0] for p in pages])
+    classes = np.concatenate([p[1] for p in pages])
+    scores = np.concatenate([p[2] for p in pages])
+    name_id = classes.astype(np.int32)
+    literals = [json.dumps(n).encode("ascii") for n in NAMES]
+    heads, tails, meta = [], [], []
+    for i in range(len(counts)):
+        path = f"/data/scans/page {i} ü.png"
+        size = {"width": 4000 + i, "height": 6000 - i} if i != 3 else None
+        srcs = [f"a/{i}.json", f"a/{i}_grid_2x2.json"][: i % 3]
+        thr = [0.5, 0.45, 1e-05, 1.0][i % 4]
+        h, t = ops.combined_head_tail(path, size, thr, srcs)
+        heads.append(h)
+        tails.append(t)
+        meta.append((path, size, thr, srcs))
+    kept = n_kept = None
+    sel = [np.arange(c) for c in counts]
+    if with_kept:  # an arbitrary ordered subset per page, as the merge's kept_idx would be
+        sel = [np.sort(rng.choice(c, size=int(rng.integers(0, c + 1)), replace=False)) if c else np.arange(0) for c in counts]
+        sel[4] = rng.permutation(counts[4])[:900]  # pick order need not be ascending
+        kept = np.zeros(max(1, off[-1]), np.int32)
+        for i, s in enumerate(sel):
+            kept[off[i]: off[i] + len(s)] = s + off[i]
+        n_kept = np.asarray([len(s) for s in sel], np.int32)
+    docs = ops.json_combined(boxes, classes, scores, name_id, off, heads, tails, literals, kept_idx=kept, n_kept=n_kept)
+    assert len(docs) == len(counts)
+    for i, (path, size, thr, srcs) in enumerate(meta):
+        b, c, s = pages[i]
+        j = sel[i]
+        want = reference_text(path, size, thr, b[j].tolist(), c[j].tolist(), s[j].tolist(),
+                              [NAMES[int(x)] for x in c[j]], srcs)
+        assert docs[i] == want, (i, docs[i][:200], want[:200])
+        assert json.loads(docs[i])["boxes"] == b[j].tolist()  # and it parses back to the same doubles
+
+
+def test_golden_stage3_tree_is_reproduced():
+    """The reference's own stage-3 records (tests/golden/cli_tree.json.gz: what the unmodified
+    3_combine_grids.py main() wrote, stored parsed-and-compacted) re-serialised on the device; the expected
+    text is json.dumps(record, indent=2), the call at 3:441-443."""
+    from conftest import load_golden
+    tree = load_golden("cli_tree.json.gz")
+    files = {k: v for k, v in tree.items() if k.startswith("3_combined_bboxes/json/") and k.endswith("_combined.json")}
+    assert files
+    names, docs_in = [], []
+    for text in files.values():
+        d = json.loads(text)
+        docs_in.append((json.dumps(d, indent=2), d))
+        for n in d["class_names"]:
+            if n not in names:
+                names.append(n)
+    off = np.concatenate([[0], np.cumsum([len(d["boxes"]) for _, d in docs_in])]).astype(np.int64)
+    boxes = np.concatenate([np.asarray(d["boxes"], np.float64).reshape(-1, 4) for _, d in docs_in])
+    classes = np.concatenate([np.asarray(d["classes"], np.float64) for _, d in docs_in])
+    scores = np.concatenate([np.asarray(d["scores"], np.float64) for _, d in docs_in])
+    name_id = np.asarray([names.index(n) for _, d in docs_in for n in d["class_names"]], np.int32)
+    ht = [ops.combined_head_tail(d["image_path"], d["image_size"], d["parameters"]["iou_threshold"], d["source_jsons"])
+          for _, d in docs_in]
+    out = ops.json_combined(boxes, classes, scores, name_id, off, [h for h, _ in ht], [t for _, t in ht],
+                            [json.dumps(n).encode("ascii") for n in names])
+    for (text, _), got in zip(docs_in, out):
+        assert got.decode("ascii") == text

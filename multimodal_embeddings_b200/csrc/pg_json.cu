@@ -69,23 +69,25 @@ __global__ void __launch_bounds__(JSON_FMT_THREADS) json_format_kernel(
   if (k >= n) return;
   const int64_t pos = page_off[p] + k;
   const int64_t gi = kept_idx ? (int64_t)kept_idx[pos] : pos;
-  const double v[6] = {boxes[4 * gi], boxes[4 * gi + 1], boxes[4 * gi + 2], boxes[4 * gi + 3], classes[gi], scores[gi]};
   const uint32_t comma = k < n - 1 ? 1u : 0u;
-  uint32_t lens[6];
+  // characters go to a shared-memory slot (no local-memory arrays), then out as two 16-byte stores
+  __shared__ __align__(16) char fs[JSON_FMT_THREADS][JSON_SLOT];
+  char* s = fs[threadIdx.x];
+  uint32_t len_box = 0, len_class = 0, len_score = 0;
 #pragma unroll 1
   for (int q = 0; q < 6; ++q) {
-    __align__(16) char s[JSON_SLOT];
-    const int l = pg_format_double_repr(v[q], s + 1);
+    const double x = q < 4 ? boxes[4 * gi + q] : (q == 4 ? classes[gi] : scores[gi]);
+    const int l = pg_format_double_repr(x, s + 1);
     s[0] = (char)l;
-    lens[q] = (uint32_t)l;
+    if (q < 4) len_box += (uint32_t)l; else if (q == 4) len_class = (uint32_t)l; else len_score = (uint32_t)l;
     uint4* dst = reinterpret_cast<uint4*>(w.slots + (pos * 6 + q) * JSON_SLOT);
     dst[0] = reinterpret_cast<const uint4*>(s)[0];
     dst[1] = reinterpret_cast<const uint4*>(s)[1];
   }
   // "\n    [" + 4 x ("\n      " + number) + 3 commas + "\n    ]" [+ ","]
-  w.len[0][pos] = 6u + 4u * 7u + 3u + 6u + lens[0] + lens[1] + lens[2] + lens[3] + comma;
-  w.len[1][pos] = 5u + lens[4] + comma;  // "\n    " + number [+ ","]
-  w.len[2][pos] = 5u + lens[5] + comma;
+  w.len[0][pos] = 6u + 4u * 7u + 3u + 6u + len_box + comma;
+  w.len[1][pos] = 5u + len_class + comma;  // "\n    " + number [+ ","]
+  w.len[2][pos] = 5u + len_score + comma;
   const int id = name_id[gi];
   w.len[3][pos] = 5u + (uint32_t)(name_off[id + 1] - name_off[id]) + comma;
 }
@@ -161,11 +163,15 @@ __device__ __forceinline__ uint8_t* put_slot(uint8_t* o, const uint8_t* slot) {
   return o + l;
 }
 
+constexpr int JSON_STAGE_BYTES = 20 * 1024;  // 128 boxes x (43 + 4 x 24 + 1) bytes = 17.9 KB at most
+
 __global__ void __launch_bounds__(JSON_FMT_THREADS) json_emit_kernel(
     const int32_t* __restrict__ name_id, const int32_t* __restrict__ kept_idx, const int64_t* __restrict__ page_off,
     const int32_t* __restrict__ n_kept, const uint8_t* __restrict__ text, const int64_t* __restrict__ head_off,
     const int64_t* __restrict__ tail_off, const int64_t* __restrict__ name_off, JsonWs w, uint8_t* __restrict__ out,
     int64_t out_capacity, const int64_t* __restrict__ out_off, int32_t n_pages) {
+  __shared__ __align__(16) uint8_t json_stage[JSON_STAGE_BYTES + 16];
+  __shared__ __align__(16) uint8_t json_slots[JSON_FMT_THREADS * 6 * JSON_SLOT];
   if (out_off[n_pages] > out_capacity) return;  // reported through out_off[n_pages]; nothing is written
   const int p = blockIdx.y, tid = threadIdx.x;
   const int n = page_count(n_kept, page_off, p);
@@ -191,36 +197,65 @@ __global__ void __launch_bounds__(JSON_FMT_THREADS) json_emit_kernel(
     }
     copy_bytes(doc + at, text + tail_off[p], tail_len, tid, JSON_FMT_THREADS);
   }
-  const int k = blockIdx.x * JSON_FMT_THREADS + tid;
-  if (k >= n) return;
-  const int64_t pos = page_off[p] + k;
+  // The entries of this CTA's boxes are contiguous inside each of the four arrays: compose each run in
+  // shared memory — at the same 16-byte phase as its destination — and write it out with aligned 16-byte
+  // stores (byte stores straight to global cost a 32-byte sector each: 28x the traffic, measured).
+  const int k0 = blockIdx.x * JSON_FMT_THREADS;
+  if (k0 >= n) return;
+  const int cnt = n - k0 < JSON_FMT_THREADS ? n - k0 : JSON_FMT_THREADS;
+  const int k = k0 + tid;
+  const bool active = tid < cnt;
+  const int64_t pos0 = page_off[p] + k0, pos = pos0 + (active ? tid : 0);
   const int64_t gi = kept_idx ? (int64_t)kept_idx[pos] : pos;
-  const uint8_t* slot = w.slots + pos * 6 * JSON_SLOT;
+  {  // this CTA's number slots: one coalesced 16-byte-vector copy instead of dependent byte loads
+    const uint4* src = reinterpret_cast<const uint4*>(w.slots + pos0 * 6 * JSON_SLOT);
+    uint4* dst = reinterpret_cast<uint4*>(json_slots);
+    for (int i = tid; i < cnt * (6 * JSON_SLOT / 16); i += JSON_FMT_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  const uint8_t* slot = json_slots + tid * 6 * JSON_SLOT;
   const bool comma = k < n - 1;
-  {  // boxes
-    uint8_t* o = put_indent(doc + sec_at[0] + w.len[0][pos], 4);
-    *o++ = '[';
-    for (int c = 0; c < 4; ++c) {
-      o = put_indent(o, 6);
-      o = put_slot(o, slot + c * JSON_SLOT);
-      if (c < 3) *o++ = ',';
+  for (int q = 0; q < 4; ++q) {
+    const int64_t start = w.len[q][pos0];
+    const int64_t end = k0 + cnt < n ? (int64_t)w.len[q][pos0 + cnt] : w.sec[p * 4 + q];
+    const int64_t bytes = end - start;
+    uint8_t* gdst = doc + sec_at[q] + start;
+    const uint32_t phase = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
+    const bool staged = bytes <= JSON_STAGE_BYTES;  // very long class names: straight to global
+    uint8_t* base = staged ? json_stage + phase : gdst;
+    if (active) {
+      uint8_t* o = put_indent(base + (w.len[q][pos] - start), 4);
+      if (q == 0) {  // "[", four coordinates, "]"
+        *o++ = '[';
+        for (int c = 0; c < 4; ++c) {
+          o = put_indent(o, 6);
+          o = put_slot(o, slot + c * JSON_SLOT);
+          if (c < 3) *o++ = ',';
+        }
+        o = put_indent(o, 4);
+        *o++ = ']';
+      } else if (q < 3) {  // class, score
+        o = put_slot(o, slot + (3 + q) * JSON_SLOT);
+      } else {  // class name (already a JSON string literal)
+        const int id = name_id[gi];
+        const int64_t a = name_off[id], l = name_off[id + 1] - a;
+        for (int64_t i = 0; i < l; ++i) o[i] = text[a + i];
+        o += l;
+      }
+      if (comma) *o++ = ',';
     }
-    o = put_indent(o, 4);
-    *o++ = ']';
-    if (comma) *o++ = ',';
-  }
-  for (int q = 1; q < 3; ++q) {  // classes, scores
-    uint8_t* o = put_indent(doc + sec_at[q] + w.len[q][pos], 4);
-    o = put_slot(o, slot + (3 + q) * JSON_SLOT);
-    if (comma) *o++ = ',';
-  }
-  {  // class names (already JSON string literals)
-    uint8_t* o = put_indent(doc + sec_at[3] + w.len[3][pos], 4);
-    const int id = name_id[gi];
-    const int64_t a = name_off[id], l = name_off[id + 1] - a;
-    for (int64_t i = 0; i < l; ++i) o[i] = text[a + i];
-    o += l;
-    if (comma) *o++ = ',';
+    if (staged) {
+      __syncthreads();
+      const int64_t lead = bytes < ((16 - phase) & 15) ? bytes : ((16 - phase) & 15);
+      const int64_t nvec = (bytes - lead) >> 4;
+      const int64_t tail_at = lead + (nvec << 4);
+      if (tid < lead) gdst[tid] = base[tid];
+      const uint4* sv = reinterpret_cast<const uint4*>(base + lead);
+      uint4* gv = reinterpret_cast<uint4*>(gdst + lead);
+      for (int64_t i = tid; i < nvec; i += JSON_FMT_THREADS) gv[i] = sv[i];
+      if (tid < bytes - tail_at) gdst[tail_at + tid] = base[tail_at + tid];
+      __syncthreads();
+    }
   }
 }
 

@@ -56,29 +56,40 @@ constexpr int TL_BAND = 16;             // output rows per work item
 constexpr uint32_t TL_PADMARK = 0xFFFFFFFFu;
 constexpr int TL_PAD_VALUE = 114;
 
+// A tile as the kernels see it.  The pipeline kernel works on COLUMN CHUNKS of a tile (chunk_x0, chunk_w):
+// a tile whose source rows are too long for four resident CTAs per SM (TL_MAX_ROW_BYTES) is cut into
+// chunks of output columns, each staging only the source span it samples (x0 = first source pixel of the
+// chunk, x-table rebased to it).  A full tile is the chunk [0, out_w) — what the direct kernel uses.
 struct TileDev {
   int32_t x0, y0, src_w, src_h;
   int32_t new_w, new_h, pad_l, pad_t, out_w, out_h;
   int32_t xtab_off, ytab_off;
   int32_t row_bytes;  // bulk-copy size per source row (multiple of 16)
   int32_t row_skew;   // byte offset of source pixel 0 inside the staged row
+  int32_t chunk_x0, chunk_w;  // output columns [chunk_x0, chunk_x0 + chunk_w) of the tile (even / multiple of 64)
+  int32_t has_xpad, pad_;     // the chunk holds 114-valued pad columns
   int64_t out_off;    // fp16 elements from the page's output base
 };
+constexpr int TL_MAX_ROW_BYTES = 9216;  // 3 stages x 2 rows x (9216+128) B x 4 CTAs fits the 227 KB of an SM
 
 struct PgTilePlan {
   int32_t page_w = 0, page_h = 0, imgsz = 0;
   std::vector<PgTileInfo> info;
-  std::vector<TileDev> tiles;
-  std::vector<uint2> xtab;  // per tile, out_w entries: {3*s0, a0 | a1<<16} or {0, PADMARK}
+  std::vector<TileDev> tiles;       // column chunks (pipeline kernel); items index this table
+  std::vector<TileDev> tiles_full;  // whole tiles (direct validation kernel), one per PgTileInfo
+  std::vector<uint2> xtab;       // per chunk, chunk_w entries: {3*(s0 - chunk source start), a0 | a1<<16} or {0, PADMARK}
+  std::vector<uint2> xtab_full;  // per tile, out_w entries relative to the tile's x0
   std::vector<int4> ytab;   // per tile, new_h entries: {s0, s1, b0, b1}
-  std::vector<int4> items;  // {tile, oy0, nrows, 0}
+  std::vector<int4> items;  // {chunk, oy0, nrows, 0}, all grids together, ordered by the source row they start at
   int64_t out_elems = 0;
-  int32_t max_row_bytes = 0;
-  int32_t max_out_w = 0;
+  int32_t max_row_bytes = 0;  // widest staged row over the chunks
+  int32_t max_out_w = 0;      // widest chunk (px)
   // device mirrors (lazy)
   int device = -1;
   TileDev* d_tiles = nullptr;
+  TileDev* d_tiles_full = nullptr;
   uint2* d_xtab = nullptr;
+  uint2* d_xtab_full = nullptr;
   int4* d_ytab = nullptr;
   int4* d_items = nullptr;
   unsigned long long* d_counters = nullptr;  // work-item counter + retired-CTA counter (self-resetting)
@@ -111,7 +122,6 @@ extern "C" int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t
     const double bh = (double)page_h / (double)rows;
     const double ox = bw * (overlap_percentage / 100.0);
     const double oy = bh * (overlap_percentage / 100.0);
-    const size_t first_tile = plan->tiles.size();
     for (int r = 0; r < rows; ++r) {
       for (int c = 0; c < cols; ++c) {
         double xs = c * bw;                       // :401-403
@@ -164,48 +174,96 @@ extern "C" int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t
         out_off += (int64_t)3 * ti.out_h * ti.out_w;
 
         TileDev td;
+        std::memset(&td, 0, sizeof(td));
         td.x0 = ti.x0; td.y0 = ti.y0; td.src_w = sw; td.src_h = sh;
         td.new_w = ti.new_w; td.new_h = ti.new_h; td.pad_l = ti.pad_l; td.pad_t = ti.pad_t;
         td.out_w = ti.out_w; td.out_h = ti.out_h;
-        td.xtab_off = (int32_t)plan->xtab.size();
+        td.xtab_off = (int32_t)plan->xtab_full.size();
         td.ytab_off = (int32_t)plan->ytab.size();
         td.row_skew = (3 * ti.x0) & 15;
         td.row_bytes = (td.row_skew + 3 * sw + 15) & ~15;
+        td.chunk_x0 = 0; td.chunk_w = ti.out_w;
+        td.has_xpad = (ti.pad_l != 0 || ti.new_w != ti.out_w) ? 1 : 0;
         td.out_off = ti.out_offset;
+        std::vector<PgCoef> cx((size_t)ti.out_w);  // per output column; s0 < 0 marks a pad column
         for (int x = 0; x < ti.out_w; ++x) {
           const int rx = x - ti.pad_l;
           if (rx < 0 || rx >= ti.new_w) {
-            plan->xtab.push_back(make_uint2(0u, TL_PADMARK));
+            cx[x].s0 = -1;
+            plan->xtab_full.push_back(make_uint2(0u, TL_PADMARK));
           } else {
-            const PgCoef cf = pg_resize_coef(sw, ti.new_w, rx, true);
+            cx[x] = pg_resize_coef(sw, ti.new_w, rx, true);
             // when c1 == 0 the neighbour is multiplied by zero, so s1 never needs to be stored
-            plan->xtab.push_back(make_uint2((uint32_t)(3 * cf.s0), (uint32_t)cf.c0 | ((uint32_t)cf.c1 << 16)));
+            plan->xtab_full.push_back(make_uint2((uint32_t)(3 * cx[x].s0), (uint32_t)cx[x].c0 | ((uint32_t)cx[x].c1 << 16)));
           }
         }
         for (int y = 0; y < ti.new_h; ++y) {
           const PgCoef cf = pg_resize_coef(sh, ti.new_h, y, false);
           plan->ytab.push_back(make_int4(cf.s0, cf.s1, cf.c0, cf.c1));
         }
-        plan->max_row_bytes = std::max(plan->max_row_bytes, td.row_bytes);
-        plan->max_out_w = std::max(plan->max_out_w, ti.out_w);
         plan->info.push_back(ti);
-        plan->tiles.push_back(td);
-      }
-    }
-    // work items: (tile row, band, tile col)
-    for (int r = 0; r < rows; ++r) {
-      int max_h = 0;
-      for (int c = 0; c < cols; ++c) max_h = std::max(max_h, plan->tiles[first_tile + r * cols + c].out_h);
-      for (int b = 0; b * TL_BAND < max_h; ++b) {
-        for (int c = 0; c < cols; ++c) {
-          const int t = (int)first_tile + r * cols + c;
-          const int oy0 = b * TL_BAND;
-          if (oy0 >= plan->tiles[t].out_h) continue;
-          plan->items.push_back(make_int4(t, oy0, std::min(TL_BAND, plan->tiles[t].out_h - oy0), 0));
+        plan->tiles_full.push_back(td);
+
+        // column chunks: the fewest equal chunks (multiples of 64 px) whose staged rows fit TL_MAX_ROW_BYTES
+        auto chunk_span = [&](int c0, int cw, int* lo, int* hi) {  // source pixels [lo, hi) sampled by the chunk
+          int l = INT32_MAX, h = -1;
+          for (int x = c0; x < std::min(c0 + cw, (int)ti.out_w); ++x) {
+            if (cx[x].s0 < 0) continue;
+            l = std::min(l, cx[x].s0);
+            h = std::max(h, cx[x].s0 + (cx[x].c1 ? 1 : 0));
+          }
+          if (h < 0) { l = 0; h = 0; }  // nothing but pad columns: stage one pixel
+          *lo = l; *hi = h + 1;
+        };
+        int n_chunks = 1, chunk_w = ti.out_w;
+        for (;; ++n_chunks) {
+          chunk_w = n_chunks == 1 ? ti.out_w : ((ti.out_w + n_chunks - 1) / n_chunks + 63) / 64 * 64;
+          int worst = 0;
+          for (int c0 = 0; c0 < ti.out_w; c0 += chunk_w) {
+            int lo, hi;
+            chunk_span(c0, chunk_w, &lo, &hi);
+            worst = std::max(worst, ((3 * (ti.x0 + lo)) & 15) + 3 * (hi - lo) + 15);
+          }
+          if (worst <= TL_MAX_ROW_BYTES || chunk_w <= 64) break;
+        }
+        for (int c0 = 0; c0 < ti.out_w; c0 += chunk_w) {
+          TileDev ch = td;
+          int lo, hi;
+          chunk_span(c0, chunk_w, &lo, &hi);
+          ch.chunk_x0 = c0;
+          ch.chunk_w = std::min(chunk_w, (int)ti.out_w - c0);
+          ch.x0 = ti.x0 + lo;
+          ch.src_w = hi - lo;
+          ch.row_skew = (3 * ch.x0) & 15;
+          ch.row_bytes = (ch.row_skew + 3 * (hi - lo) + 15) & ~15;
+          ch.xtab_off = (int32_t)plan->xtab.size();
+          ch.has_xpad = 0;
+          for (int x = c0; x < c0 + ch.chunk_w; ++x) {
+            if (cx[x].s0 < 0) {
+              ch.has_xpad = 1;
+              plan->xtab.push_back(make_uint2(0u, TL_PADMARK));
+            } else {
+              plan->xtab.push_back(make_uint2((uint32_t)(3 * (cx[x].s0 - lo)), (uint32_t)cx[x].c0 | ((uint32_t)cx[x].c1 << 16)));
+            }
+          }
+          plan->max_row_bytes = std::max(plan->max_row_bytes, ch.row_bytes);
+          plan->max_out_w = std::max(plan->max_out_w, ch.chunk_w);
+          // work items of the chunk: bands of TL_BAND output rows, keyed by the page row their source starts at
+          for (int oy0 = 0; oy0 < ti.out_h; oy0 += TL_BAND) {
+            const int ry = std::min(std::max(oy0 - ti.pad_t, 0), ti.new_h - 1);
+            const int key = ti.y0 + plan->ytab[(size_t)td.ytab_off + ry].x;
+            plan->items.push_back(make_int4((int)plan->tiles.size(), oy0, std::min(TL_BAND, ti.out_h - oy0), key));
+          }
+          plan->tiles.push_back(ch);
         }
       }
     }
   }
+  // One launch covers every grid: order the bands by the page row they read, so that the tiles of all
+  // grids (and the 20 % overlaps inside a grid) that sample the same part of the page are in flight
+  // together and share it through L2.  Stable: columns of one tile row stay adjacent.
+  std::stable_sort(plan->items.begin(), plan->items.end(), [](const int4& l, const int4& r) { return l.w < r.w; });
+  for (int4& it : plan->items) it.w = 0;
   plan->out_elems = out_off;
   *plan_out = plan;
   return PG_OK;
@@ -213,11 +271,14 @@ extern "C" int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t
 
 static void plan_free_device(PgTilePlan* p) {
   if (p->d_tiles) cudaFree(p->d_tiles);
+  if (p->d_tiles_full) cudaFree(p->d_tiles_full);
   if (p->d_xtab) cudaFree(p->d_xtab);
+  if (p->d_xtab_full) cudaFree(p->d_xtab_full);
   if (p->d_ytab) cudaFree(p->d_ytab);
   if (p->d_items) cudaFree(p->d_items);
   if (p->d_counters) cudaFree(p->d_counters);
   p->d_tiles = nullptr; p->d_xtab = nullptr; p->d_ytab = nullptr; p->d_items = nullptr; p->d_counters = nullptr;
+  p->d_tiles_full = nullptr; p->d_xtab_full = nullptr;
   p->device = -1;
 }
 
@@ -226,7 +287,7 @@ extern "C" void pg_tile_plan_destroy(PgTilePlan* plan) {
   plan_free_device(plan);
   delete plan;
 }
-extern "C" int32_t pg_tile_plan_num_tiles(const PgTilePlan* plan) { return plan ? (int32_t)plan->tiles.size() : 0; }
+extern "C" int32_t pg_tile_plan_num_tiles(const PgTilePlan* plan) { return plan ? (int32_t)plan->info.size() : 0; }
 extern "C" int pg_tile_plan_tile(const PgTilePlan* plan, int32_t tile, PgTileInfo* info) {
   PG_REQUIRE(plan && info && tile >= 0 && tile < (int32_t)plan->info.size(), "tile index");
   *info = plan->info[tile];
@@ -244,12 +305,16 @@ static int plan_upload(PgTilePlan* p, cudaStream_t s) {
   plan_free_device(p);
   PG_CUDA_TRY(cudaMalloc(&p->d_tiles, p->tiles.size() * sizeof(TileDev)));
   PG_CUDA_TRY(cudaMalloc(&p->d_xtab, p->xtab.size() * sizeof(uint2)));
+  PG_CUDA_TRY(cudaMalloc(&p->d_tiles_full, p->tiles_full.size() * sizeof(TileDev)));
+  PG_CUDA_TRY(cudaMalloc(&p->d_xtab_full, p->xtab_full.size() * sizeof(uint2)));
   PG_CUDA_TRY(cudaMalloc(&p->d_ytab, p->ytab.size() * sizeof(int4)));
   PG_CUDA_TRY(cudaMalloc(&p->d_items, p->items.size() * sizeof(int4)));
   PG_CUDA_TRY(cudaMalloc(&p->d_counters, 2 * sizeof(unsigned long long)));
   PG_CUDA_TRY(cudaMemsetAsync(p->d_counters, 0, 2 * sizeof(unsigned long long), s));
   PG_CUDA_TRY(cudaMemcpyAsync(p->d_tiles, p->tiles.data(), p->tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice, s));
   PG_CUDA_TRY(cudaMemcpyAsync(p->d_xtab, p->xtab.data(), p->xtab.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
+  PG_CUDA_TRY(cudaMemcpyAsync(p->d_tiles_full, p->tiles_full.data(), p->tiles_full.size() * sizeof(TileDev), cudaMemcpyHostToDevice, s));
+  PG_CUDA_TRY(cudaMemcpyAsync(p->d_xtab_full, p->xtab_full.data(), p->xtab_full.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
   PG_CUDA_TRY(cudaMemcpyAsync(p->d_ytab, p->ytab.data(), p->ytab.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
   PG_CUDA_TRY(cudaMemcpyAsync(p->d_items, p->items.data(), p->items.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
   PG_CUDA_TRY(cudaStreamSynchronize(s));  // host vectors may not be pinned; one-time cost
@@ -267,22 +332,25 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+// the hot loops pass 32-bit shared-window addresses computed once (a generic->shared conversion per call
+// costs an S2R and three ALU instructions per output row)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { mbar_arrive(smem_u32(bar)); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trap (launch error), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -294,6 +362,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       if (t1 - t0 > 4000000000ull) __trap();  // 4 s
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait(smem_u32(bar), parity); }
+__device__ __forceinline__ int4 lds128(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -513,26 +587,33 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
   }
 
   // ===================== consumers =====================
-  const uint32_t smem_base = smem_u32(smem);
+  uint32_t smem_base = smem_u32(smem);
+  uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]), msg0 = smem_u32(&msg[0]);
+  // opaque to the optimiser: otherwise it re-derives each address from SR_CgaCtaId on every output row
+  asm volatile("" : "+r"(smem_base), "+r"(full0), "+r"(empty0), "+r"(msg0));
   const uint32_t pad_pair = pack_unit_half2(TL_PAD_VALUE, TL_PAD_VALUE);
   const int px0 = warp * 64 + lane * 2;
   uint32_t xoff[ITER][2], coef[ITER][2];
-  int cached_tile = -1, cached_page = -1, out_w = 0, xpad = 0;
-  int64_t plane_w = 0, out_off = 0;   // plane size in half2 units
-  uint32_t* tile_ptr = nullptr;       // this thread's first pixel pair of row 0, R plane
+  int cached_tile = -1, cached_page = -1, out_w = 0, chunk_w = 0, chunk_x0 = 0, xpad = 0;
+  int64_t plane_b = 0, out_off = 0;   // plane size in bytes
+  uint32_t row_b = 0;                 // output row pitch in bytes
+  uint8_t* tile_ptr = nullptr;        // this thread's first pixel pair of row 0, R plane
 
   while (true) {
-    mbar_wait(&full_bar[stage], phase);
-    const int4 m = msg[stage];
+    mbar_wait(full0 + stage * 8u, phase);
+    const int4 m = lds128(msg0 + stage * 16u);
     if (m.x < 0) break;
     if (m.x != cached_tile) {
       cached_tile = m.x;
       const TileDev& t = a.tiles[m.x];
       out_w = t.out_w;
-      plane_w = ((int64_t)t.out_h * out_w) >> 1;
+      chunk_w = t.chunk_w;
+      chunk_x0 = t.chunk_x0;
+      plane_b = (int64_t)t.out_h * out_w * 2;
+      row_b = (uint32_t)out_w * 2u;
       out_off = t.out_off;
       cached_page = -1;
-      xpad = (t.pad_l != 0) || (t.new_w != out_w);
+      xpad = t.has_xpad;
       const uint32_t skew = (uint32_t)t.row_skew;
       const int xtab_off = t.xtab_off;
 #pragma unroll
@@ -541,7 +622,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
         for (int j = 0; j < 2; ++j) {
           const int ox = i * TL_PAIR_STRIDE + px0 + j;
           uint2 e = make_uint2(0u, TL_PADMARK);
-          if (ox < out_w) e = __ldg(&a.xtab[xtab_off + ox]);
+          if (ox < chunk_w) e = __ldg(&a.xtab[xtab_off + ox]);
           xoff[i][j] = pack_xoff(e.x + skew);
           coef[i][j] = e.y;
         }
@@ -550,16 +631,16 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
     if (m.y != cached_page) {
       cached_page = m.y;
       __half* page_out = a.page_desc ? a.page_desc[m.y].out : a.out + (int64_t)m.y * a.out_page_stride;
-      tile_ptr = reinterpret_cast<uint32_t*>(page_out + out_off) + (px0 >> 1);
+      tile_ptr = reinterpret_cast<uint8_t*>(page_out + out_off) + (chunk_x0 + px0) * 2;
     }
     const int oy = m.z & ~TL_MSG_PADROW;
-    uint32_t* pr = tile_ptr + (int64_t)oy * (out_w >> 1);
-    uint32_t* pg = pr + plane_w;
-    uint32_t* pb = pg + plane_w;
+    uint32_t* pr = reinterpret_cast<uint32_t*>(tile_ptr + (uint64_t)((uint32_t)oy * row_b));  // a plane is < 4 GB
+    uint32_t* pg = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(pr) + plane_b);
+    uint32_t* pb = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(pg) + plane_b);
     if (m.z & TL_MSG_PADROW) {
 #pragma unroll
       for (int i = 0; i < ITER; ++i) {
-        if (i * TL_PAIR_STRIDE + px0 < out_w) {
+        if (i * TL_PAIR_STRIDE + px0 < chunk_w) {
           __stcs(pr + i * (TL_PAIR_STRIDE / 2), pad_pair);
           __stcs(pg + i * (TL_PAIR_STRIDE / 2), pad_pair);
           __stcs(pb + i * (TL_PAIR_STRIDE / 2), pad_pair);
@@ -569,11 +650,11 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
       const uint32_t b0 = (uint32_t)m.w & 0xFFFFu, b1 = (uint32_t)m.w >> 16;
       const uint32_t row0 = smem_base + stage * stage_bytes;
       const uint32_t row1 = row0 + (uint32_t)a.row_stride;
-      if (xpad) tiler_row<ITER, true>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, out_w, px0);
-      else tiler_row<ITER, false>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, out_w, px0);
+      if (xpad) tiler_row<ITER, true>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, px0);
+      else tiler_row<ITER, false>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, px0);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    if (lane == 0) mbar_arrive(empty0 + stage * 8u);
     if (++stage == TL_STAGES) { stage = 0; phase ^= 1u; }
   }
 }
@@ -742,8 +823,10 @@ extern "C" int pg_tile_letterbox_direct(PgTilePlan* plan, const uint8_t* pages, 
   cudaStream_t s = (cudaStream_t)stream;
   rc = plan_upload(plan, s);
   if (rc != PG_OK) return rc;
-  const TilerArgs a = make_args(plan, pages, n_pages, pitch, page_stride, out_f16, out_page_stride);
-  const int n_tiles = (int)plan->tiles.size();
+  TilerArgs a = make_args(plan, pages, n_pages, pitch, page_stride, out_f16, out_page_stride);
+  a.tiles = plan->d_tiles_full;  // whole tiles and their own x tables: independent of the chunking
+  a.xtab = plan->d_xtab_full;
+  const int n_tiles = (int)plan->tiles_full.size();
   const int64_t gy = (int64_t)n_tiles * n_pages;
   PG_REQUIRE(gy <= 65535, "direct kernel: n_tiles*n_pages must be <= 65535");
   dim3 grid(64, (unsigned)gy);

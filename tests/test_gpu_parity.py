@@ -82,6 +82,27 @@ def test_tiler_batch_of_pages_and_padding_values():
             assert info["pad_t"] > 0 and np.all(got[:, : info["pad_t"], :] == pad)
 
 
+def test_tiler_reference_default_grids_full_size():
+    """The reference's default run (1_doclayout_bboxes.py:718 `--grids 2x2,3x3,4x4` after the full-page pass):
+    30 tiles per 8000x6000 page, whose rows need four different shared-memory rings — one launch per ring.
+    Pipeline == direct kernel on every tile, three tiles of three grids against cv2."""
+    grids = [(1, 1), (2, 2), (3, 3), (4, 4)]
+    plan = ops.TilePlan(8000, 6000, grids, 20.0)
+    assert len(plan.tiles) == 30
+    pages = ops.synth_pages(plan, 2, synth.PAGE_SEED0 + 7)
+    out = plan.run(pages)
+    out_d = plan.run(pages, direct=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out_d)
+    host = pages[0].cpu().numpy()[:, : 3 * 8000].reshape(6000, 8000, 3)
+    first = {(1, 1): 0, (2, 2): 1, (3, 3): 5, (4, 4): 14}
+    for (rows, cols), t0 in first.items():
+        cells = ot.split_array_into_grid(host, rows, cols, 20.0)
+        t = t0 + len(cells) - 1  # the last tile of the grid
+        ref = ot.u8_to_f16_unit(ot.letterbox_tile_cv2(cells[-1]["image"]))
+        assert np.array_equal(plan.tile_view(out, 0, t).cpu().numpy(), ref), (rows, cols)
+
+
 def test_tiler_full_size_page_cross_check():
     """cfg3 shape (8000x6000, 4x4): pipeline == direct kernel everywhere, and two tiles
     against cv2.  Size-independent property: two independent kernels agree bit-for-bit."""
@@ -132,20 +153,20 @@ def test_tiler_random_shapes_and_imgsz_sweep():
             assert np.array_equal(plan.tile_view(out, 0, t).cpu().numpy(), ref), (w, h, rows, cols, ov, imgsz, auto, t)
 
 
-def test_tiler_very_wide_tile_uses_shallower_ring():
-    """A 1x1 grid on a 14000 px wide page needs 42 KB per staged row: 3 stages do not fit in shared memory,
-    the launcher falls back to a 2-deep ring; beyond that it must report PG_ERR_UNSUPPORTED."""
-    w, h = 14000, 300
+@pytest.mark.parametrize("w,h", [(14000, 300), (40000, 64)])
+def test_tiler_very_wide_tile_is_cut_into_column_chunks(w, h):
+    """A 1x1 grid on a 14000 / 40000 px wide page: 42 / 120 KB per source row.  The plan cuts such a tile into
+    chunks of output columns that each stage only the source span they sample (<= 9 KB), so the row length is
+    not a limit any more; the result equals cv2 and the (unchunked) direct kernel."""
     page = np.random.default_rng(5).integers(0, 256, (h, w, 3), dtype=np.uint8)
     plan = ops.TilePlan(w, h, [(1, 1)], 20.0, 1024, 32, True)
-    out = plan.run(ops.upload_pages([page], plan))
+    pages = ops.upload_pages([page], plan)
+    out = plan.run(pages)
+    out_d = plan.run(pages, direct=True)
     torch.cuda.synchronize()
+    assert torch.equal(out, out_d)
     ref = ot.u8_to_f16_unit(ot.letterbox_tile_cv2(page, 1024, 32, True))
     assert np.array_equal(plan.tile_view(out, 0, 0).cpu().numpy(), ref)
-    from multimodal_embeddings_b200._lib import PageGeomError
-    huge = ops.TilePlan(40000, 64, [(1, 1)], 20.0, 1024, 32, True)
-    with pytest.raises(PageGeomError, match="unsupported"):
-        huge.run(huge.alloc_pages(1))
 
 
 def test_tiler_heterogeneous_batch_one_launch():

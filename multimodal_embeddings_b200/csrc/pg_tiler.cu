@@ -110,6 +110,8 @@ extern "C" int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t
   plan->page_h = page_h;
   plan->imgsz = imgsz;
   int64_t out_off = 0;
+  int max_row_bytes = TL_MAX_ROW_BYTES;
+  if (const char* e = getenv("PG_TILER_MAX_ROW_BYTES")) max_row_bytes = std::max(64, atoi(e));  // test / tuning knob
   for (int g = 0; g < n_grids; ++g) {
     const int rows = grid_rows[g], cols = grid_cols[g];
     if (rows <= 0 || cols <= 0) {
@@ -224,7 +226,7 @@ extern "C" int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t
             chunk_span(c0, chunk_w, &lo, &hi);
             worst = std::max(worst, ((3 * (ti.x0 + lo)) & 15) + 3 * (hi - lo) + 15);
           }
-          if (worst <= TL_MAX_ROW_BYTES || chunk_w <= 64) break;
+          if (worst <= max_row_bytes || chunk_w <= 64) break;
         }
         for (int c0 = 0; c0 < ti.out_w; c0 += chunk_w) {
           TileDev ch = td;

@@ -123,10 +123,14 @@ def test_tiler_full_size_page_cross_check():
     assert torch.equal(again[0], pages[1])
 
 
-def test_tiler_random_shapes_and_imgsz_sweep():
+@pytest.mark.parametrize("max_row_bytes", [None, 700, 190])
+def test_tiler_random_shapes_and_imgsz_sweep(max_row_bytes, monkeypatch):
     """Random page shapes / grids / overlaps / letterbox sizes: every instantiation of the pipeline kernel
     (1, 2 and 4 pixel-pair iterations, imgsz 320..2048) against the direct kernel everywhere and against
-    cv2 on two tiles per case."""
+    cv2 on two tiles per case.  Run again with the column-chunk threshold forced down (a plan-time knob), so
+    that these small tiles are cut into many chunks: chunk borders, rebased x tables, pad-only chunks."""
+    if max_row_bytes is not None:
+        monkeypatch.setenv("PG_TILER_MAX_ROW_BYTES", str(max_row_bytes))
     rng = np.random.default_rng(77)
     cases = [(3000, 2200, 1, 1, 0.0, 2048, True), (2100, 1500, 2, 1, 35.0, 1280, False), (801, 613, 1, 3, 20.0, 320, True)]
     for _ in range(9):
@@ -166,6 +170,24 @@ def test_tiler_very_wide_tile_is_cut_into_column_chunks(w, h):
     torch.cuda.synchronize()
     assert torch.equal(out, out_d)
     ref = ot.u8_to_f16_unit(ot.letterbox_tile_cv2(page, 1024, 32, True))
+    assert np.array_equal(plan.tile_view(out, 0, 0).cpu().numpy(), ref)
+
+
+def test_tiler_chunks_made_only_of_pad_columns():
+    """A 7000x35000 strip letterboxed into a 1024 square (auto=False): 205 real columns between 409/410 pad
+    columns, 21 KB source rows -> sixteen 64-column chunks, most of them nothing but pad (they stage one
+    pixel and never sample it)."""
+    w, h = 7000, 35000
+    plan = ops.TilePlan(w, h, [(1, 1)], 20.0, 1024, 32, False)
+    info = plan.tiles[0]
+    assert (info["out_w"], info["out_h"], info["new_w"]) == (1024, 1024, 205) and info["pad_l"] >= 384
+    pages = ops.synth_pages(plan, 1, synth.PAGE_SEED0 + 3)
+    out = plan.run(pages)
+    out_d = plan.run(pages, direct=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out_d)
+    host = pages[0].cpu().numpy()[:, : 3 * w].reshape(h, w, 3)
+    ref = ot.u8_to_f16_unit(ot.letterbox_tile_cv2(host, 1024, 32, False))
     assert np.array_equal(plan.tile_view(out, 0, 0).cpu().numpy(), ref)
 
 

@@ -191,6 +191,20 @@ def print_reference_line(args, spec):
 
 
 # ------------------------------------------------------------------------------------------------
+def enable_records(pipe, dets, page_ids):
+    """--records: page-invariant text of the stage-3 documents (3_combine_grids.py:282-291) for the shard."""
+    import json as _json
+    import numpy as np
+    from multimodal_embeddings_b200 import ops, synth
+    classes = np.concatenate([d["classes"] for d in dets])
+    names = sorted(set(synth.class_names_of(classes)))
+    lut = {c: names.index(nm) for c, nm in zip(classes.tolist(), synth.class_names_of(classes))}
+    name_id = np.asarray([lut[c] for c in classes.tolist()], np.int32)
+    ht = [ops.combined_head_tail(f"/corpus/page_{g:06d}.png", {"width": int(d["width"]), "height": int(d["height"])}, 0.5,
+                                 [f"/corpus/2_edge_box_filtered/json/page_{g:06d}_grid.json"]) for g, d in zip(page_ids, dets)]
+    pipe.enable_records([h for h, _ in ht], [t for _, t in ht], [_json.dumps(nm).encode("ascii") for nm in names], name_id)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -206,6 +220,8 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="run the box stages after the tiler on one stream")
     ap.add_argument("--corpus-stats", action="store_true", help="accumulate + all-reduce corpus histograms (cfg5)")
     ap.add_argument("--tiler-only", action="store_true", help="profiling helper: time the tiler alone")
+    ap.add_argument("--records", action="store_true",
+                    help="also lay out the stage-3 JSON records on the device every step (pg_json_combined, +4 kernels)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     spec = workload_spec(args.workload)
@@ -261,6 +277,8 @@ def main():
         dets = [synth.page_detections(w, h, rows, cols, 20.0, spec["boxes"], synth.PAGE_SEED0 + gi) for gi in idxs]
         pipe = PagePipeline(plan, len(idxs), corpus_stats=args.corpus_stats, overlap=not args.no_overlap)
         host = pipe.set_detections(dets)
+        if args.records:
+            enable_records(pipe, dets, [first_page + j for j in range(len(idxs))])
         pipes.append((plan, pipe, pages, host, dets))
     else:  # mixed page sizes: ONE heterogeneous tiler batch + ONE box pipeline for the whole shard
         page_sizes = [sizes[(first_page + i) % len(sizes)] for i in range(ppg)]
@@ -273,11 +291,15 @@ def main():
                 for j, (w, h) in enumerate(page_sizes)]
         pipe = PagePipeline(batch, ppg, corpus_stats=args.corpus_stats, overlap=not args.no_overlap)
         host = pipe.set_detections(dets)
+        if args.records:
+            enable_records(pipe, dets, [first_page + j for j in range(ppg)])
         pipes.append((batch, pipe, pages, host, dets))
     torch.cuda.synchronize()
 
     def is_batch(t):
         return isinstance(t, ops.TileBatch)
+
+    kernels_per_step = KERNELS_PER_STEP + (4 if args.records else 0)
 
     def tiler_alone(t, pipe, pages):
         return t.run() if is_batch(t) else t.run(pages, out=pipe.tiles_out)
@@ -404,7 +426,7 @@ def main():
                    "streams": "tiler (low priority) || box stages (high priority)" if not args.no_overlap else "single stream",
                    "stages": "tiler only" if args.tiler_only else "tile+letterbox, translate+edge filter, NMS merge, width median, column peaks"},
         "roofline": roofline, "clocks": clocks, "merge_stats_last_group": nms_stats, "corpus": corpus,
-        "gpu_launches": (len(pipes) if args.tiler_only else KERNELS_PER_STEP * len(pipes)) * args.steps,
+        "gpu_launches": (len(pipes) if args.tiler_only else kernels_per_step * len(pipes)) * args.steps,
     }
 
     # ---- e2e: same metric through the host-buffer API, H2D of pages+detections and D2H of results timed

@@ -82,6 +82,7 @@ class PagePipeline:
             self.col_hist = self.hist[PG_WIDTH_HIST_BINS:]
         self.gauss = ops.gauss_table()
         self.max_bins = ops.MAX_DENSITY_BINS
+        self.records = False
 
     # ---------------------------------------------------------------- detections
     def set_detections(self, dets: Sequence[dict], stream=None, host_staging: Optional[dict] = None):
@@ -207,6 +208,51 @@ class PagePipeline:
                                 self.min_confidence, self.max_cols, ptr(self.centers), ptr(self.col_widths),
                                 ptr(self.n_cols), ptr(self.col_ws), self.max_bins, ptr(self.col_spans), ptr(self.col_span_n),
                                 ptr(self.col_hist), s))
+        if self.records:
+            self._run_records(stream)
+
+    # ---------------------------------------------------------------- stage-3 records (J1-J4)
+    def enable_records(self, heads: Sequence[bytes], tails: Sequence[bytes], names: Sequence[bytes], name_id,
+                       bytes_per_box: int = 260) -> None:
+        """Have every step also lay out the `<base>_combined.json` documents of the shard on the device
+        (pg_json_combined, 4 more kernels on the box stream).  heads/tails: ops.combined_head_tail per page;
+        names: JSON string literals; name_id[box] indexes names.  Call after set_detections."""
+        p, n = self.n_pages, self.n_boxes
+        assert len(heads) == p and len(tails) == p and n > 0
+        pieces = list(heads) + list(tails) + list(names)
+        offs = np.concatenate([[0], np.cumsum([len(x) for x in pieces])]).astype(np.int64)
+        self.rec_text = torch.frombuffer(bytearray(b"".join(pieces) + b"\0"), dtype=torch.uint8).cuda()
+        self.rec_head_off = torch.from_numpy(offs[:p + 1].copy()).cuda()
+        self.rec_tail_off = torch.from_numpy(offs[p:2 * p + 1].copy()).cuda()
+        self.rec_name_off = torch.from_numpy(offs[2 * p:].copy()).cuda()
+        self.rec_name_id = ops._dev(name_id, torch.int32)
+        self.rec_ws_bytes = int(lib().pg_json_workspace_bytes(n, p))
+        self.rec_ws = torch.empty(self.rec_ws_bytes, dtype=torch.uint8, device="cuda")
+        self.rec_capacity = int(offs[2 * p]) + 80 * p + n * bytes_per_box
+        self.rec_out = torch.empty(self.rec_capacity, dtype=torch.uint8, device="cuda")
+        self.rec_off = torch.zeros(p + 1, dtype=torch.int64, device="cuda")
+        self.records = True
+
+    def _run_records(self, stream) -> None:
+        check(lib().pg_json_combined(ptr(self.boxes_page), ptr(self.classes), ptr(self.scores), ptr(self.rec_name_id),
+                                     ptr(self.kept2), ptr(self.page_off), ptr(self.n_kept2), self.n_pages, self.n_boxes,
+                                     self.max_per_page, ptr(self.rec_text), ptr(self.rec_head_off), ptr(self.rec_tail_off),
+                                     ptr(self.rec_name_off), ptr(self.rec_out), self.rec_capacity, ptr(self.rec_off),
+                                     ptr(self.rec_ws), self.rec_ws_bytes, stream.cuda_stream))
+
+    def records_to_host(self) -> List[bytes]:
+        """The documents of the last step (synchronises).  A shard whose text outgrew the buffer is re-run with
+        the exact size — the device reports it in rec_off[n_pages]."""
+        torch.cuda.synchronize()
+        off = self.rec_off.cpu().numpy()
+        if int(off[-1]) > self.rec_capacity:
+            self.rec_capacity = int(off[-1])
+            self.rec_out = torch.empty(self.rec_capacity, dtype=torch.uint8, device="cuda")
+            self._run_records(torch.cuda.current_stream())
+            torch.cuda.synchronize()
+            off = self.rec_off.cpu().numpy()
+        host = self.rec_out[:int(off[-1])].cpu().numpy().tobytes()
+        return [host[off[i]:off[i + 1]] for i in range(self.n_pages)]
 
     def allreduce_corpus_stats(self):
         """K6: the one exchange step of the path — integer histograms summed over ranks

@@ -1,5 +1,7 @@
 """Whole hot path chained on the device (PagePipeline, the object bench.py times) against the oracle,
 in both launch orders (two streams / one stream), plus the corpus histograms and their running exchange."""
+import json
+
 import numpy as np
 import pytest
 
@@ -41,6 +43,14 @@ def test_pipeline_matches_oracle_and_accumulates_corpus_histograms(workload, ove
     plan, imgs, dets, pages = workload
     pipe = PagePipeline(plan, len(imgs), corpus_stats=True, overlap=overlap)
     pipe.set_detections(dets)
+    # stage-3 records laid out on the device in the same step (deliberately small buffer: forces the re-run path)
+    all_classes = np.concatenate([d["classes"] for d in dets])
+    names = sorted(set(synth.class_names_of(all_classes)))
+    name_id = np.asarray([names.index(nm) for nm in synth.class_names_of(all_classes)], np.int32)
+    meta = [(f"/scans/p{i}.png", {"width": W, "height": H}, [f"/scans/2/p{i}_grid_{ROWS}x{COLS}.json"]) for i in range(len(imgs))]
+    ht = [ops.combined_head_tail(path, size, 0.5, srcs) for path, size, srcs in meta]
+    pipe.enable_records([h for h, _ in ht], [t for _, t in ht], [json.dumps(nm).encode("ascii") for nm in names],
+                        name_id, bytes_per_box=12 if overlap else 260)
     for _ in range(2):  # the second pass re-uses every buffer and the self-resetting work counters
         pipe.run(pages)
         pipe.exchange_corpus_stats_async()
@@ -64,6 +74,15 @@ def test_pipeline_matches_oracle_and_accumulates_corpus_histograms(workload, ove
         ref_w += np.bincount(np.clip(widths.astype(np.int64), 0, PG_WIDTH_HIST_BINS - 1), minlength=PG_WIDTH_HIST_BINS)
         for c in cc:
             ref_c[min(PG_COL_HIST_BINS - 1, int(c) * 1000 // W)] += 1
+    docs = pipe.records_to_host()
+    for p, (d, (path, size, srcs)) in enumerate(zip(dets, meta)):
+        final = oracle_page(d)[0]
+        bp = d["boxes_local"] + d["cells"][d["box_cell"]][:, [0, 1, 0, 1]]
+        want = json.dumps({"image_path": path, "image_size": size, "parameters": {"iou_threshold": 0.5},
+                           "boxes": bp[final].tolist(), "classes": d["classes"][final].tolist(),
+                           "scores": d["scores"][final].tolist(), "class_names": synth.class_names_of(d["classes"][final]),
+                           "source_jsons": srcs}, indent=2)
+        assert docs[p].decode("ascii") == want
     hist = pipe.hist.cpu().numpy()
     assert np.array_equal(hist[:PG_WIDTH_HIST_BINS], 2 * ref_w) and np.array_equal(hist[PG_WIDTH_HIST_BINS:], 2 * ref_c)
     assert np.array_equal(total.cpu().numpy(), hist)  # one rank: the running exchange is the local total

@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="run the box stages after the tiler on one stream")
     ap.add_argument("--corpus-stats", action="store_true", help="accumulate + all-reduce corpus histograms (cfg5)")
     ap.add_argument("--tiler-only", action="store_true", help="profiling helper: time the tiler alone")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the step from a CUDA graph captured after warm-up (one launch per step instead of 12-16)")
     ap.add_argument("--records", action="store_true",
                     help="also lay out the stage-3 JSON records on the device every step (pg_json_combined, +4 kernels)")
     args = ap.parse_args()
@@ -310,10 +312,14 @@ def main():
     def input_bytes(pages):
         return sum(p.numel() for p in pages) if isinstance(pages, list) else pages.numel()
 
+    graphs = []
+
     def step(ev=None):
         for k, (plan, pipe, pages, _, _) in enumerate(pipes):
             if args.tiler_only:
                 tiler_alone(plan, pipe, pages)
+            elif graphs:
+                graphs[k].replay()
             else:
                 pipe.run(pages, tiler_events=ev[k] if ev is not None else None)
         if args.corpus_stats and not cfg5:  # running exchange every step (cfg5 reduces once, at the end of the corpus)
@@ -329,6 +335,18 @@ def main():
 
     tiler_ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in pipes]
                 for _ in range(args.steps)]
+    graph_tiler_ms = None
+    if args.graph and not args.tiler_only:
+        # the tiler's duration inside the step cannot be read from a replayed graph: take it from three eager
+        # steps first, then capture
+        for s_i in range(3):
+            step(tiler_ev[s_i])
+        torch.cuda.synchronize()
+        graph_tiler_ms = sum(a.elapsed_time(b) for evs in tiler_ev[:3] for (a, b) in evs) / 3
+        graphs.extend(pipe.capture(pages) for _, pipe, pages, _, _ in pipes)
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
@@ -341,7 +359,7 @@ def main():
     sampler.start()
     e0.record(stream)
     for s_i in range(args.steps):
-        step(None if args.tiler_only else tiler_ev[s_i])
+        step(None if args.tiler_only or graphs else tiler_ev[s_i])
     if cfg5:  # the one exchange step of the path: integer histograms summed over ranks (NCCL over NVLink)
         for _, pipe, _, _, _ in pipes:
             pipe.allreduce_corpus_stats()
@@ -384,7 +402,7 @@ def main():
     if args.tiler_only:
         tiler_ms = ms / args.steps
     else:
-        tiler_ms = sum(a.elapsed_time(b) for evs in tiler_ev for (a, b) in evs) / args.steps
+        tiler_ms = graph_tiler_ms if graphs else sum(a.elapsed_time(b) for evs in tiler_ev for (a, b) in evs) / args.steps
     tiler_bytes = sum(tiler_alg_bytes(plan, pipe) for plan, pipe, _, _, _ in pipes)
     achieved = tiler_bytes / (tiler_ms * 1e-3) / 1e9
     traffic = None
@@ -423,7 +441,8 @@ def main():
         "config": {"workload": spec["name"], "pages_per_gpu": ppg, "global_pages_per_step": ppg * world,
                    "parallelism": f"page-sharded x{world}, no collective" + (" + hist all-reduce" if args.corpus_stats else ""),
                    "l2": f"inputs {sum(input_bytes(p[2]) for p in pipes) / 1e9:.1f} GB/step per GPU >> 126 MB L2 (no flush needed)",
-                   "streams": "tiler (low priority) || box stages (high priority)" if not args.no_overlap else "single stream",
+                   "streams": ("tiler (low priority) || box stages (high priority)" if not args.no_overlap else "single stream")
+                   + (", step replayed from a CUDA graph (tiler duration from 3 eager steps before capture)" if graphs else ""),
                    "stages": "tiler only" if args.tiler_only else "tile+letterbox, translate+edge filter, NMS merge, width median, column peaks"},
         "roofline": roofline, "clocks": clocks, "merge_stats_last_group": nms_stats, "corpus": corpus,
         "gpu_launches": (len(pipes) if args.tiler_only else kernels_per_step * len(pipes)) * args.steps,

@@ -39,6 +39,35 @@ def oracle_page(d):
 
 
 @pytest.mark.parametrize("overlap", [True, False])
+def test_graph_replay_equals_eager_step(workload, overlap):
+    """The step captured into a CUDA graph (fork/join over both streams) and replayed gives the eager results."""
+    plan, imgs, dets, pages = workload
+    pipe = PagePipeline(plan, len(imgs), overlap=overlap)
+    pipe.set_detections(dets)
+    pipe.run(pages)
+    torch.cuda.synchronize()
+    want = {k: v.clone() for k, v in pipe.results_to_host().items()}
+    tiles = pipe.tiles_out.clone()
+    graph = pipe.capture(pages)
+    for name in ("kept2", "n_kept2", "median", "centers", "n_cols"):
+        getattr(pipe, name).zero_()
+    pipe.tiles_out.zero_()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    pipe.check_status()
+    got = pipe.results_to_host()
+    for k in want:
+        if k == "kept2":  # entries past n_kept of a page are scratch
+            for p in range(len(imgs)):
+                n = int(want["n_kept2"][p])
+                assert torch.equal(got[k][p * NB: p * NB + n], want[k][p * NB: p * NB + n])
+        else:
+            assert torch.equal(got[k], want[k]), k
+    assert torch.equal(pipe.tiles_out, tiles)
+
+
+@pytest.mark.parametrize("overlap", [True, False])
 def test_pipeline_matches_oracle_and_accumulates_corpus_histograms(workload, overlap):
     plan, imgs, dets, pages = workload
     pipe = PagePipeline(plan, len(imgs), corpus_stats=True, overlap=overlap)

@@ -28,6 +28,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
+from .records import load_record, write_sidecar
+
 FMT = "%(asctime)s - %(name)s - %(levelname)s - %(message)s"
 IMAGE_EXTENSIONS = (".jpg", ".jpeg", ".png", ".bmp", ".tiff", ".tif", ".webp")
 
@@ -352,6 +354,8 @@ def main_stage3(argv: Optional[Sequence[str]] = None) -> int:
     p.add_argument("--output_folder", required=True)
     p.add_argument("--iou_threshold", type=float, default=0.5)
     p.add_argument("--viz_alpha", type=float, default=0.3)
+    p.add_argument("--sidecar", action="store_true",
+                   help="extension: also write <base>_combined.pgrec (raw arrays) for this implementation's stages 4/5")
     args = p.parse_args(argv)
     out_json = os.path.join(args.output_folder, "json")
     os.makedirs(out_json, exist_ok=True)
@@ -394,9 +398,14 @@ def main_stage3(argv: Optional[Sequence[str]] = None) -> int:
             ht = [ops.combined_head_tail(x[6], x[7], args.iou_threshold, x[1]) for x in pooled]
             docs = ops.json_combined(boxes, classes, scores, name_id, off, [h for h, _ in ht], [t for _, t in ht],
                                      [json.dumps(nm).encode("ascii") for nm in table], kept_idx=kept, n_kept=n_kept)
-            for x, doc in zip(pooled, docs):
-                with open(os.path.join(out_json, f"{x[0]}_combined.json"), "wb") as f:
+            for i, (x, doc) in enumerate(zip(pooled, docs)):
+                json_path = os.path.join(out_json, f"{x[0]}_combined.json")
+                with open(json_path, "wb") as f:
                     f.write(doc)
+                if args.sidecar:  # raw arrays for this implementation's stages 4/5 (records.py)
+                    idx = kept[off[i]: off[i] + n_kept[i]]
+                    write_sidecar(json_path, x[6], x[7], {"iou_threshold": args.iou_threshold}, x[1], boxes[idx],
+                                  classes[idx], scores[idx], list(table), name_id[idx])
             pooled = []
         for i, (base, paths, b, s, c, n, image_path, image_size) in enumerate(pooled):
             idx = (kept[off[i]: off[i] + n_kept[i]] - off[i]).tolist()
@@ -438,8 +447,7 @@ def main_stage4(argv: Optional[Sequence[str]] = None) -> int:
     pages = []
     for path in files:
         try:  # 4:103-151
-            with open(path) as f:
-                d = json.load(f)
+            d = load_record(path)  # the .pgrec sidecar when stage 3 wrote one, else the JSON text
             size = d.get("image_size", {}) or {}
             names, boxes = d.get("class_names", []), d.get("boxes", [])
             n = min(len(names), len(boxes))
@@ -525,8 +533,7 @@ def main_stage5(argv: Optional[Sequence[str]] = None) -> int:
             failures += 1
             continue
         try:  # 5:337-400
-            with open(path) as f:
-                layout = json.load(f)
+            layout = load_record(path)  # the .pgrec sidecar when stage 3 wrote one, else the JSON text
             with open(mpath) as f:
                 median_width = json.load(f).get("median_width", 0)
             if median_width <= 0:

@@ -61,3 +61,46 @@ def test_stage_argv_surfaces_match_reference():
     with pytest.raises(SystemExit):
         cli.main_stage2(["--input_folder", "x"])  # --output_folder is required
     assert cli.get_image_paths("/nonexistent") == []
+
+
+def test_record_sidecar_round_trip_and_staleness(tmp_path):
+    """records.py: the binary sidecar of a stage-3 record gives back exactly what json.load gives for the
+    JSON file (numbers bit for bit), and is ignored when stale, truncated or foreign."""
+    import json
+    import os
+    import time
+
+    import numpy as np
+
+    from multimodal_embeddings_b200 import records
+    rng = np.random.default_rng(3)
+    n = 257
+    boxes = rng.uniform(0, 8000, (n, 4)).astype(np.float32).astype(np.float64)
+    classes = rng.integers(0, 3, n).astype(np.float64)
+    scores = rng.random(n)
+    names = ["title", "plain_text", 'fig "x" é']
+    name_id = classes.astype(np.int32)
+    doc = {"image_path": "/p/a b.png", "image_size": {"width": 8000, "height": 6000}, "parameters": {"iou_threshold": 0.5},
+           "boxes": boxes.tolist(), "classes": classes.tolist(), "scores": scores.tolist(),
+           "class_names": [names[i] for i in name_id], "source_jsons": ["x.json", "x_grid_2x2.json"]}
+    jp = str(tmp_path / "a b_combined.json")
+    with open(jp, "w") as f:
+        json.dump(doc, f, indent=2)
+    assert records.read_sidecar(jp) is None and records.load_record(jp) == doc
+    sp = records.write_sidecar(jp, doc["image_path"], doc["image_size"], doc["parameters"], doc["source_jsons"],
+                               boxes, classes, scores, names, name_id)
+    rec = records.load_record(jp)
+    assert isinstance(rec["boxes"], np.ndarray) and list(rec) == list(doc)
+    as_lists = {k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in rec.items()}
+    assert as_lists == doc
+    # stale: the JSON was rewritten after the sidecar
+    os.utime(sp, (time.time() - 100, time.time() - 100))
+    assert records.read_sidecar(jp) is None and records.load_record(jp) == doc
+    os.utime(sp, None)
+    assert records.read_sidecar(jp) is not None
+    # truncated / foreign bytes are refused, never mis-read
+    raw = open(sp, "rb").read()
+    for bad in (raw[:-4], b"NOTPGREC" + raw[8:], raw[:17] + b"\xff" + raw[18:], raw[:20] + b"}" + raw[21:]):
+        with open(sp, "wb") as f:
+            f.write(bad)
+        assert records.read_sidecar(jp) is None

@@ -12,13 +12,33 @@ import cli_tree
 pytestmark = pytest.mark.gpu
 
 
-def test_cli_stages_2_to_5_match_reference_outputs(tmp_path):
+@pytest.mark.parametrize("sidecar", [False, True])
+def test_cli_stages_2_to_5_match_reference_outputs(tmp_path, sidecar, monkeypatch):
+    """sidecar=True: stage 3 also drops the binary `.pgrec` records and stages 4/5 must take their numbers
+    from them (json.load of a stage-3 file is made to fail) — the JSON outputs stay identical."""
     golden = load_golden("cli_tree.json.gz")
     root = str(tmp_path)
     cli_tree.build_stage1_tree(root)
     argv = cli_tree.stage_argv(root)
-    for stage, main in ((2, cli.main_stage2), (3, cli.main_stage3), (4, cli.main_stage4), (5, cli.main_stage5)):
+    if sidecar:
+        argv[3] = argv[3] + ["--sidecar"]
+    for stage, main in ((2, cli.main_stage2), (3, cli.main_stage3)):
         assert main(argv[stage]) == 0
+    if sidecar:
+        import glob
+        import os
+        from multimodal_embeddings_b200 import records
+        jsons = glob.glob(os.path.join(root, "3_combined_bboxes", "json", "*_combined.json"))
+        assert jsons and all(os.path.exists(records.sidecar_path(j)) for j in jsons)
+        real_load = json.load
+
+        def guarded(f, *a, **k):
+            assert "_combined.json" not in getattr(f, "name", ""), "stage-3 JSON text was parsed despite the sidecar"
+            return real_load(f, *a, **k)
+        monkeypatch.setattr(json, "load", guarded)
+    for stage, main in ((4, cli.main_stage4), (5, cli.main_stage5)):
+        assert main(argv[stage]) == 0
+    monkeypatch.undo()
     got = cli_tree.collect_outputs(root)
     assert sorted(got) == sorted(golden)
     for name in golden:

@@ -273,8 +273,8 @@ extern "C" int pg_json_combined(const double* boxes, const double* classes, cons
                                 void* ws, int64_t ws_bytes, void* stream) {
   PG_REQUIRE(n_pages >= 0 && n_boxes >= 0 && max_boxes_per_page >= 0 && out_capacity >= 0, "sizes");
   if (n_pages == 0) return PG_OK;
-  PG_REQUIRE(boxes && classes && scores && name_id && page_off && text && head_off && tail_off && name_off && out &&
-                 out_off && ws, "null device pointer");
+  PG_REQUIRE(page_off && text && head_off && tail_off && name_off && out && out_off && ws, "null device pointer");
+  PG_REQUIRE(n_boxes == 0 || (boxes && classes && scores && name_id), "null device pointer (box arrays)");
   if (ws_bytes < pg_json_workspace_bytes(n_boxes, n_pages)) {
     pg_set_error("workspace: pg_json_combined needs %lld bytes, got %lld",
                  (long long)pg_json_workspace_bytes(n_boxes, n_pages), (long long)ws_bytes);

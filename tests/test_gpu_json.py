@@ -114,3 +114,13 @@ def test_golden_stage3_tree_is_reproduced():
                             [json.dumps(n).encode("ascii") for n in names])
     for (text, _), got in zip(docs_in, out):
         assert got.decode("ascii") == text
+
+
+def test_shard_without_any_box():
+    """Two pages, no detections at all: four empty arrays per document, exactly as json.dump prints them."""
+    meta = [("/a.png", {"width": 10, "height": 20}, 0.5, []), ("/b.png", None, 0.25, ["s.json"])]
+    ht = [ops.combined_head_tail(*m) for m in meta]
+    docs = ops.json_combined(np.zeros((0, 4)), np.zeros(0), np.zeros(0), np.zeros(0, np.int32), np.zeros(3, np.int64),
+                             [h for h, _ in ht], [t for _, t in ht], [b'"plain_text"'])
+    for doc, (path, size, thr, srcs) in zip(docs, meta):
+        assert doc == reference_text(path, size, thr, [], [], [], [], srcs)

@@ -1002,7 +1002,9 @@ __global__ void __launch_bounds__(DEN_THREADS) column_density_kernel(
     const int64_t* __restrict__ page_off, const int32_t* __restrict__ page_wh, const double* __restrict__ median,
     int max_window, const DenEntry* __restrict__ list, const int32_t* __restrict__ list_n, double* ws_all,
     int max_bins) {
-  __shared__ DenEntry stage[DEN_THREADS / 32][32];
+  // The eight warps of a CTA walk the same span list: it is staged through shared memory by the whole CTA,
+  // 256 spans at a time, double-buffered (the next chunk's loads are in flight under this chunk's arithmetic).
+  __shared__ DenEntry buf[2][DEN_THREADS];
   const int p = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const ColGeom g = col_geom(page_wh[2 * p], page_wh[2 * p + 1], median[p], max_bins, max_window);
   if (!g.ok || !g.in_range || (int)blockIdx.x * DEN_THREADS >= g.nbins) return;
@@ -1011,57 +1013,58 @@ __global__ void __launch_bounds__(DEN_THREADS) column_density_kernel(
   const int seg0 = ((int)blockIdx.x * (DEN_THREADS / 32) + warp) * 32;
   const int bin = seg0 + lane;
   double d = 0.0;
-  DenEntry nxt;
-  nxt.left = 1; nxt.right = -1; nxt.center = 0; nxt.pad = 0; nxt.half = 1.0; nxt.inv_half = 1.0;
-  if (lane < n) nxt = lst[lane];
-  for (int e0 = 0; e0 < n; e0 += 32) {
-    const int e = e0 + lane;
-    const DenEntry mine = nxt;
-    if (e + 32 < n) nxt = lst[e + 32];  // prefetch the next 32 spans under this chunk's arithmetic
-    int L = 1, R = -1;  // padding lanes overlap nothing (R < 0 <= seg0)
-    __syncwarp();
-    if (e < n) {
-      stage[warp][lane] = mine;
-      L = mine.left; R = mine.right;
-    }
-    __syncwarp();
-    unsigned bits = __ballot_sync(0xffffffffu, L <= seg0 + 31 && R >= seg0);
-    // Four spans at a time: their weights are independent (ILP hides the fp64 latency), the adds stay
-    // in box order (:139-144).  A bin outside a span adds +0.0, which leaves any d >= 0 bit-identical.
-    while (bits) {
-      DenEntry en[4];
-      bool ok[4];
-      int slow = 0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        ok[q] = bits != 0;
-        const int l = ok[q] ? __ffs(bits) - 1 : 0;
-        bits &= bits - 1;              // 0 stays 0
-        en[q] = stage[warp][l];        // broadcast
-        slow |= en[q].pad;
-      }
-      double w4[4];
-      if (!slow) {  // warp-uniform; straight-line code so the four chains interleave
+  DenEntry none;  // overlaps nothing (right < 0 <= seg0)
+  none.left = 1; none.right = -1; none.center = 0; none.pad = 0; none.half = 1.0; none.inv_half = 1.0;
+  const int n_chunks = (n + DEN_THREADS - 1) / DEN_THREADS;
+  if (n_chunks > 0) buf[0][tid] = tid < n ? lst[tid] : none;
+  __syncthreads();
+  for (int c = 0; c < n_chunks; ++c) {
+    const DenEntry* cur = buf[c & 1];
+    DenEntry pre = none;
+    const int nx = (c + 1) * DEN_THREADS + tid;
+    if (nx < n) pre = lst[nx];
+    for (int sub = 0; sub < DEN_THREADS / 32 && c * DEN_THREADS + sub * 32 < n; ++sub) {
+      const DenEntry* grp = cur + sub * 32;
+      unsigned bits = __ballot_sync(0xffffffffu, grp[lane].left <= seg0 + 31 && grp[lane].right >= seg0);
+      // Four spans at a time: their weights are independent (ILP hides the fp64 latency), the adds stay
+      // in box order (:139-144).  A bin outside a span adds +0.0, which leaves any d >= 0 bit-identical.
+      while (bits) {
+        DenEntry en[4];
+        bool ok[4];
+        int slow = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const bool in = ok[q] && bin >= en[q].left && bin <= en[q].right;
-          const double wgt = pg_density_weight_rcp(bin, en[q].center, en[q].half, en[q].inv_half);
-          w4[q] = in ? wgt : 0.0;
+          ok[q] = bits != 0;
+          const int l = ok[q] ? __ffs(bits) - 1 : 0;
+          bits &= bits - 1;              // 0 stays 0
+          en[q] = grp[l];                // broadcast
+          slow |= en[q].pad;
         }
-      } else {
+        double w4[4];
+        if (!slow) {  // warp-uniform; straight-line code so the four chains interleave
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const bool in = ok[q] && bin >= en[q].left && bin <= en[q].right;
-          w4[q] = 0.0;
-          if (in) w4[q] = en[q].pad ? pg_density_weight(bin, en[q].left, en[q].right, en[q].center)
-                                    : pg_density_weight_rcp(bin, en[q].center, en[q].half, en[q].inv_half);
+          for (int q = 0; q < 4; ++q) {
+            const bool in = ok[q] && bin >= en[q].left && bin <= en[q].right;
+            const double wgt = pg_density_weight_rcp(bin, en[q].center, en[q].half, en[q].inv_half);
+            w4[q] = in ? wgt : 0.0;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const bool in = ok[q] && bin >= en[q].left && bin <= en[q].right;
+            w4[q] = 0.0;
+            if (in) w4[q] = en[q].pad ? pg_density_weight(bin, en[q].left, en[q].right, en[q].center)
+                                      : pg_density_weight_rcp(bin, en[q].center, en[q].half, en[q].inv_half);
+          }
         }
+        d = d + w4[0];
+        d = d + w4[1];
+        d = d + w4[2];
+        d = d + w4[3];
       }
-      d = d + w4[0];
-      d = d + w4[1];
-      d = d + w4[2];
-      d = d + w4[3];
     }
+    buf[(c + 1) & 1][tid] = pre;  // the other buffer: nobody reads it during this chunk
+    __syncthreads();
   }
   if (bin < g.nbins) ws_all[(int64_t)p * 2 * max_bins + bin] = d;
 }

@@ -13,7 +13,9 @@ stage 1 hands the letterboxed fp16 tiles to a detector object (synthetic or repl
 detections ship here) — and the JPEG visualisations (--viz_alpha is accepted and ignored).
 Extra flags, all optional: --no_image_check lets stages 2-5 run on JSON trees whose page images
 are absent (page size then comes from the JSON), --detections/--replay_folder/--boxes_per_page
-choose stage 1's detection source.
+choose stage 1's detection source, --sidecar (stage 3) also writes the binary record.
+Under `torchrun --nproc-per-node N` every stage shards its sorted work list by rank (one process per GPU, no
+communication); the union of the ranks' output files equals the single-process output.
 """
 from __future__ import annotations
 
@@ -42,6 +44,25 @@ def _logger(name: str) -> logging.Logger:
         lg.addHandler(h)
         lg.setLevel(logging.INFO)
     return lg
+
+
+def _my_share(items: list) -> list:
+    """Multi-GPU launches (`torchrun --nproc-per-node N <stage>.py ...` sets RANK / WORLD_SIZE / LOCAL_RANK):
+    pages are independent (1:749, 2:206, 3:431, 4:263, 5:569), so rank r simply takes the r-th contiguous block of
+    the stage's sorted work list and the union of the ranks' output files is the single-process output — no
+    communication.  Also binds the process to its GPU."""
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world <= 1:
+        return items
+    try:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)) % torch.cuda.device_count())
+    except ImportError:
+        pass
+    from .pipeline import shard_pages
+    r = shard_pages(len(items), rank, world)
+    return items[r.start:r.stop]
 
 
 def _dump(obj, path):
@@ -145,6 +166,7 @@ def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
     if not image_paths:
         logger.error(f"No images found in {args.input_folder}")
         return 0
+    image_paths = _my_share(image_paths)
     detector = ReplayDetector(args.replay_folder) if args.detections == "replay" else SyntheticDetector(args.boxes_per_page)
     processed = errors = 0
     import cv2
@@ -246,7 +268,7 @@ def main_stage2(argv: Optional[Sequence[str]] = None) -> int:
     os.makedirs(os.path.join(args.output_folder, "visualizations"), exist_ok=True)
 
     def run_folder(in_folder, out_folder):
-        paths = sorted(os.path.join(r, f) for r, _, fs in os.walk(in_folder) for f in fs if f.endswith(".json"))
+        paths = _my_share(sorted(os.path.join(r, f) for r, _, fs in os.walk(in_folder) for f in fs if f.endswith(".json")))
         ok = err = 0
         for path in paths:
             try:
@@ -365,7 +387,7 @@ def main_stage3(argv: Optional[Sequence[str]] = None) -> int:
         logger.error(f"No JSON files found in {args.input_folder}")
         return 0
     pooled = []
-    for base, paths in groups.items():
+    for base, paths in _my_share(list(groups.items())):
         b, s, c, n, image_path, image_size = pool_documents(paths, logger)
         if not b:
             logger.warning(f"No boxes found for {base}")
@@ -444,6 +466,7 @@ def main_stage4(argv: Optional[Sequence[str]] = None) -> int:
     if not files:
         logger.error(f"No JSON files found in {json_folder}")
         return 0
+    files = _my_share(files)
     pages = []
     for path in files:
         try:  # 4:103-151
@@ -525,6 +548,7 @@ def main_stage5(argv: Optional[Sequence[str]] = None) -> int:
     if not files:
         logger.error(f"No JSON files found in {args.input_folder}")
         return 0
+    files = _my_share(files)
     jobs, failures = [], 0
     for path in files:
         mpath = find_matching_median_json(path, args.median_folder)

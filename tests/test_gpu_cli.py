@@ -88,3 +88,33 @@ def test_cli_stage1_writes_reference_schema(tmp_path):
                           "source_jsons"]
     assert comb["scores"] == sorted(comb["scores"], reverse=True) and len(comb["boxes"]) > 10
     assert (tmp_path / "s4" / "json" / "scan A_combined_median_width.json").exists()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_cli_rank_sharding_union_equals_single_process(tmp_path, world, monkeypatch):
+    """Stages 2-5 run once per rank (RANK / WORLD_SIZE as torchrun sets them; here sequentially on one GPU) into
+    the same tree: every rank writes a disjoint subset and the union is the reference's output, file for file."""
+    import os
+    golden = load_golden("cli_tree.json.gz")
+    root = str(tmp_path)
+    cli_tree.build_stage1_tree(root)
+    argv = cli_tree.stage_argv(root)
+    monkeypatch.setenv("WORLD_SIZE", str(world))
+    written = []
+    for stage, main in ((2, cli.main_stage2), (3, cli.main_stage3), (4, cli.main_stage4), (5, cli.main_stage5)):
+        seen = set()
+        for rank in range(world):
+            monkeypatch.setenv("RANK", str(rank))
+            monkeypatch.setenv("LOCAL_RANK", "0")
+            assert main(argv[stage]) == 0
+            out_dir = argv[stage][argv[stage].index("--output_folder") + 1]
+            now = {os.path.join(r, f) for r, _, fs in os.walk(out_dir) for f in fs if f.endswith(".json")}
+            written.append((stage, rank, len(now - seen)))
+            seen = now
+    monkeypatch.undo()
+    got = cli_tree.collect_outputs(root)
+    assert sorted(got) == sorted(golden)
+    for name in golden:
+        assert got[name] == golden[name], name
+    assert sum(n for s, _, n in written if s == 3) == len([k for k in golden if k.startswith("3_combined_bboxes/")])
+    assert any(n > 0 for s, r, n in written if s == 3 and r > 0)  # the later ranks really did part of the work

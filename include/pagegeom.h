@@ -219,6 +219,24 @@ int pg_json_combined(const double* boxes /*dev [N,4]*/, const double* classes /*
                      uint8_t* out /*dev*/, int64_t out_capacity, int64_t* out_off /*dev [P+1]*/,
                      void* ws, int64_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------ R1-R3 record reader
+ * The numbers of a record's "boxes" / "classes" / "scores" arrays, text -> f64 on the device: what json.load's
+ * float() does for the reference's stage-4/5 readers (4_extract_median_widths.py:103-151,
+ * 5_detect_column_centers.py:337-400), correctly rounded for every token of <= 17 significant digits
+ * (everything json.dump prints; csrc/pg_fmt.h).  `ranges` (dev, [R,2] begin/end byte offsets into `text`) are
+ * regions holding only numbers, brackets, commas and whitespace — the caller locates them and parses the
+ * record's few strings itself.  range_block_off (dev [R+1]) = exclusive prefix of ceil(len_r / PG_JSON_PARSE_BLOCK).
+ * Range r's numbers land, in text order, in values[val_off[r] .. val_off[r+1]) (nothing is stored beyond
+ * `capacity`; val_off[R] is the total, so a short buffer is detected and the call repeated); n_bad[r] counts
+ * tokens that need the host's float() (more than 17 digits, malformed). */
+#define PG_JSON_PARSE_BLOCK 2048 /* text bytes per CTA (256 threads x 8 consecutive bytes) */
+int32_t pg_json_parse_block_bytes(void);
+int64_t pg_json_parse_workspace_bytes(int64_t total_blocks);
+int pg_json_parse_numbers(const uint8_t* text /*dev*/, const int64_t* ranges /*dev [R,2]*/, int32_t n_ranges,
+                          const int64_t* range_block_off /*dev [R+1]*/, int64_t total_blocks,
+                          double* values /*dev [capacity]*/, int64_t capacity, int64_t* val_off /*dev [R+1]*/,
+                          int32_t* n_bad /*dev [R]*/, void* ws, int64_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ test hooks
  * Host evaluations of the same inline arithmetic the kernels are compiled from
  * (csrc/pg_math.h, csrc/pg_fmt.h).  Used by the CPU test-suite only; not a compute path. */
@@ -226,6 +244,10 @@ int pg_json_combined(const double* boxes /*dev [N,4]*/, const double* classes /*
 int32_t pg_hostcheck_format_double(double x, char* buf);
 /* the same for n values, value i at buf + 24*i with length len[i]; returns the total length */
 int64_t pg_hostcheck_format_doubles(const double* x, int64_t n, char* buf, int32_t* len);
+/* the reader's number conversion (csrc/pg_fmt.h: pg_parse_json_number): token i starts at text + tok_off[i];
+ * out[i] = its value, consumed[i] = bytes used (0: not convertible here, host fallback); returns the count > 0 */
+int64_t pg_hostcheck_parse_numbers(const char* text, int64_t text_len, const int64_t* tok_off, int64_t n,
+                                   double* out, int32_t* consumed);
 double pg_hostcheck_iou(const double* a, const double* b);
 /* the divide-free predicate the merge kernel uses for `iou > thr` (must equal pg_hostcheck_iou(a,b) > thr) */
 int32_t pg_hostcheck_iou_gt(const double* a, const double* b, double thr);

@@ -72,8 +72,12 @@ SIGNATURES = {
     "pg_json_workspace_bytes": (_I64, [_I64, _I32]),
     "pg_json_combined": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P,
                                    _P, _I64, _P]),
+    "pg_json_parse_block_bytes": (_I32, []),
+    "pg_json_parse_workspace_bytes": (_I64, [_I64]),
+    "pg_json_parse_numbers": (C.c_int, [_P, _P, _I32, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P]),
     "pg_hostcheck_format_double": (_I32, [_F64, _P]),
     "pg_hostcheck_format_doubles": (_I64, [_P, _I64, _P, _P]),
+    "pg_hostcheck_parse_numbers": (_I64, [_P, _I64, _P, _I64, _P, _P]),
     "pg_hostcheck_iou": (_F64, [_P, _P]),
     "pg_hostcheck_iou_gt": (_I32, [_P, _P, _F64]),
     "pg_hostcheck_iou_gt_f32": (_I32, [_P, _P, _F64]),

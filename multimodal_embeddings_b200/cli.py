@@ -30,7 +30,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .records import load_record, write_sidecar
+from .records import load_records, write_sidecar
 
 FMT = "%(asctime)s - %(name)s - %(levelname)s - %(message)s"
 IMAGE_EXTENSIONS = (".jpg", ".jpeg", ".png", ".bmp", ".tiff", ".tif", ".webp")
@@ -467,10 +467,17 @@ def main_stage4(argv: Optional[Sequence[str]] = None) -> int:
         logger.error(f"No JSON files found in {json_folder}")
         return 0
     files = _my_share(files)
+    # the records of the whole batch: the .pgrec sidecar where stage 3 wrote one, else the JSON text with its
+    # number arrays converted on the GPU in one call (records.load_records), else json.load
+    try:
+        recs = load_records(files)
+    except Exception as e:
+        logger.error(f"Batch record reader failed ({e}); reading the files one by one")
+        recs = {}
     pages = []
     for path in files:
         try:  # 4:103-151
-            d = load_record(path)  # the .pgrec sidecar when stage 3 wrote one, else the JSON text
+            d = recs[path] if path in recs else load_records([path])[path]
             size = d.get("image_size", {}) or {}
             names, boxes = d.get("class_names", []), d.get("boxes", [])
             n = min(len(names), len(boxes))
@@ -549,6 +556,11 @@ def main_stage5(argv: Optional[Sequence[str]] = None) -> int:
         logger.error(f"No JSON files found in {args.input_folder}")
         return 0
     files = _my_share(files)
+    try:
+        recs = load_records(files)  # sidecar / device-parsed text / json.load, per file (records.load_records)
+    except Exception as e:
+        logger.error(f"Batch record reader failed ({e}); reading the files one by one")
+        recs = {}
     jobs, failures = [], 0
     for path in files:
         mpath = find_matching_median_json(path, args.median_folder)
@@ -557,7 +569,7 @@ def main_stage5(argv: Optional[Sequence[str]] = None) -> int:
             failures += 1
             continue
         try:  # 5:337-400
-            layout = load_record(path)  # the .pgrec sidecar when stage 3 wrote one, else the JSON text
+            layout = recs[path] if path in recs else load_records([path])[path]
             with open(mpath) as f:
                 median_width = json.load(f).get("median_width", 0)
             if median_width <= 0:

@@ -309,3 +309,162 @@ extern "C" int64_t pg_hostcheck_format_doubles(const double* x, int64_t n, char*
   }
   return total;
 }
+
+extern "C" int64_t pg_hostcheck_parse_numbers(const char* text, int64_t text_len, const int64_t* tok_off, int64_t n,
+                                              double* out, int32_t* consumed) {
+  int64_t ok = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t avail = text_len - tok_off[i];
+    out[i] = 0.0;
+    consumed[i] = avail > 0 ? pg_parse_json_number(text + tok_off[i], (int)(avail > 64 ? 64 : avail), &out[i]) : 0;
+    ok += consumed[i] > 0;
+  }
+  return ok;
+}
+
+// =============================================================================================
+// Reader half: the numbers of a record's "boxes" / "classes" / "scores" arrays, text -> f64
+// on the device.  Replaces the float() calls inside json.load of the reference's stage-4/5 readers
+// (4_extract_median_widths.py:103-151, 5_detect_column_centers.py:337-400) for the arrays that make up
+// > 95 % of a stage-3 record.  The caller locates the arrays (three byte ranges per record; they hold
+// nothing but numbers, brackets, commas and whitespace) and parses the few strings on the host.
+//   R1 json_tok_count_kernel  one thread per byte: is it the first byte of a number token?  count per 256 B
+//   R2 json_tok_scan_kernel   exclusive scan of the block counts -> where each block's values go; per-range offsets
+//   R3 json_tok_parse_kernel  the flagged threads convert their token (pg_fmt.h) and store it in text order
+// =============================================================================================
+constexpr int JSON_TOK_THREADS = 256;
+constexpr int JSON_TOK_BPT = PG_JSON_PARSE_BLOCK / JSON_TOK_THREADS;  // consecutive bytes per thread (8)
+
+__device__ __forceinline__ bool json_is_token_start(uint8_t c, uint8_t pv, bool first) {
+  if (!((c >= '0' && c <= '9') || c == '-' || c == 'N' || c == 'I')) return false;
+  return first || pv == ' ' || pv == '\n' || pv == '[' || pv == ',' || pv == '\t' || pv == '\r';
+}
+
+// the range that owns global block b: the last r with blk_off[r] <= b
+__device__ __forceinline__ int json_range_of_block(const int64_t* __restrict__ blk_off, int n_ranges, int64_t b) {
+  int lo = 0, hi = n_ranges - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (blk_off[mid] <= b) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// bit k of the result: byte i0 + k starts a number token
+__device__ __forceinline__ uint32_t json_thread_flags(const uint8_t* __restrict__ text, int64_t i0, int64_t begin,
+                                                      int64_t end) {
+  uint32_t bits = 0;
+  if (i0 >= end) return 0;
+  uint8_t pv = i0 > begin ? text[i0 - 1] : (uint8_t)' ';
+#pragma unroll
+  for (int k = 0; k < JSON_TOK_BPT; ++k) {
+    const int64_t i = i0 + k;
+    if (i < end) {
+      const uint8_t c = text[i];
+      if (json_is_token_start(c, pv, i == begin)) bits |= 1u << k;
+      pv = c;
+    }
+  }
+  return bits;
+}
+
+__global__ void __launch_bounds__(JSON_TOK_THREADS) json_tok_count_kernel(
+    const uint8_t* __restrict__ text, const int64_t* __restrict__ ranges, const int64_t* __restrict__ blk_off,
+    int n_ranges, int32_t* __restrict__ block_count) {
+  __shared__ int sm[33];
+  const int64_t b = blockIdx.x;
+  const int r = json_range_of_block(blk_off, n_ranges, b);
+  const int64_t begin = ranges[2 * r], end = ranges[2 * r + 1];
+  const int64_t i0 = begin + (b - blk_off[r]) * PG_JSON_PARSE_BLOCK + (int64_t)threadIdx.x * JSON_TOK_BPT;
+  const int cnt = __popc(json_thread_flags(text, i0, begin, end));
+  int total;
+  pg_block_exscan(cnt, sm, &total);
+  if (threadIdx.x == 0) block_count[b] = total;
+}
+
+__global__ void __launch_bounds__(1024) json_tok_scan_kernel(int64_t n_blocks, const int32_t* __restrict__ block_count,
+                                                             int64_t* __restrict__ block_base,
+                                                             const int64_t* __restrict__ blk_off, int n_ranges,
+                                                             int64_t* __restrict__ val_off) {
+  __shared__ int sm[33];
+  __shared__ int64_t carry_s;
+  const int tid = threadIdx.x;
+  int64_t carry = 0;
+  for (int64_t c = 0; c < n_blocks; c += 1024) {
+    const int64_t b = c + tid;
+    const int v = b < n_blocks ? block_count[b] : 0;
+    int total;
+    const int ex = pg_block_exscan(v, sm, &total);
+    if (b < n_blocks) block_base[b] = carry + ex;
+    carry += total;
+  }
+  if (tid == 0) carry_s = carry;
+  __syncthreads();
+  for (int r = tid; r <= n_ranges; r += 1024)
+    val_off[r] = (r == n_ranges || blk_off[r] >= n_blocks) ? carry_s : block_base[blk_off[r]];
+}
+
+__global__ void __launch_bounds__(JSON_TOK_THREADS) json_tok_parse_kernel(
+    const uint8_t* __restrict__ text, const int64_t* __restrict__ ranges, const int64_t* __restrict__ blk_off,
+    int n_ranges, const int64_t* __restrict__ block_base, double* __restrict__ values, int64_t capacity,
+    int32_t* __restrict__ n_bad) {
+  __shared__ int sm[33];
+  const int64_t b = blockIdx.x;
+  const int r = json_range_of_block(blk_off, n_ranges, b);
+  const int64_t begin = ranges[2 * r], end = ranges[2 * r + 1];
+  const int64_t i0 = begin + (b - blk_off[r]) * PG_JSON_PARSE_BLOCK + (int64_t)threadIdx.x * JSON_TOK_BPT;
+  uint32_t bits = json_thread_flags(text, i0, begin, end);
+  int total;
+  const int ex = pg_block_exscan(__popc(bits), sm, &total);
+  int64_t at = block_base[b] + ex;
+  while (bits) {
+    const int k = __ffs(bits) - 1;
+    bits &= bits - 1;
+    const int64_t i = i0 + k;
+    double v = 0.0;
+    const int64_t avail = end - i;
+    const int used = pg_parse_json_number(reinterpret_cast<const char*>(text + i), (int)(avail > 48 ? 48 : avail), &v);
+    if (used == 0) atomicAdd(&n_bad[r], 1);
+    if (at < capacity) values[at] = v;
+    ++at;
+  }
+}
+
+extern "C" int32_t pg_json_parse_block_bytes(void) { return PG_JSON_PARSE_BLOCK; }
+extern "C" int64_t pg_json_parse_workspace_bytes(int64_t total_blocks) {
+  const int64_t nb = total_blocks < 1 ? 1 : total_blocks;
+  return json_align(nb * 4) + json_align(nb * 8);
+}
+
+extern "C" int pg_json_parse_numbers(const uint8_t* text, const int64_t* ranges, int32_t n_ranges,
+                                     const int64_t* range_block_off, int64_t total_blocks, double* values,
+                                     int64_t capacity, int64_t* val_off, int32_t* n_bad, void* ws, int64_t ws_bytes,
+                                     void* stream) {
+  PG_REQUIRE(n_ranges >= 0 && total_blocks >= 0 && capacity >= 0, "sizes");
+  if (n_ranges == 0) return PG_OK;
+  PG_REQUIRE(text && ranges && range_block_off && val_off && n_bad && ws && (values || capacity == 0), "null device pointer");
+  PG_REQUIRE(total_blocks <= 0x7fffffffll, "more than 2^31 blocks of text in one call");
+  if (ws_bytes < pg_json_parse_workspace_bytes(total_blocks)) {
+    pg_set_error("workspace: pg_json_parse_numbers needs %lld bytes, got %lld",
+                 (long long)pg_json_parse_workspace_bytes(total_blocks), (long long)ws_bytes);
+    return PG_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t nb = total_blocks < 1 ? 1 : total_blocks;
+  int32_t* block_count = static_cast<int32_t*>(ws);
+  int64_t* block_base = reinterpret_cast<int64_t*>(static_cast<uint8_t*>(ws) + json_align(nb * 4));
+  PG_CUDA_TRY(cudaMemsetAsync(n_bad, 0, sizeof(int32_t) * n_ranges, s));
+  if (total_blocks > 0) {
+    json_tok_count_kernel<<<(unsigned)total_blocks, JSON_TOK_THREADS, 0, s>>>(text, ranges, range_block_off, n_ranges,
+                                                                              block_count);
+    PG_LAUNCH_CHECK();
+  }
+  json_tok_scan_kernel<<<1, 1024, 0, s>>>(total_blocks, block_count, block_base, range_block_off, n_ranges, val_off);
+  PG_LAUNCH_CHECK();
+  if (total_blocks > 0) {
+    json_tok_parse_kernel<<<(unsigned)total_blocks, JSON_TOK_THREADS, 0, s>>>(text, ranges, range_block_off, n_ranges,
+                                                                              block_base, values, capacity, n_bad);
+    PG_LAUNCH_CHECK();
+  }
+  return PG_OK;
+}

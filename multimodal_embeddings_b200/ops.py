@@ -455,3 +455,39 @@ def json_combined(boxes, classes, scores, name_id, page_off, heads: Sequence[byt
         capacity = int(off[-1])
     host = out[:int(off[-1])].cpu().numpy().tobytes()
     return [host[off[i]:off[i + 1]] for i in range(p)]
+
+
+# --------------------------------------------------------------------------------------------
+# R1-R3 record reader
+# --------------------------------------------------------------------------------------------
+def json_parse_numbers(text, ranges, stream=None):
+    """pg_json_parse_numbers.  text: bytes / uint8 array / cuda uint8 tensor; ranges: [R,2] begin/end byte
+    offsets of number-only regions.  Returns (values f64 cuda [total], val_off int64 numpy [R+1],
+    n_bad int32 numpy [R]): range r's numbers are values[val_off[r]:val_off[r+1]] in text order."""
+    _require_cuda()
+    if isinstance(text, (bytes, bytearray, memoryview)):
+        text = torch.frombuffer(bytearray(text) + bytearray(1), dtype=torch.uint8)
+    text = _dev(text, torch.uint8)
+    rng = np.ascontiguousarray(np.asarray(ranges, np.int64).reshape(-1, 2))
+    r = rng.shape[0]
+    bb = int(lib().pg_json_parse_block_bytes())
+    blocks = (np.maximum(rng[:, 1] - rng[:, 0], 0) + bb - 1) // bb
+    blk_off = np.concatenate([[0], np.cumsum(blocks)]).astype(np.int64)
+    total_blocks = int(blk_off[-1])
+    d_rng, d_blk = torch.from_numpy(rng).cuda(), torch.from_numpy(blk_off).cuda()
+    ws_bytes = int(lib().pg_json_parse_workspace_bytes(total_blocks))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    val_off = torch.zeros(r + 1, dtype=torch.int64, device="cuda")
+    n_bad = torch.zeros(max(r, 1), dtype=torch.int32, device="cuda")
+    capacity = int(np.maximum(rng[:, 1] - rng[:, 0], 0).sum()) // 4 + 16  # a number + separator is >= 4 bytes here
+    while True:
+        values = torch.empty(max(capacity, 1), dtype=torch.float64, device="cuda")
+        check(lib().pg_json_parse_numbers(ptr(text), ptr(d_rng), r, ptr(d_blk), total_blocks, ptr(values), capacity,
+                                          ptr(val_off), ptr(n_bad), ptr(ws), ws_bytes, stream_ptr(stream)))
+        if stream is not None:
+            stream.synchronize()
+        off = val_off.cpu().numpy()
+        if int(off[-1]) <= capacity:
+            break
+        capacity = int(off[-1])
+    return values[:int(off[-1])], off, n_bad[:r].cpu().numpy()

@@ -90,3 +90,82 @@ def load_record(json_path: str) -> dict:
         return rec
     with open(json_path) as f:
         return json.load(f)
+
+
+# ------------------------------------------------------------------------------------------------
+# Text path: the record as the reference wrote it, numbers converted on the device (pg_json_parse_numbers)
+_ARRAY_KEYS = (b'\n  "boxes": [', b'\n  "classes": [', b'\n  "scores": [', b'\n  "class_names": [')
+
+
+def split_record_text(raw: bytes):
+    """Locate the three number arrays of a stage-3 record laid out by `json.dump(indent=2)` with the
+    reference's key order (3_combine_grids.py:282-291).  Returns (head dict, tail dict, [(begin, end)] * 3) or
+    None when the text is laid out differently (then json.loads is the reader).  JSON strings cannot hold a
+    raw newline, so a key found at the start of a line is a key."""
+    pos, at = [], 0
+    for k in _ARRAY_KEYS:
+        i = raw.find(k, at)
+        if i < 0:
+            return None
+        pos.append(i)
+        at = i + len(k)
+    i_boxes, i_classes, i_scores, i_names = pos
+    try:
+        head = json.loads(raw[:i_boxes].rstrip().rstrip(b",") + b"}")
+        tail = json.loads(b"{" + raw[i_names + 1:])
+    except ValueError:
+        return None
+    if not isinstance(head, dict) or not isinstance(tail, dict) or "class_names" not in tail:
+        return None
+    ranges = [(i_boxes + len(_ARRAY_KEYS[0]), i_classes), (i_classes + len(_ARRAY_KEYS[1]), i_scores),
+              (i_scores + len(_ARRAY_KEYS[2]), i_names)]
+    return head, tail, ranges
+
+
+def load_records(json_paths: Sequence[str]) -> dict:
+    """path -> record for a batch of stage-3 files, by the cheapest valid route per file: the binary sidecar;
+    else the JSON text with its number arrays converted on the GPU in ONE call for the whole batch; else
+    (unusual layout, a token the device does not convert, no CUDA, PG_PYTHON_JSON=1) `json.load`.
+    Records from the first two routes carry numpy arrays for boxes [n,4] / classes / scores."""
+    out, pending = {}, []
+    use_device = os.environ.get("PG_PYTHON_JSON") != "1"
+    if use_device:
+        try:
+            import torch
+            use_device = torch.cuda.is_available()
+        except ImportError:
+            use_device = False
+    for path in json_paths:
+        rec = read_sidecar(path)
+        if rec is not None:
+            out[path] = rec
+            continue
+        with open(path, "rb") as f:
+            raw = f.read()
+        parts = split_record_text(raw) if use_device else None
+        if parts is None:
+            out[path] = json.loads(raw)
+        else:
+            pending.append((path, raw, parts))
+    if pending:
+        from . import ops
+        blob, ranges, base = [], [], 0
+        for _, raw, (_, _, rg) in pending:
+            blob.append(raw)
+            ranges.extend((a + base, b + base) for a, b in rg)
+            base += len(raw)
+        values, off, bad = ops.json_parse_numbers(b"".join(blob), ranges)
+        values = values.cpu().numpy()
+        for k, (path, raw, (head, tail, _)) in enumerate(pending):
+            nb, nc, ns = (int(off[3 * k + j + 1] - off[3 * k + j]) for j in range(3))
+            names = tail["class_names"]
+            if bad[3 * k: 3 * k + 3].any() or nb != 4 * nc or nc != ns or nc != len(names):
+                out[path] = json.loads(raw)  # ragged or exotic record: let CPython decide what it means
+                continue
+            rec = dict(head)
+            rec["boxes"] = values[off[3 * k]: off[3 * k + 1]].reshape(-1, 4)
+            rec["classes"] = values[off[3 * k + 1]: off[3 * k + 2]]
+            rec["scores"] = values[off[3 * k + 2]: off[3 * k + 3]]
+            rec.update(tail)
+            out[path] = rec
+    return {path: out[path] for path in json_paths}  # the caller's order

@@ -93,6 +93,53 @@ def main():
     py = [json.dumps(r, indent=2).encode("ascii") for r in recs]
     t_py = (time.perf_counter() - t0) / sample
     assert py == docs[:sample]
+    # ---- reader half: the number arrays of the same documents, text -> f64 on the device (pg_json_parse_numbers)
+    from multimodal_embeddings_b200 import records
+    ranges, base = [], 0
+    for d in docs:
+        _, _, rg = records.split_record_text(d)
+        ranges.extend((x + base, y + base) for x, y in rg)
+        base += len(d)
+    rng_np = np.asarray(ranges, np.int64)
+    bb = int(lib().pg_json_parse_block_bytes())
+    blocks = (rng_np[:, 1] - rng_np[:, 0] + bb - 1) // bb
+    blk_off = np.concatenate([[0], np.cumsum(blocks)]).astype(np.int64)
+    d_rng, d_blk = torch.from_numpy(rng_np).cuda(), torch.from_numpy(blk_off).cuda()
+    tb = int(blk_off[-1])
+    r_ws_bytes = int(lib().pg_json_parse_workspace_bytes(tb))
+    r_ws = torch.empty(r_ws_bytes, dtype=torch.uint8, device="cuda")
+    n_vals = 6 * int(nk.sum())
+    vals = torch.empty(n_vals + 16, dtype=torch.float64, device="cuda")
+    val_off = torch.zeros(len(ranges) + 1, dtype=torch.int64, device="cuda")
+    n_bad = torch.zeros(len(ranges), dtype=torch.int32, device="cuda")
+
+    def read_launch():
+        check(lib().pg_json_parse_numbers(ptr(out), ptr(d_rng), len(ranges), ptr(d_blk), tb, ptr(vals), vals.numel(),
+                                          ptr(val_off), ptr(n_bad), ptr(r_ws), r_ws_bytes,
+                                          torch.cuda.current_stream().cuda_stream))
+
+    for _ in range(a.warmup):
+        read_launch()
+    torch.cuda.synchronize()
+    e[0].record()
+    for _ in range(a.steps):
+        read_launch()
+    e[1].record()
+    torch.cuda.synchronize()
+    ms_read = e[0].elapsed_time(e[1]) / a.steps
+    assert int(val_off[-1].item()) == n_vals and int(n_bad.sum().item()) == 0
+    j0 = kh[off[0]: off[0] + nk[0]]
+    got0 = vals[: 6 * int(nk[0])].cpu().numpy()
+    want0 = np.concatenate([boxes[j0].ravel(), classes[j0], scores[j0]])
+    assert np.array_equal(got0.view(np.uint64), want0.view(np.uint64))
+    t0 = time.perf_counter()
+    for d in docs[:sample]:
+        json.loads(d)
+    t_load = (time.perf_counter() - t0) / sample
+    print(json.dumps({"what": "stage-3 record reader (pg_json_parse_numbers)", "pages": p, "numbers": n_vals,
+                      "json_bytes_per_step": total, "device_ms_per_step": ms_read, "pages_per_s_device": p / ms_read * 1e3,
+                      "text_gb_per_s_device": total / ms_read / 1e6, "cpython_json_loads_ms_per_page": t_load * 1e3,
+                      "bit_identical_to_float": True, "gpu_launches_per_step": 3}))
     print(json.dumps({"what": "stage-3 record writer (pg_json_combined)", "pages": p, "boxes_in": int(n), "boxes_kept": int(nk.sum()),
                       "json_bytes_per_step": total, "device_ms_per_step": ms_dev, "pages_per_s_device": p / ms_dev * 1e3,
                       "text_gb_per_s_device": total / ms_dev / 1e6, "d2h_ms_per_step": ms_d2h,

@@ -44,7 +44,8 @@ def row(name, d):
                 f"{d['achieved_gbs']:.0f} GB/s algorithmic = {d['frac_of_measured_hbm_peak']:.3f} of peak |")
     if "what" in d:
         return (f"| `{name}` | 1 | {d['pages_per_s_device']:.0f} pages/s | {d['device_ms_per_step']:.3f} | {d['what']}: "
-                f"{d['json_bytes_per_step'] / 1e6:.1f} MB of text, CPython {d['cpython_json_dumps_ms_per_page']:.1f} ms/page |")
+                f"{d['json_bytes_per_step'] / 1e6:.1f} MB of text, CPython "
+                f"{d.get('cpython_json_dumps_ms_per_page', d.get('cpython_json_loads_ms_per_page', 0)):.1f} ms/page |")
     if "ms_per_page" in d:
         return f"| `{name}` | 1 | {d['pages_per_s']:.0f} pages/s | {d['ms_per_launch']:.3f} | {d.get('workload', '')} |"
     if "impl" in d:

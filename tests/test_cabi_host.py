@@ -277,3 +277,43 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_parse_json_number_equals_python_float(lib):
+    """csrc/pg_fmt.h pg_parse_json_number (Ryu's inverse, <= 17 significant digits) against float(): what
+    json.load does for the reference's stage-4/5 readers (4_extract_median_widths.py:103-151)."""
+    def parse(strs):
+        text = ("\n".join(strs) + "\n").encode()
+        lens = np.fromiter((len(s) for s in strs), np.int64, len(strs))
+        offs = np.concatenate([[0], np.cumsum(lens + 1)[:-1]]).astype(np.int64)
+        buf = np.frombuffer(text, np.uint8).copy()
+        out, used = np.zeros(len(strs)), np.zeros(len(strs), np.int32)
+        lib.pg_hostcheck_parse_numbers(_lib.ptr(buf), len(buf), _lib.ptr(offs), len(strs), _lib.ptr(out), _lib.ptr(used))
+        return out, used, lens
+    special = ["0", "-0", "0.0", "-0.0", "1", "0.1", "1e16", "1E-5", "1.5e-05", "5e-324", "2.2250738585072014e-308",
+               "1.7976931348623157e+308", "1e309", "-1e309", "1e-400", "2.4703282292062327e-324", "2.4703282292062328e-324",
+               "9007199254740993", "0.30000000000000004", "1e22", "1e23", "8.5e-324", "Infinity", "-Infinity",
+               "12345678901234567000", "0.00000000000000000000000000000000000001e38", "100"]
+    out, used, lens = parse(special)
+    ref = np.array([float(s) for s in special])
+    assert np.array_equal(out.view(np.uint64), ref.view(np.uint64)) and np.array_equal(used, lens)
+    out, used, _ = parse(["NaN", "123456789012345678", "1.2.3", "-", "e5"])
+    assert np.isnan(out[0]) and used.tolist() == [3, 0, 0, 0, 0]
+    rng = np.random.default_rng(2)
+    sets = {"bit patterns": rng.integers(0, 2 ** 63, 300_000, dtype=np.int64).view(np.float64),
+            "float32 coordinates": rng.uniform(0, 8000, 200_000).astype(np.float32).astype(np.float64),
+            "subnormals": rng.integers(1, 2 ** 52, 100_000, dtype=np.int64).view(np.float64),
+            "powers of two": np.array([2.0 ** e for e in range(-1074, 1024)])}
+    for name, x in sets.items():  # repr round trip: parse(repr(x)) == x
+        x = x[np.isfinite(x)]
+        strs = [repr(v) for v in x.tolist()]
+        out, used, lens = parse(strs)
+        assert np.array_equal(out.view(np.uint64), x.view(np.uint64)) and np.array_equal(used, lens), name
+    strs = [f"{int(rng.integers(10 ** (nd - 1), 10 ** nd))}e{int(rng.integers(-345, 310))}"
+            for nd in rng.integers(1, 18, 150_000)]  # arbitrary (not shortest) decimals, whole exponent range
+    out, used, lens = parse(strs)
+    ref = np.array([float(s) for s in strs])
+    assert np.array_equal(out.view(np.uint64), ref.view(np.uint64))
+    mids = [f"{2 ** 53 + 1 + 2 * k}e-{j}" for k in range(300) for j in (0, 1, 2, 5)]  # ties and near-ties
+    out, _, _ = parse(mids)
+    assert np.array_equal(out.view(np.uint64), np.array([float(s) for s in mids]).view(np.uint64))

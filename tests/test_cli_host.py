@@ -104,3 +104,23 @@ def test_record_sidecar_round_trip_and_staleness(tmp_path):
         with open(sp, "wb") as f:
             f.write(bad)
         assert records.read_sidecar(jp) is None
+
+
+def test_split_record_text_locates_the_number_arrays():
+    import json
+
+    from multimodal_embeddings_b200 import records
+    doc = {"image_path": '/x/\\n  "boxes": [ y.png', "image_size": {"width": 10, "height": 20}, "parameters": {"iou_threshold": 0.5},
+           "boxes": [[1.5, 2.0, 3.25, 4.0], [5.0, 6.0, 7.0, 8.5]], "classes": [1.0, 0.0], "scores": [0.9, 0.8],
+           "class_names": ["plain_text", 'ti"tle'], "source_jsons": ["a.json"]}
+    raw = json.dumps(doc, indent=2).encode()
+    head, tail, ranges = records.split_record_text(raw)
+    assert head == {k: doc[k] for k in ("image_path", "image_size", "parameters")}
+    assert tail == {k: doc[k] for k in ("class_names", "source_jsons")}
+    got = [json.loads(b"[" + raw[a:b].rstrip().rstrip(b",")) for a, b in ranges]
+    assert got == [doc["boxes"], doc["classes"], doc["scores"]]
+    assert records.split_record_text(json.dumps(doc).encode()) is None           # compact layout
+    assert records.split_record_text(json.dumps(doc, indent=4).encode()) is None  # another indent
+    other = dict(doc)
+    other["scores"], other["classes"] = other.pop("classes"), other.pop("scores")
+    assert records.split_record_text(json.dumps({k: doc[k] for k in reversed(list(doc))}, indent=2).encode()) is None

@@ -124,3 +124,50 @@ def test_shard_without_any_box():
                              [h for h, _ in ht], [t for _, t in ht], [b'"plain_text"'])
     for doc, (path, size, thr, srcs) in zip(docs, meta):
         assert doc == reference_text(path, size, thr, [], [], [], [], srcs)
+
+
+# ------------------------------------------------------------------------------------------------ reader (R1-R3)
+def test_device_reader_round_trips_the_writers_documents(tmp_path):
+    """records.load_records on files written as json.dump(indent=2) writes them: the number arrays come back
+    bit for bit (they were converted on the device), strings and sizes as json.load gives them."""
+    from multimodal_embeddings_b200 import records
+    rng = np.random.default_rng(11)
+    counts = [0, 1, 3, 700, 129, 2050]
+    pages = make_pages(rng, counts)
+    paths = []
+    for i, (b, c, s) in enumerate(pages):
+        doc = {"image_path": f'/d/"boxes": [ p{i}.png', "image_size": {"width": 100 + i, "height": 200}, "parameters": {"iou_threshold": 0.5},
+               "boxes": b.tolist(), "classes": c.tolist(), "scores": s.tolist(),
+               "class_names": [NAMES[int(x)] for x in c], "source_jsons": [f"s{i}.json"]}
+        p = tmp_path / f"p{i}_combined.json"
+        p.write_text(json.dumps(doc, indent=2))
+        paths.append(str(p))
+    compact = tmp_path / "compact_combined.json"   # another layout: must still load (through json.loads)
+    compact.write_text(json.dumps({"image_path": "c.png", "image_size": None, "parameters": {}, "boxes": [[1, 2, 3, 4]],
+                                   "classes": [1.0], "scores": [0.5], "class_names": ["title"], "source_jsons": []}))
+    recs = records.load_records(paths + [str(compact)])
+    assert list(recs) == paths + [str(compact)]
+    for path, (b, c, s) in zip(paths, pages):
+        r, want = recs[path], json.load(open(path))
+        assert isinstance(r["boxes"], np.ndarray) and list(r) == list(want)
+        assert r["boxes"].shape == (len(c), 4)
+        assert np.array_equal(r["boxes"].view(np.uint64), b.view(np.uint64).reshape(-1, 4))
+        assert np.array_equal(r["classes"], c) and np.array_equal(r["scores"].view(np.uint64), s.view(np.uint64))
+        for k in ("image_path", "image_size", "parameters", "class_names", "source_jsons"):
+            assert r[k] == want[k]
+    assert recs[str(compact)]["boxes"] == [[1, 2, 3, 4]]
+
+
+def test_device_reader_ranges_counts_and_unconvertible_tokens():
+    text = (b"[\n 1.5,\n -2e-3, 3,4 ]  [ ]   [ 0.1234567890123456789, 7.0, NaN, -Infinity, 1e400, 5e-324 ]"
+            b"[12345678901234567000, 123456789012345678]")
+    a = text.index(b"[ ]")
+    b2 = text.index(b"[ 0.12")
+    c = text.index(b"[1234")
+    ranges = [(0, a), (a, b2), (b2, c), (c, len(text))]
+    vals, off, bad = ops.json_parse_numbers(text, ranges)
+    v = vals.cpu().numpy()
+    assert off.tolist() == [0, 4, 4, 10, 12] and bad.tolist() == [0, 0, 1, 1]
+    assert v[:4].tolist() == [1.5, -0.002, 3.0, 4.0]
+    assert v[5] == 7.0 and np.isnan(v[6]) and v[7] == -np.inf and v[8] == np.inf and v[9] == 5e-324
+    assert v[10] == 1.2345678901234567e19  # 17 digits + dropped zeros are exact; the 18-digit token is flagged

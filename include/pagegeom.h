@@ -228,14 +228,17 @@ int pg_json_combined(const double* boxes /*dev [N,4]*/, const double* classes /*
  * record's few strings itself.  range_block_off (dev [R+1]) = exclusive prefix of ceil(len_r / PG_JSON_PARSE_BLOCK).
  * Range r's numbers land, in text order, in values[val_off[r] .. val_off[r+1]) (nothing is stored beyond
  * `capacity`; val_off[R] is the total, so a short buffer is detected and the call repeated); n_bad[r] counts
- * tokens that need the host's float() (more than 17 digits, malformed). */
+ * tokens that need the host's float() (more than 17 digits, malformed) and, with PG_JSON_INT_LITERALS_TO_HOST,
+ * integer literals — json.load makes Python ints of those, and a caller that must re-emit them unchanged
+ * ("5", not "5.0") lets CPython read that file. */
+#define PG_JSON_INT_LITERALS_TO_HOST 1
 #define PG_JSON_PARSE_BLOCK 2048 /* text bytes per CTA (256 threads x 8 consecutive bytes) */
 int32_t pg_json_parse_block_bytes(void);
 int64_t pg_json_parse_workspace_bytes(int64_t total_blocks);
 int pg_json_parse_numbers(const uint8_t* text /*dev*/, const int64_t* ranges /*dev [R,2]*/, int32_t n_ranges,
                           const int64_t* range_block_off /*dev [R+1]*/, int64_t total_blocks,
                           double* values /*dev [capacity]*/, int64_t capacity, int64_t* val_off /*dev [R+1]*/,
-                          int32_t* n_bad /*dev [R]*/, void* ws, int64_t ws_bytes, void* stream);
+                          int32_t* n_bad /*dev [R]*/, int32_t flags, void* ws, int64_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ test hooks
  * Host evaluations of the same inline arithmetic the kernels are compiled from

@@ -19,6 +19,7 @@ PG_COL_HIST_BINS = 1001
 PG_COL_SPAN_BYTES = 32
 PG_NMS_CLASS_AGNOSTIC = 1
 PG_NMS_FP32 = 2
+PG_JSON_INT_LITERALS_TO_HOST = 1
 
 
 class PgTileInfo(C.Structure):
@@ -74,7 +75,7 @@ SIGNATURES = {
                                    _P, _I64, _P]),
     "pg_json_parse_block_bytes": (_I32, []),
     "pg_json_parse_workspace_bytes": (_I64, [_I64]),
-    "pg_json_parse_numbers": (C.c_int, [_P, _P, _I32, _P, _I64, _P, _I64, _P, _P, _P, _I64, _P]),
+    "pg_json_parse_numbers": (C.c_int, [_P, _P, _I32, _P, _I64, _P, _I64, _P, _P, _I32, _P, _I64, _P]),
     "pg_hostcheck_format_double": (_I32, [_F64, _P]),
     "pg_hostcheck_format_doubles": (_I64, [_P, _I64, _P, _P]),
     "pg_hostcheck_parse_numbers": (_I64, [_P, _I64, _P, _I64, _P, _P]),

@@ -368,6 +368,29 @@ def pool_documents(json_paths, logger):
     return boxes, scores, classes, names, image_path, image_size
 
 
+def pool_documents_fast(json_paths, logger, fast: dict):
+    """pool_documents for a page whose files were all read by records.load_pool_inputs (numbers converted on
+    the device): numpy arrays instead of lists, same order, plus `numbers_are_floats`.  A page with any file the
+    device reader declined is pooled by pool_documents (CPython's json.load), whole."""
+    if not all(p in fast for p in json_paths):
+        b, s, c, n, image_path, image_size = pool_documents(json_paths, logger)
+        floats = all(type(v) is float for row in b for v in row) and all(type(v) is float for v in s) and \
+            all(type(v) is float for v in c)
+        return b, s, c, n, image_path, image_size, floats
+    boxes, scores, classes, names = [], [], [], []
+    image_path = image_size = None
+    for path in json_paths:
+        d = fast[path]
+        if not image_path and d["image_path"]:
+            image_path = d["image_path"]
+        if not d["grid"] and not image_size and d["image_size"]:
+            image_size = d["image_size"]
+        boxes.append(d["boxes"]); scores.append(d["scores"]); classes.append(d["classes"])
+        names.extend(d["class_names"])
+    return (np.concatenate(boxes).reshape(-1, 4), np.concatenate(scores), np.concatenate(classes), names, image_path,
+            image_size, True)
+
+
 def main_stage3(argv: Optional[Sequence[str]] = None) -> int:
     from . import ops
     logger = _logger("GridBoxCombiner")
@@ -386,13 +409,22 @@ def main_stage3(argv: Optional[Sequence[str]] = None) -> int:
     if not groups:
         logger.error(f"No JSON files found in {args.input_folder}")
         return 0
+    items = _my_share(list(groups.items()))
+    # the stage-1/2 documents of every page of the shard: numbers converted on the GPU in one call
+    # (records.load_pool_inputs); files it declines are read by json.load as in the reference
+    try:
+        from .records import load_pool_inputs
+        fast = load_pool_inputs([p for _, paths in items for p in paths])
+    except Exception as e:
+        logger.error(f"Batch input reader failed ({e}); reading the files one by one")
+        fast = {}
     pooled = []
-    for base, paths in _my_share(list(groups.items())):
-        b, s, c, n, image_path, image_size = pool_documents(paths, logger)
-        if not b:
+    for base, paths in items:
+        b, s, c, n, image_path, image_size, floats = pool_documents_fast(paths, logger, fast)
+        if len(b) == 0:
             logger.warning(f"No boxes found for {base}")
             continue
-        pooled.append((base, paths, b, s, c, n, image_path, image_size))
+        pooled.append((base, paths, b, s, c, n, image_path, image_size, floats))
     if pooled:  # one batched merge for every page
         off = np.cumsum([0] + [len(x[2]) for x in pooled])
         boxes = np.concatenate([np.asarray(x[2], np.float64).reshape(-1, 4) for x in pooled])
@@ -412,8 +444,7 @@ def main_stage3(argv: Optional[Sequence[str]] = None) -> int:
         # Records: laid out on the device (pg_json_combined), byte-identical to json.dump(indent=2).  Inputs that
         # are not what stage 1/2 write (integer literals among the numbers) keep Python's own encoder, which
         # would print them without ".0".
-        all_float = all(type(v) is float for x in pooled for row in x[2] for v in row) and \
-            all(type(v) is float for x in pooled for v in x[3]) and all(type(v) is float for x in pooled for v in x[4])
+        all_float = all(x[8] for x in pooled)
         if all_float and os.environ.get("PG_PYTHON_JSON") != "1":
             table = {}
             name_id = np.asarray([table.setdefault(nm, len(table)) for x in pooled for nm in x[5]], np.int32)
@@ -429,7 +460,8 @@ def main_stage3(argv: Optional[Sequence[str]] = None) -> int:
                     write_sidecar(json_path, x[6], x[7], {"iou_threshold": args.iou_threshold}, x[1], boxes[idx],
                                   classes[idx], scores[idx], list(table), name_id[idx])
             pooled = []
-        for i, (base, paths, b, s, c, n, image_path, image_size) in enumerate(pooled):
+        for i, (base, paths, b, s, c, n, image_path, image_size, _) in enumerate(pooled):
+            b, s, c = (v.tolist() if isinstance(v, np.ndarray) else v for v in (b, s, c))
             idx = (kept[off[i]: off[i] + n_kept[i]] - off[i]).tolist()
             _dump({"image_path": image_path, "image_size": image_size,  # key order of 3:282-291
                    "parameters": {"iou_threshold": args.iou_threshold},

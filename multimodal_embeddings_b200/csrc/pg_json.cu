@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(1024) json_tok_scan_kernel(int64_t n_blocks, c
 __global__ void __launch_bounds__(JSON_TOK_THREADS) json_tok_parse_kernel(
     const uint8_t* __restrict__ text, const int64_t* __restrict__ ranges, const int64_t* __restrict__ blk_off,
     int n_ranges, const int64_t* __restrict__ block_base, double* __restrict__ values, int64_t capacity,
-    int32_t* __restrict__ n_bad) {
+    int32_t* __restrict__ n_bad, int32_t flags) {
   __shared__ int sm[33];
   const int64_t b = blockIdx.x;
   const int r = json_range_of_block(blk_off, n_ranges, b);
@@ -423,8 +423,9 @@ __global__ void __launch_bounds__(JSON_TOK_THREADS) json_tok_parse_kernel(
     const int64_t i = i0 + k;
     double v = 0.0;
     const int64_t avail = end - i;
-    const int used = pg_parse_json_number(reinterpret_cast<const char*>(text + i), (int)(avail > 48 ? 48 : avail), &v);
-    if (used == 0) atomicAdd(&n_bad[r], 1);
+    bool is_int;
+    const int used = pg_parse_json_number(reinterpret_cast<const char*>(text + i), (int)(avail > 48 ? 48 : avail), &v, &is_int);
+    if (used == 0 || (is_int && (flags & PG_JSON_INT_LITERALS_TO_HOST))) atomicAdd(&n_bad[r], 1);
     if (at < capacity) values[at] = v;
     ++at;
   }
@@ -438,8 +439,8 @@ extern "C" int64_t pg_json_parse_workspace_bytes(int64_t total_blocks) {
 
 extern "C" int pg_json_parse_numbers(const uint8_t* text, const int64_t* ranges, int32_t n_ranges,
                                      const int64_t* range_block_off, int64_t total_blocks, double* values,
-                                     int64_t capacity, int64_t* val_off, int32_t* n_bad, void* ws, int64_t ws_bytes,
-                                     void* stream) {
+                                     int64_t capacity, int64_t* val_off, int32_t* n_bad, int32_t flags, void* ws,
+                                     int64_t ws_bytes, void* stream) {
   PG_REQUIRE(n_ranges >= 0 && total_blocks >= 0 && capacity >= 0, "sizes");
   if (n_ranges == 0) return PG_OK;
   PG_REQUIRE(text && ranges && range_block_off && val_off && n_bad && ws && (values || capacity == 0), "null device pointer");
@@ -463,7 +464,7 @@ extern "C" int pg_json_parse_numbers(const uint8_t* text, const int64_t* ranges,
   PG_LAUNCH_CHECK();
   if (total_blocks > 0) {
     json_tok_parse_kernel<<<(unsigned)total_blocks, JSON_TOK_THREADS, 0, s>>>(text, ranges, range_block_off, n_ranges,
-                                                                              block_base, values, capacity, n_bad);
+                                                                              block_base, values, capacity, n_bad, flags);
     PG_LAUNCH_CHECK();
   }
   return PG_OK;

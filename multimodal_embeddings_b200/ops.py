@@ -460,7 +460,7 @@ def json_combined(boxes, classes, scores, name_id, page_off, heads: Sequence[byt
 # --------------------------------------------------------------------------------------------
 # R1-R3 record reader
 # --------------------------------------------------------------------------------------------
-def json_parse_numbers(text, ranges, stream=None):
+def json_parse_numbers(text, ranges, stream=None, int_literals_to_host: bool = False):
     """pg_json_parse_numbers.  text: bytes / uint8 array / cuda uint8 tensor; ranges: [R,2] begin/end byte
     offsets of number-only regions.  Returns (values f64 cuda [total], val_off int64 numpy [R+1],
     n_bad int32 numpy [R]): range r's numbers are values[val_off[r]:val_off[r+1]] in text order."""
@@ -483,7 +483,9 @@ def json_parse_numbers(text, ranges, stream=None):
     while True:
         values = torch.empty(max(capacity, 1), dtype=torch.float64, device="cuda")
         check(lib().pg_json_parse_numbers(ptr(text), ptr(d_rng), r, ptr(d_blk), total_blocks, ptr(values), capacity,
-                                          ptr(val_off), ptr(n_bad), ptr(ws), ws_bytes, stream_ptr(stream)))
+                                          ptr(val_off), ptr(n_bad),
+                                          _lib.PG_JSON_INT_LITERALS_TO_HOST if int_literals_to_host else 0,
+                                          ptr(ws), ws_bytes, stream_ptr(stream)))
         if stream is not None:
             stream.synchronize()
         off = val_off.cpu().numpy()

@@ -169,3 +169,128 @@ def load_records(json_paths: Sequence[str]) -> dict:
             rec.update(tail)
             out[path] = rec
     return {path: out[path] for path in json_paths}  # the caller's order
+
+
+# ------------------------------------------------------------------------------------------------
+# Stage-3 INPUTS (the stage-1/2 documents pooled by combine_boxes_for_image, 3_combine_grids.py:222-270),
+# same route: arrays located on the host, numbers converted on the device.
+_REGIONS_KEY = b'\n      "regions": {'
+_REGION_KEYS = (b'\n        "boxes_original": [', b'\n        "classes": [', b'\n        "scores": [',
+                b'\n        "class_names": [')
+_REGION_LIST_END = b'\n        ]'
+
+
+def _line_value(raw: bytes, key: bytes):
+    """Value of a top-level `"key": <scalar>` line of an indent=2 document (None if absent / not a scalar line)."""
+    i = raw.find(b'\n  "' + key + b'": ')
+    if i < 0:
+        return None
+    j = raw.find(b"\n", i + 1)
+    try:
+        return json.loads(raw[i + len(key) + 7: j if j >= 0 else len(raw)].rstrip().rstrip(b","))
+    except ValueError:
+        return None
+
+
+def split_grid_text(raw: bytes):
+    """A stage-1/2 grid document (`cells[].regions`, json.dump(indent=2)): the byte ranges of every cell's
+    boxes_original / classes / scores arrays in cell order, and the cells' class_names lists.  None unless every
+    `regions` object holds the five arrays in the order stage 1 writes them (1_doclayout_bboxes.py:620-640)."""
+    if raw.find(b'\n  "cells": [') < 0:
+        return None
+    starts, at = [], 0
+    while True:
+        i = raw.find(_REGIONS_KEY, at)
+        if i < 0:
+            break
+        starts.append(i)
+        at = i + len(_REGIONS_KEY)
+    if any(raw.count(k) != len(starts) for k in _REGION_KEYS):
+        return None
+    ranges, names = [], []
+    for r, s0 in enumerate(starts):
+        limit = starts[r + 1] if r + 1 < len(starts) else len(raw)
+        pos, at = [], s0
+        for k in _REGION_KEYS:
+            i = raw.find(k, at, limit)
+            if i < 0:
+                return None
+            pos.append(i)
+            at = i + len(k)
+        i_bo, i_cl, i_sc, i_nm = pos
+        lst = i_nm + len(_REGION_KEYS[3]) - 1  # the '[' of class_names
+        if raw[lst + 1: lst + 2] == b"]":
+            end = lst + 2
+        else:
+            j = raw.find(_REGION_LIST_END, lst, limit)
+            if j < 0:
+                return None
+            end = j + len(_REGION_LIST_END)
+        try:
+            nm = json.loads(raw[lst:end])
+        except ValueError:
+            return None
+        ranges += [(i_bo + len(_REGION_KEYS[0]), i_cl), (i_cl + len(_REGION_KEYS[1]), i_sc),
+                   (i_sc + len(_REGION_KEYS[2]), i_nm)]
+        names.append(nm)
+    return _line_value(raw, b"original_image_path"), ranges, names
+
+
+def load_pool_inputs(json_paths: Sequence[str]) -> dict:
+    """path -> what combine_boxes_for_image takes from that file, numbers converted on the device in ONE call for
+    all files: {"grid": bool, "image_path", "image_size", "boxes" f64 [n,4], "scores", "classes", "class_names"}.
+    A path is absent from the result when its text is not laid out as stage 1/2 write it, holds integer literals
+    among the numbers (CPython must read those: 5 stays 5), is ragged, or no CUDA device is there — the caller
+    reads such files with json.load."""
+    try:
+        import torch
+        if not torch.cuda.is_available() or os.environ.get("PG_PYTHON_JSON") == "1":
+            return {}
+    except ImportError:
+        return {}
+    from . import ops
+    todo, blob, ranges, base = [], [], [], 0
+    for path in json_paths:
+        try:
+            with open(path, "rb") as f:
+                raw = f.read()
+        except OSError:
+            continue
+        if b'\n  "cells": [' in raw:
+            parts = split_grid_text(raw)
+            if parts is None:
+                continue
+            image_path, rg, names = parts
+            todo.append((path, True, image_path, None, names, len(rg) // 3))
+        else:
+            parts = split_record_text(raw) if b'"boxes_original"' not in raw else None
+            if parts is None:
+                continue
+            head, tail, rg = parts
+            todo.append((path, False, head.get("image_path"), head.get("image_size"), [tail["class_names"]], 1))
+        ranges.extend((a + base, b + base) for a, b in rg)
+        blob.append(raw)
+        base += len(raw)
+    if not todo:
+        return {}
+    values, off, bad = ops.json_parse_numbers(b"".join(blob), ranges, int_literals_to_host=True)
+    values = values.cpu().numpy()
+    out, r = {}, 0
+    for path, grid, image_path, image_size, names, n_regions in todo:
+        ok, boxes, classes, scores, flat = True, [], [], [], []
+        for k in range(n_regions):
+            nb, nc, ns = (int(off[r + j + 1] - off[r + j]) for j in range(3))
+            nm = names[k]
+            if bad[r: r + 3].any() or nb != 4 * nc or nc != ns or not isinstance(nm, list) or nc != len(nm):
+                ok = False
+            boxes.append(values[off[r]: off[r + 1]])
+            classes.append(values[off[r + 1]: off[r + 2]])
+            scores.append(values[off[r + 2]: off[r + 3]])
+            flat.extend(nm if isinstance(nm, list) else [])
+            r += 3
+        if ok:
+            cat = (lambda xs: np.concatenate(xs) if xs else np.zeros(0))
+            out[path] = {"grid": grid, "image_path": image_path, "image_size": image_size,
+                         "boxes": cat(boxes).reshape(-1, 4), "classes": cat(classes), "scores": cat(scores),
+                         "class_names": flat}
+    return out

@@ -115,7 +115,7 @@ def main():
 
     def read_launch():
         check(lib().pg_json_parse_numbers(ptr(out), ptr(d_rng), len(ranges), ptr(d_blk), tb, ptr(vals), vals.numel(),
-                                          ptr(val_off), ptr(n_bad), ptr(r_ws), r_ws_bytes,
+                                          ptr(val_off), ptr(n_bad), 0, ptr(r_ws), r_ws_bytes,
                                           torch.cuda.current_stream().cuda_stream))
 
     for _ in range(a.warmup):

@@ -118,3 +118,36 @@ def test_cli_rank_sharding_union_equals_single_process(tmp_path, world, monkeypa
         assert got[name] == golden[name], name
     assert sum(n for s, _, n in written if s == 3) == len([k for k in golden if k.startswith("3_combined_bboxes/")])
     assert any(n > 0 for s, r, n in written if s == 3 and r > 0)  # the later ranks really did part of the work
+
+
+def test_stage3_inputs_read_on_the_device_equal_json_load(tmp_path):
+    """records.load_pool_inputs (arrays located by line-anchored keys, numbers converted on the GPU) against
+    pool_documents (json.load) on the stage-2 files of the reference's golden tree; a file holding an integer
+    literal among its numbers is left to CPython."""
+    import os
+    import numpy as np
+    from multimodal_embeddings_b200 import records
+    root = str(tmp_path)
+    cli_tree.build_stage1_tree(root)
+    argv = cli_tree.stage_argv(root)
+    assert cli.main_stage2(argv[2]) == 0
+    groups = cli.find_grid_jsons(os.path.join(root, "2_edge_box_filtered"))
+    paths = [p for ps in groups.values() for p in ps]
+    fast = records.load_pool_inputs(paths)
+    assert sorted(fast) == sorted(paths)
+    lg = cli._logger("GridBoxCombiner")
+    for base, ps in groups.items():
+        b, s, c, n, ip, isz = cli.pool_documents(ps, lg)
+        fb, fs, fc, fn, fip, fisz, floats = cli.pool_documents_fast(ps, lg, fast)
+        assert floats and isinstance(fb, np.ndarray) and fb.shape == (len(b), 4)
+        assert fb.tolist() == b and fs.tolist() == s and fc.tolist() == c and fn == n and (fip, fisz) == (ip, isz)
+    # an integer literal among the numbers: that file must not be taken by the device reader
+    victim = paths[0]
+    doc = json.load(open(victim))
+    target = doc["cells"][0]["regions"] if "cells" in doc else doc
+    key = "boxes_original" if "cells" in doc else "boxes"
+    if target[key]:
+        target[key][0][0] = 7
+        json.dump(doc, open(victim, "w"), indent=2)
+        again = records.load_pool_inputs(paths)
+        assert victim not in again and len(again) == len(paths) - 1

@@ -171,3 +171,15 @@ def test_device_reader_ranges_counts_and_unconvertible_tokens():
     assert v[:4].tolist() == [1.5, -0.002, 3.0, 4.0]
     assert v[5] == 7.0 and np.isnan(v[6]) and v[7] == -np.inf and v[8] == np.inf and v[9] == 5e-324
     assert v[10] == 1.2345678901234567e19  # 17 digits + dropped zeros are exact; the 18-digit token is flagged
+
+
+def test_device_reader_dense_text_outgrows_the_first_buffer():
+    """Two-byte tokens ("7,") are denser than the wrapper's first capacity guess: the total reported in
+    val_off[R] makes it retry with the exact size; order and values must be intact across 2 KB block borders."""
+    rng = np.random.default_rng(4)
+    digits = rng.integers(0, 10, 30000)
+    text = ("[" + ",".join(str(int(d)) for d in digits) + "]").encode()
+    split = 12345 * 2 + 1  # a range border in the middle of the list (just after a comma)
+    vals, off, bad = ops.json_parse_numbers(text, [(0, split), (split, len(text))])
+    assert off.tolist() == [0, 12345, 30000] and bad.tolist() == [0, 0]
+    assert np.array_equal(vals.cpu().numpy(), digits.astype(np.float64))

@@ -205,8 +205,8 @@ def split_grid_text(raw: bytes):
             break
         starts.append(i)
         at = i + len(_REGIONS_KEY)
-    if any(raw.count(k) != len(starts) for k in _REGION_KEYS):
-        return None
+    # (each key is looked up inside its own `regions` object only — `limit` below — so a missing or misplaced
+    # array fails the file; counting the keys over the whole text as a cross-check cost more than the parse)
     ranges, names = [], []
     for r, s0 in enumerate(starts):
         limit = starts[r + 1] if r + 1 < len(starts) else len(raw)

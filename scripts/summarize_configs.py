@@ -42,6 +42,10 @@ def row(name, d):
     if "grids" in d:
         return (f"| `{name}` | 1 | {d['pages_per_s']:.0f} pages/s | {d['ms_per_launch']:.3f} | {d['grids']}: {d['tiles_per_page']} tiles/page, "
                 f"{d['achieved_gbs']:.0f} GB/s algorithmic = {d['frac_of_measured_hbm_peak']:.3f} of peak |")
+    if "seconds_device_json" in d:
+        return (f"| `{name}` | 1 | {d['pages_per_s_device_json']:.1f} pages/s | {1e3 * d['seconds_device_json']:.0f} | {d['what']}: "
+                f"{d['input_json_mb']:.1f} MB in, {d['output_json_mb']:.1f} MB out; CPython json {d['pages_per_s_cpython_json']:.1f} "
+                f"pages/s ({d['speedup']:.1f}x slower), identical files |")
     if "what" in d:
         return (f"| `{name}` | 1 | {d['pages_per_s_device']:.0f} pages/s | {d['device_ms_per_step']:.3f} | {d['what']}: "
                 f"{d['json_bytes_per_step'] / 1e6:.1f} MB of text, CPython "

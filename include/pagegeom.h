@@ -219,6 +219,35 @@ int pg_json_combined(const double* boxes /*dev [N,4]*/, const double* classes /*
                      uint8_t* out /*dev*/, int64_t out_capacity, int64_t* out_off /*dev [P+1]*/,
                      void* ws, int64_t ws_bytes, void* stream);
 
+/* Generic form of the writer, for the other json.dump(indent=2) schemas of the reference (the nested
+ * cells[].regions documents of stages 1/2: 1_doclayout_bboxes.py:592-594,645-647, 2_edge_box_filter.py:485-487).
+ * The output is a flat list of segments: a piece of host-encoded text followed by one array printed from device
+ * data (nothing after the text for PG_JSON_KIND_TEXT).  A document is any run of consecutive segments; the
+ * caller cuts it out of `out` with seg_out_off (dev [S+1], always written; if seg_out_off[S] > out_capacity
+ * nothing is written to `out`).  Element k of a segment is box kept_idx[start + k] (or start + k when kept_idx is
+ * NULL) of data[data_id]: f64 [N,4] for BOX4, f64 [N] for SCALAR, int32 [N] name ids for NAME (name i is
+ * text[name_off[i] .. name_off[i+1]), a JSON string literal).  elem_off (dev [S+1]) = exclusive prefix of the
+ * segments' counts (0 for TEXT).  `indent` = spaces in front of an entry (the array's key sits at indent - 2). */
+#define PG_JSON_KIND_TEXT 0
+#define PG_JSON_KIND_BOX4 1
+#define PG_JSON_KIND_SCALAR 2
+#define PG_JSON_KIND_NAME 3
+typedef struct PgJsonSegment {
+  int64_t head_begin, head_end; /* text[head_begin .. head_end) precedes the array */
+  int64_t start;                /* first element */
+  int32_t count;                /* elements (0: prints "[]") */
+  int32_t kind;                 /* PG_JSON_KIND_* */
+  int32_t data_id;              /* index into data[] */
+  int32_t indent;
+} PgJsonSegment;
+int64_t pg_json_segments_workspace_bytes(int64_t n_elems, int32_t n_segs);
+int pg_json_segments(const PgJsonSegment* segs /*dev [S]*/, int32_t n_segs, const int64_t* elem_off /*dev [S+1]*/,
+                     int64_t n_elems, const void* const* data /*host array of <= 8 dev pointers*/, int32_t n_data,
+                     const int32_t* kept_idx /*dev or NULL*/, const uint8_t* text /*dev*/,
+                     const int64_t* name_off /*dev or NULL when no NAME segment*/, uint8_t* out /*dev*/,
+                     int64_t out_capacity, int64_t* seg_out_off /*dev [S+1]*/, void* ws, int64_t ws_bytes,
+                     void* stream);
+
 /* ------------------------------------------------------------------ R1-R3 record reader
  * The numbers of a record's "boxes" / "classes" / "scores" arrays, text -> f64 on the device: what json.load's
  * float() does for the reference's stage-4/5 readers (4_extract_median_widths.py:103-151,

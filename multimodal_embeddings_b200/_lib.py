@@ -73,6 +73,8 @@ SIGNATURES = {
     "pg_json_workspace_bytes": (_I64, [_I64, _I32]),
     "pg_json_combined": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P,
                                    _P, _I64, _P]),
+    "pg_json_segments_workspace_bytes": (_I64, [_I64, _I32]),
+    "pg_json_segments": (C.c_int, [_P, _I32, _P, _I64, _P, _I32, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
     "pg_json_parse_block_bytes": (_I32, []),
     "pg_json_parse_workspace_bytes": (_I64, [_I64]),
     "pg_json_parse_numbers": (C.c_int, [_P, _P, _I32, _P, _I64, _P, _I64, _P, _P, _I32, _P, _I64, _P]),

@@ -469,3 +469,185 @@ extern "C" int pg_json_parse_numbers(const uint8_t* text, const int64_t* ranges,
   }
   return PG_OK;
 }
+
+// =============================================================================================
+// Generic form of the writer: documents as a flat list of SEGMENTS — a piece of host-encoded text followed
+// by one array printed from device data — so that any of the reference's json.dump(indent=2) schemas
+// (the nested cells[].regions of stages 1/2 included) can be laid out on the device.  A segment prints
+//     head text, then  "[]"                                   if it has no elements,
+//                      "[" entries "\n" <indent-2 spaces> "]"  otherwise,
+// where an entry is, at `indent` spaces:  BOX4   "\n<indent>[" 4 x "\n<indent+2>number"(",") "\n<indent>]"
+//                                          SCALAR "\n<indent>number"      NAME "\n<indent>"string literal"
+// each followed by "," unless it is the last.  KIND_TEXT segments are text only (the end of a file).
+// Numbers are formatted twice (once for their length, once in place) instead of going through slots: this
+// path serves the command-line stages, whose volume is a few MB per page.
+//   S1 seg_len_kernel    one thread per element: its entry length
+//   S2 seg_scan_kernel   one CTA per segment: entry offsets, segment size
+//   S3 json_offsets_kernel (shared with J3): segment offsets in the output
+//   S4 seg_head_kernel   one CTA per segment: head text and brackets;  seg_emit_kernel: one thread per element
+// =============================================================================================
+constexpr int SEG_MAX_DATA = 8;
+struct SegData {
+  const void* ptr[SEG_MAX_DATA];
+};
+
+__device__ __forceinline__ int seg_of_elem(const int64_t* __restrict__ elem_off, int n_segs, int64_t e) {
+  int lo = 0, hi = n_segs - 1;
+  while (lo < hi) {  // the last segment whose first element is <= e (empty segments share an offset with a later one)
+    const int mid = (lo + hi + 1) >> 1;
+    if (elem_off[mid] <= e) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ int64_t seg_body_len(const PgJsonSegment& sg, int64_t entries) {
+  if (sg.kind == PG_JSON_KIND_TEXT) return 0;
+  return sg.count == 0 ? 2 : 1 + entries + 1 + (sg.indent - 2) + 1;
+}
+
+__global__ void __launch_bounds__(128) seg_len_kernel(const PgJsonSegment* __restrict__ segs, int n_segs,
+                                                      const int64_t* __restrict__ elem_off, int64_t n_elems, SegData data,
+                                                      const int32_t* __restrict__ kept_idx,
+                                                      const int64_t* __restrict__ name_off, uint32_t* __restrict__ len) {
+  __shared__ char scratch[128][PG_FMT_MAX_DOUBLE + 8];
+  const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (e >= n_elems) return;
+  const int s = seg_of_elem(elem_off, n_segs, e);
+  const PgJsonSegment sg = segs[s];
+  const int64_t k = e - elem_off[s];
+  const int64_t pos = sg.start + k;
+  const int64_t gi = kept_idx ? (int64_t)kept_idx[pos] : pos;
+  const uint32_t comma = k < sg.count - 1 ? 1u : 0u;
+  const uint32_t ind = (uint32_t)sg.indent;
+  char* buf = scratch[threadIdx.x];
+  uint32_t l;
+  if (sg.kind == PG_JSON_KIND_BOX4) {
+    const double* b = static_cast<const double*>(data.ptr[sg.data_id]) + 4 * gi;
+    l = (2u + ind) + 4u * (3u + ind) + 3u + (2u + ind);
+    for (int c = 0; c < 4; ++c) l += (uint32_t)pg_format_double_repr(b[c], buf);
+  } else if (sg.kind == PG_JSON_KIND_SCALAR) {
+    l = 1u + ind + (uint32_t)pg_format_double_repr(static_cast<const double*>(data.ptr[sg.data_id])[gi], buf);
+  } else {
+    const int id = static_cast<const int32_t*>(data.ptr[sg.data_id])[gi];
+    l = 1u + ind + (uint32_t)(name_off[id + 1] - name_off[id]);
+  }
+  len[e] = l + comma;
+}
+
+__global__ void __launch_bounds__(256) seg_scan_kernel(const PgJsonSegment* __restrict__ segs,
+                                                       const int64_t* __restrict__ elem_off, uint32_t* __restrict__ len,
+                                                       int64_t* __restrict__ seg_len) {
+  __shared__ int sm[33];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const PgJsonSegment sg = segs[s];
+  const int64_t base = elem_off[s];
+  const int n = sg.kind == PG_JSON_KIND_TEXT ? 0 : sg.count;
+  int64_t carry = 0;
+  for (int c = 0; c < n; c += 256) {
+    const int k = c + tid;
+    const int v = k < n ? (int)len[base + k] : 0;
+    int total;
+    const int ex = pg_block_exscan(v, sm, &total);
+    if (k < n) len[base + k] = (uint32_t)(carry + ex);
+    carry += total;
+  }
+  if (tid == 0) seg_len[s] = (sg.head_end - sg.head_begin) + seg_body_len(sg, carry);
+}
+
+__global__ void __launch_bounds__(128) seg_head_kernel(const PgJsonSegment* __restrict__ segs, int n_segs,
+                                                       const uint8_t* __restrict__ text, uint8_t* __restrict__ out,
+                                                       int64_t capacity, const int64_t* __restrict__ seg_out_off) {
+  if (seg_out_off[n_segs] > capacity) return;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const PgJsonSegment sg = segs[s];
+  uint8_t* o = out + seg_out_off[s];
+  const int64_t hl = sg.head_end - sg.head_begin;
+  for (int64_t i = tid; i < hl; i += 128) o[i] = text[sg.head_begin + i];
+  if (tid == 0 && sg.kind != PG_JSON_KIND_TEXT) {
+    o[hl] = '[';
+    uint8_t* end = out + seg_out_off[s + 1];
+    end[-1] = ']';
+    if (sg.count > 0) {
+      uint8_t* q = end - 1 - (sg.indent - 2) - 1;
+      *q++ = '\n';
+      for (int i = 0; i < sg.indent - 2; ++i) *q++ = ' ';
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) seg_emit_kernel(const PgJsonSegment* __restrict__ segs, int n_segs,
+                                                       const int64_t* __restrict__ elem_off, int64_t n_elems, SegData data,
+                                                       const int32_t* __restrict__ kept_idx, const uint8_t* __restrict__ text,
+                                                       const int64_t* __restrict__ name_off,
+                                                       const uint32_t* __restrict__ len, uint8_t* __restrict__ out,
+                                                       int64_t capacity, const int64_t* __restrict__ seg_out_off) {
+  if (seg_out_off[n_segs] > capacity) return;
+  const int64_t e = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (e >= n_elems) return;
+  const int s = seg_of_elem(elem_off, n_segs, e);
+  const PgJsonSegment sg = segs[s];
+  const int64_t k = e - elem_off[s];
+  const int64_t pos = sg.start + k;
+  const int64_t gi = kept_idx ? (int64_t)kept_idx[pos] : pos;
+  uint8_t* o = out + seg_out_off[s] + (sg.head_end - sg.head_begin) + 1 + len[e];
+  o = put_indent(o, sg.indent);
+  if (sg.kind == PG_JSON_KIND_BOX4) {
+    const double* b = static_cast<const double*>(data.ptr[sg.data_id]) + 4 * gi;
+    *o++ = '[';
+    for (int c = 0; c < 4; ++c) {
+      o = put_indent(o, sg.indent + 2);
+      o += pg_format_double_repr(b[c], reinterpret_cast<char*>(o));
+      if (c < 3) *o++ = ',';
+    }
+    o = put_indent(o, sg.indent);
+    *o++ = ']';
+  } else if (sg.kind == PG_JSON_KIND_SCALAR) {
+    o += pg_format_double_repr(static_cast<const double*>(data.ptr[sg.data_id])[gi], reinterpret_cast<char*>(o));
+  } else {
+    const int id = static_cast<const int32_t*>(data.ptr[sg.data_id])[gi];
+    const int64_t a = name_off[id], l = name_off[id + 1] - a;
+    for (int64_t i = 0; i < l; ++i) o[i] = text[a + i];
+    o += l;
+  }
+  if (k < sg.count - 1) *o++ = ',';
+}
+
+extern "C" int64_t pg_json_segments_workspace_bytes(int64_t n_elems, int32_t n_segs) {
+  return json_align((n_elems < 1 ? 1 : n_elems) * 4) + json_align((int64_t)(n_segs < 1 ? 1 : n_segs) * 8);
+}
+
+extern "C" int pg_json_segments(const PgJsonSegment* segs, int32_t n_segs, const int64_t* elem_off, int64_t n_elems,
+                                const void* const* data, int32_t n_data, const int32_t* kept_idx, const uint8_t* text,
+                                const int64_t* name_off, uint8_t* out, int64_t out_capacity, int64_t* seg_out_off,
+                                void* ws, int64_t ws_bytes, void* stream) {
+  PG_REQUIRE(n_segs >= 0 && n_elems >= 0 && n_data >= 0 && n_data <= SEG_MAX_DATA && out_capacity >= 0, "sizes");
+  if (n_segs == 0) return PG_OK;
+  PG_REQUIRE(segs && elem_off && text && out && seg_out_off && ws && (data || n_data == 0), "null pointer");
+  if (ws_bytes < pg_json_segments_workspace_bytes(n_elems, n_segs)) {
+    pg_set_error("workspace: pg_json_segments needs %lld bytes, got %lld",
+                 (long long)pg_json_segments_workspace_bytes(n_elems, n_segs), (long long)ws_bytes);
+    return PG_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  SegData d;
+  for (int i = 0; i < SEG_MAX_DATA; ++i) d.ptr[i] = i < n_data ? data[i] : nullptr;
+  uint32_t* len = static_cast<uint32_t*>(ws);
+  int64_t* seg_len = reinterpret_cast<int64_t*>(static_cast<uint8_t*>(ws) + json_align((n_elems < 1 ? 1 : n_elems) * 4));
+  const unsigned eg = (unsigned)((n_elems + 127) / 128);
+  if (n_elems > 0) {
+    seg_len_kernel<<<eg, 128, 0, s>>>(segs, n_segs, elem_off, n_elems, d, kept_idx, name_off, len);
+    PG_LAUNCH_CHECK();
+  }
+  seg_scan_kernel<<<n_segs, 256, 0, s>>>(segs, elem_off, len, seg_len);
+  PG_LAUNCH_CHECK();
+  json_offsets_kernel<<<1, 1024, 0, s>>>(n_segs, seg_len, seg_out_off);
+  PG_LAUNCH_CHECK();
+  seg_head_kernel<<<n_segs, 128, 0, s>>>(segs, n_segs, text, out, out_capacity, seg_out_off);
+  PG_LAUNCH_CHECK();
+  if (n_elems > 0) {
+    seg_emit_kernel<<<eg, 128, 0, s>>>(segs, n_segs, elem_off, n_elems, d, kept_idx, text, name_off, len, out,
+                                       out_capacity, seg_out_off);
+    PG_LAUNCH_CHECK();
+  }
+  return PG_OK;
+}

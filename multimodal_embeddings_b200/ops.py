@@ -493,3 +493,90 @@ def json_parse_numbers(text, ranges, stream=None, int_literals_to_host: bool = F
             break
         capacity = int(off[-1])
     return values[:int(off[-1])], off, n_bad[:r].cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------
+# Generic writer: any json.dump(indent=2) document with device-resident arrays (pg_json_segments)
+# --------------------------------------------------------------------------------------------
+SEGMENT_DTYPE = np.dtype([("head_begin", "<i8"), ("head_end", "<i8"), ("start", "<i8"), ("count", "<i4"),
+                          ("kind", "<i4"), ("data_id", "<i4"), ("indent", "<i4")])
+JSON_KIND_TEXT, JSON_KIND_BOX4, JSON_KIND_SCALAR, JSON_KIND_NAME = 0, 1, 2, 3
+
+
+class DeviceArray:
+    """Placeholder inside a document handed to render_documents: the JSON array printed at this place is
+    elements [start, start + count) (positions into `kept_idx`, or box indices without one) of data[data_id]."""
+    __slots__ = ("kind", "data_id", "start", "count")
+
+    def __init__(self, kind: int, data_id: int, start: int, count: int):
+        self.kind, self.data_id, self.start, self.count = int(kind), int(data_id), int(start), int(count)
+
+
+def render_documents(docs: Sequence, data: Sequence, names: Sequence[bytes] = (), kept_idx=None, stream=None) -> List[bytes]:
+    """`json.dumps(doc, indent=2)` for every doc, with each DeviceArray placeholder printed on the device from
+    `data` (cuda tensors: f64 [N,4] for BOX4, f64 [N] for SCALAR, int32 [N] ids into `names` for NAME; names are
+    JSON string literals).  The text around the arrays is encoded by CPython itself (a dump of the document with
+    a sentinel string at each placeholder), so key order, escaping and nesting are whatever json.dumps does."""
+    import json
+    import re
+    _require_cuda()
+    marks: List[DeviceArray] = []
+
+    def sentinel(o):
+        if not isinstance(o, DeviceArray):
+            raise TypeError(f"Object of type {type(o).__name__} is not JSON serializable")
+        marks.append(o)
+        return f"\x00PGARR{len(marks) - 1}\x00"
+
+    pat = re.compile(rb'"\\u0000PGARR(\d+)\\u0000"')
+    pieces, segs, doc_first = [], [], []
+    for doc in docs:
+        text = json.dumps(doc, indent=2, default=sentinel).encode("ascii")
+        doc_first.append(len(segs))
+        at = 0
+        for m in pat.finditer(text):
+            head = text[at:m.start()]
+            nl = head.rfind(b"\n")
+            line = head[nl + 1:]
+            key_indent = len(line) - len(line.lstrip(b" "))
+            a = marks[int(m.group(1))]
+            segs.append((len(pieces), a.start, a.count, a.kind, a.data_id, key_indent + 2))
+            pieces.append(head)
+            at = m.end()
+        segs.append((len(pieces), 0, 0, JSON_KIND_TEXT, 0, 0))
+        pieces.append(text[at:])
+    doc_first.append(len(segs))
+    n_text = len(pieces)
+    pieces.extend(names)
+    lens = np.fromiter((len(x) for x in pieces), np.int64, len(pieces))
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    seg_arr = np.zeros(len(segs), SEGMENT_DTYPE)
+    for i, (pi, start, count, kind, data_id, indent) in enumerate(segs):
+        seg_arr[i] = (offs[pi], offs[pi + 1], start, count, kind, data_id, indent)
+    elem_off = np.concatenate([[0], np.cumsum(seg_arr["count"].astype(np.int64))]).astype(np.int64)
+    n_elems, n_segs = int(elem_off[-1]), len(segs)
+    d_text = torch.frombuffer(bytearray(b"".join(pieces) + b"\0"), dtype=torch.uint8).cuda()
+    d_segs = torch.from_numpy(seg_arr.view(np.uint8).reshape(-1)).cuda()
+    d_elem = torch.from_numpy(elem_off).cuda()
+    d_name = torch.from_numpy(offs[n_text:].copy()).cuda() if len(names) else None
+    if kept_idx is not None:
+        kept_idx = _dev(kept_idx, torch.int32)
+    data = [t if isinstance(t, torch.Tensor) and t.is_cuda else _dev(t, torch.int32 if np.asarray(t).dtype.kind in "iu" else torch.float64)
+            for t in data]
+    ptrs = (C.c_void_p * max(len(data), 1))(*[t.data_ptr() for t in data])
+    ws_bytes = int(lib().pg_json_segments_workspace_bytes(n_elems, n_segs))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    seg_off = torch.zeros(n_segs + 1, dtype=torch.int64, device="cuda")
+    capacity = int(lens[:n_text].sum()) + 4 * n_segs + 40 * n_elems
+    while True:
+        out = torch.empty(max(capacity, 1), dtype=torch.uint8, device="cuda")
+        check(lib().pg_json_segments(ptr(d_segs), n_segs, ptr(d_elem), n_elems, ptrs, len(data), ptr(kept_idx), ptr(d_text),
+                                     ptr(d_name), ptr(out), capacity, ptr(seg_off), ptr(ws), ws_bytes, stream_ptr(stream)))
+        if stream is not None:
+            stream.synchronize()
+        off = seg_off.cpu().numpy()
+        if int(off[-1]) <= capacity:
+            break
+        capacity = int(off[-1])
+    host = out[:int(off[-1])].cpu().numpy().tobytes()
+    return [host[off[doc_first[i]]:off[doc_first[i + 1]]] for i in range(len(docs))]

@@ -183,3 +183,56 @@ def test_device_reader_dense_text_outgrows_the_first_buffer():
     vals, off, bad = ops.json_parse_numbers(text, [(0, split), (split, len(text))])
     assert off.tolist() == [0, 12345, 30000] and bad.tolist() == [0, 0]
     assert np.array_equal(vals.cpu().numpy(), digits.astype(np.float64))
+
+
+# ------------------------------------------------------------------------------------------------ generic writer
+def test_render_documents_equals_json_dumps_on_nested_schemas():
+    """ops.render_documents (pg_json_segments): documents shaped like the reference's stage-1/2 grid files
+    (cells[].regions with five arrays per cell, arrays at indent 8), like its standard files, and odd ones
+    (an array as a list element, empty arrays, a document without any array) against json.dumps(indent=2)."""
+    rng = np.random.default_rng(21)
+    n = 3000
+    local = rng.uniform(0, 3000, (n, 4)).astype(np.float32).astype(np.float64)
+    orig = local + rng.integers(0, 5000, (n, 1)).astype(np.float64)
+    cls = rng.integers(0, len(NAMES), n).astype(np.float64)
+    sc = rng.uniform(0, 1, n).astype(np.float32).astype(np.float64)
+    name_id = cls.astype(np.int32)
+    kept = rng.permutation(n).astype(np.int32)  # an arbitrary indirection, as kept_idx is
+    data = [local, orig, cls, sc, name_id]
+    literals = [json.dumps(x).encode("ascii") for x in NAMES]
+    A = ops.DeviceArray
+
+    def arrays(start, count):  # placeholders and what they must print
+        j = kept[start:start + count]
+        ph = {"boxes": A(ops.JSON_KIND_BOX4, 0, start, count), "boxes_original": A(ops.JSON_KIND_BOX4, 1, start, count),
+              "classes": A(ops.JSON_KIND_SCALAR, 2, start, count), "scores": A(ops.JSON_KIND_SCALAR, 3, start, count),
+              "class_names": A(ops.JSON_KIND_NAME, 4, start, count)}
+        real = {"boxes": local[j].tolist(), "boxes_original": orig[j].tolist(), "classes": cls[j].tolist(),
+                "scores": sc[j].tolist(), "class_names": [NAMES[i] for i in name_id[j]]}
+        return ph, real
+
+    docs, want = [], []
+    at = 0
+    for f in range(3):  # grid documents
+        cells_ph, cells_real = [], []
+        for c, cnt in enumerate([0, 1, 130, 517, 2][: 3 + f]):
+            ph, real = arrays(at, cnt)
+            at += cnt
+            meta = {"cell_path": f"/g/é{f}_{c}.png", "cell_json_path": f"/g/{f}_{c}.json",
+                    "cell_coordinates": {"x_start": 0, "y_start": 0, "x_end": 2280.6, "y_end": 3360.6}, "row": 1, "col": c + 1}
+            cells_ph.append({**meta, "regions": ph})
+            cells_real.append({**meta, "regions": real})
+        tail = {"grid_config": {"rows": 2, "cols": 2, "overlap_percentage": 20.0}}
+        docs.append({"original_image_path": f'/p/"{f}".png', "cells": cells_ph, **tail})
+        want.append({"original_image_path": f'/p/"{f}".png', "cells": cells_real, **tail})
+    ph, real = arrays(at, 333)  # a standard document (arrays at indent 4), one array used twice
+    docs.append({"image_path": "s.png", "image_size": {"width": 1, "height": 2}, **ph, "again": ph["scores"]})
+    want.append({"image_path": "s.png", "image_size": {"width": 1, "height": 2}, **real, "again": real["scores"]})
+    docs.append({"k": [1, ph["classes"], "x", [ph["boxes"]]], "none": None})  # arrays as list elements, nested
+    want.append({"k": [1, real["classes"], "x", [real["boxes"]]], "none": None})
+    docs.append({"plain": True, "v": [1.5, "no arrays here"]})
+    want.append({"plain": True, "v": [1.5, "no arrays here"]})
+    got = ops.render_documents(docs, data, literals, kept_idx=kept)
+    assert len(got) == len(docs)
+    for g, w in zip(got, want):
+        assert g == json.dumps(w, indent=2).encode("ascii")

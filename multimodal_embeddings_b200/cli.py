@@ -270,8 +270,24 @@ def main_stage2(argv: Optional[Sequence[str]] = None) -> int:
     def run_folder(in_folder, out_folder):
         paths = _my_share(sorted(os.path.join(r, f) for r, _, fs in os.walk(in_folder) for f in fs if f.endswith(".json")))
         ok = err = 0
+        # Grid documents laid out as stage 1 writes them go through three device calls for the whole folder —
+        # numbers text -> f64, edge filter with every cell as its own page, filtered documents -> text
+        # (records.filter_grid_files); the results are written in the loop below, in the reference's file order,
+        # so that an error in another file stops the run at the same place as in the reference.
+        try:
+            from .records import filter_grid_files
+            fast = filter_grid_files(paths, args.edge_threshold, lambda sk: _grid_page_size(sk, args.no_image_check),
+                                     api._cell_tuple)
+        except Exception as e:
+            logger.error(f"Batch path failed ({e}); processing the files one by one")
+            fast = {}
         for path in paths:
             try:
+                if path in fast:
+                    with open(os.path.join(out_folder, os.path.basename(path)), "wb") as f:
+                        f.write(fast[path])
+                    ok += 1
+                    continue
                 with open(path) as f:
                     regions = json.load(f)
                 target = os.path.join(out_folder, os.path.basename(path))

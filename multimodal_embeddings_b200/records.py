@@ -294,3 +294,166 @@ def load_pool_inputs(json_paths: Sequence[str]) -> dict:
                          "boxes": cat(boxes).reshape(-1, 4), "classes": cat(classes), "scores": cat(scores),
                          "class_names": flat}
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Stage 2 on grid documents, batched: read -> edge filter -> write, numbers never visiting the host
+_REGION_KEYS5 = (b'\n        "boxes": [',) + _REGION_KEYS
+
+
+def split_grid_text_full(raw: bytes):
+    """Like split_grid_text, with the cell-local `boxes` as well: (skeleton dict — the document with the five
+    arrays of every `regions` emptied —, [(begin, end)] * 4 per cell in the order boxes, boxes_original,
+    classes, scores, class_names lists per cell), or None."""
+    if raw.find(b'\n  "cells": [') < 0:
+        return None
+    starts, at = [], 0
+    while True:
+        i = raw.find(_REGIONS_KEY, at)
+        if i < 0:
+            break
+        starts.append(i)
+        at = i + len(_REGIONS_KEY)
+    ranges, names, skel, prev = [], [], [], 0
+    empty = b"],".join(_REGION_KEYS5) + b"]"
+    for r, s0 in enumerate(starts):
+        limit = starts[r + 1] if r + 1 < len(starts) else len(raw)
+        pos, at = [], s0
+        for k in _REGION_KEYS5:
+            i = raw.find(k, at, limit)
+            if i < 0:
+                return None
+            pos.append(i)
+            at = i + len(k)
+        i_b, i_bo, i_cl, i_sc, i_nm = pos
+        lst = i_nm + len(_REGION_KEYS5[4]) - 1
+        if raw[lst + 1: lst + 2] == b"]":
+            end = lst + 2
+        else:
+            j = raw.find(_REGION_LIST_END, lst, limit)
+            if j < 0:
+                return None
+            end = j + len(_REGION_LIST_END)
+        try:
+            nm = json.loads(raw[lst:end])
+        except ValueError:
+            return None
+        ranges += [(i_b + len(_REGION_KEYS5[0]), i_bo), (i_bo + len(_REGION_KEYS5[1]), i_cl),
+                   (i_cl + len(_REGION_KEYS5[2]), i_sc), (i_sc + len(_REGION_KEYS5[3]), i_nm)]
+        names.append(nm)
+        skel += [raw[prev:i_b], empty]
+        prev = end
+    skel.append(raw[prev:])
+    try:
+        skeleton = json.loads(b"".join(skel))
+    except ValueError:
+        return None
+    cells = skeleton.get("cells") if isinstance(skeleton, dict) else None
+    if not isinstance(cells, list) or len(cells) != len(starts) or any(
+            not isinstance(c, dict) or "regions" not in c for c in cells):
+        return None
+    return skeleton, ranges, names
+
+
+def filter_grid_files(json_paths: Sequence[str], threshold, page_size_of, cell_tuple) -> dict:
+    """Stage 2 (filter_grid_info, 2_edge_box_filter.py:148-237, and its json.dump :485-487) for a batch of grid
+    documents in three device calls: pg_json_parse_numbers for every array of every cell of every file,
+    pg_edge_filter with each cell as its own page, pg_json_segments for the filtered documents.  Returns
+    path -> the bytes of the output file for the files it could take; the others (layout, integer literals,
+    unknown page size, ragged arrays) are left to the per-file path.  `page_size_of(skeleton)` -> (W, H) or None;
+    `cell_tuple(cell_coordinates, W, H)` -> [x_start, y_start, x_end, y_end]."""
+    try:
+        import torch
+        if not torch.cuda.is_available() or os.environ.get("PG_PYTHON_JSON") == "1":
+            return {}
+    except ImportError:
+        return {}
+    from . import ops
+    files, blob, base = [], [], 0
+    for path in json_paths:
+        try:
+            with open(path, "rb") as f:
+                raw = f.read()
+        except OSError:
+            continue
+        parts = split_grid_text_full(raw) if b'\n  "cells": [' in raw else None
+        if parts is None:
+            continue
+        skeleton, rg, names = parts
+        if not ("grid_config" in skeleton or "grid_info" in skeleton) or "original_image_path" not in skeleton:
+            continue
+        try:
+            size = page_size_of(skeleton)
+            tuples = [cell_tuple(c["cell_coordinates"], size[0], size[1]) for c in skeleton["cells"]] if size else None
+            meta = [(c["cell_path"], c["cell_json_path"], c["cell_coordinates"]) for c in skeleton["cells"]]
+        except Exception:
+            continue
+        if not size or any(len(t) != 4 for t in tuples) or not meta and skeleton["cells"]:
+            continue
+        files.append((path, skeleton, [(a + base, b + base) for a, b in rg], names, size, tuples))
+        blob.append(raw)
+        base += len(raw)
+    if not files:
+        return {}
+    # ranges kind-major, so that the converted numbers come out as four contiguous arrays over all cells
+    ranges = [r for kind in range(4) for f in files for r in f[2][kind::4]]
+    n_cells = len(ranges) // 4
+    values, off, bad = ops.json_parse_numbers(b"".join(blob), ranges, int_literals_to_host=True)
+    cnt = np.diff(off).reshape(4, n_cells)
+    ok_cell = (bad.reshape(4, n_cells) == 0).all(0) & (cnt[0] == 4 * cnt[2]) & (cnt[1] == 4 * cnt[2]) & (cnt[3] == cnt[2])
+    flat_names, c = [], 0
+    for f in files:
+        for nm in f[3]:
+            if not isinstance(nm, list) or len(nm) != cnt[2][c] or any(not isinstance(x, str) for x in nm):
+                ok_cell[c] = False
+            flat_names.append(nm if isinstance(nm, list) else [])
+            c += 1
+    # per-file verdict; a declined file's cells simply stay unused in the arrays
+    take, c = [], 0
+    for f in files:
+        k = len(f[3])
+        take.append(bool(ok_cell[c:c + k].all()))
+        c += k
+    if not all(take):  # a ragged / exotic file would shift the per-kind arrays: redo the batch without it
+        good = [f[0] for f, t in zip(files, take) if t]
+        return filter_grid_files(good, threshold, page_size_of, cell_tuple) if good else {}
+    n = int(cnt[2].sum())
+    boxes_local = values[off[0]: off[n_cells]].view(-1, 4)
+    boxes_orig = values[off[n_cells]: off[2 * n_cells]].view(-1, 4)
+    classes = values[off[2 * n_cells]: off[3 * n_cells]]
+    scores = values[off[3 * n_cells]: off[4 * n_cells]]
+    cell_off = np.concatenate([[0], np.cumsum(cnt[2])]).astype(np.int64)
+    table, name_id = {}, np.zeros(max(n, 1), np.int32)
+    for ci, nm in enumerate(flat_names):
+        name_id[cell_off[ci]: cell_off[ci + 1]] = [table.setdefault(x, len(table)) for x in nm]
+    page_wh = np.asarray([f[4] for f in files for _ in f[3]], np.int32).reshape(-1, 2)
+    cells = np.asarray([t for f in files for t in f[5]], np.float64).reshape(-1, 4)
+    box_cell = np.repeat(np.arange(n_cells, dtype=np.int32), cnt[2])
+    if n:
+        _, _, kept, n_kept = ops.edge_filter(boxes_orig, box_cell, cells, page_wh, cell_off, threshold,
+                                             boxes_are_local=False, want_boxes_page=False)
+        n_kept_h = n_kept.cpu().numpy()
+    else:
+        kept, n_kept_h = np.zeros(1, np.int32), np.zeros(n_cells, np.int32)
+    A = ops.DeviceArray
+    docs, doc_paths, c = [], [], 0
+    for f, good in zip(files, take):
+        path, skeleton = f[0], f[1]
+        if good:
+            filtered = {"original_image_path": skeleton["original_image_path"], "cells": []}
+            if "grid_config" in skeleton:
+                filtered["grid_config"] = skeleton["grid_config"]
+            for j, cell in enumerate(skeleton["cells"]):
+                s, k = int(cell_off[c + j]), int(n_kept_h[c + j])
+                filtered["cells"].append({
+                    "cell_path": cell["cell_path"], "cell_json_path": cell["cell_json_path"],
+                    "cell_coordinates": cell["cell_coordinates"], "row": cell.get("row", 0), "col": cell.get("col", 0),
+                    "regions": {"boxes": A(ops.JSON_KIND_BOX4, 0, s, k), "boxes_original": A(ops.JSON_KIND_BOX4, 1, s, k),
+                                "classes": A(ops.JSON_KIND_SCALAR, 2, s, k), "scores": A(ops.JSON_KIND_SCALAR, 3, s, k),
+                                "class_names": A(ops.JSON_KIND_NAME, 4, s, k)}})
+            docs.append(filtered)
+            doc_paths.append(path)
+        c += len(f[3])
+    literals = [json.dumps(x).encode("ascii") for x in table] or [b'""']
+    texts = ops.render_documents(docs, [boxes_local, boxes_orig, classes, scores, name_id], literals, kept_idx=kept)
+    return dict(zip(doc_paths, texts))

@@ -151,3 +151,35 @@ def test_stage3_inputs_read_on_the_device_equal_json_load(tmp_path):
         json.dump(doc, open(victim, "w"), indent=2)
         again = records.load_pool_inputs(paths)
         assert victim not in again and len(again) == len(paths) - 1
+
+
+def test_stage2_batch_path_equals_per_file_path(tmp_path):
+    """records.filter_grid_files (read, edge filter and write on the device for all grid files at once) against
+    the per-file path — reference_api.filter_grid_info + json.dumps — on the synthetic stage-1 tree; it must
+    actually take every grid file, and decline one that holds an integer literal among its numbers."""
+    import glob
+    import os
+    from multimodal_embeddings_b200 import records
+    from multimodal_embeddings_b200 import reference_api as api
+    root = str(tmp_path)
+    s1 = cli_tree.build_stage1_tree(root)
+    paths = sorted(glob.glob(os.path.join(s1, "json", "*.json")))
+    grid = [p for p in paths if "_grid_" in os.path.basename(p)]
+    size_of = lambda sk: cli._grid_page_size(sk, True)  # noqa: E731
+    fast = records.filter_grid_files(paths, 10, size_of, api._cell_tuple)
+    assert sorted(fast) == grid and grid
+    n_removed = 0
+    for p in grid:
+        doc = json.load(open(p))
+        want = api.filter_grid_info(doc, 10, image_size=size_of(doc))
+        assert fast[p].decode("ascii") == json.dumps(want, indent=2)
+        n_removed += sum(len(c["regions"]["boxes"]) for c in doc["cells"]) - sum(len(c["regions"]["boxes"]) for c in want["cells"])
+    assert n_removed > 0  # the filter really dropped boxes
+    victim = next(p for p in grid if any(c["regions"]["scores"] for c in json.load(open(p))["cells"]))
+    doc = json.load(open(victim))
+    cell = next(c for c in doc["cells"] if c["regions"]["scores"])
+    cell["regions"]["boxes"][0][1] = 3
+    json.dump(doc, open(victim, "w"), indent=2)
+    again = records.filter_grid_files(paths, 10, size_of, api._cell_tuple)
+    rest = [p for p in grid if p != victim]
+    assert sorted(again) == rest and all(again[p] == fast[p] for p in rest)

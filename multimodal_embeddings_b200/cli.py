@@ -276,8 +276,13 @@ def main_stage2(argv: Optional[Sequence[str]] = None) -> int:
         # so that an error in another file stops the run at the same place as in the reference.
         try:
             from .records import filter_grid_files
+            def standard_ok(doc):  # the image check of 2:381-412 for full-page documents
+                if args.no_image_check:
+                    return True
+                return any(doc.get(k) and os.path.exists(doc[k]) for k in ("image_path", "original_image_path"))
+
             fast = filter_grid_files(paths, args.edge_threshold, lambda sk: _grid_page_size(sk, args.no_image_check),
-                                     api._cell_tuple)
+                                     api._cell_tuple, standard_ok)
         except Exception as e:
             logger.error(f"Batch path failed ({e}); processing the files one by one")
             fast = {}

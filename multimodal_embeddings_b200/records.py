@@ -355,13 +355,16 @@ def split_grid_text_full(raw: bytes):
     return skeleton, ranges, names
 
 
-def filter_grid_files(json_paths: Sequence[str], threshold, page_size_of, cell_tuple) -> dict:
+def filter_grid_files(json_paths: Sequence[str], threshold, page_size_of, cell_tuple, standard_ok=None) -> dict:
     """Stage 2 (filter_grid_info, 2_edge_box_filter.py:148-237, and its json.dump :485-487) for a batch of grid
     documents in three device calls: pg_json_parse_numbers for every array of every cell of every file,
     pg_edge_filter with each cell as its own page, pg_json_segments for the filtered documents.  Returns
     path -> the bytes of the output file for the files it could take; the others (layout, integer literals,
     unknown page size, ragged arrays) are left to the per-file path.  `page_size_of(skeleton)` -> (W, H) or None;
-    `cell_tuple(cell_coordinates, W, H)` -> [x_start, y_start, x_end, y_end]."""
+    `cell_tuple(cell_coordinates, W, H)` -> [x_start, y_start, x_end, y_end].
+    With `standard_ok(doc_without_arrays) -> bool`, full-page documents (no `cells`, no `cell_coordinates`: stage 2
+    copies them, "Non-grid image detected, not filtering any boxes", 2:92-100) take the same route: read and
+    re-written on the device, every box kept."""
     try:
         import torch
         if not torch.cuda.is_available() or os.environ.get("PG_PYTHON_JSON") == "1":
@@ -376,7 +379,27 @@ def filter_grid_files(json_paths: Sequence[str], threshold, page_size_of, cell_t
                 raw = f.read()
         except OSError:
             continue
-        parts = split_grid_text_full(raw) if b'\n  "cells": [' in raw else None
+        if b'\n  "cells": [' not in raw:
+            if standard_ok is None or b'"boxes_original"' in raw or b'"cell_coordinates"' in raw:
+                continue
+            parts = split_record_text(raw)
+            if parts is None:
+                continue
+            head, tail, rg = parts
+            tail = dict(tail)
+            names = tail.pop("class_names")
+            try:
+                if not standard_ok({**head, **tail}):
+                    continue
+            except Exception:
+                continue
+            # one pseudo-cell; its `boxes` array stands in for both box kinds so that the arrays stay aligned
+            files.append((path, ("standard", head, tail), [(a + base, b + base) for a, b in (rg[0], rg[0], rg[1], rg[2])],
+                          [names], (1, 1), [[0, 0, 1, 1]]))
+            blob.append(raw)
+            base += len(raw)
+            continue
+        parts = split_grid_text_full(raw)
         if parts is None:
             continue
         skeleton, rg, names = parts
@@ -432,14 +455,27 @@ def filter_grid_files(json_paths: Sequence[str], threshold, page_size_of, cell_t
     if n:
         _, _, kept, n_kept = ops.edge_filter(boxes_orig, box_cell, cells, page_wh, cell_off, threshold,
                                              boxes_are_local=False, want_boxes_page=False)
-        n_kept_h = n_kept.cpu().numpy()
+        n_kept_h = n_kept.cpu().numpy().copy()
+        c = 0
+        for f in files:  # full-page documents keep every box, in order
+            if isinstance(f[1], tuple):
+                a, b = int(cell_off[c]), int(cell_off[c + 1])
+                kept[a:b] = torch.arange(a, b, dtype=torch.int32, device=kept.device)
+                n_kept_h[c] = b - a
+            c += len(f[3])
     else:
         kept, n_kept_h = np.zeros(1, np.int32), np.zeros(n_cells, np.int32)
     A = ops.DeviceArray
     docs, doc_paths, c = [], [], 0
     for f, good in zip(files, take):
         path, skeleton = f[0], f[1]
-        if good:
+        if good and isinstance(skeleton, tuple):
+            _, head, tail = skeleton
+            s, k = int(cell_off[c]), int(n_kept_h[c])
+            docs.append({**head, "boxes": A(ops.JSON_KIND_BOX4, 0, s, k), "classes": A(ops.JSON_KIND_SCALAR, 2, s, k),
+                         "scores": A(ops.JSON_KIND_SCALAR, 3, s, k), "class_names": A(ops.JSON_KIND_NAME, 4, s, k), **tail})
+            doc_paths.append(path)
+        elif good:
             filtered = {"original_image_path": skeleton["original_image_path"], "cells": []}
             if "grid_config" in skeleton:
                 filtered["grid_config"] = skeleton["grid_config"]

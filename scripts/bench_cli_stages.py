@@ -2,7 +2,7 @@
 reader + writer and with CPython's json on both sides (PG_PYTHON_JSON=1) — what the §8f rank-2 work buys the
 drop-in command line.  Prints one JSON line.
 
-    python scripts/bench_cli_stage3.py [--pages 16] [--boxes 10000]
+    python scripts/bench_cli_stages.py [--pages 16] [--boxes 10000]
 """
 import argparse
 import json
@@ -60,7 +60,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pages", type=int, default=16)
     ap.add_argument("--boxes", type=int, default=10000)
+    ap.add_argument("--stage", type=int, default=3, choices=[2, 3])
     a = ap.parse_args()
+    main_fn = cli.main_stage3 if a.stage == 3 else cli.main_stage2
+    extra = [] if a.stage == 3 else ["--no_image_check"]
     with tempfile.TemporaryDirectory() as tmp:
         src = os.path.join(tmp, "2_edge_box_filtered")
         in_bytes = write_tree(src, a.pages, a.boxes)
@@ -70,13 +73,15 @@ def main():
             if mode == "cpython":
                 os.environ["PG_PYTHON_JSON"] = "1"
             t0 = time.perf_counter()
-            assert cli.main_stage3(["--input_folder", src, "--output_folder", out]) == 0
+            assert main_fn(["--input_folder", src, "--output_folder", out] + extra) == 0
             times[mode] = time.perf_counter() - t0
             os.environ.pop("PG_PYTHON_JSON", None)
             outs[mode] = {f: open(os.path.join(out, "json", f), "rb").read() for f in sorted(os.listdir(os.path.join(out, "json")))}
-        assert outs["device"] == outs["cpython"] and len(outs["device"]) == a.pages
+        assert outs["device"] == outs["cpython"] and len(outs["device"]) == a.pages * (1 if a.stage == 3 else 4)
         out_bytes = sum(len(v) for v in outs["device"].values())
-        print(json.dumps({"what": "stage-3 CLI wall time (read 4 stage-2 files per page, merge, write the record)",
+        what = ("stage-3 CLI wall time (read 4 stage-2 files per page, merge, write the record)" if a.stage == 3 else
+                "stage-2 CLI wall time (read 4 stage-1 files per page, edge filter, write 4 files)")
+        print(json.dumps({"what": what,
                           "pages": a.pages, "boxes_per_page_in": a.boxes, "input_json_mb": in_bytes / 1e6,
                           "output_json_mb": out_bytes / 1e6, "seconds_device_json": times["device"],
                           "seconds_cpython_json": times["cpython"], "pages_per_s_device_json": a.pages / times["device"],

@@ -168,6 +168,12 @@ def test_stage2_batch_path_equals_per_file_path(tmp_path):
     size_of = lambda sk: cli._grid_page_size(sk, True)  # noqa: E731
     fast = records.filter_grid_files(paths, 10, size_of, api._cell_tuple)
     assert sorted(fast) == grid and grid
+    both = records.filter_grid_files(paths, 10, size_of, api._cell_tuple, standard_ok=lambda doc: True)
+    assert sorted(both) == paths and all(both[p] == fast[p] for p in grid)
+    for p in paths:
+        if p not in grid:  # full-page documents are copied (2:92-100): what json.dump of the loaded file gives
+            assert both[p].decode("ascii") == json.dumps(api.filter_edge_boxes(json.load(open(p)), 10), indent=2)
+    assert records.filter_grid_files(paths, 10, size_of, api._cell_tuple, standard_ok=lambda doc: False).keys() == fast.keys()
     n_removed = 0
     for p in grid:
         doc = json.load(open(p))

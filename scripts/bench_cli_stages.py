@@ -60,27 +60,39 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pages", type=int, default=16)
     ap.add_argument("--boxes", type=int, default=10000)
-    ap.add_argument("--stage", type=int, default=3, choices=[2, 3])
+    ap.add_argument("--stage", type=int, default=3, choices=[2, 3, 4, 5])
     a = ap.parse_args()
-    main_fn = cli.main_stage3 if a.stage == 3 else cli.main_stage2
-    extra = [] if a.stage == 3 else ["--no_image_check"]
     with tempfile.TemporaryDirectory() as tmp:
-        src = os.path.join(tmp, "2_edge_box_filtered")
-        in_bytes = write_tree(src, a.pages, a.boxes)
+        s2 = os.path.join(tmp, "2_edge_box_filtered")
+        in_bytes = write_tree(s2, a.pages, a.boxes)
+        s3, s4 = os.path.join(tmp, "3_combined_bboxes"), os.path.join(tmp, "4_medians_extracted")
+        if a.stage >= 4:  # the later stages read what the earlier ones wrote
+            assert cli.main_stage3(["--input_folder", s2, "--output_folder", s3]) == 0
+            in_bytes = sum(os.path.getsize(os.path.join(s3, "json", f)) for f in os.listdir(os.path.join(s3, "json")))
+        if a.stage == 5:
+            assert cli.main_stage4(["--input_folder", os.path.join(s3, "json"), "--output_folder", s4, "--no_image_check"]) == 0
+        main_fn = {2: cli.main_stage2, 3: cli.main_stage3, 4: cli.main_stage4, 5: cli.main_stage5}[a.stage]
+        argv = {2: ["--input_folder", s2, "--no_image_check"], 3: ["--input_folder", s2],
+                4: ["--input_folder", os.path.join(s3, "json"), "--no_image_check"],
+                5: ["--input_folder", os.path.join(s3, "json"), "--median_folder", os.path.join(s4, "json"),
+                    "--no_image_check"]}[a.stage]
+        files_per_page = {2: 4, 3: 1, 4: 1, 5: 1}[a.stage]
         times, outs = {}, {}
         for mode in ("warmup", "device", "cpython"):
-            out = os.path.join(tmp, f"3_{mode}")
+            out = os.path.join(tmp, f"out_{mode}")
             if mode == "cpython":
                 os.environ["PG_PYTHON_JSON"] = "1"
             t0 = time.perf_counter()
-            assert main_fn(["--input_folder", src, "--output_folder", out] + extra) == 0
+            assert main_fn(argv + ["--output_folder", out]) == 0
             times[mode] = time.perf_counter() - t0
             os.environ.pop("PG_PYTHON_JSON", None)
             outs[mode] = {f: open(os.path.join(out, "json", f), "rb").read() for f in sorted(os.listdir(os.path.join(out, "json")))}
-        assert outs["device"] == outs["cpython"] and len(outs["device"]) == a.pages * (1 if a.stage == 3 else 4)
+        assert outs["device"] == outs["cpython"] and len(outs["device"]) == a.pages * files_per_page
         out_bytes = sum(len(v) for v in outs["device"].values())
-        what = ("stage-3 CLI wall time (read 4 stage-2 files per page, merge, write the record)" if a.stage == 3 else
-                "stage-2 CLI wall time (read 4 stage-1 files per page, edge filter, write 4 files)")
+        what = {2: "stage-2 CLI wall time (read 4 stage-1 files per page, edge filter, write 4 files)",
+                3: "stage-3 CLI wall time (read 4 stage-2 files per page, merge, write the record)",
+                4: "stage-4 CLI wall time (read the stage-3 record, width median, write a small file)",
+                5: "stage-5 CLI wall time (read the stage-3 record and the median, column peaks, write a small file)"}[a.stage]
         print(json.dumps({"what": what,
                           "pages": a.pages, "boxes_per_page_in": a.boxes, "input_json_mb": in_bytes / 1e6,
                           "output_json_mb": out_bytes / 1e6, "seconds_device_json": times["device"],

@@ -472,15 +472,19 @@ struct TilerArgs {
 //   x = tile (-1: no more work), y = page, z = output row | TL_MSG_PADROW, w = b0 | b1 << 16
 constexpr int TL_MSG_PADROW = 1 << 30;
 
-// one output row for this thread's pixel pairs; XPAD: the tile has 114-valued columns
+// One output row.  Per iteration a warp covers 64 consecutive pixels and lane L computes pixels L (j = 0) and
+// 32 + L (j = 1): ADJACENT lanes read ADJACENT source pixels, so one LDS instruction of the warp spans half as
+// many shared-memory words as with a pixel pair per lane (the kernel's l1tex pipe was 92 % busy with 2.3
+// wavefronts per LDS).  The half2 pairs for the stores are formed by one exchange with the neighbouring lane:
+// even lanes store pixels (L, L+1), odd lanes store (32+L-1, 32+L).  XPAD: the chunk has 114-valued columns.
 template <int ITER, bool XPAD>
 __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const uint32_t (&xoff)[ITER][2],
                                           const uint32_t (&coef)[ITER][2], uint32_t b0, uint32_t b1,
-                                          uint32_t* pr, uint32_t* pg, uint32_t* pb, int out_w, int px0) {
+                                          uint32_t* pr, uint32_t* pg, uint32_t* pb, int out_w, int warp_px, int store_px,
+                                          uint32_t pair_sel) {
 #pragma unroll
   for (int i = 0; i < ITER; ++i) {
-    const int ox = i * TL_PAIR_STRIDE + px0;
-    if (ox < out_w) {
+    if (i * TL_PAIR_STRIDE + warp_px < out_w) {  // warp-uniform: the exchange below needs every lane
       // pg_vpass split in two: the 32-bit products of each source row (rounding +2 folded into the
       // row-0 product's addend), then both pixels of the pair finished 16 bits to a lane.
       uint32_t ab[2], ag[2], ar[2], bb[2], bg[2], br[2];
@@ -500,15 +504,20 @@ __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const ui
       }
       // BGR -> RGB planes
       // pr/pg/pb already point at this thread's first pixel pair of the row in each plane
-      __stcs(pr + i * (TL_PAIR_STRIDE / 2), vpass_pair_half2(ar, br));
-      __stcs(pg + i * (TL_PAIR_STRIDE / 2), vpass_pair_half2(ag, bg));
-      __stcs(pb + i * (TL_PAIR_STRIDE / 2), vpass_pair_half2(ab, bb));
+      const uint32_t vr = vpass_pair_half2(ar, br), vg = vpass_pair_half2(ag, bg), vb = vpass_pair_half2(ab, bb);
+      const uint32_t nr = __shfl_xor_sync(0xffffffffu, vr, 1), ng = __shfl_xor_sync(0xffffffffu, vg, 1),
+                     nb = __shfl_xor_sync(0xffffffffu, vb, 1);
+      if (i * TL_PAIR_STRIDE + store_px < out_w) {
+        __stcs(pr + i * (TL_PAIR_STRIDE / 2), __byte_perm(vr, nr, pair_sel));
+        __stcs(pg + i * (TL_PAIR_STRIDE / 2), __byte_perm(vg, ng, pair_sel));
+        __stcs(pb + i * (TL_PAIR_STRIDE / 2), __byte_perm(vb, nb, pair_sel));
+      }
     }
   }
 }
 
 template <int ITER, int TL_STAGES>
-__global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const TilerArgs a) {
+__global__ void __launch_bounds__(TL_THREADS, ITER <= 2 ? 4 : 2) tile_letterbox_kernel(const TilerArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[TL_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TL_STAGES];
@@ -598,7 +607,9 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
   // opaque to the optimiser: otherwise it re-derives each address from SR_CgaCtaId on every output row
   asm volatile("" : "+r"(smem_base), "+r"(full0), "+r"(empty0), "+r"(msg0));
   const uint32_t pad_pair = pack_unit_half2(TL_PAD_VALUE, TL_PAD_VALUE);
-  const int px0 = warp * 64 + lane * 2;
+  const int warp_px = warp * 64;                                              // first pixel of the warp's 64
+  const int store_px = warp_px + ((lane & 1) ? 31 + lane : lane);             // first pixel of the pair this lane stores
+  const uint32_t pair_sel = (lane & 1) ? 0x3276u : 0x5410u;                   // (nb.hi, own.hi) : (own.lo, nb.lo)
   uint32_t xoff[ITER][2], coef[ITER][2];
   int cached_tile = -1, cached_page = -1, out_w = 0, chunk_w = 0, chunk_x0 = 0, xpad = 0;
   int64_t plane_b = 0, out_off = 0;   // plane size in bytes
@@ -626,7 +637,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
       for (int i = 0; i < ITER; ++i) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int ox = i * TL_PAIR_STRIDE + px0 + j;
+          const int ox = i * TL_PAIR_STRIDE + warp_px + j * 32 + lane;
           uint2 e = make_uint2(0u, TL_PADMARK);
           if (ox < chunk_w) e = __ldg(&a.xtab[xtab_off + ox]);
           xoff[i][j] = pack_xoff(e.x + skew);
@@ -637,7 +648,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
     if (m.y != cached_page) {
       cached_page = m.y;
       __half* page_out = a.page_desc ? a.page_desc[m.y].out : a.out + (int64_t)m.y * a.out_page_stride;
-      tile_ptr = reinterpret_cast<uint8_t*>(page_out + out_off) + (chunk_x0 + px0) * 2;
+      tile_ptr = reinterpret_cast<uint8_t*>(page_out + out_off) + (chunk_x0 + store_px) * 2;
     }
     const int oy = m.z & ~TL_MSG_PADROW;
     uint32_t* pr = reinterpret_cast<uint32_t*>(tile_ptr + (uint64_t)((uint32_t)oy * row_b));  // a plane is < 4 GB
@@ -646,7 +657,7 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
     if (m.z & TL_MSG_PADROW) {
 #pragma unroll
       for (int i = 0; i < ITER; ++i) {
-        if (i * TL_PAIR_STRIDE + px0 < chunk_w) {
+        if (i * TL_PAIR_STRIDE + store_px < chunk_w) {
           __stcs(pr + i * (TL_PAIR_STRIDE / 2), pad_pair);
           __stcs(pg + i * (TL_PAIR_STRIDE / 2), pad_pair);
           __stcs(pb + i * (TL_PAIR_STRIDE / 2), pad_pair);
@@ -656,8 +667,8 @@ __global__ void __launch_bounds__(TL_THREADS, 2) tile_letterbox_kernel(const Til
       const uint32_t b0 = (uint32_t)m.w & 0xFFFFu, b1 = (uint32_t)m.w >> 16;
       const uint32_t row0 = smem_base + stage * stage_bytes;
       const uint32_t row1 = row0 + (uint32_t)a.row_stride;
-      if (xpad) tiler_row<ITER, true>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, px0);
-      else tiler_row<ITER, false>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, px0);
+      if (xpad) tiler_row<ITER, true>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, warp_px, store_px, pair_sel);
+      else tiler_row<ITER, false>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, warp_px, store_px, pair_sel);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + stage * 8u);

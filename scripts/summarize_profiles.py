@@ -36,16 +36,66 @@ def launches():
     return "\n".join(out), agg, total, len(rows), sum(mine.values()) / total
 
 
-def raw_metrics():
-    rep = os.path.join(SRC, "tiler_full.ncu-rep")
+def raw_rows(name):
+    """One dict {metric: (value, unit)} per captured launch of gpurun_out/prof/<name>.ncu-rep ([] if absent)."""
+    rep = os.path.join(SRC, name + ".ncu-rep")
+    if not os.path.exists(rep):
+        return []
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    return {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
+    hdr, units = rows[0], rows[1]
+    return [{h: (v[i], units[i]) for i, h in enumerate(hdr)} for v in rows[2:] if len(v) == len(hdr)]
+
+
+def raw_metrics():
+    return raw_rows("tiler_full")[0]
+
+
+MERGE_KEYS = [
+    "gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__grid_size", "launch__block_size",
+    "launch__registers_per_thread", "launch__waves_per_multiprocessor", "smsp__inst_executed.sum",
+    "dram__bytes_read.sum", "dram__bytes_write.sum",
+]
+
+
+def merge_profile():
+    """cfg4 merge kernels (ncu --set full of one pg_nms_merge call): SM / L1 throughput per kernel."""
+    rows = raw_rows("merge_full")
+    if not rows:
+        return
+    plain = None
+    try:
+        plain = json.load(open(os.path.join(SRC, "merge_plain.json")))
+    except Exception:
+        pass
+    with open(os.path.join(DST, f"{TAG}_merge_ncu_full.md"), "w") as f:
+        f.write(f"# {TAG}: cfg4 merge (`pg_nms_merge`, 8 pages x 100 000 boxes) — ncu --set full --clock-control none, one call\n\n")
+        f.write("Command: `python scripts/bench_merge_stress.py` (the five kernels of the fourth call; the three before it are warm-up).\n"
+                "The merge is bound by SM issue (fp64 compares in the mask kernel) and shared-memory/L1 traffic, not by HBM: the\n"
+                "whole input is 4.8 MB per page.  Durations under ncu are cold-cache and serialised.\n\n")
+        if plain:
+            f.write(f"Same command without ncu: `{json.dumps(plain)}`\n\n")
+        names = [re.sub(r"\(.*", "", r["Kernel Name"][0]) for r in rows]
+        f.write("| metric | " + " | ".join(f"`{n}`" for n in names) + " | unit |\n|---|" + "---:|" * len(names) + "---|\n")
+        for k in MERGE_KEYS:
+            if any(k in r for r in rows):
+                f.write(f"| `{k}` | " + " | ".join(r.get(k, ("", ""))[0] for r in rows) + f" | {next(r[k][1] for r in rows if k in r)} |\n")
+        f.write("\nTop warp stall reasons per issue-active cycle:\n\n")
+        for n, r in zip(names, rows):
+            st = sorted(((float(v[0].replace(",", "")), k.split("issue_stalled_")[1].split("_per")[0]) for k, v in r.items()
+                         if "issue_stalled" in k and "per_issue_active" in k and v[0]), reverse=True)[:5]
+            f.write(f"* `{n}`: " + ", ".join(f"{nm} {v:.2f}" for v, nm in st) + "\n")
 
 
 def main():
     os.makedirs(DST, exist_ok=True)
+    merge_profile()
     table, agg, total, n_launch, _ = launches()
     m = raw_metrics()
 

@@ -5,8 +5,13 @@
 // shard.  None of them is HBM-bound (a page's boxes are a few hundred KB); they are organised
 // so that the dependent chain per page is short and pages run side by side on different SMs.
 #include <cfloat>
+#include <cstdlib>
+
+#include <cooperative_groups.h>
 
 #include "pg_common.cuh"
+
+namespace cg = cooperative_groups;
 
 // =============================================================================================
 // K2 — edge-touch filter (+ fused cell->page translation)
@@ -89,6 +94,10 @@ extern "C" int pg_edge_filter(const double* boxes, int32_t boxes_are_local, cons
 //               box, typical depth is 3-6 rounds;
 //   F  emit     sort the kept boxes by priority (normalised bitonic network in shared memory,
 //               global-memory network for > 8192 survivors) and write global indices in pick order.
+// Pages of >= 32 768 boxes (cfg4: 100 000) would leave E and F on one CTA per page; when the pages
+// of a launch number fewer than the SMs, E and F instead run on one thread-block CLUSTER per page
+// (up to 8 CTAs, cluster barrier between rounds / network stages, flags and counts exchanged
+// through distributed shared memory): nms_resolve_cluster_kernel, nms_emit_cluster_kernel.
 // =============================================================================================
 constexpr int NMS_GY = 128;     // y cells (7-bit digit)
 constexpr int NMS_GX_MAX = 64;  // x strips (6-bit digit), chosen per page from the mean box width
@@ -589,6 +598,115 @@ __global__ void __launch_bounds__(1024) nms_resolve_kernel(const int64_t* __rest
   }
 }
 
+// ---- E (large pages): resolve on one thread-block cluster per page ---------------------------
+// The same Jacobi rounds, the page's blocks dealt round-robin to the warps of all CTAs of the cluster.
+// A round reads only the state words of the previous round (double-buffered), so one cluster barrier
+// per round orders everything; the state lives in global memory behind volatile (L1-bypassing)
+// accesses, the per-round "anything still undecided" flags and the final per-CTA counts travel
+// through distributed shared memory.
+constexpr int NMS_CLUSTER_MAX = 8;
+
+__global__ void __launch_bounds__(1024) nms_resolve_cluster_kernel(const int64_t* __restrict__ page_off,
+                                                                   const int32_t* __restrict__ n_sel, NmsWs ws,
+                                                                   int32_t* __restrict__ n_kept) {
+  __shared__ int scan_smem[34];
+  __shared__ int pend_x[2][NMS_CLUSTER_MAX];  // [round parity][CTA rank]
+  __shared__ int tot_x[NMS_CLUSTER_MAX];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int csize = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int p = blockIdx.x / csize, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const PageSpan sp = page_span(page_off, n_sel, p);
+  if (ws.stats[0] != PG_OK) {  // the same word for every CTA of the cluster: all of them leave here
+    if (rank == 0 && tid == 0) n_kept[p] = -1;
+    return;
+  }
+  volatile uint32_t* kept = ws.st_kept;
+  volatile uint32_t* undec = ws.st_undec;
+  const int64_t nbc = ws.nb_cap;
+  for (int b = rank * (int)blockDim.x + tid; b < sp.nb; b += csize * (int)blockDim.x) {
+    const int valid = min(32, sp.m - b * 32);
+    undec[sp.blk0 + b] = valid >= 32 ? 0xffffffffu : ((1u << valid) - 1u);
+    kept[sp.blk0 + b] = 0u;
+  }
+  __threadfence();
+  cluster.sync();
+  int cur = 0, rounds = 0;
+  while (true) {
+    const int64_t rc = (int64_t)cur * nbc, rn = (int64_t)(cur ^ 1) * nbc;
+    int pending = 0;
+    for (int b = rank * nwarps + warp; b < sp.nb; b += csize * nwarps) {
+      const int64_t I = sp.blk0 + b;
+      const uint32_t u = undec[rc + I], k = kept[rc + I];
+      if (u == 0u) {
+        if (lane == 0) { undec[rn + I] = 0u; kept[rn + I] = k; }
+        continue;
+      }
+      const bool mine = (u >> lane) & 1u;
+      bool sup = false, wait = false;
+      const int64_t e0 = ws.cand_off[I], e1 = e0 + ws.cand_cnt[I];
+      for (int64_t e = e0; e < e1; ++e) {
+        const int jbk = ws.ent_j[e];
+        if (jbk < 0) continue;
+        const uint32_t m = mine ? ws.ent_mask[e * 32 + lane] : 0u;
+        const uint32_t kj = kept[rc + jbk], uj = undec[rc + jbk];
+        if (m & kj) sup = true;
+        else if (m & uj) wait = true;
+      }
+      const unsigned bk = __ballot_sync(0xffffffffu, mine && !sup && !wait);
+      const unsigned bs = __ballot_sync(0xffffffffu, mine && sup);
+      const uint32_t un = u & ~(bk | bs);
+      if (lane == 0) { kept[rn + I] = k | bk; undec[rn + I] = un; }
+      pending |= (un != 0u);
+    }
+    const int any_local = __syncthreads_or(pending);
+    const int par = rounds & 1;
+    if (tid < csize) *cluster.map_shared_rank(&pend_x[par][rank], tid) = any_local;
+    __threadfence();
+    cluster.sync();
+    int any = 0;
+    for (int q = 0; q < csize; ++q) any |= pend_x[par][q];
+    cur ^= 1;
+    ++rounds;
+    if (!any) break;
+  }
+  // compact the kept boxes into (score, position) lists: CTA r owns a contiguous range of blocks
+  const int64_t rc = (int64_t)cur * nbc;
+  const int per = (sp.nb + csize - 1) / csize;
+  const int lo = min(sp.nb, rank * per), hi = min(sp.nb, lo + per);
+  int cnt = 0;
+  for (int b = lo + tid; b < hi; b += blockDim.x) cnt += __popc(kept[rc + sp.blk0 + b]);
+  int mine_total;
+  pg_block_exscan(cnt, scan_smem, &mine_total);
+  if (tid < csize) *cluster.map_shared_rank(&tot_x[rank], tid) = mine_total;
+  cluster.sync();
+  int running = 0, all = 0;
+  for (int q = 0; q < csize; ++q) {
+    if (q < rank) running += tot_x[q];
+    all += tot_x[q];
+  }
+  for (int b0 = lo; b0 < hi; b0 += blockDim.x) {
+    const int b = b0 + tid;
+    const uint32_t k = b < hi ? kept[rc + sp.blk0 + b] : 0u;
+    int total;
+    const int ex = pg_block_exscan(__popc(k), scan_smem, &total);
+    uint32_t bits = k;
+    int64_t dst = sp.base + running + ex;
+    while (bits) {
+      const int l = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const SBox* sb = ws.sbox + (sp.blk0 + b) * 32 + l;
+      ws.kscore[dst] = sb->score;
+      ws.kpos[dst] = (int32_t)sb->k;
+      ++dst;
+    }
+    running += total;
+  }
+  if (rank == 0 && tid == 0) {
+    n_kept[p] = all;
+    atomicMax((unsigned long long*)&ws.stats[2], (unsigned long long)rounds);
+  }
+}
+
 // ---- F: emit -------------------------------------------------------------------------------
 constexpr int EMIT_SMEM_ELEMS = 8192;
 
@@ -655,6 +773,158 @@ __global__ void __launch_bounds__(1024) nms_emit_kernel(const int32_t* __restric
   }
 }
 
+// ---- F (large pages): emit on one thread-block cluster per page -------------------------------
+// The same normalised bitonic network on K > 8192 survivors, cut at chunks of EMIT_SMEM_ELEMS:
+// every step whose partner distance stays inside a chunk runs in shared memory (each CTA owns the
+// chunks rank, rank + csize, ...), the few steps that cross chunks run on the L2-resident arrays with
+// all CTAs of the cluster sharing the comparators; a cluster barrier separates the stages.  Elements at
+// or above K are virtual +inf: a comparator (i, pr) has i < pr and is skipped when pr >= K.
+__device__ __forceinline__ void emit_cswap_global(unsigned long long* keys, int32_t* idx, int i, int pr) {
+  const unsigned long long a = __ldcg(keys + i), b = __ldcg(keys + pr);
+  const int32_t ia = __ldcg(idx + i), ib = __ldcg(idx + pr);
+  if (b < a || (b == a && ib < ia)) {
+    __stcg(keys + i, b); __stcg(keys + pr, a); __stcg(idx + i, ib); __stcg(idx + pr, ia);
+  }
+}
+
+__global__ void __launch_bounds__(1024) nms_emit_cluster_kernel(const int32_t* __restrict__ sel_idx,
+                                                                const int64_t* __restrict__ page_off, NmsWs ws,
+                                                                const int32_t* __restrict__ n_kept,
+                                                                int32_t* __restrict__ kept_idx) {
+  extern __shared__ __align__(16) unsigned char emit_smem[];
+  constexpr int CH = EMIT_SMEM_ELEMS;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int csize = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int p = blockIdx.x / csize, tid = threadIdx.x;
+  const int K = n_kept[p];  // the same for every CTA of the cluster
+  if (K <= 0) return;
+  const int64_t base = page_off[p];
+  int n2 = 1;
+  while (n2 < K) n2 <<= 1;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(emit_smem);
+  int32_t* idx = reinterpret_cast<int32_t*>(emit_smem + (size_t)CH * 8);
+  unsigned long long* gkeys = reinterpret_cast<unsigned long long*>(ws.kscore + base);
+  int32_t* gidx = ws.kpos + base;
+  if (n2 <= CH) {  // few survivors on this page: one CTA, no cluster barrier on this path for anyone
+    if (rank != 0) return;
+    for (int i = tid; i < K; i += blockDim.x) { keys[i] = score_desc_key(ws.kscore[base + i]); idx[i] = ws.kpos[base + i]; }
+    __syncthreads();
+    bitonic_sort_pairs(keys, idx, K, n2);
+    for (int i = tid; i < K; i += blockDim.x) {
+      const int k = idx[i];
+      kept_idx[base + i] = sel_idx ? sel_idx[base + k] : (int32_t)(base + k);
+    }
+    return;
+  }
+  const int nch = n2 / CH;
+  // stage 0: every chunk sorted on its own (k = 2 .. CH), scores turned into sortable keys on the way in
+  for (int c = rank; c < nch; c += csize) {
+    const int cb = c * CH;
+    if (cb >= K) break;
+    const int kc = min(CH, K - cb);
+    for (int i = tid; i < kc; i += blockDim.x) { keys[i] = score_desc_key(ws.kscore[base + cb + i]); idx[i] = gidx[cb + i]; }
+    __syncthreads();
+    bitonic_sort_pairs(keys, idx, kc, CH);
+    for (int i = tid; i < kc; i += blockDim.x) { __stcg(gkeys + cb + i, keys[i]); __stcg(gidx + cb + i, idx[i]); }
+    __syncthreads();
+  }
+  __threadfence();
+  cluster.sync();
+  for (int k = 2 * CH; k <= n2; k <<= 1) {
+    // steps that cross chunks: all CTAs of the cluster, straight on the workspace arrays
+    for (int j = k >> 1; j >= CH; j >>= 1) {
+      for (int t = rank * (int)blockDim.x + tid; t < (n2 >> 1); t += csize * (int)blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int pr = (j == (k >> 1)) ? (i ^ (k - 1)) : (i ^ j);
+        if (pr < K) emit_cswap_global(gkeys, gidx, i, pr);
+      }
+      __threadfence();
+      cluster.sync();
+    }
+    // the remaining steps j = CH/2 .. 1 stay inside a chunk
+    const bool last = (k == n2);
+    for (int c = rank; c < nch; c += csize) {
+      const int cb = c * CH;
+      if (cb >= K) break;
+      const int kc = min(CH, K - cb);
+      for (int i = tid; i < kc; i += blockDim.x) { keys[i] = __ldcg(gkeys + cb + i); idx[i] = __ldcg(gidx + cb + i); }
+      __syncthreads();
+      for (int j = CH >> 1; j > 0; j >>= 1) {
+        for (int t = tid; t < (CH >> 1); t += blockDim.x) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const int pr = i ^ j;
+          if (pr < kc) {
+            const unsigned long long a = keys[i], b = keys[pr];
+            const int32_t ia = idx[i], ib = idx[pr];
+            if (b < a || (b == a && ib < ia)) { keys[i] = b; keys[pr] = a; idx[i] = ib; idx[pr] = ia; }
+          }
+        }
+        __syncthreads();
+      }
+      if (last) {
+        for (int i = tid; i < kc; i += blockDim.x) {
+          const int kk = idx[i];
+          kept_idx[base + cb + i] = sel_idx ? sel_idx[base + kk] : (int32_t)(base + kk);
+        }
+      } else {
+        for (int i = tid; i < kc; i += blockDim.x) { __stcg(gkeys + cb + i, keys[i]); __stcg(gidx + cb + i, idx[i]); }
+      }
+      __syncthreads();
+    }
+    if (!last) {
+      __threadfence();
+      cluster.sync();
+    }
+  }
+}
+
+// Cluster width for the resolve/emit pair of a launch: 1 = one CTA per page (the default kernels).
+// Clusters pay off when a page is large and the launch has fewer pages than SMs.
+static int nms_cluster_width(int32_t n_pages, int32_t max_boxes_per_page, int sms, int emit_smem) {
+  int min_boxes = 32768;
+  if (const char* e = getenv("PG_NMS_CLUSTER_MIN_BOXES")) min_boxes = atoi(e);  // test / tuning knob; <= 0 disables
+  if (min_boxes <= 0 || max_boxes_per_page < min_boxes) return 1;
+  int c = NMS_CLUSTER_MAX;
+  while (c > 1 && (int64_t)n_pages * c > sms) c >>= 1;
+  if (c == 1) return 1;
+  // the device must be able to co-schedule such a cluster (1024 threads and the emit ring per CTA)
+  static int launchable[NMS_CLUSTER_MAX + 1] = {0};  // 0 unknown, 1 yes, -1 no
+  if (launchable[c] == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)c);
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = (size_t)emit_smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n1 = 0, n2 = 0;
+    const cudaError_t e1 = cudaOccupancyMaxActiveClusters(&n1, nms_emit_cluster_kernel, &cfg);
+    cfg.dynamicSmemBytes = 0;
+    const cudaError_t e2 = cudaOccupancyMaxActiveClusters(&n2, nms_resolve_cluster_kernel, &cfg);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) cudaGetLastError();
+    launchable[c] = (e1 == cudaSuccess && e2 == cudaSuccess && n1 > 0 && n2 > 0) ? 1 : -1;
+  }
+  return launchable[c] > 0 ? c : 1;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cluster(void (*kernel)(KArgs...), int n_pages, int width, size_t smem, cudaStream_t s,
+                                  Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_pages * width));
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)width; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 extern "C" int pg_nms_merge(const double* boxes, const double* scores, const double* classes,
                             const int32_t* sel_idx, const int64_t* page_off, const int32_t* n_sel,
                             int32_t n_pages, int64_t n_boxes, int32_t max_boxes_per_page, double iou_threshold,
@@ -669,7 +939,6 @@ extern "C" int pg_nms_merge_ex(const double* boxes, const double* scores, const 
                                int32_t n_pages, int64_t n_boxes, int32_t max_boxes_per_page, double iou_threshold,
                                int32_t mode, int32_t* kept_idx, int32_t* n_kept, void* workspace,
                                size_t workspace_bytes, void* stream) {
-  (void)max_boxes_per_page;
   PG_REQUIRE(n_pages >= 0 && n_boxes >= 0, "sizes");
   PG_REQUIRE((mode & ~(PG_NMS_CLASS_AGNOSTIC | PG_NMS_FP32)) == 0, "mode");
   if (n_pages == 0) return PG_OK;
@@ -692,6 +961,7 @@ extern "C" int pg_nms_merge_ex(const double* boxes, const double* scores, const 
   cudaStream_t s = (cudaStream_t)stream;
   const int emit_smem = EMIT_SMEM_ELEMS * 12;
   PG_CUDA_TRY(cudaFuncSetAttribute(nms_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem));
+  PG_CUDA_TRY(cudaFuncSetAttribute(nms_emit_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem));
   PG_CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 8 * sizeof(int64_t), s));
   const int all_pairs = !(iou_threshold >= 0.0);  // thr < 0: disjoint boxes (IoU 0) suppress too
   nms_bin_kernel<<<n_pages, 1024, 0, s>>>(boxes, scores, classes, sel_idx, page_off, n_sel, n_pages, ws);
@@ -709,6 +979,13 @@ extern "C" int pg_nms_merge_ex(const double* boxes, const double* scores, const 
   const unsigned mask_grid = (unsigned)(mask_want < mask_slots ? (mask_want < 1 ? 1 : mask_want) : mask_slots);
   nms_mask_kernel<<<mask_grid, 256, 0, s>>>(ws, iou_threshold);
   PG_LAUNCH_CHECK();
+  const int width = nms_cluster_width(n_pages, max_boxes_per_page, sms, emit_smem);
+  if (width > 1) {
+    PG_CUDA_TRY(launch_cluster(nms_resolve_cluster_kernel, n_pages, width, 0, s, page_off, n_sel, ws, n_kept));
+    PG_CUDA_TRY(launch_cluster(nms_emit_cluster_kernel, n_pages, width, (size_t)emit_smem, s, sel_idx, page_off, ws,
+                               (const int32_t*)n_kept, kept_idx));
+    return PG_OK;
+  }
   nms_resolve_kernel<<<n_pages, 1024, 0, s>>>(page_off, n_sel, ws, n_kept);
   PG_LAUNCH_CHECK();
   nms_emit_kernel<<<n_pages, 1024, emit_smem, s>>>(sel_idx, page_off, ws, n_kept, kept_idx);

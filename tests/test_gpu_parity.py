@@ -357,6 +357,82 @@ def test_nms_dense_stress_100k_boxes():
     assert int(n2[0].item()) == len(ref) and np.array_equal(kept2[: len(ref)].cpu().numpy(), np.arange(len(ref)))
 
 
+def _pooled(cfgs, dups=3):
+    bs, ss, cs, off = [], [], [], [0]
+    for (w, h, r, c, n, seed) in cfgs:
+        d = synth.page_detections(w, h, r, c, 20.0, n, seed, dups=dups)
+        bs.append(d["boxes_local"] + d["cells"][d["box_cell"]][:, [0, 1, 0, 1]] if n else np.zeros((0, 4)))
+        ss.append(d["scores"]); cs.append(d["classes"]); off.append(off[-1] + n)
+    return np.concatenate(bs), np.concatenate(ss), np.concatenate(cs), off
+
+
+@pytest.mark.parametrize("name,cfgs,dups,oracle_pages", [
+    # six pages incl. an empty and a one-box page: width 8, every page below 8192 survivors (rank-0 emit path)
+    ("mixed", [(8000, 6000, 4, 4, 10000, 31), (3801, 5601, 2, 2, 2000, 32), (2000, 2000, 2, 2, 1, 33),
+               (2778, 4187, 3, 3, 3333, 34), (640, 480, 1, 1, 0, 35), (4000, 5443, 2, 2, 33, 36)], 3, [0, 2, 3, 4]),
+    # one page whose survivors need two 8192-element chunks
+    ("two_chunks", [(8000, 6000, 4, 4, 30000, 41)], 3, [0]),
+    # three large pages side by side, 8 CTAs each
+    ("three_pages", [(8000, 6000, 4, 4, 40000, 42), (8000, 6000, 4, 4, 50000, 43), (6000, 8000, 3, 3, 35000, 44)], 6, []),
+    # > 65536 survivors: 16 chunks over 8 CTAs (two chunks per CTA); a lattice of disjoint boxes plus duplicates
+    ("sixteen_chunks", None, 1, []),
+    # 30 pages: the cluster narrows to 4 CTAs so that the launch still fits the SMs
+    ("width4", [(4000, 3000, 2, 2, 3000 + 37 * i, 50 + i) for i in range(30)], 3, [7]),
+])
+def test_nms_cluster_kernels_equal_single_cta_kernels(name, cfgs, dups, oracle_pages, monkeypatch):
+    """Resolve/emit on one thread-block cluster per page (taken for pages of >= 32768 boxes; forced here through
+    PG_NMS_CLUSTER_MIN_BOXES) against the one-CTA-per-page kernels, and against the oracle on some pages."""
+    if cfgs is None:
+        rng = np.random.default_rng(46)
+        gx, gy = np.meshgrid(np.arange(300) * 26.0, np.arange(300) * 20.0)
+        lat = np.stack([gx.ravel(), gy.ravel(), gx.ravel() + 18.0, gy.ravel() + 12.0], 1)
+        dup = lat[rng.choice(len(lat), 30000, replace=False)] + rng.normal(0, 0.7, (30000, 4))
+        boxes = np.concatenate([lat, dup]).astype(np.float32).astype(np.float64)
+        boxes = boxes[rng.permutation(len(boxes))]
+        scores = rng.uniform(0.1, 0.99, len(boxes)).astype(np.float32).astype(np.float64)
+        scores[5000:5600] = scores[5000]
+        classes = rng.integers(0, 3, len(boxes)).astype(np.float64)
+        off, cfgs = [0, len(boxes)], [None]
+    else:
+        boxes, scores, classes, off = _pooled(cfgs, dups)
+    if name == "mixed":
+        scores[100:140] = scores[100]
+    mx = int(np.diff(off).max())
+    out = {}
+    for knob in ("0", "1"):
+        monkeypatch.setenv("PG_NMS_CLUSTER_MIN_BOXES", knob)
+        ws = ops.NmsWorkspace(len(boxes), len(cfgs), pairs_per_block=96)
+        kept, n_kept, ws = ops.nms_merge(boxes, scores, classes, off, 0.5, max_boxes_per_page=mx, workspace=ws)
+        assert ws.stats()["status"] == 0
+        out[knob] = (kept.cpu().numpy(), n_kept.cpu().numpy(), ws.stats()["rounds"])
+    (k0, n0, r0), (k1, n1, r1) = out["0"], out["1"]
+    assert np.array_equal(n0, n1) and r0 == r1
+    for i in range(len(cfgs)):
+        assert np.array_equal(k0[off[i]: off[i] + n0[i]], k1[off[i]: off[i] + n1[i]]), (name, i)
+    if name == "sixteen_chunks":
+        assert n1[0] > 65536
+    if name == "two_chunks":
+        assert 8192 < n1[0] <= 16384
+    for i in oracle_pages:
+        sl = slice(off[i], off[i + 1])
+        ref = nms_pick_order_c(boxes[sl], scores[sl], classes[sl], 0.5)
+        assert n1[i] == len(ref) and np.array_equal(k1[off[i]: off[i] + n1[i]] - off[i], ref), (name, i)
+
+
+def test_nms_cluster_kernels_report_workspace_overflow(monkeypatch):
+    monkeypatch.setenv("PG_NMS_CLUSTER_MIN_BOXES", "1")
+    n = 3000
+    boxes = np.tile(np.array([[10.0, 10.0, 50.0, 60.0]]), (n, 1))
+    scores = np.linspace(0.9, 0.1, n)
+    classes = (np.arange(n) % 3).astype(np.float64)
+    ws = ops.NmsWorkspace(n, 1, pairs_per_block=128)
+    kept, n_kept, ws = ops.nms_merge(boxes, scores, classes, [0, n], 0.5, max_boxes_per_page=n, workspace=ws)
+    assert ws.stats()["status"] == 0 and kept[: int(n_kept[0].item())].cpu().numpy().tolist() == [0, 1, 2]
+    small = ops.NmsWorkspace(n, 1, pairs_per_block=2)
+    _, n_kept2, small = ops.nms_merge(boxes, scores, classes, [0, n], 0.5, max_boxes_per_page=n, workspace=small)
+    assert small.stats()["status"] == 3 and int(n_kept2[0].item()) == -1
+
+
 def test_nms_adversarial_identical_boxes_and_workspace_overflow():
     n = 3000
     boxes = np.tile(np.array([[10.0, 10.0, 50.0, 60.0]]), (n, 1))

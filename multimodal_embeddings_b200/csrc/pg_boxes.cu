@@ -101,6 +101,7 @@ extern "C" int pg_edge_filter(const double* boxes, int32_t boxes_are_local, cons
 // =============================================================================================
 constexpr int NMS_GY = 128;     // y cells (7-bit digit)
 constexpr int NMS_GX_MAX = 64;  // x strips (6-bit digit), chosen per page from the mean box width
+constexpr int NMS_CLUSTER_MAX = 8;  // CTAs per page when a launch has few, large pages
 
 struct __align__(16) SBox {  // one box in spatial order
   double x0, y0, x1, y1;
@@ -257,6 +258,11 @@ __device__ __forceinline__ void block_stable_pass(int m, int* hist, int* scan_sm
 }
 
 // ---- A: bin --------------------------------------------------------------------------------
+__device__ __forceinline__ void nms_blocked_copy(const double* __restrict__ boxes, const double* __restrict__ scores,
+                                                 const double* __restrict__ classes, const int32_t* __restrict__ sel_idx,
+                                                 const PageSpan& sp, const int32_t* sorted, const NmsWs& ws, int p,
+                                                 int wfirst, int wstride);
+
 __global__ void __launch_bounds__(1024) nms_bin_kernel(const double* __restrict__ boxes,
                                                        const double* __restrict__ scores,
                                                        const double* __restrict__ classes,
@@ -323,7 +329,17 @@ __global__ void __launch_bounds__(1024) nms_bin_kernel(const double* __restrict_
                                 [cellid](int e) { return cellid[e] >> 7; }, sorted);
 
   // blocked copy + block bounding boxes
-  for (int b = warp; b < sp.nb; b += (blockDim.x >> 5)) {
+  nms_blocked_copy(boxes, scores, classes, sel_idx, sp, sorted, ws, p, warp, blockDim.x >> 5);
+}
+
+// Blocked AoS copy of a page in spatial order + block / sub-block bounding boxes; block b is handled by the
+// warp whose index is congruent to b modulo `wstride` (the warps of one CTA, or of all CTAs of a cluster).
+__device__ __forceinline__ void nms_blocked_copy(const double* __restrict__ boxes, const double* __restrict__ scores,
+                                                 const double* __restrict__ classes, const int32_t* __restrict__ sel_idx,
+                                                 const PageSpan& sp, const int32_t* sorted, const NmsWs& ws, int p,
+                                                 int wfirst, int wstride) {
+  const int lane = threadIdx.x & 31;
+  for (int b = wfirst; b < sp.nb; b += wstride) {
     const int pos = b * 32 + lane;
     const bool valid = pos < sp.m;
     SBox sb;
@@ -359,6 +375,150 @@ __global__ void __launch_bounds__(1024) nms_bin_kernel(const double* __restrict_
     }
     if ((lane & 7) == 0) ws.subbox[(sp.blk0 + b) * 4 + (lane >> 3)] = make_float4(gx0, gy0, gx1, gy1);
   }
+}
+
+// ---- A (large pages): bin on one thread-block cluster per page --------------------------------
+// One stable counting-sort pass over the cluster: global warp g = rank * 32 + warp owns a contiguous chunk
+// of the input, so (digit, g, position) order == (digit, input order).  Each CTA publishes its per-digit
+// totals to every CTA of the cluster through distributed shared memory; the bases follow locally.
+template <int NDIG, typename ElemOf, typename DigitOf>
+__device__ __forceinline__ void cluster_stable_pass(cg::cluster_group& cluster, int csize, int rank, int m, int* hist,
+                                                    int* all_tot, int* scan_smem, ElemOf elem, DigitOf digit,
+                                                    int32_t* dst) {
+  static_assert(NDIG <= 1024, "one thread per digit");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 32 * NDIG; i += 1024) hist[i] = 0;
+  __syncthreads();
+  const int tw = csize * 32;
+  const int chunk = (((m + tw - 1) / tw) + 31) & ~31;
+  const int lo = min(m, (rank * 32 + warp) * chunk), hi = min(m, lo + chunk);
+  for (int i = lo + lane; i < hi; i += 32) atomicAdd(&hist[warp * NDIG + digit(elem(i))], 1);
+  __syncthreads();
+  if (tid < NDIG) {
+    int t = 0;
+    for (int w = 0; w < 32; ++w) t += hist[w * NDIG + tid];
+    for (int q = 0; q < csize; ++q) *cluster.map_shared_rank(&all_tot[rank * NDIG + tid], q) = t;
+  }
+  cluster.sync();
+  {
+    int v = 0, before = 0;
+    if (tid < NDIG) {
+      for (int q = 0; q < csize; ++q) {
+        const int t = all_tot[q * NDIG + tid];
+        v += t;
+        if (q < rank) before += t;
+      }
+    }
+    int total;
+    const int ex = pg_block_exscan(v, scan_smem, &total);  // digit bases of the whole page
+    if (tid < NDIG) {
+      int running = ex + before;
+      for (int w = 0; w < 32; ++w) {
+        const int t = hist[w * NDIG + tid];
+        hist[w * NDIG + tid] = running;
+        running += t;
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = lo; c < hi; c += 32) {
+    const int i = c + lane;
+    const bool act = i < hi;
+    const int e = act ? elem(i) : 0;
+    const int d = act ? digit(e) : -1 - lane;
+    const unsigned grp = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(grp) - 1;
+    const int rk = __popc(grp & ((1u << lane) - 1u));
+    int basepos = 0;
+    if (act && lane == leader) {
+      basepos = hist[warp * NDIG + d];
+      hist[warp * NDIG + d] = basepos + __popc(grp);
+    }
+    basepos = __shfl_sync(0xffffffffu, basepos, leader);
+    if (act) dst[basepos + rk] = e;
+    __syncwarp();
+  }
+  __threadfence();
+  cluster.sync();  // dst complete and visible to the whole cluster; all_tot free for the next pass
+}
+
+__global__ void __launch_bounds__(1024) nms_bin_cluster_kernel(const double* __restrict__ boxes,
+                                                               const double* __restrict__ scores,
+                                                               const double* __restrict__ classes,
+                                                               const int32_t* __restrict__ sel_idx,
+                                                               const int64_t* __restrict__ page_off,
+                                                               const int32_t* __restrict__ n_sel, int n_pages, NmsWs ws) {
+  __shared__ int hist[32 * NMS_GY];
+  __shared__ int all_tot[NMS_CLUSTER_MAX * NMS_GY];
+  __shared__ double red[5][32];
+  __shared__ double ext_x[NMS_CLUSTER_MAX][5];
+  __shared__ int scan_smem[34];
+  static_assert(NMS_GX_MAX <= NMS_GY, "hist / all_tot are sized for the wider digit");
+  cg::cluster_group cluster = cg::this_cluster();
+  const int csize = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int p = blockIdx.x / csize, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ctid = rank * (int)blockDim.x + tid, cthreads = csize * (int)blockDim.x;
+  const PageSpan sp = page_span(page_off, n_sel, p);
+  const int64_t blk_next = (p + 1 < n_pages) ? (page_off[p + 1] >> 5) + p + 1 : ws.nb_cap;
+  for (int64_t b = sp.blk0 + sp.nb + ctid; b < blk_next; b += cthreads) ws.blk_page[b] = -1;
+
+  // extent of the box centres and mean box width
+  double mnx = DBL_MAX, mny = DBL_MAX, mxx = -DBL_MAX, mxy = -DBL_MAX, sw = 0.0;
+  for (int k = ctid; k < sp.m; k += cthreads) {
+    const int64_t gi = sel_idx ? (int64_t)sel_idx[sp.base + k] : sp.base + k;
+    const double2 a = *reinterpret_cast<const double2*>(boxes + 4 * gi);
+    const double2 b = *reinterpret_cast<const double2*>(boxes + 4 * gi + 2);
+    const double cx = (a.x + b.x) * 0.5, cy = (a.y + b.y) * 0.5;
+    mnx = fmin(mnx, cx); mxx = fmax(mxx, cx); mny = fmin(mny, cy); mxy = fmax(mxy, cy);
+    sw += fabs(b.x - a.x);
+  }
+  mnx = warp_min_d(mnx); mny = warp_min_d(mny); mxx = warp_max_d(mxx); mxy = warp_max_d(mxy); sw = warp_sum_d(sw);
+  if (lane == 0) { red[0][warp] = mnx; red[1][warp] = mny; red[2][warp] = mxx; red[3][warp] = mxy; red[4][warp] = sw; }
+  __syncthreads();
+  if (warp == 0) {
+    const double a = warp_min_d(red[0][lane]), b = warp_min_d(red[1][lane]);
+    const double c = warp_max_d(red[2][lane]), d = warp_max_d(red[3][lane]), e = warp_sum_d(red[4][lane]);
+    if (lane == 0) { red[0][0] = a; red[1][0] = b; red[2][0] = c; red[3][0] = d; red[4][0] = e; }
+  }
+  __syncthreads();
+  if (tid < 5 * csize) *cluster.map_shared_rank(&ext_x[rank][tid % 5], tid / 5) = red[tid % 5][0];
+  cluster.sync();
+  mnx = ext_x[0][0]; mny = ext_x[0][1]; mxx = ext_x[0][2]; mxy = ext_x[0][3];
+  double sw_all = ext_x[0][4];
+  for (int q = 1; q < csize; ++q) {  // the same order in every CTA: all of them derive the same grid
+    mnx = fmin(mnx, ext_x[q][0]); mny = fmin(mny, ext_x[q][1]);
+    mxx = fmax(mxx, ext_x[q][2]); mxy = fmax(mxy, ext_x[q][3]);
+    sw_all += ext_x[q][4];
+  }
+  int gxn = 1;
+  if (sp.m > 0 && mxx > mnx) {
+    const double meanw = sw_all / (double)sp.m;
+    const double s = meanw > 0.0 ? (mxx - mnx) / meanw : 1.0;
+    gxn = s >= (double)NMS_GX_MAX ? NMS_GX_MAX : (s >= 1.0 ? (int)s + 1 : 1);
+    if (gxn > NMS_GX_MAX) gxn = NMS_GX_MAX;
+  }
+  const double sx = (mxx > mnx) ? (double)gxn / (mxx - mnx) : 0.0;
+  const double sy = (mxy > mny) ? (double)NMS_GY / (mxy - mny) : 0.0;
+
+  for (int k = ctid; k < sp.m; k += cthreads) {
+    const int64_t gi = sel_idx ? (int64_t)sel_idx[sp.base + k] : sp.base + k;
+    const double2 a = *reinterpret_cast<const double2*>(boxes + 4 * gi);
+    const double2 b = *reinterpret_cast<const double2*>(boxes + 4 * gi + 2);
+    const double fx = ((a.x + b.x) * 0.5 - mnx) * sx, fy = ((a.y + b.y) * 0.5 - mny) * sy;
+    const int gx = (fx >= 0.0) ? (fx < (double)(gxn - 1) ? (int)fx : gxn - 1) : 0;
+    const int gy = (fy >= 0.0) ? (fy < (double)(NMS_GY - 1) ? (int)fy : NMS_GY - 1) : 0;
+    ws.cellid[sp.base + k] = gx * NMS_GY + gy;
+  }
+  __threadfence();
+  cluster.sync();  // the passes read cell ids written by other CTAs
+  const int32_t* cellid = ws.cellid + sp.base;
+  int32_t* tmp = ws.kpos + sp.base;
+  int32_t* sorted = ws.sorted_pos + sp.base;
+  cluster_stable_pass<NMS_GY>(cluster, csize, rank, sp.m, hist, all_tot, scan_smem, [](int i) { return i; },
+                              [cellid](int e) { return cellid[e] & (NMS_GY - 1); }, tmp);
+  cluster_stable_pass<NMS_GX_MAX>(cluster, csize, rank, sp.m, hist, all_tot, scan_smem, [tmp](int i) { return tmp[i]; },
+                                  [cellid](int e) { return cellid[e] >> 7; }, sorted);
+  nms_blocked_copy(boxes, scores, classes, sel_idx, sp, sorted, ws, p, rank * 32 + warp, csize * 32);
 }
 
 __device__ __forceinline__ bool bbox_hit(const double* a, const double* b) {
@@ -604,8 +764,6 @@ __global__ void __launch_bounds__(1024) nms_resolve_kernel(const int64_t* __rest
 // per round orders everything; the state lives in global memory behind volatile (L1-bypassing)
 // accesses, the per-round "anything still undecided" flags and the final per-CTA counts travel
 // through distributed shared memory.
-constexpr int NMS_CLUSTER_MAX = 8;
-
 __global__ void __launch_bounds__(1024) nms_resolve_cluster_kernel(const int64_t* __restrict__ page_off,
                                                                    const int32_t* __restrict__ n_sel, NmsWs ws,
                                                                    int32_t* __restrict__ n_kept) {
@@ -904,7 +1062,10 @@ static int nms_cluster_width(int32_t n_pages, int32_t max_boxes_per_page, int sm
     cfg.dynamicSmemBytes = 0;
     const cudaError_t e2 = cudaOccupancyMaxActiveClusters(&n2, nms_resolve_cluster_kernel, &cfg);
     if (e1 != cudaSuccess || e2 != cudaSuccess) cudaGetLastError();
-    launchable[c] = (e1 == cudaSuccess && e2 == cudaSuccess && n1 > 0 && n2 > 0) ? 1 : -1;
+    int n3 = 0;
+    const cudaError_t e3 = cudaOccupancyMaxActiveClusters(&n3, nms_bin_cluster_kernel, &cfg);
+    if (e3 != cudaSuccess) cudaGetLastError();
+    launchable[c] = (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && n1 > 0 && n2 > 0 && n3 > 0) ? 1 : -1;
   }
   return launchable[c] > 0 ? c : 1;
 }
@@ -964,14 +1125,21 @@ extern "C" int pg_nms_merge_ex(const double* boxes, const double* scores, const 
   PG_CUDA_TRY(cudaFuncSetAttribute(nms_emit_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem));
   PG_CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 8 * sizeof(int64_t), s));
   const int all_pairs = !(iou_threshold >= 0.0);  // thr < 0: disjoint boxes (IoU 0) suppress too
-  nms_bin_kernel<<<n_pages, 1024, 0, s>>>(boxes, scores, classes, sel_idx, page_off, n_sel, n_pages, ws);
-  PG_LAUNCH_CHECK();
-  const unsigned cand_grid = (unsigned)((ws.nb_cap + 7) / 8);
-  nms_cand_kernel<<<cand_grid, 256, 0, s>>>(page_off, n_sel, ws, all_pairs);
-  PG_LAUNCH_CHECK();
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // per-page kernels (bin, resolve, emit): one CTA per page, or one cluster per page for few large pages
+  const int width = nms_cluster_width(n_pages, max_boxes_per_page, sms, emit_smem);
+  if (width > 1) {
+    PG_CUDA_TRY(launch_cluster(nms_bin_cluster_kernel, n_pages, width, 0, s, boxes, scores, classes, sel_idx, page_off,
+                               n_sel, (int)n_pages, ws));
+  } else {
+    nms_bin_kernel<<<n_pages, 1024, 0, s>>>(boxes, scores, classes, sel_idx, page_off, n_sel, n_pages, ws);
+    PG_LAUNCH_CHECK();
+  }
+  const unsigned cand_grid = (unsigned)((ws.nb_cap + 7) / 8);
+  nms_cand_kernel<<<cand_grid, 256, 0, s>>>(page_off, n_sel, ws, all_pairs);
+  PG_LAUNCH_CHECK();
   const int64_t mask_want = (ws.ent_cap + 8 * MASK_UNIT - 1) / (8 * MASK_UNIT);
   int mask_per_sm = 3;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mask_per_sm, nms_mask_kernel, 256, 0);
@@ -979,7 +1147,6 @@ extern "C" int pg_nms_merge_ex(const double* boxes, const double* scores, const 
   const unsigned mask_grid = (unsigned)(mask_want < mask_slots ? (mask_want < 1 ? 1 : mask_want) : mask_slots);
   nms_mask_kernel<<<mask_grid, 256, 0, s>>>(ws, iou_threshold);
   PG_LAUNCH_CHECK();
-  const int width = nms_cluster_width(n_pages, max_boxes_per_page, sms, emit_smem);
   if (width > 1) {
     PG_CUDA_TRY(launch_cluster(nms_resolve_cluster_kernel, n_pages, width, 0, s, page_off, n_sel, ws, n_kept));
     PG_CUDA_TRY(launch_cluster(nms_emit_cluster_kernel, n_pages, width, (size_t)emit_smem, s, sel_idx, page_off, ws,

@@ -581,13 +581,19 @@ __global__ void __launch_bounds__(256) nms_cand_kernel(const int64_t* __restrict
 // of J that outrank box i (:112), may share its class (:130) and are not provably disjoint from it
 // (:65); runs of 8 boxes of J whose bounds miss block I are skipped warp-wide.  Phase 2 evaluates the
 // exact predicate (exact class compare, pg_iou_gt) on the marked pairs only.  The kernel is bound by
-// shared-memory bandwidth, hence the compact records.
+// shared-memory bandwidth, hence the compact records and the plane layout of the full boxes (the AoS
+// layout cost 4-way bank conflicts on every store and on the lane-indexed reads of phase 2).
 constexpr int MASK_UNIT = 4;  // consecutive entries per work unit (mostly the same I)
 struct __align__(16) SLite {
   float x0, y0, x1, y1;  // box rounded outwards: disjoint here => disjoint in fp64
   double score;
   int k;                 // pooled position, -1 = padding lane
   uint32_t ch;           // class hash: equal classes => equal hashes
+};
+struct __align__(16) SLiteB {  // the second half of SLite, as stored in shared memory
+  double score;
+  int k;
+  uint32_t ch;
 };
 __device__ __forceinline__ SLite slite_of(const SBox& b) {
   SLite s;
@@ -602,8 +608,11 @@ __device__ __forceinline__ SLite slite_of(const SBox& b) {
 }
 
 __global__ void __launch_bounds__(256) nms_mask_kernel(NmsWs ws, double thr) {
-  __shared__ SBox jb[8][32];
-  __shared__ SLite jl[8][32];
+  // boxes of J: full-precision fields as planes (8-byte words, box index innermost: stores and the
+  // lane-indexed reads of phase 2 are free of bank conflicts), prefilter records as two 16-byte halves
+  __shared__ double jbf[8][6][32];  // x0, y0, x1, y1, area, cls
+  __shared__ float4 jla[8][32];     // outward-rounded fp32 bounds
+  __shared__ SLiteB jlb[8][32];     // score, position, class hash
   if (ws.stats[ST_STATUS] != PG_OK) return;
   const long long total = ws.stats[ST_ENT_TOTAL];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -629,8 +638,13 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(NmsWs ws, double thr) {
       __syncwarp();
       {
         const SBox bj = ws.sbox[(int64_t)J * 32 + lane];
-        jb[wib][lane] = bj;
-        jl[wib][lane] = slite_of(bj);
+        const SLite lj = slite_of(bj);
+        jbf[wib][0][lane] = bj.x0; jbf[wib][1][lane] = bj.y0; jbf[wib][2][lane] = bj.x1; jbf[wib][3][lane] = bj.y1;
+        jbf[wib][4][lane] = bj.area; jbf[wib][5][lane] = bj.cls;
+        jla[wib][lane] = make_float4(lj.x0, lj.y0, lj.x1, lj.y1);
+        SLiteB lb;
+        lb.score = lj.score; lb.k = lj.k; lb.ch = lj.ch;
+        jlb[wib][lane] = lb;
       }
       // which runs of 8 boxes of J can touch block I at all (warp-uniform)
       bool ghit = false;
@@ -648,10 +662,11 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(NmsWs ws, double thr) {
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const int jj = g * 8 + t;
-            const SLite lj = jl[wib][jj];  // broadcast LDS.128 x2
-            const bool outranks = (lj.score > li.score) || (lj.score == li.score && lj.k < li.k);
-            const bool apart = lj.x1 < li.x0 || li.x1 < lj.x0 || lj.y1 < li.y0 || li.y1 < lj.y0;
-            const bool c = (lj.k >= 0) & (li.k >= 0) & outranks & ((lj.ch == li.ch) | agnostic) & (!apart | all_pairs);
+            const float4 la = jla[wib][jj];  // broadcast LDS.128 x2
+            const SLiteB lb = jlb[wib][jj];
+            const bool outranks = (lb.score > li.score) || (lb.score == li.score && lb.k < li.k);
+            const bool apart = la.z < li.x0 || li.x1 < la.x || la.w < li.y0 || li.y1 < la.y;
+            const bool c = (lb.k >= 0) & (li.k >= 0) & outranks & ((lb.ch == li.ch) | agnostic) & (!apart | all_pairs);
             cand |= (c ? 1u : 0u) << jj;
           }
         }
@@ -662,11 +677,12 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(NmsWs ws, double thr) {
         if (cand) {
           const int jj = __ffs(cand) - 1;
           cand &= cand - 1;
-          const SBox bj = jb[wib][jj];
-          if (agnostic || bj.cls == bi.cls) {
-            const bool hit = f32 ? pg_iou_gt_f32((float)bj.x0, (float)bj.y0, (float)bj.x1, (float)bj.y1, (float)bj.area,
+          if (agnostic || jbf[wib][5][jj] == bi.cls) {
+            const double jx0 = jbf[wib][0][jj], jy0 = jbf[wib][1][jj], jx1 = jbf[wib][2][jj], jy1 = jbf[wib][3][jj];
+            const double jarea = jbf[wib][4][jj];
+            const bool hit = f32 ? pg_iou_gt_f32((float)jx0, (float)jy0, (float)jx1, (float)jy1, (float)jarea,
                                                  (float)bi.x0, (float)bi.y0, (float)bi.x1, (float)bi.y1, (float)bi.area, thr)
-                                 : pg_iou_gt(bj.x0, bj.y0, bj.x1, bj.y1, bj.area, bi.x0, bi.y0, bi.x1, bi.y1, bi.area, thr);
+                                 : pg_iou_gt(jx0, jy0, jx1, jy1, jarea, bi.x0, bi.y0, bi.x1, bi.y1, bi.area, thr);
             if (hit) mask |= 1u << jj;
           }
         }
@@ -680,6 +696,41 @@ __global__ void __launch_bounds__(256) nms_mask_kernel(NmsWs ws, double thr) {
 }
 
 // ---- E: resolve ----------------------------------------------------------------------------
+// The candidate entries of block I against the state words of round `rc`: box `lane` of I is suppressed
+// if a kept box of some J suppresses it, and has to wait while an undecided one might.  The entry
+// headers (block id and the two state words of J) are fetched 32 at a time, one per lane; only entries
+// whose J still has kept or undecided boxes touch their 128-byte mask row, four rows in flight.
+__device__ __forceinline__ void resolve_scan_entries(const NmsWs& ws, const volatile uint32_t* kept,
+                                                     const volatile uint32_t* undec, int64_t rc, int64_t I, bool mine,
+                                                     int lane, bool& sup, bool& wait) {
+  const int64_t e0 = ws.cand_off[I], e1 = e0 + ws.cand_cnt[I];
+  for (int64_t eb = e0; eb < e1; eb += 32) {
+    const int64_t me = eb + lane;
+    const int jbk = me < e1 ? ws.ent_j[me] : -1;  // global block id, -1 = no suppressor in that block
+    uint32_t kj = 0u, uj = 0u;
+    if (jbk >= 0) { kj = kept[rc + jbk]; uj = undec[rc + jbk]; }
+    unsigned live = __ballot_sync(0xffffffffu, (kj | uj) != 0u);
+    while (live) {
+      int q[4];
+      uint32_t m[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        q[t] = live ? __ffs(live) - 1 : -1;
+        live &= live - 1;  // 0 stays 0
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) m[t] = (mine && q[t] >= 0) ? ws.ent_mask[(eb + q[t]) * 32 + lane] : 0u;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint32_t kq = __shfl_sync(0xffffffffu, kj, q[t] & 31), uq = __shfl_sync(0xffffffffu, uj, q[t] & 31);
+        if (m[t] & kq) sup = true;
+        else if (m[t] & uq) wait = true;
+      }
+      if (__all_sync(0xffffffffu, !mine || sup)) return;  // every undecided box of I is suppressed already
+    }
+  }
+}
+
 __global__ void __launch_bounds__(1024) nms_resolve_kernel(const int64_t* __restrict__ page_off,
                                                            const int32_t* __restrict__ n_sel, NmsWs ws,
                                                            int32_t* __restrict__ n_kept) {
@@ -713,15 +764,7 @@ __global__ void __launch_bounds__(1024) nms_resolve_kernel(const int64_t* __rest
       }
       const bool mine = (u >> lane) & 1u;
       bool sup = false, wait = false;
-      const int64_t e0 = ws.cand_off[I], e1 = e0 + ws.cand_cnt[I];
-      for (int64_t e = e0; e < e1; ++e) {
-        const int jbk = ws.ent_j[e];  // global block id, -1 = no suppressor in that block
-        if (jbk < 0) continue;
-        const uint32_t m = mine ? ws.ent_mask[e * 32 + lane] : 0u;
-        const uint32_t kj = kept[rc + jbk], uj = undec[rc + jbk];
-        if (m & kj) sup = true;
-        else if (m & uj) wait = true;
-      }
+      resolve_scan_entries(ws, kept, undec, rc, I, mine, lane, sup, wait);
       const unsigned bk = __ballot_sync(0xffffffffu, mine && !sup && !wait);
       const unsigned bs = __ballot_sync(0xffffffffu, mine && sup);
       const uint32_t un = u & ~(bk | bs);
@@ -801,15 +844,7 @@ __global__ void __launch_bounds__(1024) nms_resolve_cluster_kernel(const int64_t
       }
       const bool mine = (u >> lane) & 1u;
       bool sup = false, wait = false;
-      const int64_t e0 = ws.cand_off[I], e1 = e0 + ws.cand_cnt[I];
-      for (int64_t e = e0; e < e1; ++e) {
-        const int jbk = ws.ent_j[e];
-        if (jbk < 0) continue;
-        const uint32_t m = mine ? ws.ent_mask[e * 32 + lane] : 0u;
-        const uint32_t kj = kept[rc + jbk], uj = undec[rc + jbk];
-        if (m & kj) sup = true;
-        else if (m & uj) wait = true;
-      }
+      resolve_scan_entries(ws, kept, undec, rc, I, mine, lane, sup, wait);
       const unsigned bk = __ballot_sync(0xffffffffu, mine && !sup && !wait);
       const unsigned bs = __ballot_sync(0xffffffffu, mine && sup);
       const uint32_t un = u & ~(bk | bs);

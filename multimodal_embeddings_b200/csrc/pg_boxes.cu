@@ -115,6 +115,7 @@ struct NmsWs {
   int32_t* cellid;     // [N]
   SBox* sbox;          // [NB*32]
   double* bbox;        // [NB*4]
+  double* sbbox;       // [(NB/32 + P + 1)*4]  bounds of each run of 32 blocks of a page ("super-block")
   float4* bboxf;       // [NB]    the same, rounded outwards to fp32 (conservative prefilter only)
   float4* subbox;      // [NB*4]  outward-rounded fp32 bounds of each run of 8 boxes inside a block
   int32_t* blk_page;   // [NB]
@@ -150,6 +151,7 @@ static size_t nms_layout(int64_t n, int32_t n_pages, int32_t pairs_per_block, ui
   w.cellid = (int32_t*)take((size_t)n * 4);
   w.sbox = (SBox*)take((size_t)nb * 32 * sizeof(SBox));
   w.bbox = (double*)take((size_t)nb * 4 * 8);
+  w.sbbox = (double*)take((size_t)((nb >> 5) + n_pages + 1) * 4 * 8);
   w.bboxf = (float4*)take((size_t)nb * sizeof(float4));
   w.subbox = (float4*)take((size_t)nb * 4 * sizeof(float4));
   w.blk_page = (int32_t*)take((size_t)nb * 4);
@@ -526,9 +528,50 @@ __device__ __forceinline__ bool bbox_hit(const double* a, const double* b) {
 }
 
 // ---- B: candidates -------------------------------------------------------------------------
+// Bounding boxes of the super-blocks (32 consecutive blocks of a page = 1024 boxes in spatial order; they
+// never span pages: page p's super-blocks start at (blk0 >> 5) + p).  One warp per block, the warps of
+// blocks that do not open a super-block leave at once.
+__global__ void __launch_bounds__(256) nms_super_kernel(const int64_t* __restrict__ page_off,
+                                                        const int32_t* __restrict__ n_sel, NmsWs ws) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t I = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (I >= ws.nb_cap) return;
+  const int p = ws.blk_page[I];
+  if (p < 0) return;
+  const PageSpan sp = page_span(page_off, n_sel, p);
+  const int b = (int)(I - sp.blk0);
+  if (b & 31) return;
+  const bool valid = b + lane < sp.nb;
+  const double* bb = ws.bbox + 4 * (I + lane);
+  const double x0 = warp_min_d(valid ? bb[0] : DBL_MAX), y0 = warp_min_d(valid ? bb[1] : DBL_MAX);
+  const double x1 = warp_max_d(valid ? bb[2] : -DBL_MAX), y1 = warp_max_d(valid ? bb[3] : -DBL_MAX);
+  if (lane == 0) {
+    double* o = ws.sbbox + 4 * ((sp.blk0 >> 5) + p + (b >> 5));
+    o[0] = x0; o[1] = y0; o[2] = x1; o[3] = y1;
+  }
+}
+
 // One warp per block I: count the blocks J of the page whose bounding boxes intersect bbox(I),
-// reserve that many entries with one atomicAdd, then list them (entries of one I stay contiguous;
-// their global order depends on the atomics but nothing downstream depends on it).
+// reserve that many entries with one atomicAdd, then list them (entries of one I stay contiguous and
+// ascending in J; their global order depends on the atomics but nothing downstream depends on it).
+// Two levels: the super-blocks of the page first, then the 32 blocks of each super-block that is hit.
+template <typename OnHit>
+__device__ __forceinline__ void cand_walk(const NmsWs& ws, const PageSpan& sp, int p, const double* bbI, int all_pairs,
+                                          int lane, OnHit on_hit) {
+  const int ns = (sp.nb + 31) >> 5;
+  const double* sb = ws.sbbox + 4 * ((sp.blk0 >> 5) + p);
+  for (int s0 = 0; s0 < ns; s0 += 32) {
+    const bool sh = (s0 + lane < ns) && (all_pairs || bbox_hit(bbI, sb + 4 * (s0 + lane)));
+    unsigned sm = __ballot_sync(0xffffffffu, sh);
+    while (sm) {
+      const int j = (s0 + __ffs(sm) - 1) * 32 + lane;
+      sm &= sm - 1;
+      const bool hit = (j < sp.nb) && (all_pairs || bbox_hit(bbI, ws.bbox + 4 * (sp.blk0 + j)));
+      on_hit(j, hit, __ballot_sync(0xffffffffu, hit));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) nms_cand_kernel(const int64_t* __restrict__ page_off,
                                                        const int32_t* __restrict__ n_sel, NmsWs ws, int all_pairs) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -544,11 +587,7 @@ __global__ void __launch_bounds__(256) nms_cand_kernel(const int64_t* __restrict
 #pragma unroll
   for (int q = 0; q < 4; ++q) bbI[q] = ws.bbox[4 * I + q];
   int cnt = 0;
-  for (int j0 = 0; j0 < sp.nb; j0 += 32) {
-    bool hit = false;
-    if (j0 + lane < sp.nb) hit = all_pairs || bbox_hit(bbI, ws.bbox + 4 * (sp.blk0 + j0 + lane));
-    cnt += __popc(__ballot_sync(0xffffffffu, hit));
-  }
+  cand_walk(ws, sp, p, bbI, all_pairs, lane, [&](int, bool, unsigned hits) { cnt += __popc(hits); });
   long long off = 0;
   if (lane == 0) off = (long long)atomicAdd((unsigned long long*)&ws.stats[ST_ENT_TOTAL], (unsigned long long)cnt);
   off = __shfl_sync(0xffffffffu, off, 0);
@@ -560,17 +599,14 @@ __global__ void __launch_bounds__(256) nms_cand_kernel(const int64_t* __restrict
   }
   if (!fits) return;
   long long e = off;
-  for (int j0 = 0; j0 < sp.nb; j0 += 32) {
-    bool hit = false;
-    if (j0 + lane < sp.nb) hit = all_pairs || bbox_hit(bbI, ws.bbox + 4 * (sp.blk0 + j0 + lane));
-    const unsigned hits = __ballot_sync(0xffffffffu, hit);
+  cand_walk(ws, sp, p, bbI, all_pairs, lane, [&](int j, bool hit, unsigned hits) {
     if (hit) {
       const long long slot = e + __popc(hits & ((1u << lane) - 1u));
-      ws.ent_j[slot] = (int32_t)(sp.blk0 + j0 + lane);
+      ws.ent_j[slot] = (int32_t)(sp.blk0 + j);
       ws.ent_i[slot] = (int32_t)I;
     }
     e += __popc(hits);
-  }
+  });
 }
 
 // ---- C: masks ------------------------------------------------------------------------------
@@ -1173,6 +1209,8 @@ extern "C" int pg_nms_merge_ex(const double* boxes, const double* scores, const 
     PG_LAUNCH_CHECK();
   }
   const unsigned cand_grid = (unsigned)((ws.nb_cap + 7) / 8);
+  nms_super_kernel<<<cand_grid, 256, 0, s>>>(page_off, n_sel, ws);
+  PG_LAUNCH_CHECK();
   nms_cand_kernel<<<cand_grid, 256, 0, s>>>(page_off, n_sel, ws, all_pairs);
   PG_LAUNCH_CHECK();
   const int64_t mask_want = (ws.ent_cap + 8 * MASK_UNIT - 1) / (8 * MASK_UNIT);

@@ -19,7 +19,7 @@ import torch
 from . import ops
 from ._lib import PG_COL_HIST_BINS, PG_COL_SPAN_BYTES, PG_WIDTH_HIST_BINS, check, lib, ptr, stream_ptr
 
-KERNELS_PER_STEP = 12  # tiler, edge filter, 5 NMS kernels, class flags, width median, column prep + density + peaks
+KERNELS_PER_STEP = 13  # tiler, edge filter, 6 NMS kernels, class flags, width median, column prep + density + peaks
 
 
 def shard_pages(n_pages_total: int, rank: int, world: int) -> range:
@@ -179,7 +179,7 @@ class PagePipeline:
 
     def capture(self, pages: torch.Tensor) -> "torch.cuda.CUDAGraph":
         """One step captured into a CUDA graph (both streams: the fork/join through events is recorded as graph
-        dependencies).  Replaying it costs one launch instead of 12-16 ctypes calls + launches — what matters
+        dependencies).  Replaying it costs one launch instead of 13-17 ctypes calls + launches — what matters
         for short steps (cfg2: 19 pages, 0.4 ms).  Run at least one eager step first: plans upload their
         tables lazily, which is not capturable."""
         graph = torch.cuda.CUDAGraph()

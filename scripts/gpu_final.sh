@@ -21,7 +21,7 @@ kill $SMI
 # 2. cfg4 merge kernels, full set (north_star: SM / L1 throughput of the merge); the plain run first
 MCMD="python scripts/bench_merge_stress.py"
 step 60 "merge plain" bash -c "timeout 200 $MCMD > $O/merge_plain.json 2> $O/merge_plain.err" && \
-step 90 "merge ncu full" bash -c "timeout 400 ncu --set full --clock-control none --import-source on -k regex:nms_ -s 15 -c 5 -f -o $O/merge_full $MCMD > $O/ncu_merge.log 2>&1"
+step 90 "merge ncu full" bash -c "timeout 400 ncu --set full --clock-control none --import-source on -k regex:nms_ -s 18 -c 6 -f -o $O/merge_full $MCMD > $O/ncu_merge.log 2>&1"
 # 3. launch list of the bench command (serialised under ncu: shares, not absolutes)
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-overlap"
 step 90 "launch plain" bash -c "timeout 200 $CMD > $O/plain_launches.log 2>&1" && \
@@ -32,6 +32,11 @@ step 40 "bench tiler-only" bash -c "timeout 200 python bench.py --tiler-only --n
 step 50 "bench reference" bash -c "timeout 200 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference.json 2>> $O/bench_default.err"
 # 5. the dominant kernel, full set, at the bench's 64 pages per launch
 CMD2="python bench.py --tiler-only --steps 1 --warmup 3 --no-cpu-baseline"
-step 100 "tiler ncu full" bash -c "timeout $(( $(left) > 60 ? $(left) : 60 )) ncu --set full --clock-control none --import-source on -k regex:tile_letterbox -s 3 -c 1 -f -o $O/tiler_full $CMD2 > $O/ncu_tiler.log 2>&1"
+[ -n "$SKIP_TILER_NCU" ] || step 100 "tiler ncu full" bash -c "timeout $(( $(left) > 60 ? $(left) : 60 )) ncu --set full --clock-control none --import-source on -k regex:tile_letterbox -s 3 -c 1 -f -o $O/tiler_full $CMD2 > $O/ncu_tiler.log 2>&1"
+# 6. optionally the GPU tests a change did not touch yet (PYTEST_K = a -k expression), in the time that is left
+if [ -n "$PYTEST_K" ] && [ "$(left)" -gt 40 ]; then
+  timeout $(left) python -m pytest tests -m gpu -q -k "$PYTEST_K" --maxfail=5 -p no:cacheprovider > gpurun_out/pytest_rest.log 2>&1
+  echo "pytest rest exit $?"; tail -4 gpurun_out/pytest_rest.log
+fi
 ls -la $O
 echo "total $(( $(date +%s) - T0 )) s"

@@ -8,7 +8,7 @@ echo "stress exit $?"; cat gpurun_out/merge_stress.json; tail -3 gpurun_out/merg
 PG_NMS_CLUSTER_MIN_BOXES=0 timeout 120 python scripts/bench_merge_stress.py > gpurun_out/merge_stress_nocluster.json 2>> gpurun_out/merge_stress.err
 echo "stress (one CTA per page) exit $?"; cat gpurun_out/merge_stress_nocluster.json
 # per-kernel durations of one call (serialised, cold-cache)
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:nms_ -s 15 -c 5 --csv --log-file gpurun_out/merge_launches.csv python scripts/bench_merge_stress.py > gpurun_out/ncu_merge_launches.log 2>&1
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:nms_ -s 18 -c 6 --csv --log-file gpurun_out/merge_launches.csv python scripts/bench_merge_stress.py > gpurun_out/ncu_merge_launches.log 2>&1
 echo "ncu exit $?"; grep -v "^==" gpurun_out/merge_launches.csv | python -c "
 import csv,sys
 for r in csv.DictReader(sys.stdin):

@@ -24,8 +24,9 @@ def launches():
             rows.append((int(row["ID"]), re.sub(r"\(.*", "", row["Kernel Name"]), float(row["Metric Value"].replace(",", ""))))
     til = [i for i, r in enumerate(rows) if "tile_letterbox_kernel" in r[1]]
     start = til[-1]  # last timed step
+    stop = max(i for i, r in enumerate(rows) if "column_peaks_kernel" in r[1]) + 1  # what follows is the status check
     agg = collections.OrderedDict()
-    for i in range(start, len(rows)):
+    for i in range(start, stop):
         agg[rows[i][1]] = agg.get(rows[i][1], 0.0) + rows[i][2]
     total = sum(agg.values())
     mine = {k: v for k, v in agg.items() if not k.startswith("void at::")}
@@ -76,7 +77,7 @@ def merge_profile():
         pass
     with open(os.path.join(DST, f"{TAG}_merge_ncu_full.md"), "w") as f:
         f.write(f"# {TAG}: cfg4 merge (`pg_nms_merge`, 8 pages x 100 000 boxes) — ncu --set full --clock-control none, one call\n\n")
-        f.write("Command: `python scripts/bench_merge_stress.py` (the five kernels of the fourth call; the three before it are warm-up).\n"
+        f.write("Command: `python scripts/bench_merge_stress.py` (the six kernels of the fourth call; the three before it are warm-up).\n"
                 "The merge is bound by SM issue (fp64 compares in the mask kernel) and shared-memory/L1 traffic, not by HBM: the\n"
                 "whole input is 4.8 MB per page.  Durations under ncu are cold-cache and serialised.\n\n")
         if plain:

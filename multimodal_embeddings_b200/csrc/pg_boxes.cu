@@ -643,7 +643,8 @@ __device__ __forceinline__ SLite slite_of(const SBox& b) {
   return s;
 }
 
-__global__ void __launch_bounds__(256) nms_mask_kernel(NmsWs ws, double thr) {
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) nms_mask_kernel(NmsWs ws, double thr) {
   // boxes of J: full-precision fields as planes (8-byte words, box index innermost: stores and the
   // lane-indexed reads of phase 2 are free of bank conflicts), prefilter records as two 16-byte halves
   __shared__ double jbf[8][6][32];  // x0, y0, x1, y1, area, cls
@@ -1215,10 +1216,13 @@ extern "C" int pg_nms_merge_ex(const double* boxes, const double* scores, const 
   PG_LAUNCH_CHECK();
   const int64_t mask_want = (ws.ent_cap + 8 * MASK_UNIT - 1) / (8 * MASK_UNIT);
   int mask_per_sm = 3;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mask_per_sm, nms_mask_kernel, 256, 0);
+  int mask_occ = 3;
+  if (const char* e = getenv("PG_NMS_MASK_OCC")) mask_occ = atoi(e);  // tuning knob: 3 (76 registers) or 4 (64)
+  void (*mask_kernel)(NmsWs, double) = mask_occ == 4 ? nms_mask_kernel<4> : nms_mask_kernel<3>;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mask_per_sm, mask_kernel, 256, 0);
   const int64_t mask_slots = (int64_t)sms * (mask_per_sm > 0 ? mask_per_sm : 1);
   const unsigned mask_grid = (unsigned)(mask_want < mask_slots ? (mask_want < 1 ? 1 : mask_want) : mask_slots);
-  nms_mask_kernel<<<mask_grid, 256, 0, s>>>(ws, iou_threshold);
+  mask_kernel<<<mask_grid, 256, 0, s>>>(ws, iou_threshold);
   PG_LAUNCH_CHECK();
   if (width > 1) {
     PG_CUDA_TRY(launch_cluster(nms_resolve_cluster_kernel, n_pages, width, 0, s, page_off, n_sel, ws, n_kept));

@@ -132,7 +132,12 @@ int pg_edge_filter(const double* boxes /*dev [N,4]*/, int32_t boxes_are_local,
  * Replaces calculate_iou / apply_non_max_suppression (3_combine_grids.py:46-138) on
  * the pooled boxes of combine_boxes_for_image (3_combine_grids.py:222-267).
  * Output: kept_idx = global box indices in pick order (score descending, earlier
- * pooled position first on ties), page p's picks stored from page_off[p]. */
+ * pooled position first on ties), page p's picks stored from page_off[p].
+ * max_boxes_per_page is a scheduling hint (0 = unknown), never a correctness input: from 32768 boxes
+ * on a page, and while n_pages * 8 fits the SMs, the per-page kernels (bin, resolve, emit) run on one
+ * thread-block cluster per page instead of one CTA per page; results are identical either way.
+ * Environment knobs read at each call: PG_NMS_CLUSTER_MIN_BOXES (that threshold; <= 0 disables the
+ * cluster kernels), PG_NMS_MASK_OCC (3 or 4 resident CTAs per SM for the mask kernel). */
 size_t pg_nms_workspace_bytes(int64_t n_boxes, int32_t n_pages, int32_t pairs_per_block);
 int pg_nms_merge(const double* boxes /*dev [N,4]*/, const double* scores /*dev [N]*/,
                  const double* classes /*dev [N]*/, const int32_t* sel_idx /*dev or NULL*/,

@@ -1117,7 +1117,7 @@ static int nms_cluster_width(int32_t n_pages, int32_t max_boxes_per_page, int sm
   int c = NMS_CLUSTER_MAX;
   while (c > 1 && (int64_t)n_pages * c > sms) c >>= 1;
   if (c == 1) return 1;
-  // the device must be able to co-schedule such a cluster (1024 threads and the emit ring per CTA)
+  // the device must be able to co-schedule such a cluster (1024 threads and the 96 KB emit buffer per CTA)
   static int launchable[NMS_CLUSTER_MAX + 1] = {0};  // 0 unknown, 1 yes, -1 no
   if (launchable[c] == 0) {
     cudaLaunchConfig_t cfg = {};

@@ -626,11 +626,6 @@ struct __align__(16) SLite {
   int k;                 // pooled position, -1 = padding lane
   uint32_t ch;           // class hash: equal classes => equal hashes
 };
-struct __align__(16) SLiteB {  // the second half of SLite, as stored in shared memory
-  double score;
-  int k;
-  uint32_t ch;
-};
 __device__ __forceinline__ SLite slite_of(const SBox& b) {
   SLite s;
   s.x0 = __double2float_rd(fmin(b.x0, b.x1)); s.y0 = __double2float_rd(fmin(b.y0, b.y1));
@@ -643,23 +638,53 @@ __device__ __forceinline__ SLite slite_of(const SBox& b) {
   return s;
 }
 
+// One prefilter test of the mask kernel as a single predicate chain (nine instructions, no branch, no
+// materialised booleans): box j outranks box i (3_combine_grids.py:112: higher score, earlier position on ties),
+// carries the same class hash (:130) and is not provably disjoint from it (:65; `!(a < b)` keeps the
+// unordered case, like the C expression).  Returns bits | bit when all of that holds.
+__device__ __forceinline__ uint32_t prefilter_or(uint32_t bits, uint32_t bit, double sj, double si, int kj, int ki,
+                                                 uint32_t chj, uint32_t chi, float4 bj, float ix0, float iy0, float ix1,
+                                                 float iy1) {
+  asm("{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.eq.f64 p, %2, %3;\n\t"
+      "setp.lt.and.s32 p, %4, %5, p;\n\t"
+      "setp.gt.or.f64 p, %2, %3, p;\n\t"
+      "setp.eq.and.u32 p, %6, %7, p;\n\t"
+      "setp.geu.and.f32 p, %8, %9, p;\n\t"    // !(bj.z < ix0)
+      "setp.geu.and.f32 p, %10, %11, p;\n\t"  // !(ix1 < bj.x)
+      "setp.geu.and.f32 p, %12, %13, p;\n\t"  // !(bj.w < iy0)
+      "setp.geu.and.f32 p, %14, %15, p;\n\t"  // !(iy1 < bj.y)
+      "@p or.b32 %0, %0, %1;\n\t"
+      "}"
+      : "+r"(bits)
+      : "r"(bit), "d"(sj), "d"(si), "r"(kj), "r"(ki), "r"(chj), "r"(chi), "f"(bj.z), "f"(ix0), "f"(ix1), "f"(bj.x),
+        "f"(bj.w), "f"(iy0), "f"(iy1), "f"(bj.y));
+  return bits;
+}
+
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS) nms_mask_kernel(NmsWs ws, double thr) {
   // boxes of J: full-precision fields as planes (8-byte words, box index innermost: stores and the
   // lane-indexed reads of phase 2 are free of bank conflicts), prefilter records as two 16-byte halves
   __shared__ double jbf[8][6][32];  // x0, y0, x1, y1, area, cls
-  __shared__ float4 jla[8][32];     // outward-rounded fp32 bounds
-  __shared__ SLiteB jlb[8][32];     // score, position, class hash
+  __shared__ float4 jla[8][32];     // outward-rounded fp32 bounds (all of the plane when nothing may be skipped)
+  __shared__ int4 jlb[8][32];       // score (lo, hi), position, class hash (0 when classes are ignored)
   if (ws.stats[ST_STATUS] != PG_OK) return;
   const long long total = ws.stats[ST_ENT_TOTAL];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long gw = (long long)blockIdx.x * 8 + wib, nw = (long long)gridDim.x * 8;
   const bool all_pairs = !(thr >= 0.0);  // thr < 0: IoU 0 already suppresses, nothing can be skipped
   const bool agnostic = (ws.mode & PG_NMS_CLASS_AGNOSTIC) != 0, f32 = (ws.mode & PG_NMS_FP32) != 0;
+  // the two launch-wide switches are folded into the records, so that the 1024 prefilter tests of an entry
+  // are plain compare chains: class hashes masked to 0 when classes are ignored, bounds opened to the whole
+  // plane when every same-class pair has to be tested
+  const uint32_t ch_keep = agnostic ? 0u : 0xffffffffu;
   int cached = -1;
   SBox bi;
   bi.k = -1;
   SLite li = slite_of(bi);
+  uint32_t li_ch = 0u;
   float4 bbI = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long u = gw; u * MASK_UNIT < total; u += nw) {
     for (int q = 0; q < MASK_UNIT; ++q) {
@@ -669,6 +694,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) nms_mask_kernel(NmsWs ws, doubl
       if (I != cached) {
         bi = ws.sbox[(int64_t)I * 32 + lane];
         li = slite_of(bi);
+        li_ch = li.ch & ch_keep;
         bbI = ws.bboxf[I];
         cached = I;
       }
@@ -678,10 +704,11 @@ __global__ void __launch_bounds__(256, MIN_CTAS) nms_mask_kernel(NmsWs ws, doubl
         const SLite lj = slite_of(bj);
         jbf[wib][0][lane] = bj.x0; jbf[wib][1][lane] = bj.y0; jbf[wib][2][lane] = bj.x1; jbf[wib][3][lane] = bj.y1;
         jbf[wib][4][lane] = bj.area; jbf[wib][5][lane] = bj.cls;
-        jla[wib][lane] = make_float4(lj.x0, lj.y0, lj.x1, lj.y1);
-        SLiteB lb;
-        lb.score = lj.score; lb.k = lj.k; lb.ch = lj.ch;
-        jlb[wib][lane] = lb;
+        // padding lanes of J are disjoint from everything, real boxes from nothing when all pairs must be tested
+        jla[wib][lane] = lj.k < 0 ? make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY)
+                                  : (all_pairs ? make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY)
+                                               : make_float4(lj.x0, lj.y0, lj.x1, lj.y1));
+        jlb[wib][lane] = make_int4(__double2loint(lj.score), __double2hiint(lj.score), lj.k, (int)(lj.ch & ch_keep));
       }
       // which runs of 8 boxes of J can touch block I at all (warp-uniform)
       bool ghit = false;
@@ -700,14 +727,13 @@ __global__ void __launch_bounds__(256, MIN_CTAS) nms_mask_kernel(NmsWs ws, doubl
           for (int t = 0; t < 8; ++t) {
             const int jj = g * 8 + t;
             const float4 la = jla[wib][jj];  // broadcast LDS.128 x2
-            const SLiteB lb = jlb[wib][jj];
-            const bool outranks = (lb.score > li.score) || (lb.score == li.score && lb.k < li.k);
-            const bool apart = la.z < li.x0 || li.x1 < la.x || la.w < li.y0 || li.y1 < la.y;
-            const bool c = (lb.k >= 0) & (li.k >= 0) & outranks & ((lb.ch == li.ch) | agnostic) & (!apart | all_pairs);
-            cand |= (c ? 1u : 0u) << jj;
+            const int4 lb = jlb[wib][jj];
+            cand = prefilter_or(cand, 1u << jj, __hiloint2double(lb.y, lb.x), li.score, lb.z, li.k, (uint32_t)lb.w, li_ch,
+                                la, li.x0, li.y0, li.x1, li.y1);
           }
         }
       }
+      if (li.k < 0) cand = 0u;  // padding lane of I
       // phase 2 (exact, only on the marked pairs; lanes walk their own bit lists)
       uint32_t mask = 0;
       while (__any_sync(0xffffffffu, cand != 0)) {

@@ -1,7 +1,8 @@
-"""Host models of the two cluster-wide algorithms of the large-page merge kernels (csrc/pg_boxes.cu):
-the index arithmetic restated in numpy, checked against a plain sort.  They pin the decomposition itself
-(which comparators run where, which counts go where); the kernels are checked on the GPU in
-tests/test_gpu_parity.py::test_nms_cluster_kernels_equal_single_cta_kernels."""
+"""Host models of the merge algorithms (csrc/pg_boxes.cu) restated in numpy and checked against plain sorts and the
+sequential greedy loop: the chunked bitonic network and the cluster counting-sort pass of the large-page kernels,
+and the Jacobi rounds of the resolve kernels.  They pin the algorithms themselves (which comparators run where,
+which counts go where, why rounds reach the greedy result); the kernels are checked on the GPU in
+tests/test_gpu_parity.py."""
 import numpy as np
 import pytest
 
@@ -125,3 +126,52 @@ def test_cluster_counting_sort_pass_is_a_stable_sort(m, csize):
     tmp = cluster_stable_pass_model(ident, lambda e: cell[e] & 127, 128, csize)
     srt = cluster_stable_pass_model(tmp, lambda e: cell[e] >> 7, 64, csize)
     assert np.array_equal(srt, np.argsort(cell, kind="stable"))
+
+
+def jacobi_resolve_model(sup):
+    """nms_resolve: sup[i] = the boxes that outrank i, share its class and overlap it beyond the threshold.
+    Every round reads the state of the previous round only (double-buffered kept/undecided words):
+    undecided -> suppressed if a suppressor is kept, -> kept if none of its suppressors is still undecided."""
+    n = len(sup)
+    kept = np.zeros(n, bool)
+    undec = np.ones(n, bool)
+    rounds = 0
+    while undec.any():
+        k2, u2 = kept.copy(), undec.copy()
+        for i in np.nonzero(undec)[0]:
+            s = sup[i]
+            if kept[s].any():
+                u2[i] = False
+            elif not undec[s].any():
+                k2[i], u2[i] = True, False
+        kept, undec = k2, u2
+        rounds += 1
+        assert rounds <= n
+    return kept, rounds
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_jacobi_rounds_reach_the_greedy_fixed_point(seed):
+    """The sequential loop of apply_non_max_suppression (3_combine_grids.py:104-136) against the round-based
+    resolution, on random boxes with score ties and several classes."""
+    from oracle import boxes as ob
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 400))
+    xy = rng.uniform(0, 300, (n, 2))
+    wh = rng.uniform(5, 80, (n, 2))
+    boxes = np.concatenate([xy, xy + wh], 1)
+    scores = rng.choice(np.round(rng.uniform(0.1, 0.9, 40), 2), n)  # heavy ties
+    classes = rng.integers(0, 3, n).astype(np.float64)
+    thr = float(rng.choice([0.5, 0.2, 0.0]))
+    picks = ob.nms_pick_order(boxes.tolist(), scores.tolist(), classes.tolist(), thr)
+    sup = []
+    for i in range(n):
+        s = [j for j in range(n) if j != i and classes[j] == classes[i]
+             and (scores[j] > scores[i] or (scores[j] == scores[i] and j < i))
+             and ob.iou(boxes[j].tolist(), boxes[i].tolist()) > thr]
+        sup.append(np.asarray(s, np.int64))
+    kept, rounds = jacobi_resolve_model(sup)
+    assert sorted(picks) == np.nonzero(kept)[0].tolist()
+    # emit: survivors ordered by (score descending, earlier position first) == the reference's pick order
+    order = sorted(np.nonzero(kept)[0].tolist(), key=lambda i: (-scores[i], i))
+    assert order == picks

@@ -200,6 +200,25 @@ int pg_assign_columns(const double* boxes /*dev [N,4]*/, const int32_t* sel_idx,
                       const int32_t* centers /*dev [P,max_cols]*/, const int32_t* n_cols /*dev [P]*/,
                       int32_t max_cols, int32_t* col_of_box /*dev [N]*/, void* stream);
 
+/* ------------------------------------------------------------------ K6 corpus-histogram exchange
+ * The one exchange step of the path (the reference is a single process and has no analogue):
+ * the per-rank integer histograms pg_width_median / pg_column_peaks accumulate (width_hist, col_hist) are
+ * summed over the ranks, in place, with ONE ncclAllReduce(ncclUint32, ncclSum) over NVLink.  Integer sums are
+ * order-independent: the totals are bit-identical for any number of GPUs.
+ *   pg_hist_allreduce(hist, n, comm, stream)   `comm` is an ncclComm_t (passed as void* so that this header does
+ *                                              not need nccl.h); asynchronous on `stream`.
+ * For callers that do not hold an NCCL communicator: rank 0 makes an id with pg_comm_unique_id, sends the 128
+ * bytes to every rank by whatever means the host has (the Python side uses torch.distributed), and every rank
+ * calls pg_comm_create (collective); pg_comm_nccl() is the ncclComm_t to pass above.  NCCL is bound at run time
+ * (libnccl.so.2, sharing the host process's copy when it has one); without it these return PG_ERR_UNSUPPORTED. */
+typedef struct PgComm PgComm;
+int pg_comm_nccl_version(void); /* 0: NCCL not available */
+int pg_comm_unique_id(uint8_t id[128]);
+int pg_comm_create(const uint8_t id[128], int32_t world, int32_t rank, PgComm** comm);
+void pg_comm_destroy(PgComm* comm);
+void* pg_comm_nccl(PgComm* comm);
+int pg_hist_allreduce(uint32_t* hist /*dev [n_bins]*/, size_t n_bins, void* nccl_comm /*ncclComm_t*/, void* stream);
+
 /* ------------------------------------------------------------------ J1-J4 stage-3 record writer
  * Replaces `json.dump(result, f, indent=2)` (3_combine_grids.py:441-443) of the dict built by
  * combine_boxes_for_image (3:282-291): the documents of n_pages pages are laid out on the device, byte for

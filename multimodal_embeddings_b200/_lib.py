@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpagegeom.so")
 
 PG_OK = 0
+PG_ERR_WORKSPACE = 3
 PG_FLAG_PLAIN_TEXT = 1
 PG_FLAG_TITLE = 2
 PG_WIDTH_HIST_BINS = 16384
@@ -70,6 +71,12 @@ SIGNATURES = {
     "pg_column_peaks": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I32, _F64, _I32,
                                   _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
     "pg_assign_columns": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _P, _P, _I32, _P, _P]),
+    "pg_comm_nccl_version": (C.c_int, []),
+    "pg_comm_unique_id": (C.c_int, [_P]),
+    "pg_comm_create": (C.c_int, [_P, _I32, _I32, _P]),
+    "pg_comm_destroy": (None, [_P]),
+    "pg_comm_nccl": (_P, [_P]),
+    "pg_hist_allreduce": (C.c_int, [_P, C.c_size_t, _P, _P]),
     "pg_json_workspace_bytes": (_I64, [_I64, _I32]),
     "pg_json_combined": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P,
                                    _P, _I64, _P]),

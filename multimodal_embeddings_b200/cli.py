@@ -84,14 +84,14 @@ def _image_size(path) -> Optional[Tuple[int, int]]:
 # =============================================================================================
 class SyntheticDetector:
     """Stands in for DocLayout-YOLO (weights unavailable offline): deterministic per-tile detections
-    from multimodal_embeddings_b200.synth, keyed by page name."""
+    from multimodal_embeddings_b200.synth, keyed by page name.  `--detections synthetic` only."""
 
     def __init__(self, boxes_per_page: int = 2000, seed: int = 0xB200):
         self.boxes_per_page, self.seed = boxes_per_page, seed
 
-    def detect_page(self, base: str, width: int, height: int, rows: int, cols: int, overlap: float, tiles):
+    def detect_page(self, base: str, width: int, height: int, rows: int, cols: int, overlap: float, tiles, **_):
         from . import synth
-        n = max(1, self.boxes_per_page * rows * cols // max(1, rows * cols))
+        n = max(1, self.boxes_per_page)
         seed = (self.seed + sum(ord(c) * (i + 1) for i, c in enumerate(base)) + 97 * rows + cols) & 0x7FFFFFFF
         d = synth.page_detections(width, height, rows, cols, overlap, n, seed)
         out = []
@@ -109,13 +109,53 @@ class ReplayDetector:
     def __init__(self, folder: str):
         self.folder = folder
 
-    def detect_page(self, base, width, height, rows, cols, overlap, tiles):
+    def detect_page(self, base, width, height, rows, cols, overlap, tiles, **_):
         name = f"{base}.json" if (rows, cols) == (1, 1) else f"{base}_grid_{rows}x{cols}.json"
         with open(os.path.join(self.folder, "json", name)) as f:
             d = json.load(f)
         if "cells" in d:
             return [{k: c["regions"][k] for k in ("boxes", "classes", "scores", "class_names")} for c in d["cells"]]
         return [{k: d[k] for k in ("boxes", "classes", "scores", "class_names")}]
+
+
+class DocLayoutYoloDetector:
+    """The reference's network (1_doclayout_bboxes.py:178-179) fed with this path's letterboxed tiles instead of
+    image files.  Needs the third-party `doclayout_yolo` package and a local weights file (`--model_path`);
+    neither exists offline, so this class is exercised only where they are installed — and refuses loudly
+    otherwise.  The tiles are already what LetterBox -> /255 produces, so the network is called on the tensors
+    and its boxes are mapped back to tile pixels by undoing the letterbox (ultralytics' scale_boxes:
+    subtract the pad, divide by the gain, clip)."""
+
+    def __init__(self, model_path: str, conf: float, device: Optional[str]):
+        if not model_path or not os.path.exists(model_path):
+            raise FileNotFoundError(f"Model file not found at {model_path}")  # 1:119-121
+        try:
+            from doclayout_yolo import YOLOv10
+        except ImportError as e:
+            raise RuntimeError("--model_path needs the doclayout_yolo package, which is not installed here; "
+                               "use --detector module:factory or --detections replay/synthetic") from e
+        self.model, self.conf, self.device = YOLOv10(model_path), conf, device or "cuda"
+
+    def detect_page(self, base, width, height, rows, cols, overlap, tiles, tile_infos=None, **_):
+        out = []
+        for t, info in zip(tiles, tile_infos):
+            res = self.model.predict(t.unsqueeze(0).float(), imgsz=max(t.shape[1:]), conf=self.conf, device=self.device)[0]
+            b = res.boxes.xyxy.float().cpu().numpy().copy()
+            gain = min(info["new_w"] / (info["x1"] - info["x0"]), info["new_h"] / (info["y1"] - info["y0"]))
+            b[:, [0, 2]] = np.clip((b[:, [0, 2]] - info["pad_l"]) / gain, 0, info["x1"] - info["x0"])
+            b[:, [1, 3]] = np.clip((b[:, [1, 3]] - info["pad_t"]) / gain, 0, info["y1"] - info["y0"])
+            out.append({"boxes": b, "classes": res.boxes.cls.cpu().numpy(), "scores": res.boxes.conf.cpu().numpy()})
+        return out
+
+
+def load_detector_plugin(spec: str, args):
+    """`--detector module:factory`: factory(args) returns an object with
+    detect_page(base, width, height, rows, cols, overlap, tiles, tile_names=, tile_sizes=, tile_infos=) ->
+    one dict per tile {boxes [n,4] xyxy in tile pixels, classes [n], scores [n]} BEFORE the per-tile NMS
+    (the command line applies 1:217-225 itself); `tiles` are the letterboxed fp16 CHW tensors on the GPU."""
+    import importlib
+    mod, _, attr = spec.partition(":")
+    return getattr(importlib.import_module(mod), attr or "Detector")(args)
 
 
 def get_image_paths(input_folder):
@@ -128,8 +168,14 @@ def get_image_paths(input_folder):
     return sorted(paths)
 
 
+def _take(values, keep):
+    if isinstance(values, np.ndarray):
+        return values[keep].tolist()
+    return [values[i] for i in keep]
+
+
 def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
-    from . import ops
+    from . import ops, synth
     from .reference_api import nms_per_tile, parse_grid_configs, translate_coordinates_to_original
     logger = _logger("DocLayoutAnalyzer")
     p = argparse.ArgumentParser(description="Document Layout Analysis")
@@ -145,13 +191,39 @@ def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
     p.add_argument("--grids", type=str, default="2x2,3x3,4x4")
     p.add_argument("--overlap", type=float, default=20.0)
     p.add_argument("--disable_grid", action="store_true")
-    p.add_argument("--detections", choices=["synthetic", "replay"], default="synthetic")
+    p.add_argument("--detector", help="extension: detector plug-in, module:factory (load_detector_plugin)")
+    p.add_argument("--detections", choices=["synthetic", "replay"],
+                   help="extension: synthetic detections (benchmarks/tests) or replay of a stage-1 JSON folder")
     p.add_argument("--replay_folder")
     p.add_argument("--boxes_per_page", type=int, default=2000)
     p.add_argument("--imgsz", type=int, default=1024)
+    p.add_argument("--write_tiles", action="store_true", help="also write the tile images of 1:568 (grid_RxC/images)")
+    p.add_argument("--batch_pages", type=int, default=16, help="pages tiled per launch")
     args = p.parse_args(argv)
     if args.device == "cpu":
         logger.error("--device cpu: this implementation has no CPU path (libpagegeom.so is CUDA only)")
+        return 2
+    # The detector.  The reference downloads DocLayout-YOLO weights here (1:125-129); there is no silent
+    # substitute: without a plug-in, a weights file or an explicit --detections choice the run is refused.
+    try:
+        if args.detector:
+            detector = load_detector_plugin(args.detector, args)
+        elif args.detections == "replay":
+            if not args.replay_folder:
+                raise RuntimeError("--detections replay needs --replay_folder")
+            detector = ReplayDetector(args.replay_folder)
+        elif args.detections == "synthetic":
+            logger.warning("--detections synthetic: boxes, classes and scores in the output are FABRICATED "
+                           "(multimodal_embeddings_b200.synth), not detections of the input images")
+            detector = SyntheticDetector(args.boxes_per_page)
+        elif args.model_path:
+            detector = DocLayoutYoloDetector(args.model_path, args.conf_threshold, args.device)
+        else:
+            raise RuntimeError("no detector: DocLayout-YOLO weights cannot be downloaded here. Give --model_path "
+                               "(with the doclayout_yolo package installed), --detector module:factory, "
+                               "--detections replay --replay_folder DIR, or --detections synthetic")
+    except Exception as e:
+        logger.error(f"Error loading model: {str(e)}")
         return 2
     json_folder = os.path.join(args.output_folder, "json")
     os.makedirs(json_folder, exist_ok=True)
@@ -167,70 +239,108 @@ def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
         logger.error(f"No images found in {args.input_folder}")
         return 0
     image_paths = _my_share(image_paths)
-    detector = ReplayDetector(args.replay_folder) if args.detections == "replay" else SyntheticDetector(args.boxes_per_page)
+    grids = [(1, 1)] + grid_configs
+    params = {"conf_threshold": args.conf_threshold, "iou_threshold": args.iou_threshold}
     processed = errors = 0
-    import cv2
-    for image_path in image_paths:
+    stop = False
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1))
+    for b0 in range(0, len(image_paths), max(1, args.batch_pages)):
+        if stop:
+            break
+        chunk = image_paths[b0:b0 + max(1, args.batch_pages)]
+        # decode on host threads (cv2 releases the GIL), upload through pinned staging, ONE tiler launch for every
+        # tile of every grid of every page of the chunk (pages of different sizes: PgTileBatch)
+        decoded = list(pool.map(ops.decode_page, chunk))
+        live = [(path, page) for path, page in zip(chunk, decoded) if page is not None]
+        for path, page in zip(chunk, decoded):
+            if page is None:  # detect_regions -> None -> process_image False (1:240-242, 466-482)
+                logger.error(f"Error detecting regions in {os.path.basename(path)}: cannot decode image")
+                errors += 1
+        if not live:
+            continue
         try:
-            page = cv2.imread(image_path)  # host decode (out of scope)
-            if page is None:
-                raise RuntimeError(f"Failed to load image: {image_path}")
-            h, w = page.shape[:2]
-            base, ext = os.path.splitext(os.path.basename(image_path))
-            grids = [(1, 1)] + grid_configs
-            plan = ops.TilePlan(w, h, grids, args.overlap, args.imgsz)
-            tiles = plan.run(ops.upload_pages([page], plan))  # every tile of every grid in ONE launch
-            params = {"conf_threshold": args.conf_threshold, "iou_threshold": args.iou_threshold}
-            t0 = 0
-            for rows, cols in grids:
-                n_t = rows * cols
-                views = [plan.tile_view(tiles, 0, t0 + k) for k in range(n_t)]
-                dets = detector.detect_page(base, w, h, rows, cols, args.overlap, views)
-                # per-tile class-agnostic NMS of detect_regions (1:217-225), all tiles of the grid in one launch
-                keeps = nms_per_tile([d["boxes"] for d in dets], [d["scores"] for d in dets], args.iou_threshold)
-                dets = [{k: [d[k][i] for i in keep.tolist()] for k in ("boxes", "classes", "scores", "class_names")}
-                        for d, keep in zip(dets, keeps)]
-                if (rows, cols) == (1, 1) and t0 == 0:  # full-page pass, 1:446-482 / schema 1:227-235
-                    d = dets[0]
-                    _dump({"image_path": image_path, "image_size": {"width": w, "height": h}, "parameters": params,
-                           "boxes": d["boxes"], "classes": d["classes"], "scores": d["scores"],
-                           "class_names": d["class_names"]}, os.path.join(json_folder, f"{base}.json"))
-                else:  # 1:513-654
-                    grid_folder = os.path.join(args.output_folder, f"grid_{rows}x{cols}")
-                    for sub in ("images", "json", "visualizations", "visualizations_original_coords"):
-                        os.makedirs(os.path.join(grid_folder, sub), exist_ok=True)
-                    info = {"original_image_path": image_path,
-                            "grid_config": {"rows": rows, "cols": cols, "overlap_percentage": args.overlap}, "cells": []}
-                    for k, d in enumerate(dets):
-                        ti = plan.tiles[t0 + k]
-                        cc = plan.cell_coordinates(t0 + k)
-                        cell_name = f"{base}_row{ti['row']}_col{ti['col']}{ext}"
-                        cell_path = os.path.join(grid_folder, "images", cell_name)
-                        cell_json = os.path.join(grid_folder, "json", cell_name.replace(ext, ".json"))
-                        orig = translate_coordinates_to_original(d["boxes"], cc)
-                        cell_regions = {"image_path": cell_path,
-                                        "image_size": {"width": ti["x1"] - ti["x0"], "height": ti["y1"] - ti["y0"]},
-                                        "parameters": params, "boxes": d["boxes"], "classes": d["classes"],
-                                        "scores": d["scores"], "class_names": d["class_names"],
-                                        "cell_coordinates": cc, "original_image_path": image_path,
-                                        "boxes_original": orig,
-                                        "grid_info": {"rows": rows, "cols": cols, "row": ti["row"], "col": ti["col"]}}
-                        _dump(cell_regions, cell_json)
-                        info["cells"].append({"cell_path": cell_path, "cell_json_path": cell_json, "cell_coordinates": cc,
-                                              "row": ti["row"], "col": ti["col"],
-                                              "regions": {"boxes": d["boxes"], "boxes_original": orig,
-                                                          "classes": d["classes"], "scores": d["scores"],
-                                                          "class_names": d["class_names"]}})
-                    if info["cells"]:
-                        _dump(info, os.path.join(json_folder, f"{base}_grid_{rows}x{cols}.json"))
-                t0 += n_t
-            processed += 1
-        except Exception as e:  # 1:778-783
-            errors += 1
-            logger.error(f"Error processing {os.path.basename(image_path)}: {str(e)}")
+            batch = ops.TileBatch([(pg.shape[1], pg.shape[0]) for _, pg in live], grids, args.overlap, args.imgsz)
+            batch.bind(ops.upload_pages_pinned([pg for _, pg in live]))
+            batch.run()
+        except Exception as e:
+            errors += len(live)
+            logger.error(f"Error processing {os.path.basename(live[0][0])}: {str(e)}")
             if not args.skip_errors:
                 logger.error("Stopping due to error. Use --skip_errors to continue despite errors.")
                 break
+            continue
+        for pi, (image_path, page) in enumerate(live):
+            try:
+                h, w = page.shape[:2]
+                plan = batch.plan_of(pi)
+                base, ext = os.path.splitext(os.path.basename(image_path))
+                t0 = 0
+                for rows, cols in grids:
+                    n_t = rows * cols
+                    infos = plan.tiles[t0:t0 + n_t]
+                    full_page = (rows, cols) == (1, 1) and t0 == 0
+                    names = [os.path.basename(image_path)] if full_page else \
+                        [f"{base}_row{ti['row']}_col{ti['col']}{ext}" for ti in infos]
+                    sizes = [(ti["x1"] - ti["x0"], ti["y1"] - ti["y0"]) for ti in infos]
+                    views = [batch.tile_view(pi, t0 + k) for k in range(n_t)]
+                    dets = detector.detect_page(base, w, h, rows, cols, args.overlap, views, tile_names=names,
+                                                tile_sizes=sizes, tile_infos=infos)
+                    # per-tile class-agnostic NMS of detect_regions (1:217-225), all tiles of the grid in one launch
+                    keeps = nms_per_tile([d["boxes"] for d in dets], [d["scores"] for d in dets], args.iou_threshold)
+                    kept = []
+                    for d, keep in zip(dets, keeps):
+                        keep = keep.tolist()
+                        classes = _take(d["classes"], keep)
+                        cn = _take(d["class_names"], keep) if "class_names" in d else \
+                            [synth.ID_TO_NAMES[int(c)] for c in classes]  # 1:233
+                        kept.append({"boxes": _take(d["boxes"], keep), "classes": classes,
+                                     "scores": _take(d["scores"], keep), "class_names": cn})
+                    if full_page:  # full-page pass, 1:446-482 / schema 1:227-235
+                        d = kept[0]
+                        _dump({"image_path": image_path, "image_size": {"width": w, "height": h}, "parameters": params,
+                               "boxes": d["boxes"], "classes": d["classes"], "scores": d["scores"],
+                               "class_names": d["class_names"]}, os.path.join(json_folder, f"{base}.json"))
+                    else:  # 1:513-654
+                        grid_folder = os.path.join(args.output_folder, f"grid_{rows}x{cols}")
+                        for sub in ("images", "json", "visualizations", "visualizations_original_coords"):
+                            os.makedirs(os.path.join(grid_folder, sub), exist_ok=True)
+                        info = {"original_image_path": image_path,
+                                "grid_config": {"rows": rows, "cols": cols, "overlap_percentage": args.overlap}, "cells": []}
+                        for k, d in enumerate(kept):
+                            ti = infos[k]
+                            cc = plan.cell_coordinates(t0 + k)
+                            cell_path = os.path.join(grid_folder, "images", names[k])
+                            cell_json = os.path.join(grid_folder, "json", names[k].replace(ext, ".json"))
+                            if args.write_tiles:  # the slice of 1:424-430, written as 1:568 does
+                                import cv2
+                                cv2.imwrite(cell_path, page[ti["y0"]:ti["y1"], ti["x0"]:ti["x1"]])
+                            orig = translate_coordinates_to_original(d["boxes"], cc)
+                            cell_regions = {"image_path": cell_path,
+                                            "image_size": {"width": sizes[k][0], "height": sizes[k][1]},
+                                            "parameters": params, "boxes": d["boxes"], "classes": d["classes"],
+                                            "scores": d["scores"], "class_names": d["class_names"],
+                                            "cell_coordinates": cc, "original_image_path": image_path,
+                                            "boxes_original": orig,
+                                            "grid_info": {"rows": rows, "cols": cols, "row": ti["row"], "col": ti["col"]}}
+                            _dump(cell_regions, cell_json)
+                            info["cells"].append({"cell_path": cell_path, "cell_json_path": cell_json, "cell_coordinates": cc,
+                                                  "row": ti["row"], "col": ti["col"],
+                                                  "regions": {"boxes": d["boxes"], "boxes_original": orig,
+                                                              "classes": d["classes"], "scores": d["scores"],
+                                                              "class_names": d["class_names"]}})
+                        if info["cells"]:
+                            _dump(info, os.path.join(json_folder, f"{base}_grid_{rows}x{cols}.json"))
+                    t0 += n_t
+                processed += 1
+            except Exception as e:  # 1:778-783
+                errors += 1
+                logger.error(f"Error processing {os.path.basename(image_path)}: {str(e)}")
+                if not args.skip_errors:
+                    logger.error("Stopping due to error. Use --skip_errors to continue despite errors.")
+                    stop = True
+                    break
+    pool.shutdown()
     logger.info(f"Processing complete. Successfully processed {processed} images with {errors} errors. "
                 f"Results saved to {args.output_folder}")
     return 0
@@ -452,16 +562,10 @@ def main_stage3(argv: Optional[Sequence[str]] = None) -> int:
         scores = np.concatenate([np.asarray(x[3], np.float64) for x in pooled])
         classes = np.concatenate([np.asarray(x[4], np.float64) for x in pooled])
         ws = ops.NmsWorkspace(len(boxes), len(pooled), 64 if args.iou_threshold >= 0 else int(max(np.diff(off)) // 32 + 2))
+        # status checked inside (a workspace overflow is retried with the dense bound, anything else raises)
         kept, n_kept, ws = ops.nms_merge(boxes, scores, classes, off, args.iou_threshold, workspace=ws,
-                                         max_boxes_per_page=int(max(np.diff(off))))
+                                         max_boxes_per_page=int(max(np.diff(off))), check_status=True)
         kept, n_kept = kept.cpu().numpy(), n_kept.cpu().numpy()
-        st = ws.stats()
-        if st["status"] != 0:
-            dense = ops.NmsWorkspace(len(boxes), len(pooled), int(max(np.diff(off)) // 32 + 2))
-            kept, n_kept, ws = ops.nms_merge(boxes, scores, classes, off, args.iou_threshold, workspace=dense)
-            kept, n_kept = kept.cpu().numpy(), n_kept.cpu().numpy()
-            if ws.stats()["status"] != 0:
-                raise RuntimeError(f"pg_nms_merge failed: {ws.stats()}")
         # Records: laid out on the device (pg_json_combined), byte-identical to json.dump(indent=2).  Inputs that
         # are not what stage 1/2 write (integer literals among the numbers) keep Python's own encoder, which
         # would print them without ".0".
@@ -531,7 +635,7 @@ def main_stage4(argv: Optional[Sequence[str]] = None) -> int:
     for path in files:
         try:  # 4:103-151
             d = recs[path] if path in recs else load_records([path])[path]
-            size = d.get("image_size", {}) or {}
+            size = d.get("image_size", {})  # null (grid-only pooling, 3:249-250) raises here like 4:122-124: no file
             names, boxes = d.get("class_names", []), d.get("boxes", [])
             n = min(len(names), len(boxes))
             pages.append((path, d.get("image_path", ""), size.get("width", 0), size.get("height", 0), boxes[:n], names[:n]))

@@ -966,8 +966,11 @@ __global__ void __launch_bounds__(1024) nms_resolve_cluster_kernel(const int64_t
 // ---- F: emit -------------------------------------------------------------------------------
 constexpr int EMIT_SMEM_ELEMS = 8192;
 
-// ascending u64 key == descending score (positive and negative doubles, -0.0 < +0.0)
+// ascending u64 key == descending score (positive and negative doubles).  -0.0 is folded onto +0.0 first: the
+// suppression ranking (prefilter_or), like Python's max()/index of 3_combine_grids.py:112, compares VALUES, so
+// a -0.0 and a +0.0 score tie and the earlier pooled position wins — the emitted pick order must agree with it.
 __device__ __forceinline__ unsigned long long score_desc_key(double s) {
+  if (s == 0.0) s = 0.0;
   unsigned long long b = (unsigned long long)__double_as_longlong(s);
   b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);  // ascending-orderable
   return ~b;

@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdlib>
@@ -74,7 +75,18 @@ struct TileDev {
   int32_t has_xpad, pad_;     // the chunk holds 114-valued pad columns
   int64_t out_off;    // fp16 elements from the page's output base
 };
-constexpr int TL_MAX_ROW_BYTES = 9216;  // 3 stages x 2 rows x (9216+128) B x 4 CTAs fits the 227 KB of an SM
+constexpr int TL_MAX_ROW_BYTES = 9216;
+// Work counters are per launch: launch k of a plan (or batch) uses slot k % 8 of a small ring, which its last CTA to
+// retire re-arms, so launches of one plan that overlap on different streams never share a counter (up to 8 in
+// flight).  A launch recorded into a CUDA graph keeps its slot for every replay; those take slots 8..15 so that a
+// replaying graph and eager launches of the same plan cannot meet either.
+constexpr int TL_COUNTER_SLOTS = 16;
+static unsigned long long* counter_slot(unsigned long long* base, std::atomic<uint32_t>& seq, cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  const bool capturing = cudaStreamIsCapturing(s, &st) == cudaSuccess && st == cudaStreamCaptureStatusActive;
+  const uint32_t k = seq.fetch_add(1u) % (TL_COUNTER_SLOTS / 2);
+  return base + 2 * (k + (capturing ? TL_COUNTER_SLOTS / 2 : 0));
+}  // 3 stages x 2 rows x (9216+128) B x 4 CTAs fits the 227 KB of an SM
 
 struct PgTilePlan {
   int32_t page_w = 0, page_h = 0, imgsz = 0;
@@ -96,7 +108,8 @@ struct PgTilePlan {
   uint2* d_xtab_full = nullptr;
   int4* d_ytab = nullptr;
   int4* d_items = nullptr;
-  unsigned long long* d_counters = nullptr;  // work-item counter + retired-CTA counter (self-resetting)
+  unsigned long long* d_counters = nullptr;  // TL_COUNTER_SLOTS x {work-item counter, retired-CTA counter}
+  std::atomic<uint32_t> launch_seq{0};
 };
 
 static double py_round_half_even(double v) { return std::nearbyint(v); }
@@ -315,8 +328,8 @@ static int plan_upload(PgTilePlan* p, cudaStream_t s) {
   PG_CUDA_TRY(cudaMalloc(&p->d_xtab_full, p->xtab_full.size() * sizeof(uint2)));
   PG_CUDA_TRY(cudaMalloc(&p->d_ytab, p->ytab.size() * sizeof(int4)));
   PG_CUDA_TRY(cudaMalloc(&p->d_items, p->items.size() * sizeof(int4)));
-  PG_CUDA_TRY(cudaMalloc(&p->d_counters, 2 * sizeof(unsigned long long)));
-  PG_CUDA_TRY(cudaMemsetAsync(p->d_counters, 0, 2 * sizeof(unsigned long long), s));
+  PG_CUDA_TRY(cudaMalloc(&p->d_counters, 2 * TL_COUNTER_SLOTS * sizeof(unsigned long long)));
+  PG_CUDA_TRY(cudaMemsetAsync(p->d_counters, 0, 2 * TL_COUNTER_SLOTS * sizeof(unsigned long long), s));
   PG_CUDA_TRY(cudaMemcpyAsync(p->d_tiles, p->tiles.data(), p->tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice, s));
   PG_CUDA_TRY(cudaMemcpyAsync(p->d_xtab, p->xtab.data(), p->xtab.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
   PG_CUDA_TRY(cudaMemcpyAsync(p->d_tiles_full, p->tiles_full.data(), p->tiles_full.size() * sizeof(TileDev), cudaMemcpyHostToDevice, s));
@@ -748,7 +761,7 @@ static TilerArgs make_args(const PgTilePlan* plan, const uint8_t* pages, int32_t
   a.total_items = (int64_t)plan->items.size() * n_pages;
   a.row_stride = (plan->max_row_bytes + 16 + 127) & ~127;
   a.items_per_cta = 1;
-  a.counters = plan->d_counters;
+  a.counters = plan->d_counters;  // the pipeline launch picks its own slot (counter_slot)
   return a;
 }
 
@@ -801,7 +814,8 @@ extern "C" int pg_tile_letterbox(PgTilePlan* plan, const uint8_t* pages, int32_t
   cudaStream_t s = (cudaStream_t)stream;
   rc = plan_upload(plan, s);
   if (rc != PG_OK) return rc;
-  const TilerArgs a = make_args(plan, pages, n_pages, pitch, page_stride, out_f16, out_page_stride);
+  TilerArgs a = make_args(plan, pages, n_pages, pitch, page_stride, out_f16, out_page_stride);
+  a.counters = counter_slot(plan->d_counters, plan->launch_seq, s);
   return dispatch_pipeline(a, plan->max_out_w, s);
 }
 
@@ -875,6 +889,7 @@ struct PgTileBatch {
   int4* d_items = nullptr;
   PageDesc* d_desc = nullptr;
   unsigned long long* d_counters = nullptr;
+  std::atomic<uint32_t> launch_seq{0};
 };
 
 static void batch_free_device(PgTileBatch* b) {
@@ -969,8 +984,8 @@ extern "C" int pg_tile_batch_bind(PgTileBatch* b, const uint8_t* const* page_ptr
     PG_CUDA_TRY(cudaMalloc(&b->d_ytab, b->ytab.size() * sizeof(int4)));
     PG_CUDA_TRY(cudaMalloc(&b->d_items, b->items.size() * sizeof(int4)));
     PG_CUDA_TRY(cudaMalloc(&b->d_desc, n * sizeof(PageDesc)));
-    PG_CUDA_TRY(cudaMalloc(&b->d_counters, 2 * sizeof(unsigned long long)));
-    PG_CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, 2 * sizeof(unsigned long long), s));
+    PG_CUDA_TRY(cudaMalloc(&b->d_counters, 2 * TL_COUNTER_SLOTS * sizeof(unsigned long long)));
+    PG_CUDA_TRY(cudaMemsetAsync(b->d_counters, 0, 2 * TL_COUNTER_SLOTS * sizeof(unsigned long long), s));
     PG_CUDA_TRY(cudaMemcpyAsync(b->d_tiles, b->tiles.data(), b->tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice, s));
     PG_CUDA_TRY(cudaMemcpyAsync(b->d_xtab, b->xtab.data(), b->xtab.size() * sizeof(uint2), cudaMemcpyHostToDevice, s));
     PG_CUDA_TRY(cudaMemcpyAsync(b->d_ytab, b->ytab.data(), b->ytab.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
@@ -1003,7 +1018,7 @@ extern "C" int pg_tile_letterbox_batch(PgTileBatch* b, void* stream) {
   a.total_items = b->total_items;
   a.row_stride = (b->max_row_bytes + 16 + 127) & ~127;
   a.items_per_cta = 1;
-  a.counters = b->d_counters;
+  a.counters = counter_slot(b->d_counters, b->launch_seq, (cudaStream_t)stream);
   return dispatch_pipeline(a, b->max_out_w, (cudaStream_t)stream);
 }
 
@@ -1050,7 +1065,9 @@ extern "C" int pg_synth_pages(uint8_t* pages, int32_t n_pages, int32_t page_w, i
   PG_REQUIRE(pitch >= (int64_t)3 * page_w && pitch % 16 == 0, "pitch");
   PG_REQUIRE(page_stride >= pitch * page_h && page_stride % 16 == 0, "page_stride");
   if (n_pages == 0) return PG_OK;
-  synth_pages_kernel<<<148 * 16, 256, 0, (cudaStream_t)stream>>>(pages, n_pages, page_w, page_h, pitch, page_stride,
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  synth_pages_kernel<<<sms * 16, 256, 0, (cudaStream_t)stream>>>(pages, n_pages, page_w, page_h, pitch, page_stride,
                                                                   seed0, first_page);
   PG_LAUNCH_CHECK();
   return PG_OK;

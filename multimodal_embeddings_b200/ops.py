@@ -190,6 +190,32 @@ def upload_pages(images: Sequence[np.ndarray], plan: TilePlan, stream=None) -> t
     return host.to("cuda", non_blocking=True)
 
 
+def decode_page(path) -> Optional[np.ndarray]:
+    """Host decode of one scan to BGR uint8 HxWx3, as the reference's cv2.imread (1_doclayout_bboxes.py:381);
+    None when the file cannot be decoded (cv2's own convention)."""
+    import cv2
+    return cv2.imread(str(path))
+
+
+def upload_pages_pinned(images: Sequence[np.ndarray], stream=None) -> List[torch.Tensor]:
+    """Host BGR pages of any sizes -> one pitched cuda tensor [H, pitch] per page (TileBatch.bind's input).
+    All pages go through ONE pinned staging buffer and one asynchronous copy."""
+    _require_cuda()
+    sizes = [(img.shape[0], row_pitch(img.shape[1])) for img in images]
+    offs = np.concatenate([[0], np.cumsum([h * p for h, p in sizes])]).astype(np.int64)
+    host = torch.empty(int(offs[-1]), dtype=torch.uint8).pin_memory()
+    hv = host.numpy()
+    for img, (h, p), o in zip(images, sizes, offs):
+        assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3
+        hv[o:o + h * p].reshape(h, p)[:, : 3 * img.shape[1]] = img.reshape(h, 3 * img.shape[1])
+    if stream is not None:
+        with torch.cuda.stream(stream):
+            dev = host.to("cuda", non_blocking=True)
+    else:
+        dev = host.to("cuda", non_blocking=True)
+    return [dev[o:o + h * p].view(h, p) for (h, p), o in zip(sizes, offs)]
+
+
 def synth_pages(plan: TilePlan, n_pages: int, seed0: int, first_page: int = 0, out: Optional[torch.Tensor] = None,
                 stream=None) -> torch.Tensor:
     _require_cuda()
@@ -257,15 +283,19 @@ class NmsWorkspace:
 
 def nms_merge(boxes, scores, classes, page_off, iou_threshold: float = 0.5, sel_idx=None, n_sel=None,
               max_boxes_per_page: int = 0, workspace: Optional[NmsWorkspace] = None, stream=None,
-              kept_idx: Optional[torch.Tensor] = None, n_kept: Optional[torch.Tensor] = None, mode: int = 0):
+              kept_idx: Optional[torch.Tensor] = None, n_kept: Optional[torch.Tensor] = None, mode: int = 0,
+              check_status: bool = False):
     """pg_nms_merge_ex.  Returns (kept_idx [N] i32 global indices in pick order, n_kept [P] i32, workspace).
-    mode: 0 = stage-3 semantics (class-aware, fp64); PG_NMS_CLASS_AGNOSTIC | PG_NMS_FP32 = torchvision.ops.nms."""
+    mode: 0 = stage-3 semantics (class-aware, fp64); PG_NMS_CLASS_AGNOSTIC | PG_NMS_FP32 = torchvision.ops.nms.
+    check_status=True synchronises and reads the status word the kernels leave in the workspace: a candidate list that
+    outgrew the workspace (PG_ERR_WORKSPACE, n_kept = -1) is re-run with the dense bound, any other error raises.
+    check_status=False (launch-only, for callers that stay asynchronous) leaves that to the caller: `workspace.stats()`."""
     _require_cuda()
     boxes = _dev(boxes, torch.float64).view(-1, 4)
     scores = _dev(scores, torch.float64)
     classes = _dev(classes, torch.float64) if classes is not None else None
-    page_off = _dev(page_off, torch.int64)
-    n, p = boxes.shape[0], page_off.numel() - 1
+    page_off_t = _dev(page_off, torch.int64)
+    n, p = boxes.shape[0], page_off_t.numel() - 1
     if sel_idx is not None:
         sel_idx = _dev(sel_idx, torch.int32)
         n_sel = _dev(n_sel, torch.int32)
@@ -275,9 +305,24 @@ def nms_merge(boxes, scores, classes, page_off, iou_threshold: float = 0.5, sel_
         kept_idx = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
     if n_kept is None:
         n_kept = torch.zeros(max(p, 1), dtype=torch.int32, device="cuda")
-    check(lib().pg_nms_merge_ex(ptr(boxes), ptr(scores), ptr(classes), ptr(sel_idx), ptr(page_off), ptr(n_sel), p, n,
-                                int(max_boxes_per_page), float(iou_threshold), int(mode), ptr(kept_idx), ptr(n_kept),
-                                workspace.ptr, workspace.nbytes, stream_ptr(stream)))
+
+    def launch(ws):
+        check(lib().pg_nms_merge_ex(ptr(boxes), ptr(scores), ptr(classes), ptr(sel_idx), ptr(page_off_t), ptr(n_sel), p,
+                                         n, int(max_boxes_per_page), float(iou_threshold), int(mode), ptr(kept_idx),
+                                    ptr(n_kept), ws.ptr, ws.nbytes, stream_ptr(stream)))
+
+    launch(workspace)
+    if check_status:
+        (stream.synchronize() if stream is not None else torch.cuda.current_stream().synchronize())
+        st = workspace.stats()
+        if st["status"] == _lib.PG_ERR_WORKSPACE:
+            longest = int(max_boxes_per_page) if max_boxes_per_page > 0 else int((page_off_t[1:] - page_off_t[:-1]).max().item())
+            workspace = NmsWorkspace(n, p, pairs_per_block=longest // 32 + 2)
+            launch(workspace)
+            (stream.synchronize() if stream is not None else torch.cuda.current_stream().synchronize())
+            st = workspace.stats()
+        if st["status"] != 0:
+            raise _lib.PageGeomError(f"pg_nms_merge_ex failed on the device: {st}")
     return kept_idx, n_kept[:p], workspace
 
 
@@ -393,6 +438,53 @@ def assign_columns(boxes, page_off, centers, n_cols, sel_idx=None, n_sel=None, s
                                   centers.shape[1] if centers.dim() == 2 else max(1, centers.numel() // max(p, 1)),
                                   ptr(out), stream_ptr(stream)))
     return out[:n]
+
+
+# --------------------------------------------------------------------------------------------
+# K6 corpus-histogram exchange
+# --------------------------------------------------------------------------------------------
+class CorpusComm:
+    """The NCCL communicator of the K6 exchange, created through the C ABI (pg_comm_*): rank 0 makes the id,
+    torch.distributed (whatever backend the process group has) carries its 128 bytes to the other ranks, and
+    every rank joins.  One process per GPU; the current CUDA device is the rank's GPU."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        _require_cuda()
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        ident = (C.c_uint8 * 128)()
+        if self.rank == 0:
+            check(lib().pg_comm_unique_id(ident))
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0)
+        ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        handle = C.c_void_p()
+        check(lib().pg_comm_create(ident, self.world, self.rank, C.byref(handle)))
+        self._h = handle
+        self.nccl = lib().pg_comm_nccl(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pg_comm_destroy(self._h)
+            self._h = None
+
+
+_COMM: Optional[CorpusComm] = None
+
+
+def corpus_comm() -> CorpusComm:
+    global _COMM
+    if _COMM is None:
+        _COMM = CorpusComm()
+    return _COMM
+
+
+def hist_allreduce(hist: torch.Tensor, stream=None) -> torch.Tensor:
+    """pg_hist_allreduce: uint32 bins (int32 storage) summed over the ranks in place, asynchronous on `stream`."""
+    _require_cuda()
+    assert hist.is_cuda and hist.is_contiguous() and hist.element_size() == 4
+    check(lib().pg_hist_allreduce(ptr(hist), hist.numel(), corpus_comm().nccl, stream_ptr(stream)))
+    return hist
 
 
 # --------------------------------------------------------------------------------------------

@@ -17,7 +17,8 @@ import numpy as np
 import torch
 
 from . import ops
-from ._lib import PG_COL_HIST_BINS, PG_COL_SPAN_BYTES, PG_WIDTH_HIST_BINS, check, lib, ptr, stream_ptr
+from ._lib import (PG_COL_HIST_BINS, PG_COL_SPAN_BYTES, PG_ERR_WORKSPACE, PG_WIDTH_HIST_BINS, check, lib, ptr,
+                   stream_ptr)
 
 KERNELS_PER_STEP = 13  # tiler, edge filter, 6 NMS kernels, class flags, width median, column prep + density + peaks
 
@@ -29,13 +30,18 @@ def shard_pages(n_pages_total: int, rank: int, world: int) -> range:
     return range(lo, min(n_pages_total, lo + per))
 
 
-def allreduce_histograms(hist: torch.Tensor) -> torch.Tensor:
+def allreduce_histograms(hist: torch.Tensor, stream=None) -> torch.Tensor:
     """K6 — the only exchange step of the path: corpus-level integer histograms (plain_text widths,
-    column centres) summed over ranks in place.  NCCL over NVLink on GPUs (gloo in the CPU tests);
-    integer sums are order-independent, so 1/2/4/8-rank results are bit-identical."""
+    column centres) summed over ranks in place.  Device histograms go through the C ABI (pg_hist_allreduce: one
+    ncclAllReduce over NVLink on a communicator libpagegeom.so owns); host tensors — the world-size-2 `gloo`
+    tests of the shard logic — through torch.distributed.  Integer sums are order-independent, so
+    1/2/4/8-rank results are bit-identical."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        if hist.is_cuda:
+            ops.hist_allreduce(hist, stream)
+        else:
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM)
     return hist
 
 
@@ -272,30 +278,27 @@ class PagePipeline:
         (NCCL over NVLink; order-independent, so 1/2/4/8-GPU results are bit-identical).
         In place, so call it ONCE, when the shard is finished."""
         if self.corpus_stats:
-            allreduce_histograms(self.hist)
+            allreduce_histograms(self.hist, torch.cuda.current_stream())
         return self.hist
 
     def exchange_corpus_stats_async(self):
         """Running form of K6, callable after every step: a snapshot of the rank's running histograms is
-        summed over ranks on NCCL's own stream, ordered after this step's box kernels only, so the exchange
-        runs under the next steps' tiler instead of serialising the ranks.  `self.hist` stays rank-local;
-        the corpus-wide totals so far are `self.hist_global` once `finish_exchange()` has been called."""
+        summed over ranks (pg_hist_allreduce) on a stream of its own, ordered after this step's box kernels only,
+        so the exchange runs under the next steps' tiler instead of serialising the ranks.  `self.hist` stays
+        rank-local; the corpus-wide totals so far are `self.hist_global` once `finish_exchange()` has been called."""
         if not self.corpus_stats:
             return
-        import torch.distributed as dist
         if not hasattr(self, "_xchg_buf"):
             self._xchg_buf = [torch.zeros_like(self.hist) for _ in range(2)]
-            self._xchg_work, self._xchg_i = [None, None], 0
+            self._xchg_i = 0
+            self.s_xchg = torch.cuda.Stream()
         k = self._xchg_i & 1
         self._xchg_i += 1
         side = self.s_box if self.overlap else torch.cuda.current_stream()
-        with torch.cuda.stream(side):
-            if self._xchg_work[k] is not None:
-                self._xchg_work[k].wait()  # stream-level: the buffer's previous exchange (two steps ago)
-                self._xchg_work[k] = None
+        self.s_xchg.wait_stream(side)  # the step's box kernels (and, stream-ordered, this buffer's previous exchange)
+        with torch.cuda.stream(self.s_xchg):
             self._xchg_buf[k].copy_(self.hist)
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                self._xchg_work[k] = dist.all_reduce(self._xchg_buf[k], op=dist.ReduceOp.SUM, async_op=True)
+            allreduce_histograms(self._xchg_buf[k], self.s_xchg)
         self.hist_global = self._xchg_buf[k]
 
     def finish_exchange(self, stream=None):
@@ -303,13 +306,9 @@ class PagePipeline:
         if not hasattr(self, "_xchg_buf"):
             return getattr(self, "hist", None)
         s = stream if stream is not None else torch.cuda.current_stream()
-        with torch.cuda.stream(s):
-            for k, w in enumerate(self._xchg_work):
-                if w is not None:
-                    w.wait()
-                    self._xchg_work[k] = None
-            if self.overlap:
-                s.wait_stream(self.s_box)
+        s.wait_stream(self.s_xchg)
+        if self.overlap:
+            s.wait_stream(self.s_box)
         return self.hist_global
 
     # ---------------------------------------------------------------- results
@@ -330,7 +329,17 @@ class PagePipeline:
                    for n in ("kept2", "n_kept2", "median", "n_bins", "centers", "col_widths", "n_cols"))
 
     def check_status(self) -> dict:
+        """After a step (synchronises): the merge's status word and the column kernel's limits.  A candidate list
+        that outgrew the NMS workspace (PG_ERR_WORKSPACE: n_kept = -1, and everything downstream of it in that
+        step is void) is handled like the command line does: the workspace is re-sized to the dense bound and the
+        box stages of the step are run again before anything is reported."""
+        torch.cuda.synchronize()
         st = self.nms_ws.stats()
+        if st["status"] == PG_ERR_WORKSPACE:
+            self.nms_ws = ops.NmsWorkspace(self.n_boxes, self.n_pages, pairs_per_block=self.max_per_page // 32 + 2)
+            self._run_boxes(torch.cuda.current_stream())
+            torch.cuda.synchronize()
+            st = self.nms_ws.stats()
         if st["status"] != 0:
             raise RuntimeError(f"NMS merge reported an error on device: {st}")
         if bool((self.n_cols < 0).any().item()):

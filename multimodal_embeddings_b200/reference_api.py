@@ -95,18 +95,9 @@ def nms_per_tile(boxes_list, scores_list, iou_threshold: float):
     if n == 0:
         return [torch.zeros(0, dtype=torch.int64) for _ in bs]
     off = np.concatenate([[0], np.cumsum(counts)])
-    kept, n_kept, ws = ops.nms_merge(np.concatenate(bs).astype(np.float64), np.concatenate(ss).astype(np.float64), None,
-                                     off, iou_threshold, max_boxes_per_page=max(counts),
-                                     mode=PG_NMS_CLASS_AGNOSTIC | PG_NMS_FP32)
-    st = ws.stats()
-    if st["status"] == 3:  # dense bound
-        dense = ops.NmsWorkspace(n, len(bs), pairs_per_block=max(counts) // 32 + 2)
-        kept, n_kept, ws = ops.nms_merge(np.concatenate(bs).astype(np.float64), np.concatenate(ss).astype(np.float64),
-                                         None, off, iou_threshold, workspace=dense,
-                                         mode=PG_NMS_CLASS_AGNOSTIC | PG_NMS_FP32)
-        st = ws.stats()
-    if st["status"] != 0:
-        raise RuntimeError(f"pg_nms_merge_ex failed on device: {st}")
+    kept, n_kept, _ = ops.nms_merge(np.concatenate(bs).astype(np.float64), np.concatenate(ss).astype(np.float64), None,
+                                    off, iou_threshold, max_boxes_per_page=max(counts),
+                                    mode=PG_NMS_CLASS_AGNOSTIC | PG_NMS_FP32, check_status=True)
     kept, n_kept = kept.cpu().numpy(), n_kept.cpu().numpy()
     return [torch.from_numpy((kept[off[i]: off[i] + n_kept[i]] - off[i]).astype(np.int64)) for i in range(len(bs))]
 
@@ -226,16 +217,8 @@ def nms_keep_indices(boxes, scores, classes, iou_threshold=0.5) -> List[int]:
         return []
     args = (np.asarray(boxes, np.float64), np.asarray(scores, np.float64), np.asarray(classes, np.float64), [0, n],
             iou_threshold)
-    kept, n_kept, ws = ops.nms_merge(*args, max_boxes_per_page=n)
+    kept, n_kept, _ = ops.nms_merge(*args, max_boxes_per_page=n, check_status=True)  # raises on a device error
     k = int(n_kept[0].item())
-    st = ws.stats()
-    if st["status"] == 3:  # candidate list outgrew the default workspace: retry with the dense bound
-        dense = ops.NmsWorkspace(n, 1, pairs_per_block=(n + 31) // 32 + 1)
-        kept, n_kept, ws = ops.nms_merge(*args, max_boxes_per_page=n, workspace=dense)
-        k = int(n_kept[0].item())
-        st = ws.stats()
-    if st["status"] != 0 or k < 0:
-        raise RuntimeError(f"pg_nms_merge failed on device: {st}")
     return kept[:k].cpu().numpy().tolist()
 
 

@@ -124,3 +124,20 @@ def test_split_record_text_locates_the_number_arrays():
     other = dict(doc)
     other["scores"], other["classes"] = other.pop("classes"), other.pop("scores")
     assert records.split_record_text(json.dumps({k: doc[k] for k in reversed(list(doc))}, indent=2).encode()) is None
+
+
+def test_stage1_refuses_to_run_without_a_detector(tmp_path, caplog):
+    """No silent substitute for the network: without --model_path / --detector / --detections the run is refused
+    (exit status 2, nothing written); --model_path without the doclayout_yolo package is refused as loudly."""
+    src = tmp_path / "in"
+    src.mkdir()
+    (src / "a.png").write_bytes(b"not an image")
+    out = tmp_path / "out"
+    assert cli.main_stage1(["--input_folder", str(src), "--output_folder", str(out)]) == 2
+    assert not out.exists()
+    weights = tmp_path / "w.pt"
+    weights.write_bytes(b"x")
+    assert cli.main_stage1(["--input_folder", str(src), "--output_folder", str(out), "--model_path", str(weights)]) == 2
+    assert cli.main_stage1(["--input_folder", str(src), "--output_folder", str(out), "--model_path", "/nonexistent.pt"]) == 2
+    assert cli.main_stage1(["--input_folder", str(src), "--output_folder", str(out), "--detections", "replay"]) == 2
+    assert not out.exists()

@@ -57,7 +57,7 @@ def test_cli_stage1_writes_reference_schema(tmp_path):
     Image.fromarray(synth.page_pixels(w, h, 9)[..., ::-1].copy()).save(src / "scan A.png")
     out = tmp_path / "out"
     assert cli.main_stage1(["--input_folder", str(src), "--output_folder", str(out), "--grids", "2x2,3x3",
-                            "--boxes_per_page", "300", "--imgsz", "512"]) == 0
+                            "--detections", "synthetic", "--boxes_per_page", "300", "--imgsz", "512"]) == 0
     std = json.load(open(out / "json" / "scan A.json"))
     assert list(std) == ["image_path", "image_size", "parameters", "boxes", "classes", "scores", "class_names"]
     assert std["image_size"] == {"width": w, "height": h}

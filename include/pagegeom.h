@@ -77,6 +77,15 @@ int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t* grid_rows
                         const int32_t* grid_cols, int32_t n_grids, double overlap_percentage,
                         int32_t imgsz, int32_t stride, int32_t auto_pad, int32_t scaleup,
                         PgTilePlan** plan);
+/* The same for pages of `channels` bytes per pixel: 3 = BGR interleaved (what pg_tile_plan_create builds), 1 = ONE
+ * grey plane — a greyscale scan decoded on the device (pg_jpeg_decode), for which cv2.imread would have replicated
+ * the plane into three equal channels (1:381).  The one-channel kernel reads the plane once and writes the same
+ * value to the three output planes: tiles bit-identical to the three-channel path on the replicated page, a third
+ * of the page bytes.  pitch >= channels*W; algorithmic bytes = channels*W*H + 2*out_elems. */
+int pg_tile_plan_create_ex(int32_t page_w, int32_t page_h, int32_t channels, const int32_t* grid_rows,
+                           const int32_t* grid_cols, int32_t n_grids, double overlap_percentage,
+                           int32_t imgsz, int32_t stride, int32_t auto_pad, int32_t scaleup,
+                           PgTilePlan** plan);
 void pg_tile_plan_destroy(PgTilePlan* plan);
 int32_t pg_tile_plan_num_tiles(const PgTilePlan* plan);
 int pg_tile_plan_tile(const PgTilePlan* plan, int32_t tile, PgTileInfo* info);
@@ -293,6 +302,37 @@ int pg_json_parse_numbers(const uint8_t* text /*dev*/, const int64_t* ranges /*d
                           double* values /*dev [capacity]*/, int64_t capacity, int64_t* val_off /*dev [R+1]*/,
                           int32_t* n_bad /*dev [R]*/, int32_t flags, void* ws, int64_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------ D1-D8 JPEG scans decoded on the device
+ * Replaces, for `.jpg` input, the `cv2.imread(image_path)` that opens the path (1_doclayout_bboxes.py:381, once
+ * per grid; 2_edge_box_filter.py:195): the files cross PCIe compressed and the pages are produced in HBM, bit for
+ * bit what cv2 (libjpeg-turbo: Huffman decode, dequantisation, "islow" integer IDCT) returns.  Baseline / extended
+ * sequential Huffman, 8-bit, one scan, greyscale (the scans of this corpus; cv2 replicates the plane into three
+ * equal channels, the tiler's one-channel plans read the single plane instead).  Anything else — progressive,
+ * colour, arithmetic coding — is PG_ERR_UNSUPPORTED at set_files time and the caller keeps its host decoder for
+ * that file.
+ *   set_files   host: parses the headers of n files lying back to back in `blob` (host memory; file i is
+ *               blob[file_off[i] .. file_off[i+1])); nothing is copied, the device gets the same blob.
+ *   decode      device, asynchronous: blob_dev = the same bytes in device memory; page i is written to
+ *               out_ptrs[i] as uint8 [height, pitches[i]] (8-byte aligned, pitch % 8 == 0).
+ *   status      after the stream has been synchronised: stats[0] = PG_OK, or PG_ERR_UNSUPPORTED when the
+ *               configured number of sync rounds (default 3; pg_jpeg_decoder_configure) did not reach the fixed
+ *               point of the chunk states — raise it and decode again; [1] = rounds that changed a state,
+ *               [2] = states replaced in round 1, [3] = chunks.
+ * Entropy decoding is parallel over fixed chunks of the unstuffed stream (default 512 bytes), self-synchronising;
+ * csrc/pg_jpeg.h describes the passes. */
+typedef struct PgJpegDecoder PgJpegDecoder;
+int pg_jpeg_decoder_create(PgJpegDecoder** dec);
+void pg_jpeg_decoder_destroy(PgJpegDecoder* dec);
+int pg_jpeg_decoder_configure(PgJpegDecoder* dec, int32_t chunk_bytes, int32_t sync_rounds);
+int pg_jpeg_decoder_set_files(PgJpegDecoder* dec, const uint8_t* blob /*host*/, const int64_t* file_off /*host [n+1]*/,
+                              int32_t n);
+int pg_jpeg_decoder_image_info(const PgJpegDecoder* dec, int32_t i, int32_t* width, int32_t* height, int32_t* channels);
+int64_t pg_jpeg_workspace_bytes(const PgJpegDecoder* dec); /* for the files of the last set_files */
+int pg_jpeg_decode(PgJpegDecoder* dec, const uint8_t* blob_dev, uint8_t* const* out_ptrs /*host array of dev ptrs*/,
+                   const int64_t* pitches /*host [n]*/, void* workspace /*dev, 256-aligned*/, int64_t workspace_bytes,
+                   void* stream);
+int pg_jpeg_decode_status(const PgJpegDecoder* dec, int64_t stats[4]);
+
 /* ------------------------------------------------------------------ test hooks
  * Host evaluations of the same inline arithmetic the kernels are compiled from
  * (csrc/pg_math.h, csrc/pg_fmt.h).  Used by the CPU test-suite only; not a compute path. */
@@ -314,6 +354,11 @@ double pg_hostcheck_density_weight(int32_t bin, int32_t left, int32_t right, int
 /* number of (right-left, |bin-center|) pairs in [0,max_span]x[0,max_n] where the reciprocal+FMA
  * form used by the density kernel differs from the true divide (must be 0) */
 int64_t pg_hostcheck_density_rcp_mismatches(int32_t max_span, int32_t max_n);
+/* the decoder's inline code (csrc/pg_jpeg.h) evaluated on the host, chunk by chunk in the kernels' order: one
+ * greyscale file -> out[height, pitch] (out NULL: header only).  stats: [0] sync rounds that changed a state,
+ * [1] states replaced in round 1, [2] chunks, [3] restart markers */
+int pg_hostcheck_jpeg_decode(const uint8_t* file, int64_t len, int32_t chunk_bytes, int32_t max_rounds, uint8_t* out,
+                             int64_t pitch, int32_t* width, int32_t* height, int64_t stats[4]);
 int pg_hostcheck_resize_row(const uint8_t* row0, const uint8_t* row1, int32_t src_w, int32_t src_h,
                             int32_t dst_w, int32_t dst_h, int32_t dy, uint8_t* out_bgr);
 

@@ -48,6 +48,7 @@ SIGNATURES = {
     "pg_version": (C.c_int, []),
     "pg_device_info": (C.c_int, [_P, _P, _P]),
     "pg_tile_plan_create": (C.c_int, [_I32, _I32, _P, _P, _I32, _F64, _I32, _I32, _I32, _I32, _P]),
+    "pg_tile_plan_create_ex": (C.c_int, [_I32, _I32, _I32, _P, _P, _I32, _F64, _I32, _I32, _I32, _I32, _P]),
     "pg_tile_plan_destroy": (None, [_P]),
     "pg_tile_plan_num_tiles": (_I32, [_P]),
     "pg_tile_plan_tile": (C.c_int, [_P, _I32, _P]),
@@ -77,6 +78,15 @@ SIGNATURES = {
     "pg_comm_destroy": (None, [_P]),
     "pg_comm_nccl": (_P, [_P]),
     "pg_hist_allreduce": (C.c_int, [_P, C.c_size_t, _P, _P]),
+    "pg_jpeg_decoder_create": (C.c_int, [_P]),
+    "pg_jpeg_decoder_destroy": (None, [_P]),
+    "pg_jpeg_decoder_configure": (C.c_int, [_P, _I32, _I32]),
+    "pg_jpeg_decoder_set_files": (C.c_int, [_P, _P, _P, _I32]),
+    "pg_jpeg_decoder_image_info": (C.c_int, [_P, _I32, _P, _P, _P]),
+    "pg_jpeg_workspace_bytes": (_I64, [_P]),
+    "pg_jpeg_decode": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P]),
+    "pg_jpeg_decode_status": (C.c_int, [_P, _P]),
+    "pg_hostcheck_jpeg_decode": (C.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, _P, _P]),
     "pg_json_workspace_bytes": (_I64, [_I64, _I32]),
     "pg_json_combined": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P,
                                    _P, _I64, _P]),

@@ -22,8 +22,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpagegeom.so")
 STAMP = LIB + ".srchash"
-SOURCES = ["pg_tiler.cu", "pg_boxes.cu", "pg_json.cu", "pg_comm.cu"]
-HEADERS = ["pg_common.cuh", "pg_math.h", "pg_fmt.h", "pg_ryu_tables.h", os.path.join("..", "..", "include", "pagegeom.h")]
+SOURCES = ["pg_tiler.cu", "pg_boxes.cu", "pg_json.cu", "pg_comm.cu", "pg_jpeg.cu"]
+HEADERS = ["pg_common.cuh", "pg_math.h", "pg_fmt.h", "pg_ryu_tables.h", "pg_jpeg.h", os.path.join("..", "..", "include", "pagegeom.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "--threads", "0", "-ldl",

@@ -1,0 +1,358 @@
+// pg_jpeg.h — baseline JPEG entropy decoding + inverse DCT as inline host/device code, shared by the CUDA
+// kernels (pg_jpeg.cu) and by the host evaluation used in the CPU test-suite (pg_hostcheck_jpeg_decode).
+//
+// Replaces, for `.jpg` scans, the `cv2.imread(image_path)` that opens every stage of the reference
+// (1_doclayout_bboxes.py:381, 2_edge_box_filter.py:195): libjpeg-turbo's sequential Huffman decoder (ITU-T T.81
+// Annex F), dequantisation and the "islow" integer IDCT (jidctint.c), restated from the published algorithm.
+// Bit-exact against cv2.imdecode (tests).
+//
+// Parallel entropy decoding.  A Huffman bit stream has no index, so it is cut into fixed CHUNKS of the
+// unstuffed stream and decoded in three passes (the self-synchronising scheme of Weissenberger & Schmidt,
+// "Massively Parallel Huffman Decoding on GPUs", adapted to JPEG block structure and restart markers):
+//   1. every chunk is decoded speculatively from its first bit as if a block started there; Huffman streams
+//      resynchronise within a few code words, so most chunks END in the true decoder state.  A chunk's exit
+//      state = (bit position, block-in-MCU index) of the first block starting at or after the chunk's end;
+//   2. sync rounds: chunk j is decoded again from chunk j-1's exit state; if the exit it reaches differs from
+//      the stored one it is replaced and chunk j+1 is redone in the next round.  Chunk 0 starts in the true
+//      state, so a round without changes means every exit state is true.  Restart markers (byte-aligned, DC
+//      predictors reset) are known true states and resynchronise a wrong decoder at once;
+//   3. a segmented scan over the chunks' block counts and DC-difference sums gives every chunk the absolute
+//      block index and DC predictors at its entry; the final pass decodes again and stores coefficients.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define PGJ_HD __host__ __device__ __forceinline__
+#else
+#define PGJ_HD inline
+#endif
+
+constexpr int PGJ_LUT_BITS = 9;
+constexpr int PGJ_MAX_BLOCKS_PER_MCU = 10;
+
+struct PgjHuff {
+  uint16_t lut[1 << PGJ_LUT_BITS];  // (length << 8) | symbol for codes of <= 9 bits; 0: longer code
+  int32_t maxcode[18];              // maxcode[l] = largest code of length l (-1: none); [17] = sentinel
+  int32_t valoff[17];               // symbol index of the first code of length l minus that code
+  uint8_t vals[256];
+};
+
+struct PgjImage {
+  int32_t width, height, n_comps;
+  int32_t mcus_w, mcus_h, bpm;                  // blocks per MCU
+  int32_t blk_comp[PGJ_MAX_BLOCKS_PER_MCU];     // component of block c of an MCU
+  int32_t blk_dx[PGJ_MAX_BLOCKS_PER_MCU], blk_dy[PGJ_MAX_BLOCKS_PER_MCU];
+  int32_t comp_h[3], comp_v[3];                 // sampling factors
+  int32_t comp_bw[3], comp_bh[3];               // blocks per row / column of the component's coefficient plane
+  int32_t comp_dc[3], comp_ac[3];               // Huffman table ids (0/1)
+  int64_t comp_coef_off[3];                     // int16 elements from the image's coefficient base
+  int32_t restart_blocks;                       // blocks per restart interval (0: no restart markers)
+  int32_t total_blocks;
+  uint16_t qt[3][64];                           // per component, natural order
+  PgjHuff huff[2][2];                           // [class: 0 DC, 1 AC][table id]
+};
+
+struct PgjStream {
+  const uint8_t* bytes;     // unstuffed entropy-coded data, readable 512 bytes beyond n_bits / 8
+  int64_t n_bits;
+  const int32_t* rst_pos;   // byte positions (in `bytes`) where restart interval k+1 starts, ascending
+  int32_t n_rst;
+};
+
+struct PgjChunkState {   // 32 bytes
+  int64_t p;             // exit: bit position of the first block starting at/after the chunk's end; -1 invalid, -2 inactive
+  int32_t c;             // block-in-MCU index there
+  int32_t n;             // blocks accepted since the chunk's entry, or since the last restart passed
+  int32_t anchor;        // -1: no restart passed inside; k: restart interval k was entered (block index k * restart_blocks)
+  int32_t dc[3];         // sums of DC differences per component since entry / the last restart
+};
+
+// natural-order index of zigzag position k
+#define PGJ_ZIGZAG_TABLE                                                                                             \
+  {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28, \
+   35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, \
+   62, 63}
+#ifdef __CUDACC__
+static __device__ const uint8_t pgj_zz_dev[64] = PGJ_ZIGZAG_TABLE;  // global memory: lanes index it divergently
+#endif
+static const uint8_t pgj_zz_host[64] = PGJ_ZIGZAG_TABLE;
+PGJ_HD int pgj_zigzag(int k) {
+#ifdef __CUDA_ARCH__
+  return __ldg(&pgj_zz_dev[k]);
+#else
+  return pgj_zz_host[k];
+#endif
+}
+
+// ---- bit reader over the unstuffed stream (big-endian bit order) ---------------------------------------
+struct PgjBits {
+  const uint8_t* base;
+  uint64_t buf;       // next bits, left-aligned
+  int32_t avail;      // valid bits in buf
+  int64_t next_word;  // index of the next 32-bit word to load
+
+  PGJ_HD uint32_t load_be(int64_t w) const {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(base + 4 * w);  // base is 4-byte aligned
+#ifdef __CUDA_ARCH__
+    return __byte_perm(v, 0u, 0x0123);
+#else
+    return (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24);
+#endif
+  }
+  PGJ_HD void seek(const uint8_t* b, int64_t p) {
+    base = b;
+    next_word = p >> 5;
+    buf = ((uint64_t)load_be(next_word) << 32) | (uint64_t)load_be(next_word + 1);
+    next_word += 2;
+    const int sh = (int)(p & 31);
+    buf <<= sh;
+    avail = 64 - sh;
+  }
+  PGJ_HD void need32() {  // at least 32 valid bits afterwards
+    if (avail < 32) {
+      buf |= (uint64_t)load_be(next_word++) << (32 - avail);
+      avail += 32;
+    }
+  }
+  PGJ_HD int64_t pos() const { return next_word * 32 - avail; }
+  PGJ_HD uint32_t peek16() const { return (uint32_t)(buf >> 48); }
+  PGJ_HD void skip(int n) { buf <<= n; avail -= n; }
+  PGJ_HD uint32_t take(int n) {  // n in 1..16
+    const uint32_t v = (uint32_t)(buf >> (64 - n));
+    skip(n);
+    return v;
+  }
+};
+
+// one Huffman symbol; -1: no such code.  Needs >= 16 valid bits.
+PGJ_HD int pgj_symbol(PgjBits& br, const PgjHuff& h) {
+  const uint32_t look = br.peek16();
+  const uint32_t e = h.lut[look >> (16 - PGJ_LUT_BITS)];
+  if (e) {
+    br.skip((int)(e >> 8));
+    return (int)(e & 0xFFu);
+  }
+  for (int l = PGJ_LUT_BITS + 1; l <= 16; ++l) {
+    const int32_t code = (int32_t)(look >> (16 - l));
+    if (code <= h.maxcode[l]) {
+      br.skip(l);
+      return h.vals[(code + h.valoff[l]) & 0xFF];
+    }
+  }
+  return -1;
+}
+
+PGJ_HD int pgj_extend(uint32_t v, int s) { return v < (1u << (s - 1)) ? (int)v - (1 << s) + 1 : (int)v; }
+
+// One block, decoded leniently: a decoder that is out of step (pass 1) must keep walking so that it can fall
+// into step, so a bit pattern that is no code word costs one bit and a run that overshoots the block ends it.
+// Neither happens to a decoder in the true state on a valid stream.  `stop`: the next restart boundary / end of the
+// scan — a block that reaches it is not a block (padding, or a decoder out of step) and false is returned.
+// Emit::dc(diff) / Emit::ac(natural index, value).
+template <class Emit>
+PGJ_HD bool pgj_block(PgjBits& br, const PgjHuff& dc, const PgjHuff& ac, int& dc_diff, Emit& emit, int64_t stop) {
+  int s;
+  while (true) {
+    br.need32();
+    s = pgj_symbol(br, dc);
+    if (s >= 0) break;
+    br.skip(1);
+    if (br.pos() >= stop) return false;
+  }
+  s &= 15;
+  int diff = 0;
+  if (s) diff = pgj_extend(br.take(s), s);
+  dc_diff = diff;
+  emit.dc(diff);
+  int k = 1;
+  while (k < 64) {
+    if (br.pos() >= stop) return false;
+    br.need32();
+    const int rs = pgj_symbol(br, ac);
+    if (rs < 0) { br.skip(1); continue; }
+    const int r = rs >> 4;
+    s = rs & 15;
+    if (s == 0) {
+      if (r != 15) break;  // EOB
+      k += 16;             // ZRL
+      continue;
+    }
+    k += r;
+    if (k > 63) { br.skip(s); break; }
+    emit.ac(pgj_zigzag(k), pgj_extend(br.take(s), s));
+    ++k;
+  }
+  return true;
+}
+
+struct PgjNoEmit {
+  PGJ_HD void dc(int) {}
+  PGJ_HD void ac(int, int) {}
+};
+
+// first restart whose boundary lies beyond bit p
+PGJ_HD int pgj_next_restart(const PgjStream& sv, int64_t p) {
+  int lo = 0, hi = sv.n_rst;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((int64_t)sv.rst_pos[mid] * 8 > p) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// Passes 1 and 2: decode (without storing anything) from state (p, c) until a block starts at or after `limit`.
+// Interval ends are found from the bits alone: the block that would cross a restart boundary (or the end of the
+// stream) is padding — or the work of a decoder that is out of step — and the decoder moves to the boundary,
+// which is a true state.
+PGJ_HD void pgj_span(const PgjStream& sv, const PgjImage& im, int64_t p, int c, int64_t limit, int anchor_in,
+                     PgjChunkState& out) {
+  int n = 0, anchor = anchor_in;
+  int d0 = 0, d1 = 0, d2 = 0;
+  int r = pgj_next_restart(sv, p - 1);  // first boundary at or beyond p
+  if (r < sv.n_rst && (int64_t)sv.rst_pos[r] * 8 == p) {
+    // p lies exactly on a boundary: the interval before it ended without padding, or the previous chunk's
+    // walk already moved here — either way restart interval r + 1 begins at p (taking it twice changes nothing)
+    anchor = r + 1;
+    c = 0;
+    ++r;
+  }
+  int64_t bound = r < sv.n_rst ? (int64_t)sv.rst_pos[r] * 8 : sv.n_bits;
+  PgjBits br;
+  br.seek(sv.bytes, p);
+  PgjNoEmit none;
+  while (p < limit && p < sv.n_bits) {
+    const int comp = im.blk_comp[c];
+    int diff = 0;
+    const bool ok = pgj_block(br, im.huff[0][im.comp_dc[comp]], im.huff[1][im.comp_ac[comp]], diff, none, bound);
+    const int64_t pe = br.pos();
+    if (!ok || pe > bound) {
+      if (bound >= sv.n_bits) { p = sv.n_bits; c = 0; break; }  // end of the scan
+      p = bound; c = 0; anchor = r + 1; n = 0; d0 = d1 = d2 = 0;
+      ++r;
+      bound = r < sv.n_rst ? (int64_t)sv.rst_pos[r] * 8 : sv.n_bits;
+      br.seek(sv.bytes, p);
+      continue;
+    }
+    ++n;
+    if (comp == 0) d0 += diff; else if (comp == 1) d1 += diff; else d2 += diff;
+    c = c + 1 == im.bpm ? 0 : c + 1;
+    p = pe;
+  }
+  out.p = p; out.c = c; out.n = n; out.anchor = anchor; out.dc[0] = d0; out.dc[1] = d1; out.dc[2] = d2;
+}
+
+// where block `blk` (scan order) of the image keeps its 64 coefficients, in int16 elements from the image's base
+PGJ_HD int64_t pgj_block_coef_index(const PgjImage& im, int blk, int c, int& comp) {
+  comp = im.blk_comp[c];
+  if (im.bpm == 1) return (int64_t)blk * 64;
+  const int mcu = blk / im.bpm;
+  const int my = mcu / im.mcus_w, mx = mcu - my * im.mcus_w;
+  const int bx = mx * im.comp_h[comp] + im.blk_dx[c], by = my * im.comp_v[comp] + im.blk_dy[c];
+  return im.comp_coef_off[comp] + ((int64_t)by * im.comp_bw[comp] + bx) * 64;
+}
+
+struct PgjStoreEmit {
+  int16_t* dst;  // the block's 64 coefficients (zero-filled beforehand)
+  int pred;
+  PGJ_HD void dc(int diff) { if (dst) dst[0] = (int16_t)(pred + diff); }
+  PGJ_HD void ac(int idx, int v) { if (dst) dst[idx] = (int16_t)v; }
+};
+
+// Pass 3: the same walk from a TRUE state with the absolute block index and the DC predictors known; stores
+// coefficients.  Interval ends are taken from the block count here (nothing speculative is left).
+PGJ_HD void pgj_span_store(const PgjStream& sv, const PgjImage& im, int64_t p, int c, int64_t limit, int blk,
+                           int pred0, int pred1, int pred2, int16_t* coef_base) {
+  int pred[3] = {pred0, pred1, pred2};
+  if (im.restart_blocks && blk > 0 && blk % im.restart_blocks == 0) {
+    // the entry lies in the padding behind a completed interval (or already on the boundary): the next block
+    // is the first of restart interval k and starts on the k-th boundary with cleared predictors
+    const int k = blk / im.restart_blocks;
+    if (k - 1 >= sv.n_rst) return;
+    p = (int64_t)sv.rst_pos[k - 1] * 8;
+    pred[0] = pred[1] = pred[2] = 0;
+    c = 0;
+  }
+  int r = pgj_next_restart(sv, p);
+  PgjBits br;
+  br.seek(sv.bytes, p);
+  while (p < limit && p < sv.n_bits && blk < im.total_blocks) {
+    int comp;
+    const int64_t ci = pgj_block_coef_index(im, blk, c, comp);
+    PgjStoreEmit emit{coef_base + ci, pred[comp]};
+    int diff = 0;
+    if (!pgj_block(br, im.huff[0][im.comp_dc[comp]], im.huff[1][im.comp_ac[comp]], diff, emit, sv.n_bits + 64)) return;  // corrupt
+    pred[comp] += diff;
+    ++blk;
+    c = c + 1 == im.bpm ? 0 : c + 1;
+    p = br.pos();
+    if (im.restart_blocks && blk % im.restart_blocks == 0) {  // interval complete: skip the padding
+      if (r >= sv.n_rst) return;
+      p = (int64_t)sv.rst_pos[r] * 8;
+      ++r;
+      pred[0] = pred[1] = pred[2] = 0;
+      c = 0;
+      br.seek(sv.bytes, p);
+    }
+  }
+}
+
+// ---- jidctint.c ("islow"): 13-bit constants, PASS1_BITS = 2 --------------------------------------------
+PGJ_HD int32_t pgj_descale(int32_t x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+PGJ_HD void pgj_idct_1d(int32_t i0, int32_t i1, int32_t i2, int32_t i3, int32_t i4, int32_t i5, int32_t i6, int32_t i7,
+                        int shift, int32_t* o) {
+  int32_t z1 = (i2 + i6) * 4433;
+  const int32_t tmp2 = z1 + i6 * (-15137);
+  const int32_t tmp3 = z1 + i2 * 6270;
+  const int32_t tmp0 = (i0 + i4) * 8192, tmp1 = (i0 - i4) * 8192;
+  const int32_t tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  int32_t t0 = i7, t1 = i5, t2 = i3, t3 = i1;
+  z1 = t0 + t3;
+  int32_t z2 = t1 + t2, z3 = t0 + t2, z4 = t1 + t3;
+  const int32_t z5 = (z3 + z4) * 9633;
+  t0 *= 2446; t1 *= 16819; t2 *= 25172; t3 *= 12299;
+  z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;
+  z3 += z5; z4 += z5;
+  t0 += z1 + z3; t1 += z2 + z4; t2 += z2 + z3; t3 += z1 + z4;
+  o[0] = pgj_descale(tmp10 + t3, shift); o[7] = pgj_descale(tmp10 - t3, shift);
+  o[1] = pgj_descale(tmp11 + t2, shift); o[6] = pgj_descale(tmp11 - t2, shift);
+  o[2] = pgj_descale(tmp12 + t1, shift); o[5] = pgj_descale(tmp12 - t1, shift);
+  o[3] = pgj_descale(tmp13 + t0, shift); o[4] = pgj_descale(tmp13 - t0, shift);
+}
+
+PGJ_HD uint8_t pgj_clamp_sample(int32_t x) {
+  x += 128;
+  return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
+}
+
+// coef: 64 quantised coefficients (natural order); q: quantisation table; out[8][8] samples
+PGJ_HD void pgj_idct_block(const int16_t* coef, const uint16_t* q, uint8_t out[64]) {
+  int32_t ws[64];
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {  // pass 1: columns
+    int32_t o[8];
+    pgj_idct_1d((int32_t)coef[x] * q[x], (int32_t)coef[8 + x] * q[8 + x], (int32_t)coef[16 + x] * q[16 + x],
+                (int32_t)coef[24 + x] * q[24 + x], (int32_t)coef[32 + x] * q[32 + x], (int32_t)coef[40 + x] * q[40 + x],
+                (int32_t)coef[48 + x] * q[48 + x], (int32_t)coef[56 + x] * q[56 + x], 11, o);
+#pragma unroll
+    for (int y = 0; y < 8; ++y) ws[8 * y + x] = o[y];
+  }
+#pragma unroll
+  for (int y = 0; y < 8; ++y) {  // pass 2: rows
+    int32_t o[8];
+    pgj_idct_1d(ws[8 * y], ws[8 * y + 1], ws[8 * y + 2], ws[8 * y + 3], ws[8 * y + 4], ws[8 * y + 5], ws[8 * y + 6],
+                ws[8 * y + 7], 18, o);
+#pragma unroll
+    for (int x = 0; x < 8; ++x) out[8 * y + x] = pgj_clamp_sample(o[x]);
+  }
+}
+
+// bytes that leave the entropy-coded segment when it is unstuffed: the zero after a data FF, and both bytes of
+// a restart marker FF D0..D7 (prev / next: neighbouring bytes, 0 outside the segment)
+PGJ_HD bool pgj_is_rst(uint8_t b) { return b >= 0xD0 && b <= 0xD7; }
+PGJ_HD bool pgj_keep_byte(uint8_t prev, uint8_t cur, uint8_t next) {
+  if (prev == 0xFF && (cur == 0x00 || pgj_is_rst(cur))) return false;
+  if (cur == 0xFF && pgj_is_rst(next)) return false;
+  return true;
+}
+PGJ_HD bool pgj_rst_starts(uint8_t cur, uint8_t next) { return cur == 0xFF && pgj_is_rst(next); }

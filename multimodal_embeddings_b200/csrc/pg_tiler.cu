@@ -90,6 +90,7 @@ static unsigned long long* counter_slot(unsigned long long* base, std::atomic<ui
 
 struct PgTilePlan {
   int32_t page_w = 0, page_h = 0, imgsz = 0;
+  int32_t channels = 3;  // 3: BGR interleaved pages (cv2.imread); 1: one grey plane (a greyscale scan decoded on the device)
   std::vector<PgTileInfo> info;
   std::vector<TileDev> tiles;       // column chunks (pipeline kernel); items index this table
   std::vector<TileDev> tiles_full;  // whole tiles (direct validation kernel), one per PgTileInfo
@@ -114,11 +115,25 @@ struct PgTilePlan {
 
 static double py_round_half_even(double v) { return std::nearbyint(v); }
 
+extern "C" int pg_tile_plan_create_ex(int32_t page_w, int32_t page_h, int32_t channels, const int32_t* grid_rows,
+                                      const int32_t* grid_cols, int32_t n_grids, double overlap_percentage,
+                                      int32_t imgsz, int32_t stride, int32_t auto_pad, int32_t scaleup,
+                                      PgTilePlan** plan_out);
 extern "C" int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t* grid_rows,
                                    const int32_t* grid_cols, int32_t n_grids, double overlap_percentage,
                                    int32_t imgsz, int32_t stride, int32_t auto_pad, int32_t scaleup,
                                    PgTilePlan** plan_out) {
+  return pg_tile_plan_create_ex(page_w, page_h, 3, grid_rows, grid_cols, n_grids, overlap_percentage, imgsz, stride,
+                                auto_pad, scaleup, plan_out);
+}
+
+extern "C" int pg_tile_plan_create_ex(int32_t page_w, int32_t page_h, int32_t channels, const int32_t* grid_rows,
+                                      const int32_t* grid_cols, int32_t n_grids, double overlap_percentage,
+                                      int32_t imgsz, int32_t stride, int32_t auto_pad, int32_t scaleup,
+                                      PgTilePlan** plan_out) {
   PG_REQUIRE(plan_out != nullptr, "plan");
+  PG_REQUIRE(channels == 1 || channels == 3, "channels must be 1 (grey plane) or 3 (BGR)");
+  const int CHN = channels;
   PG_REQUIRE(page_w > 0 && page_h > 0, "page size");
   PG_REQUIRE(n_grids > 0 && grid_rows && grid_cols, "grids");
   PG_REQUIRE(imgsz > 0 && stride > 0 && imgsz % 2 == 0, "imgsz/stride");
@@ -126,6 +141,7 @@ extern "C" int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t
   plan->page_w = page_w;
   plan->page_h = page_h;
   plan->imgsz = imgsz;
+  plan->channels = channels;
   int64_t out_off = 0;
   int max_row_bytes = TL_MAX_ROW_BYTES;
   if (const char* e = getenv("PG_TILER_MAX_ROW_BYTES")) max_row_bytes = std::max(64, atoi(e));  // test / tuning knob
@@ -199,8 +215,8 @@ extern "C" int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t
         td.out_w = ti.out_w; td.out_h = ti.out_h;
         td.xtab_off = (int32_t)plan->xtab_full.size();
         td.ytab_off = (int32_t)plan->ytab.size();
-        td.row_skew = (3 * ti.x0) & 15;
-        td.row_bytes = (td.row_skew + 3 * sw + 15) & ~15;
+        td.row_skew = (CHN * ti.x0) & 15;
+        td.row_bytes = (td.row_skew + CHN * sw + 15) & ~15;
         td.chunk_x0 = 0; td.chunk_w = ti.out_w;
         td.has_xpad = (ti.pad_l != 0 || ti.new_w != ti.out_w) ? 1 : 0;
         td.out_off = ti.out_offset;
@@ -213,7 +229,7 @@ extern "C" int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t
           } else {
             cx[x] = pg_resize_coef(sw, ti.new_w, rx, true);
             // when c1 == 0 the neighbour is multiplied by zero, so s1 never needs to be stored
-            plan->xtab_full.push_back(make_uint2((uint32_t)(3 * cx[x].s0), (uint32_t)cx[x].c0 | ((uint32_t)cx[x].c1 << 16)));
+            plan->xtab_full.push_back(make_uint2((uint32_t)(CHN * cx[x].s0), (uint32_t)cx[x].c0 | ((uint32_t)cx[x].c1 << 16)));
           }
         }
         for (int y = 0; y < ti.new_h; ++y) {
@@ -241,7 +257,7 @@ extern "C" int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t
           for (int c0 = 0; c0 < ti.out_w; c0 += chunk_w) {
             int lo, hi;
             chunk_span(c0, chunk_w, &lo, &hi);
-            worst = std::max(worst, ((3 * (ti.x0 + lo)) & 15) + 3 * (hi - lo) + 15);
+            worst = std::max(worst, ((CHN * (ti.x0 + lo)) & 15) + CHN * (hi - lo) + 15);
           }
           if (worst <= max_row_bytes || chunk_w <= 64) break;
         }
@@ -253,8 +269,8 @@ extern "C" int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t
           ch.chunk_w = std::min(chunk_w, (int)ti.out_w - c0);
           ch.x0 = ti.x0 + lo;
           ch.src_w = hi - lo;
-          ch.row_skew = (3 * ch.x0) & 15;
-          ch.row_bytes = (ch.row_skew + 3 * (hi - lo) + 15) & ~15;
+          ch.row_skew = (CHN * ch.x0) & 15;
+          ch.row_bytes = (ch.row_skew + CHN * (hi - lo) + 15) & ~15;
           ch.xtab_off = (int32_t)plan->xtab.size();
           ch.has_xpad = 0;
           for (int x = c0; x < c0 + ch.chunk_w; ++x) {
@@ -262,7 +278,7 @@ extern "C" int pg_tile_plan_create(int32_t page_w, int32_t page_h, const int32_t
               ch.has_xpad = 1;
               plan->xtab.push_back(make_uint2(0u, TL_PADMARK));
             } else {
-              plan->xtab.push_back(make_uint2((uint32_t)(3 * (cx[x].s0 - lo)), (uint32_t)cx[x].c0 | ((uint32_t)cx[x].c1 << 16)));
+              plan->xtab.push_back(make_uint2((uint32_t)(CHN * (cx[x].s0 - lo)), (uint32_t)cx[x].c0 | ((uint32_t)cx[x].c1 << 16)));
             }
           }
           plan->max_row_bytes = std::max(plan->max_row_bytes, ch.row_bytes);
@@ -314,7 +330,7 @@ extern "C" int pg_tile_plan_tile(const PgTilePlan* plan, int32_t tile, PgTileInf
 }
 extern "C" int64_t pg_tile_plan_out_elems(const PgTilePlan* plan) { return plan ? plan->out_elems : 0; }
 extern "C" int64_t pg_tile_plan_algorithmic_bytes(const PgTilePlan* plan) {
-  return plan ? (int64_t)3 * plan->page_w * plan->page_h + 2 * plan->out_elems : 0;
+  return plan ? (int64_t)plan->channels * plan->page_w * plan->page_h + 2 * plan->out_elems : 0;
 }
 
 static int plan_upload(PgTilePlan* p, cudaStream_t s) {
@@ -420,6 +436,13 @@ __device__ __forceinline__ void hpass_smem(uint32_t row_addr, uint32_t off, uint
   hr = __dp2a_lo(coef, rr, 0u);
 }
 
+// one-channel pages: the two neighbouring source bytes of a pixel at byte offset `off` of a staged row
+__device__ __forceinline__ uint32_t hpass_smem_grey(uint32_t row_addr, uint32_t off, uint32_t coef) {
+  const uint32_t a = row_addr + (off >> 16);
+  const uint32_t w0 = lds32(a), w1 = lds32(a + 4);
+  return __dp2a_lo(coef, __funnelshift_r(w0, w1, off), 0u);  // a0*S0 + a1*S1
+}
+
 __device__ __forceinline__ uint32_t pack_unit_half2(uint32_t va, uint32_t vb) {
   // fp16(v/255): v*(1/255) in fp32 then one RN conversion matches fp16(fp32(v)/255) for all 256 v
   const float k = 1.0f / 255.0f;
@@ -478,6 +501,7 @@ struct TilerArgs {
   int64_t total_items;
   int32_t row_stride;     // shared-memory bytes per staged row
   int32_t items_per_cta;  // work items a CTA may claim before it retires
+  int32_t channels;       // bytes per source pixel (3: BGR, 1: grey plane)
   unsigned long long* counters;  // [0] next item, [1] CTAs finished (self-resetting)
 };
 
@@ -490,7 +514,7 @@ constexpr int TL_MSG_PADROW = 1 << 30;
 // many shared-memory words as with a pixel pair per lane (the kernel's l1tex pipe was 92 % busy with 2.3
 // wavefronts per LDS).  The half2 pairs for the stores are formed by one exchange with the neighbouring lane:
 // even lanes store pixels (L, L+1), odd lanes store (32+L-1, 32+L).  XPAD: the chunk has 114-valued columns.
-template <int ITER, bool XPAD>
+template <int ITER, bool XPAD, int CHN>
 __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const uint32_t (&xoff)[ITER][2],
                                           const uint32_t (&coef)[ITER][2], uint32_t b0, uint32_t b1,
                                           uint32_t* pr, uint32_t* pg, uint32_t* pb, int out_w, int warp_px, int store_px,
@@ -498,6 +522,30 @@ __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const ui
 #pragma unroll
   for (int i = 0; i < ITER; ++i) {
     if (i * TL_PAIR_STRIDE + warp_px < out_w) {  // warp-uniform: the exchange below needs every lane
+      if (CHN == 1) {
+        // one grey plane in, the same value to the three output planes (what cv2.imread's replicated channels
+        // would give through the three-channel path, at a third of the arithmetic and of the page bytes)
+        uint32_t ay[2], by[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (XPAD && coef[i][j] == TL_PADMARK) {
+            ay[j] = (4u * TL_PAD_VALUE + 2u) << 16;
+            by[j] = 0u;
+          } else {
+            ay[j] = b0 * (hpass_smem_grey(row0, xoff[i][j], coef[i][j]) >> 4) + 0x20000u;
+            by[j] = b1 * (hpass_smem_grey(row1, xoff[i][j], coef[i][j]) >> 4);
+          }
+        }
+        const uint32_t vy = vpass_pair_half2(ay, by);
+        const uint32_t ny = __shfl_xor_sync(0xffffffffu, vy, 1);
+        if (i * TL_PAIR_STRIDE + store_px < out_w) {
+          const uint32_t pair = __byte_perm(vy, ny, pair_sel);
+          __stcs(pr + i * (TL_PAIR_STRIDE / 2), pair);
+          __stcs(pg + i * (TL_PAIR_STRIDE / 2), pair);
+          __stcs(pb + i * (TL_PAIR_STRIDE / 2), pair);
+        }
+        continue;
+      }
       // pg_vpass split in two: the 32-bit products of each source row (rounding +2 folded into the
       // row-0 product's addend), then both pixels of the pair finished 16 bits to a lane.
       uint32_t ab[2], ag[2], ar[2], bb[2], bg[2], br[2];
@@ -529,7 +577,7 @@ __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const ui
   }
 }
 
-template <int ITER, int TL_STAGES>
+template <int ITER, int TL_STAGES, int CHN>
 __global__ void __launch_bounds__(TL_THREADS, ITER <= 2 ? 4 : 2) tile_letterbox_kernel(const TilerArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[TL_STAGES];
@@ -579,7 +627,7 @@ __global__ void __launch_bounds__(TL_THREADS, ITER <= 2 ? 4 : 2) tile_letterbox_
         }
         const TileDev& t = a.tiles[item.x];
         const int pad_t = t.pad_t, new_h = t.new_h, ytab_off = t.ytab_off;
-        const uint8_t* src = page_src + (int64_t)t.y0 * pitch + ((3 * t.x0) & ~15);
+        const uint8_t* src = page_src + (int64_t)t.y0 * pitch + ((CHN * t.x0) & ~15);
         const uint32_t bytes = (uint32_t)t.row_bytes;
         for (int oy = item.y; oy < item.y + item.z; ++oy) {
           const int ry = oy - pad_t;
@@ -680,8 +728,8 @@ __global__ void __launch_bounds__(TL_THREADS, ITER <= 2 ? 4 : 2) tile_letterbox_
       const uint32_t b0 = (uint32_t)m.w & 0xFFFFu, b1 = (uint32_t)m.w >> 16;
       const uint32_t row0 = smem_base + stage * stage_bytes;
       const uint32_t row1 = row0 + (uint32_t)a.row_stride;
-      if (xpad) tiler_row<ITER, true>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, warp_px, store_px, pair_sel);
-      else tiler_row<ITER, false>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, warp_px, store_px, pair_sel);
+      if (xpad) tiler_row<ITER, true, CHN>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, warp_px, store_px, pair_sel);
+      else tiler_row<ITER, false, CHN>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, warp_px, store_px, pair_sel);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + stage * 8u);
@@ -699,7 +747,8 @@ __global__ void __launch_bounds__(256) tile_letterbox_direct_kernel(const TilerA
   const int64_t npairs = (int64_t)pairs_w * t.out_h;
   __half* out_tile = a.out + (int64_t)page * a.out_page_stride + t.out_off;
   const int64_t plane = (int64_t)t.out_h * t.out_w;
-  const uint8_t* src = a.pages + (int64_t)page * a.page_stride + (int64_t)t.y0 * a.pitch + 3 * (int64_t)t.x0;
+  const int chn = a.channels;
+  const uint8_t* src = a.pages + (int64_t)page * a.page_stride + (int64_t)t.y0 * a.pitch + chn * (int64_t)t.x0;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += (int64_t)gridDim.x * blockDim.x) {
     const int oy = (int)(p / pairs_w), ox = (int)(p - (int64_t)oy * pairs_w) * 2;
     const int ry = oy - t.pad_t;
@@ -714,11 +763,12 @@ __global__ void __launch_bounds__(256) tile_letterbox_direct_kernel(const TilerA
         const uint32_t a0 = e.y & 0xFFFFu, a1 = e.y >> 16;
         const uint8_t* r0 = src + (int64_t)yt.x * a.pitch + e.x;
         const uint8_t* r1 = src + (int64_t)yt.y * a.pitch + e.x;
-        const int dx = a1 ? 3 : 0;
+        const int dx = a1 ? chn : 0;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const uint32_t h0 = pg_hpass(r0[c], r0[c + dx], a0, a1);
-          const uint32_t h1 = pg_hpass(r1[c], r1[c + dx], a0, a1);
+          const int cc = chn == 3 ? c : 0;  // a grey plane feeds all three output planes
+          const uint32_t h0 = pg_hpass(r0[cc], r0[cc + dx], a0, a1);
+          const uint32_t h1 = pg_hpass(r1[cc], r1[cc + dx], a0, a1);
           v[c][j] = pg_vpass(h0, h1, (uint32_t)yt.z, (uint32_t)yt.w);
         }
       }
@@ -735,7 +785,8 @@ static int check_pages_layout(const PgTilePlan* plan, const uint8_t* pages, int3
   PG_REQUIRE(plan != nullptr, "plan");
   PG_REQUIRE(pages != nullptr && out != nullptr, "null device pointer");
   PG_REQUIRE(n_pages >= 0, "n_pages");
-  PG_REQUIRE(pitch >= (int64_t)3 * plan->page_w && pitch % 16 == 0, "pitch must be >= 3*W and a multiple of 16");
+  PG_REQUIRE(pitch >= (int64_t)plan->channels * plan->page_w && pitch % 16 == 0,
+             "pitch must be >= channels*W and a multiple of 16");
   PG_REQUIRE(page_stride >= pitch * plan->page_h && page_stride % 16 == 0, "page_stride");
   PG_REQUIRE(((uintptr_t)pages & 15) == 0, "pages must be 16-byte aligned");
   PG_REQUIRE(out_page_stride >= plan->out_elems && out_page_stride % 2 == 0, "out_page_stride");
@@ -761,12 +812,13 @@ static TilerArgs make_args(const PgTilePlan* plan, const uint8_t* pages, int32_t
   a.total_items = (int64_t)plan->items.size() * n_pages;
   a.row_stride = (plan->max_row_bytes + 16 + 127) & ~127;
   a.items_per_cta = 1;
+  a.channels = plan->channels;
   a.counters = plan->d_counters;  // the pipeline launch picks its own slot (counter_slot)
   return a;
 }
 
-template <int ITER, int TL_STAGES>
-static int launch_pipeline(TilerArgs a, cudaStream_t s) {
+template <int ITER, int TL_STAGES, int CHN>
+static int launch_pipeline_c(TilerArgs a, cudaStream_t s) {
   const size_t smem = (size_t)TL_STAGES * 2 * a.row_stride;
   int dev = 0, sms = 0, max_smem = 0;
   PG_CUDA_TRY(cudaGetDevice(&dev));
@@ -776,7 +828,7 @@ static int launch_pipeline(TilerArgs a, cudaStream_t s) {
     pg_set_error("unsupported: tile rows of %d bytes need %zu B of shared memory (max %d)", a.row_stride, smem, max_smem);
     return PG_ERR_UNSUPPORTED;
   }
-  auto kernel = tile_letterbox_kernel<ITER, TL_STAGES>;
+  auto kernel = tile_letterbox_kernel<ITER, TL_STAGES, CHN>;
   PG_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   PG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TL_THREADS, smem));
@@ -802,6 +854,11 @@ static int launch_pipeline(TilerArgs a, cudaStream_t s) {
   kernel<<<(unsigned)grid, TL_THREADS, smem, s>>>(a);
   PG_LAUNCH_CHECK();
   return PG_OK;
+}
+
+template <int ITER, int TL_STAGES>
+static int launch_pipeline(const TilerArgs& a, cudaStream_t s) {
+  return a.channels == 1 ? launch_pipeline_c<ITER, TL_STAGES, 1>(a, s) : launch_pipeline_c<ITER, TL_STAGES, 3>(a, s);
 }
 
 static int dispatch_pipeline(const TilerArgs& a, int max_out_w, cudaStream_t s);
@@ -873,6 +930,7 @@ extern "C" int pg_tile_letterbox_direct(PgTilePlan* plan, const uint8_t* pages, 
 struct PgTileBatch {
   std::vector<int32_t> page_plan;
   std::vector<int32_t> plan_w, plan_h, plan_tile_base, plan_item_base, plan_item_count;
+  int32_t channels = 3;
   std::vector<int64_t> plan_out_elems;
   std::vector<TileDev> tiles;
   std::vector<uint2> xtab;
@@ -912,6 +970,12 @@ extern "C" int pg_tile_batch_create(const PgTilePlan* const* plans, int32_t n_pl
       pg_set_error("invalid argument: plan %d is null", k);
       return PG_ERR_INVALID;
     }
+    if (k == 0) b->channels = p->channels;
+    if (p->channels != b->channels) {
+      delete b;
+      pg_set_error("invalid argument: the plans of a batch must share the channel count");
+      return PG_ERR_INVALID;
+    }
     const int32_t xb = (int32_t)b->xtab.size(), yb = (int32_t)b->ytab.size();
     b->plan_tile_base.push_back((int32_t)b->tiles.size());
     b->plan_item_base.push_back((int32_t)b->items.size());
@@ -946,7 +1010,7 @@ extern "C" int pg_tile_batch_create(const PgTilePlan* const* plans, int32_t n_pl
     d.tile_base = b->plan_tile_base[k];
     b->desc.push_back(d);
     off += b->plan_item_count[k];
-    b->alg_bytes += (int64_t)3 * b->plan_w[k] * b->plan_h[k] + 2 * b->plan_out_elems[k];
+    b->alg_bytes += (int64_t)b->channels * b->plan_w[k] * b->plan_h[k] + 2 * b->plan_out_elems[k];
   }
   b->total_items = off;
   *out = b;
@@ -970,8 +1034,8 @@ extern "C" int pg_tile_batch_bind(PgTileBatch* b, const uint8_t* const* page_ptr
   for (size_t i = 0; i < n; ++i) {
     const int k = b->page_plan[i];
     PG_REQUIRE(page_ptrs[i] && out_ptrs[i], "null page / output pointer");
-    PG_REQUIRE(((uintptr_t)page_ptrs[i] & 15) == 0 && pitches[i] % 16 == 0 && pitches[i] >= (int64_t)3 * b->plan_w[k],
-               "each page must be 16-byte aligned with pitch >= 3*W and a multiple of 16");
+    PG_REQUIRE(((uintptr_t)page_ptrs[i] & 15) == 0 && pitches[i] % 16 == 0 && pitches[i] >= (int64_t)b->channels * b->plan_w[k],
+               "each page must be 16-byte aligned with pitch >= channels*W and a multiple of 16");
     PG_REQUIRE(((uintptr_t)out_ptrs[i] & 3) == 0, "outputs must be 4-byte aligned");
     b->desc[i].src = page_ptrs[i];
     b->desc[i].out = reinterpret_cast<__half*>(out_ptrs[i]);
@@ -1018,6 +1082,7 @@ extern "C" int pg_tile_letterbox_batch(PgTileBatch* b, void* stream) {
   a.total_items = b->total_items;
   a.row_stride = (b->max_row_bytes + 16 + 127) & ~127;
   a.items_per_cta = 1;
+  a.channels = b->channels;
   a.counters = counter_slot(b->d_counters, b->launch_seq, (cudaStream_t)stream);
   return dispatch_pipeline(a, b->max_out_w, (cudaStream_t)stream);
 }

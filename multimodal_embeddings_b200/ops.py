@@ -25,9 +25,9 @@ def _require_cuda():
 MAX_DENSITY_BINS = 2048
 
 
-def row_pitch(width: int) -> int:
-    """Row pitch (bytes) of a BGR uint8 page for the tiler: 3*W rounded up to 16 (bulk-copy alignment)."""
-    return (3 * int(width) + 15) // 16 * 16
+def row_pitch(width: int, channels: int = 3) -> int:
+    """Row pitch (bytes) of a uint8 page for the tiler: channels*W rounded up to 16 (bulk-copy alignment)."""
+    return (int(channels) * int(width) + 15) // 16 * 16
 
 
 # --------------------------------------------------------------------------------------------
@@ -42,15 +42,16 @@ class TilePlan:
 
     def __init__(self, page_w: int, page_h: int, grids: Sequence[Tuple[int, int]] = ((2, 2),),
                  overlap: float = 20.0, imgsz: int = 1024, stride: int = 32, auto: bool = True,
-                 scaleup: bool = True):
-        self.page_w, self.page_h = int(page_w), int(page_h)
+                 scaleup: bool = True, channels: int = 3):
+        self.page_w, self.page_h, self.channels = int(page_w), int(page_h), int(channels)
         self.grids = [(int(r), int(c)) for r, c in grids]
         self.overlap, self.imgsz, self.stride, self.auto = float(overlap), int(imgsz), int(stride), bool(auto)
         rows = (C.c_int32 * len(self.grids))(*[g[0] for g in self.grids])
         cols = (C.c_int32 * len(self.grids))(*[g[1] for g in self.grids])
         handle = C.c_void_p()
-        check(lib().pg_tile_plan_create(self.page_w, self.page_h, rows, cols, len(self.grids), self.overlap,
-                                        self.imgsz, self.stride, int(auto), int(scaleup), C.byref(handle)))
+        check(lib().pg_tile_plan_create_ex(self.page_w, self.page_h, self.channels, rows, cols, len(self.grids),
+                                           self.overlap, self.imgsz, self.stride, int(auto), int(scaleup),
+                                           C.byref(handle)))
         self._h = handle
         self.tiles: List[dict] = []
         for t in range(lib().pg_tile_plan_num_tiles(self._h)):
@@ -59,7 +60,7 @@ class TilePlan:
             self.tiles.append({name: getattr(info, name) for name, _ in PgTileInfo._fields_})
         self.out_elems = int(lib().pg_tile_plan_out_elems(self._h))
         self.algorithmic_bytes = int(lib().pg_tile_plan_algorithmic_bytes(self._h))
-        self.pitch = row_pitch(self.page_w)
+        self.pitch = row_pitch(self.page_w, self.channels)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -93,7 +94,7 @@ class TilePlan:
 
     def run(self, pages: torch.Tensor, out: Optional[torch.Tensor] = None, stream=None,
             direct: bool = False) -> torch.Tensor:
-        """pages: cuda uint8 [P, H, pitch] (BGR interleaved rows, pitch % 16 == 0).
+        """pages: cuda uint8 [P, H, pitch] (BGR interleaved rows, or one grey plane for channels=1; pitch % 16 == 0).
         Returns fp16 [P, out_elems]; tile_view() slices a tile out of it."""
         _require_cuda()
         assert pages.is_cuda and pages.dtype == torch.uint8 and pages.dim() == 3 and pages.is_contiguous()
@@ -119,8 +120,9 @@ class TileBatch:
     tensor [H_i, pitch_i]; outputs are allocated here as one fp16 tensor per page."""
 
     def __init__(self, sizes: Sequence[Tuple[int, int]], grids: Sequence[Tuple[int, int]] = ((2, 2),),
-                 overlap: float = 20.0, imgsz: int = 1024, stride: int = 32, auto: bool = True):
+                 overlap: float = 20.0, imgsz: int = 1024, stride: int = 32, auto: bool = True, channels: int = 3):
         _require_cuda()
+        self.channels = int(channels)
         self.sizes = [(int(w), int(h)) for w, h in sizes]
         self.plans: List[TilePlan] = []
         index = {}
@@ -128,7 +130,7 @@ class TileBatch:
         for s in self.sizes:
             if s not in index:
                 index[s] = len(self.plans)
-                self.plans.append(TilePlan(s[0], s[1], grids, overlap, imgsz, stride, auto))
+                self.plans.append(TilePlan(s[0], s[1], grids, overlap, imgsz, stride, auto, channels=self.channels))
             self.page_plan.append(index[s])
         n = len(self.sizes)
         plan_arr = (C.c_void_p * len(self.plans))(*[p._h for p in self.plans])
@@ -144,7 +146,7 @@ class TileBatch:
         return self.plans[self.page_plan[page]]
 
     def alloc_pages(self) -> List[torch.Tensor]:
-        return [torch.empty((h, row_pitch(w)), dtype=torch.uint8, device="cuda") for (w, h) in self.sizes]
+        return [torch.empty((h, row_pitch(w, self.channels)), dtype=torch.uint8, device="cuda") for (w, h) in self.sizes]
 
     def bind(self, pages: Sequence[torch.Tensor], stream=None) -> List[torch.Tensor]:
         n = len(self.sizes)
@@ -214,6 +216,141 @@ def upload_pages_pinned(images: Sequence[np.ndarray], stream=None) -> List[torch
     else:
         dev = host.to("cuda", non_blocking=True)
     return [dev[o:o + h * p].view(h, p) for (h, p), o in zip(sizes, offs)]
+
+
+# --------------------------------------------------------------------------------------------
+# D1-D8 JPEG scans decoded on the device
+# --------------------------------------------------------------------------------------------
+class JpegDecoder:
+    """pg_jpeg_*: greyscale baseline JPEG files -> grey pages in HBM, bit for bit what cv2.imread returns
+    (in each of its three equal channels).  Usage per batch of files:
+
+        sizes = dec.set_files(blob, file_off)        # host: headers parsed; blob = files back to back
+        pages = dec.decode(blob_dev)                 # device, asynchronous; list of uint8 [H, pitch] tensors
+        dec.check()                                  # after a synchronisation: raises / retries on non-convergence
+
+    `blob` is a uint8 numpy array or (pinned) CPU tensor; `blob_dev` the same bytes on the GPU."""
+
+    def __init__(self, chunk_bytes: int = 0, sync_rounds: int = 4):
+        handle = C.c_void_p()
+        check(lib().pg_jpeg_decoder_create(C.byref(handle)))
+        self._h = handle
+        self.chunk_bytes, self.sync_rounds = int(chunk_bytes), int(sync_rounds)
+        self.auto_chunk = chunk_bytes <= 0
+        self.ws: Optional[torch.Tensor] = None
+        self.sizes: List[Tuple[int, int, int]] = []
+        self._last = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().pg_jpeg_decoder_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def set_files(self, blob, file_off) -> List[Tuple[int, int, int]]:
+        """Parses the headers (host).  Returns [(width, height, channels)].  Raises PageGeomError (error 4,
+        'unsupported: ...') for anything but greyscale/colour baseline Huffman files."""
+        arr = blob.numpy() if isinstance(blob, torch.Tensor) else np.asarray(blob)
+        assert arr.dtype == np.uint8 and arr.ndim == 1 and arr.flags.c_contiguous
+        off = np.ascontiguousarray(np.asarray(file_off, np.int64))
+        n = len(off) - 1
+        if self.auto_chunk:
+            # chunk ~ 24 blocks of the batch's average block length (entropy bytes / 8x8 blocks is not known before
+            # the headers are parsed, so the first pass uses 512 and a re-parse follows only when that is far off)
+            self.chunk_bytes = self.chunk_bytes or 512
+        check(lib().pg_jpeg_decoder_configure(self._h, self.chunk_bytes, self.sync_rounds))
+        check(lib().pg_jpeg_decoder_set_files(self._h, arr.ctypes.data, off.ctypes.data, n))
+        self.sizes = []
+        w, h, c = C.c_int32(), C.c_int32(), C.c_int32()
+        for i in range(n):
+            check(lib().pg_jpeg_decoder_image_info(self._h, i, C.byref(w), C.byref(h), C.byref(c)))
+            self.sizes.append((w.value, h.value, c.value))
+        if self.auto_chunk:
+            blocks = sum(((w + 7) // 8) * ((h + 7) // 8) for w, h, _ in self.sizes)
+            per_block = float(off[-1] - off[0]) / max(blocks, 1)
+            want = 64
+            while want < 24 * per_block and want < 4096:
+                want *= 2
+            want = max(want, 256)
+            if want != self.chunk_bytes:
+                self.chunk_bytes = want
+                check(lib().pg_jpeg_decoder_configure(self._h, self.chunk_bytes, self.sync_rounds))
+                check(lib().pg_jpeg_decoder_set_files(self._h, arr.ctypes.data, off.ctypes.data, n))
+        self._host = (arr, off)
+        return self.sizes
+
+    def alloc_pages(self) -> List[torch.Tensor]:
+        _require_cuda()
+        return [torch.empty((h, row_pitch(w, c)), dtype=torch.uint8, device="cuda") for w, h, c in self.sizes]
+
+    def decode(self, blob_dev: torch.Tensor, outs: Optional[Sequence[torch.Tensor]] = None, stream=None) -> List[torch.Tensor]:
+        _require_cuda()
+        assert blob_dev.is_cuda and blob_dev.dtype == torch.uint8 and blob_dev.is_contiguous()
+        if outs is None:
+            outs = self.alloc_pages()
+        n = len(self.sizes)
+        assert len(outs) == n
+        need = int(lib().pg_jpeg_workspace_bytes(self._h))
+        if self.ws is None or self.ws.numel() < need + 256:
+            self.ws = torch.empty(need + need // 8 + 256, dtype=torch.uint8, device="cuda")
+        ws_ptr = self.ws.data_ptr() + ((-self.ws.data_ptr()) % 256)
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in outs])
+        pitches = (C.c_int64 * n)(*[t.shape[1] for t in outs])
+        check(lib().pg_jpeg_decode(self._h, ptr(blob_dev), ptrs, pitches, ws_ptr, need, stream_ptr(stream)))
+        self._last = (blob_dev, list(outs), stream)
+        return list(outs)
+
+    def status(self) -> dict:
+        arr = (C.c_int64 * 4)()
+        check(lib().pg_jpeg_decode_status(self._h, arr))
+        return {"status": arr[0], "rounds_used": arr[1], "states_replaced_round1": arr[2], "chunks": arr[3]}
+
+    def check(self) -> dict:
+        """After the decode's stream has been synchronised.  If the configured sync rounds did not reach the fixed
+        point (long blocks against short chunks), the rounds are doubled and the batch decoded again."""
+        st = self.status()
+        while st["status"] != 0:
+            if self.sync_rounds >= 64:
+                raise _lib.PageGeomError(f"pg_jpeg_decode: chunk states did not converge: {st}")
+            self.sync_rounds = min(64, self.sync_rounds * 2)
+            arr, off = self._host
+            check(lib().pg_jpeg_decoder_configure(self._h, self.chunk_bytes, self.sync_rounds))
+            check(lib().pg_jpeg_decoder_set_files(self._h, arr.ctypes.data, off.ctypes.data, len(off) - 1))
+            blob_dev, outs, stream = self._last
+            self.decode(blob_dev, outs, stream)
+            (stream.synchronize() if stream is not None else torch.cuda.current_stream().synchronize())
+            st = self.status()
+        return st
+
+
+def pack_files(files: Sequence[bytes], pinned: bool = True):
+    """Files back to back, each starting on a 256-byte boundary -> (uint8 CPU tensor, int64 offsets [n+1] of the
+    files' FIRST bytes plus the end of the last).  pg_jpeg_decoder_set_files takes file i as
+    blob[off[i] .. off[i+1]); the alignment padding at a file's end is ignored by the parser (it lies behind EOI)."""
+    off = [0]
+    for f in files:
+        off.append(off[-1] + (len(f) + 255) // 256 * 256)
+    blob = torch.zeros(off[-1] + 256, dtype=torch.uint8)
+    if pinned and torch.cuda.is_available():
+        blob = blob.pin_memory()
+    view = blob.numpy()
+    for f, o in zip(files, off):
+        view[o:o + len(f)] = np.frombuffer(f, np.uint8)
+    return blob, np.asarray(off, np.int64)
+
+
+def decode_jpeg_files(files: Sequence[bytes], decoder: Optional[JpegDecoder] = None) -> List[torch.Tensor]:
+    """Convenience: greyscale JPEG files (bytes) -> grey pages on the GPU (synchronises)."""
+    dec = decoder or JpegDecoder()
+    blob, off = pack_files(files)
+    dec.set_files(blob, off)
+    pages = dec.decode(blob.to("cuda", non_blocking=True))
+    torch.cuda.current_stream().synchronize()
+    dec.check()
+    return pages
 
 
 def synth_pages(plan: TilePlan, n_pages: int, seed0: int, first_page: int = 0, out: Optional[torch.Tensor] = None,

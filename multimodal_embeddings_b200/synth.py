@@ -156,3 +156,33 @@ def page_pixels(width, height, seed):
     img = np.where(ink, rng.normal(30, 10, (height, width, 1)), bg)
     img = img + rng.normal(0, 3, (height, width, 3))
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def newspaper_page(width, height, seed):
+    """Grey uint8 [H, W] scan-like page for the compressed-input leg (bench e2e, decoder tests): text lines of
+    glyph-sized ink cells in columns with gutters, word gaps and paragraph breaks, rendered at a quarter of the
+    resolution and enlarged bilinearly (soft stroke edges), on paper with slow shading and optically blurred
+    grain.  Unlike `page_pixels` (independent noise per pixel, incompressible) it compresses like a scan: about
+    3 bits/pixel as JPEG at cv2's default quality 95, 1.4 at quality 75."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    cw, ch = (width + 3) // 4, (height + 3) // 4
+    ink = rng.random((ch, cw)) < 0.42
+    line = (np.arange(ch) % 10 >= 1) & (np.arange(ch) % 10 <= 6)
+    para = (np.arange(ch) // 10) % 9 == 8
+    ncol = max(2, round(width / 1000))
+    gutter = (np.arange(cw) % (cw / ncol)) < (cw / ncol) * 0.04
+    gaps = np.zeros(cw, bool)
+    pos = 0
+    while pos < cw:
+        pos += int(rng.integers(5, 14))
+        gaps[pos:pos + 2] = True
+        pos += 2
+    mask = ink & (line & ~para)[:, None] & ~(gutter | gaps)[None, :]
+    big = cv2.resize(np.where(mask, 40, 228).astype(np.uint8), (cw * 4, ch * 4), interpolation=cv2.INTER_LINEAR)
+    big = big[:height, :width].astype(np.float32)
+    gy, gx = np.mgrid[0:height + 64:64, 0:width + 64:64]
+    shade = (6 * np.sin(gx / 900.0 + seed % 7) + 5 * np.cos(gy / 700.0)).astype(np.float32)
+    big += cv2.resize(shade, (width, height), interpolation=cv2.INTER_LINEAR)
+    big += cv2.blur(rng.integers(-6, 7, (height, width)).astype(np.float32), (3, 3))
+    return np.clip(big, 0, 255).astype(np.uint8)

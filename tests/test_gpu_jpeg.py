@@ -1,0 +1,127 @@
+"""GPU parity of the compressed-input path: JPEG files -> pages in HBM (pg_jpeg_decode) against cv2.imdecode (what
+the reference's cv2.imread returns, 1_doclayout_bboxes.py:381), and the one-channel tiler against the
+three-channel tiler on the replicated page."""
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from multimodal_embeddings_b200 import ops, synth
+from multimodal_embeddings_b200._lib import PageGeomError
+
+pytestmark = pytest.mark.gpu
+
+
+def _page(h, w, seed, noise=4.0):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = 200 + 20 * np.sin(xx / 37.0) + 15 * np.cos(yy / 23.0) + rng.normal(0, noise, (h, w))
+    return np.clip(np.where(rng.random((h, w)) < 0.08, 40, img), 0, 255).astype(np.uint8)
+
+
+def _encode(img, q=95, rst=0, extra=()):
+    ok, buf = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_RST_INTERVAL, rst, *extra])
+    assert ok
+    return buf.tobytes()
+
+
+def _ref(data):
+    bgr = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+    assert np.array_equal(bgr[..., 0], bgr[..., 1]) and np.array_equal(bgr[..., 0], bgr[..., 2])
+    return bgr[..., 0]
+
+
+@pytest.mark.parametrize("chunk", [64, 256, 512, 4096])
+def test_decode_batch_of_mixed_files_equals_cv2(chunk):
+    """One launch sequence for files of different sizes, qualities and restart intervals (none, every MCU, every
+    7 MCUs, one per MCU row), sizes that are not multiples of 8, a single-block image."""
+    specs = [(64, 64, 95, 0), (61, 77, 75, 1), (8, 8, 95, 0), (517, 640, 30, 7), (1003, 1501, 95, 0), (1000, 760, 100, 0),
+             (333, 200, 90, 25), (1640, 1180, 85, 148), (40, 3000, 95, 0)]
+    files = [_encode(_page(h, w, 10 + i, 4 if i % 2 else 30), q, rst) for i, (h, w, q, rst) in enumerate(specs)]
+    dec = ops.JpegDecoder(chunk_bytes=chunk, sync_rounds=4)
+    pages = ops.decode_jpeg_files(files, dec)
+    for data, page, (h, w, _, _) in zip(files, pages, specs):
+        assert page.shape == (h, ops.row_pitch(w, 1))
+        assert np.array_equal(page[:, :w].cpu().numpy(), _ref(data))
+    assert dec.status()["status"] == 0
+
+
+def test_decode_full_size_scan_like_pages_equals_cv2():
+    """8000x6000 newspaper-like pages at cv2's default quality and at 75, automatic chunk size."""
+    files = [_encode(synth.newspaper_page(8000, 6000, 5), 95), _encode(synth.newspaper_page(8000, 6000, 6), 75),
+             _encode(synth.newspaper_page(7934, 5755, 7), 95, rst=992)]
+    dec = ops.JpegDecoder()
+    pages = ops.decode_jpeg_files(files, dec)
+    st = dec.status()
+    assert st["status"] == 0 and st["rounds_used"] <= dec.sync_rounds
+    for data, page in zip(files, pages):
+        ref = _ref(data)
+        assert np.array_equal(page[:, :ref.shape[1]].cpu().numpy(), ref)
+
+
+def test_decode_retries_with_more_rounds_when_the_states_have_not_converged():
+    """Quality 100 on a noisy page: blocks of ~1000 bits against 64-byte chunks, one sync round configured — the
+    status word reports it and check() decodes again with more rounds until the fixed point is reached."""
+    data = _encode(_page(600, 800, 3, 40), 100)
+    dec = ops.JpegDecoder(chunk_bytes=64, sync_rounds=1)
+    blob, off = ops.pack_files([data])
+    dec.set_files(blob, off)
+    pages = dec.decode(blob.cuda())
+    torch.cuda.synchronize()
+    assert dec.status()["status"] != 0
+    st = dec.check()
+    assert st["status"] == 0 and dec.sync_rounds > 1
+    assert np.array_equal(pages[0][:, :800].cpu().numpy(), _ref(data))
+
+
+def test_unsupported_files_are_refused_at_parse_time():
+    g = _page(64, 64, 1)
+    ok, prog = cv2.imencode(".jpg", g, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    dec = ops.JpegDecoder()
+    with pytest.raises(PageGeomError, match="unsupported"):
+        dec.set_files(*ops.pack_files([prog.tobytes()]))
+    colour = _encode(np.stack([g, g, 255 - g], -1))
+    blob, off = ops.pack_files([colour])
+    assert dec.set_files(blob, off) == [(64, 64, 3)]
+    with pytest.raises(PageGeomError, match="unsupported"):
+        dec.decode(blob.cuda())
+
+
+@pytest.mark.parametrize("w,h,grids", [(8000, 6000, [(4, 4)]), (8000, 6000, [(1, 1), (2, 2), (3, 3), (4, 4)]),
+                                       (3801, 5601, [(2, 2)]), (1501, 1003, [(1, 1), (2, 3)]), (40000, 700, [(1, 2)])])
+def test_one_channel_tiler_equals_three_channel_tiler_on_the_replicated_page(w, h, grids):
+    """channels=1 plans: tiles bit-identical to the BGR path fed with the plane replicated three times (what
+    cv2.imread returns for a greyscale scan), through the staged kernel and the direct validation kernel, incl. the
+    reference's default 30-tile grid set and tiles cut into column chunks."""
+    g = synth.newspaper_page(w, h, 11)
+    plan3 = ops.TilePlan(w, h, grids, 20.0)
+    plan1 = ops.TilePlan(w, h, grids, 20.0, channels=1)
+    assert plan1.out_elems == plan3.out_elems and plan1.tiles == plan3.tiles
+    assert plan1.algorithmic_bytes == w * h + 2 * plan1.out_elems
+    want = plan3.run(ops.upload_pages([np.repeat(g[..., None], 3, -1)], plan3))
+    page1 = torch.zeros((1, h, plan1.pitch), dtype=torch.uint8)
+    page1[0, :, :w] = torch.from_numpy(g)
+    page1 = page1.cuda()
+    got = plan1.run(page1)
+    got_direct = plan1.run(page1, direct=True)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want) and torch.equal(got_direct, want)
+
+
+def test_jpeg_to_tiles_equals_cv2_imread_to_tiles():
+    """The whole front of the path on compressed input: files -> device decode -> one-channel tiler batch (pages of
+    different sizes in one launch) against cv2.imdecode -> BGR upload -> three-channel tiler batch."""
+    sizes = [(1501, 1003), (777, 1001), (2400, 1800)]
+    files = [_encode(synth.newspaper_page(w, h, 20 + i), 95) for i, (w, h) in enumerate(sizes)]
+    pages = ops.decode_jpeg_files(files)
+    grids = [(1, 1), (2, 2)]
+    b1 = ops.TileBatch(sizes, grids, 20.0, channels=1)
+    b1.bind(pages)
+    b1.run()
+    bgr = [cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_COLOR) for f in files]
+    b3 = ops.TileBatch(sizes, grids, 20.0)
+    b3.bind(ops.upload_pages_pinned(bgr))
+    b3.run()
+    torch.cuda.synchronize()
+    for a, b in zip(b1.outs, b3.outs):
+        assert torch.equal(a, b)

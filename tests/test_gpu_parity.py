@@ -342,6 +342,25 @@ def test_nms_synthetic_batch_vs_oracle(thr):
         assert np.array_equal(kept[off[i]: off[i] + n_kept[i]] - off[i], ref), (i, thr)
 
 
+def test_nms_signed_zero_scores_tie_by_position():
+    """-0.0 and +0.0 scores compare EQUAL in the reference (`max()` / `index`, 3_combine_grids.py:112), so the
+    earlier pooled position wins whatever the sign bit; the emitted pick order must follow the same rule as the
+    suppression ranking (advisor finding: the sort key used to order -0.0 after +0.0)."""
+    rng = np.random.default_rng(77)
+    n = 600
+    xy = rng.uniform(0, 900, (n, 2))
+    boxes = np.concatenate([xy, xy + rng.uniform(30, 120, (n, 2))], 1)
+    classes = rng.integers(0, 2, n).astype(np.float64)
+    scores = np.where(rng.random(n) < 0.5, -0.0, 0.0)
+    scores[::7] = rng.choice([0.25, -0.25], len(scores[::7]))
+    assert np.signbit(scores).any() and (scores == 0).sum() > 100
+    for thr in (0.5, 0.1):
+        ref = nms_pick_order_c(boxes, scores, classes, thr)
+        from oracle import boxes as ob
+        assert list(ref) == ob.nms_pick_order(boxes.tolist(), scores.tolist(), classes.tolist(), thr)
+        assert api.nms_keep_indices(boxes, scores, classes, thr) == list(ref)
+
+
 def test_nms_dense_stress_100k_boxes():
     """cfg4: 100k boxes on one page (the reference needs ~10^3 s here; the C oracle ~10 s)."""
     d = synth.page_detections(8000, 6000, 4, 4, 20.0, 100000, 77, dups=6)

@@ -1,0 +1,96 @@
+"""CPU checks of the JPEG path: the numpy restatement (oracle/jpeg.py) against cv2.imdecode — the call the
+reference makes through cv2.imread (1_doclayout_bboxes.py:381) — and the decoder's own inline code
+(csrc/pg_jpeg.h), evaluated on the host chunk by chunk in the kernels' order, against cv2 as well."""
+import ctypes as C
+
+import cv2
+import numpy as np
+import pytest
+
+from multimodal_embeddings_b200 import synth
+from multimodal_embeddings_b200._lib import PageGeomError, check, lib
+from oracle import jpeg as oj
+
+SUBSAMPLING = {"444": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, "420": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420,
+               "422": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, "440": cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440}
+
+
+def _page(h, w, seed, noise=4.0):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = 200 + 20 * np.sin(xx / 37.0) + 15 * np.cos(yy / 23.0) + rng.normal(0, noise, (h, w))
+    return np.clip(np.where(rng.random((h, w)) < 0.08, 40, img), 0, 255).astype(np.uint8)
+
+
+def _encode(img, q=95, rst=0, extra=()):
+    ok, buf = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_RST_INTERVAL, rst, *extra])
+    assert ok
+    return buf.tobytes()
+
+
+def host_decode(data: bytes, chunk_bytes: int, max_rounds: int = 1 << 20):
+    L = lib()
+    w, h, st = C.c_int32(), C.c_int32(), (C.c_int64 * 4)()
+    b = np.frombuffer(data, np.uint8)
+    check(L.pg_hostcheck_jpeg_decode(b.ctypes.data, len(b), chunk_bytes, max_rounds, None, 0, C.byref(w), C.byref(h), st))
+    pitch = (w.value + 15) // 16 * 16
+    out = np.zeros((h.value, pitch), np.uint8)
+    check(L.pg_hostcheck_jpeg_decode(b.ctypes.data, len(b), chunk_bytes, max_rounds, out.ctypes.data, pitch, C.byref(w),
+                                     C.byref(h), st))
+    return out[:, :w.value], {"rounds": st[0], "replaced_round1": st[1], "chunks": st[2], "restarts": st[3]}
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (61, 77), (8, 8), (17, 130)])
+@pytest.mark.parametrize("q", [95, 30, 100])
+def test_numpy_restatement_equals_cv2(shape, q):
+    """oracle/jpeg.py: grey and colour (4:4:4, 4:2:0, 4:2:2, 4:4:0), with and without restart markers."""
+    h, w = shape
+    for rst in (0, 3):
+        g = _page(h, w, 1)
+        data = _encode(g, q, rst)
+        assert np.array_equal(oj.decode(data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR))
+        c = np.stack([g, np.roll(g, 3, 1), 255 - g], -1)
+        for ss in SUBSAMPLING.values():
+            data = _encode(c, q, rst, (cv2.IMWRITE_JPEG_SAMPLING_FACTOR, ss))
+            assert np.array_equal(oj.decode(data), cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR))
+
+
+@pytest.mark.parametrize("shape,noise", [((64, 64), 4), ((61, 77), 40), ((8, 8), 4), ((200, 333), 4), ((517, 640), 40)])
+def test_chunked_decoder_inline_code_equals_cv2(shape, noise):
+    """The three-pass chunked entropy decoder + islow IDCT of csrc/pg_jpeg.h on the host: every chunk size from far
+    below a block (a block then spans several chunks) to far above, restart intervals of 1 and 7 MCUs (restart
+    boundaries inside chunks, on chunk edges, intervals ending without padding), qualities 30-100."""
+    h, w = shape
+    for q in (95, 75, 30, 100):
+        for rst in (0, 1, 7):
+            data = _encode(_page(h, w, 7, noise), q, rst)
+            ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+            assert np.array_equal(ref[..., 0], ref[..., 1]) and np.array_equal(ref[..., 0], ref[..., 2])
+            for chunk in (8, 16, 64, 512, 4096):
+                got, st = host_decode(data, chunk)
+                assert np.array_equal(got, ref[..., 0]), (shape, q, rst, chunk, st)
+                assert st["restarts"] == (0 if rst == 0 else max(0, -(-(-(-h // 8) * -(-w // 8)) // rst) - 1))
+
+
+def test_chunk_states_converge_in_a_few_rounds_on_a_scan_like_page():
+    """Self-synchronisation is what makes the scheme parallel: on a newspaper-like page the speculative pass ends
+    most chunks in the true state and the sync rounds fix the rest quickly."""
+    g = synth.newspaper_page(2000, 1500, 3)
+    for q, chunk, max_rounds in ((95, 512, 4), (75, 512, 3), (95, 2048, 3)):
+        data = _encode(g, q)
+        got, st = host_decode(data, chunk)
+        assert np.array_equal(got, cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE))
+        assert st["rounds"] <= max_rounds and st["replaced_round1"] < 0.25 * st["chunks"], st
+
+
+def test_parser_refuses_what_the_device_path_does_not_decode():
+    g = _page(40, 40, 2)
+    ok, prog = cv2.imencode(".jpg", g, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    L = lib()
+    w, h, st = C.c_int32(), C.c_int32(), (C.c_int64 * 4)()
+    for data in (prog.tobytes(), b"\x89PNG\r\n\x1a\n" + bytes(64), _encode(g)[:60]):
+        b = np.frombuffer(data, np.uint8)
+        rc = L.pg_hostcheck_jpeg_decode(b.ctypes.data, len(b), 512, 8, None, 0, C.byref(w), C.byref(h), st)
+        assert rc == 4 and b"unsupported" in L.pg_last_error()  # PG_ERR_UNSUPPORTED
+    with pytest.raises(PageGeomError):
+        check(4)

@@ -147,3 +147,19 @@ def test_width_median_and_columns(r4, r5, seed):
             c, cw = ob.column_centers(boxes, names, scores, w, h, med, conf)
             assert [float(x) for x in c] == [float(x) for x in c_ref]
             assert [float(x) for x in cw] == [float(x) for x in w_ref]
+
+
+def test_nms_signed_zero_scores(r3):
+    """The reference on scores of both zero signs: max()/index compare values, so -0.0 ties with +0.0 and the
+    earlier position wins; both oracles (Python and C) must agree with it."""
+    from oracle.nms_fast import nms_pick_order_c
+    rng = np.random.default_rng(78)
+    n = 300
+    xy = rng.uniform(0, 600, (n, 2))
+    boxes = np.concatenate([xy, xy + rng.uniform(30, 120, (n, 2))], 1)
+    classes = rng.integers(0, 2, n).astype(np.float64)
+    scores = np.where(rng.random(n) < 0.5, -0.0, 0.0)
+    scores[::5] = 0.5
+    _, _, _, picked = r3.apply_non_max_suppression(boxes.tolist(), scores.tolist(), classes.tolist(), list(range(n)), 0.3)
+    assert picked == ob.nms_pick_order(boxes.tolist(), scores.tolist(), classes.tolist(), 0.3)
+    assert picked == list(nms_pick_order_c(boxes, scores, classes, 0.3))

@@ -104,30 +104,49 @@ class ClockSampler:
 _W = {}
 
 
-def _cpu_worker_init(w, h, rows, cols, n_boxes, seed):
-    import numpy as np
+E2E_JPEG_QUALITY = 95  # cv2.imwrite's default: what the reference's stage 0 writes for a .jpg scan (0_orientation.py:267)
+
+
+def e2e_scan_file(w, h, page_index, quality=E2E_JPEG_QUALITY):
+    """One scan as the file the path starts from: a grey newspaper-like page (synth.newspaper_page, a pure function
+    of the global page index) as a JPEG at cv2's default quality.  Both arms read these bytes."""
+    import cv2
+    from multimodal_embeddings_b200 import synth
+    ok, buf = cv2.imencode(".jpg", synth.newspaper_page(w, h, synth.PAGE_SEED0 + page_index), [cv2.IMWRITE_JPEG_QUALITY, quality])
+    assert ok
+    return buf.tobytes()
+
+
+def _cpu_worker_init(file_bytes, w, h, rows, cols, n_boxes, seed):
+    """Worker processes are SPAWNED (a forked child of a process that has used OpenCV's or CUDA's thread pools
+    deadlocks in them); the scan's file bytes come from the parent."""
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
     from multimodal_embeddings_b200 import synth
     try:
         import cv2
         cv2.setNumThreads(1)
     except Exception:
         pass
-    rng = np.random.default_rng(seed + os.getpid())
-    _W["page"] = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    _W["file"] = file_bytes
     _W["det"] = synth.page_detections(w, h, rows, cols, 20.0, n_boxes, seed)
     _W["cfg"] = (w, h, rows, cols)
 
 
 def _cpu_one_page(_):
-    """Reference algorithm for one page, function level: grid split + cv2
-    letterbox + /255, translate + edge filter, pooled pure-Python NMS, width median, columns."""
+    """Reference algorithm for one page, function level: the scan decoded as cv2.imread does
+    (1:381), grid split + cv2 letterbox + /255, translate + edge filter, pooled pure-Python NMS, width median,
+    columns."""
+    import cv2
+    import numpy as np
     from multimodal_embeddings_b200 import synth
     from oracle import boxes as ob
     from oracle import tiler as ot
     w, h, rows, cols = _W["cfg"]
     d = _W["det"]
     t0 = time.perf_counter()
-    tiles = ot.tile_page(_W["page"], rows, cols, 20.0)
+    page = cv2.imdecode(np.frombuffer(_W["file"], np.uint8), cv2.IMREAD_COLOR)
+    tiles = ot.tile_page(page, rows, cols, 20.0)
     cells = [{"coordinates": c["coordinates"]} for c, _ in tiles]
     boxes_page = []
     for b, ci in zip(d["boxes_local"].tolist(), d["box_cell"].tolist()):
@@ -145,15 +164,17 @@ def _cpu_one_page(_):
     return time.perf_counter() - t0, len(fb), len(cols_out[0])
 
 
-def run_cpu_arm(spec, steps, warmup, budget_s=150.0, pages_per_step=None):
+def run_cpu_arm(spec, steps, warmup, budget_s=150.0, pages_per_step=None, file_bytes=None):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     w, h = spec["sizes"][0]
     rows, cols = spec["grid"]
-    ctx = mp.get_context("fork")
+    if file_bytes is None:
+        file_bytes = e2e_scan_file(w, h, 0)
+    ctx = mp.get_context("spawn")
     pps = pages_per_step or cores
     times = []
-    with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(w, h, rows, cols, spec["boxes"], 0xB200)) as pool:
+    with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(file_bytes, w, h, rows, cols, spec["boxes"], 0xB200)) as pool:
         done = 0
         for it in range(warmup + steps):
             t0 = time.perf_counter()
@@ -176,8 +197,9 @@ def run_cpu_arm(spec, steps, warmup, budget_s=150.0, pages_per_step=None):
 def print_reference_line(args, spec):
     r = run_cpu_arm(spec, args.steps, args.warmup)
     sample = (f"{r['pages_per_step']} page(s) per step, one per worker process on {r['cores']} host cores; "
-              "oracle port of the reference scripts at function level: cv2 letterbox tiles, translate+edge "
-              "filter, pure-Python greedy NMS, width median, column peaks (no PNG/JSON codec time)")
+              "oracle port of the reference scripts at function level: cv2.imdecode of the page's JPEG file "
+              f"(quality {E2E_JPEG_QUALITY}, the bytes the e2e leg uploads), cv2 letterbox tiles, translate+edge "
+              "filter, pure-Python greedy NMS, width median, column peaks (no JSON / visualisation time)")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
@@ -214,7 +236,11 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5"])
     ap.add_argument("--total-pages", type=int, default=0, help="cfg5: corpus size (default 102400)")
     ap.add_argument("--pages-per-gpu", type=int, default=64)
-    ap.add_argument("--e2e-pages", type=int, default=8)
+    ap.add_argument("--e2e-pages", type=int, default=16, help="pages per end-to-end step")
+    ap.add_argument("--e2e-input", default="jpeg", choices=["jpeg", "raw"],
+                    help="what crosses PCIe in the e2e leg: the scans' JPEG files (decoded on the device) or raw BGR pages")
+    ap.add_argument("--no-corpus", action="store_true", help="skip the K6 corpus sub-run (cfg5 in small)")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the sustained-rate loop (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling helper: skip the host-buffer leg")
     ap.add_argument("--no-overlap", action="store_true", help="run the box stages after the tiler on one stream")
@@ -242,6 +268,7 @@ def main():
 
     from multimodal_embeddings_b200 import build as pg_build
     from multimodal_embeddings_b200 import ops, synth
+    from multimodal_embeddings_b200._lib import lib as lib_handle
     from multimodal_embeddings_b200.pipeline import KERNELS_PER_STEP, PagePipeline
 
     if not torch.cuda.is_available():
@@ -424,7 +451,10 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "tile_letterbox_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": ("constant from the committed ncu --set full capture (profiles/tiler_traffic.json), "
+                                   "not measured in this run") if traffic is not None else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": tiler_bytes, "kernel_ms_per_launch": tiler_ms / max(1, len(pipes)),
                 "kernel_share_of_step": tiler_ms / (ms / args.steps),
                 "timed": "inside the timed region" + ("" if args.no_overlap or args.tiler_only
@@ -458,8 +488,127 @@ def main():
         "gpu_launches": (len(pipes) if args.tiler_only else kernels_per_step * len(pipes)) * args.steps,
     }
 
-    # ---- e2e: same metric through the host-buffer API, H2D of pages+detections and D2H of results timed
-    if not args.no_e2e and not args.tiler_only:
+    # ---- K6 on the record: a small cfg5 — corpus histograms over a fixed 512-page corpus (64 distinct pages, the
+    # same on every rank, so the totals are identical for any N), ONE pg_hist_allreduce at the end
+    if not args.no_corpus and not args.tiler_only and not cfg5 and args.workload == "cfg3":
+        import hashlib
+        from multimodal_embeddings_b200._lib import PG_WIDTH_HIST_BINS
+        from multimodal_embeddings_b200.pipeline import corpus_median_width
+        plan0, _, pages0, _, _ = pipes[0]
+        corpus_pages = 512
+        c_steps = max(1, corpus_pages // (ppg * world))
+        cdets = pipes[0][4] if first_page == 0 else \
+            [synth.page_detections(plan0.page_w, plan0.page_h, rows, cols, 20.0, spec["boxes"], synth.PAGE_SEED0 + gi)
+             for gi in range(ppg)]
+        cpipe = PagePipeline(plan0, ppg, corpus_stats=True, overlap=not args.no_overlap)
+        cpipe.set_detections(cdets)
+        cpipe.run(pages0)
+        torch.cuda.synchronize()
+        cpipe.check_status()
+        cpipe.hist.zero_()
+        if world > 1:
+            ops.corpus_comm()  # communicator set-up (collective) outside the timed exchange
+            dist.barrier()
+        torch.cuda.synchronize()
+        c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        c0.record(stream)
+        for _ in range(c_steps):
+            cpipe.run(pages0)
+        c1.record(stream)
+        cpipe.allreduce_corpus_stats()
+        c2.record(stream)
+        torch.cuda.synchronize()
+        hh = cpipe.hist.cpu().numpy()
+        col = hh[PG_WIDTH_HIST_BINS:]
+        line["corpus"] = {"pages": ppg * world * c_steps, "steps_per_rank": c_steps,
+                          "plain_text_boxes": int(hh[:PG_WIDTH_HIST_BINS].sum()),
+                          "median_plain_text_width_px": corpus_median_width(cpipe.hist[:PG_WIDTH_HIST_BINS]),
+                          "columns_found": int(col.sum()), "modal_column_centre_permille": int(col.argmax()),
+                          "hist_sha256": hashlib.sha256(hh.tobytes()).hexdigest()[:16],
+                          "exchange": "pg_hist_allreduce (one ncclAllReduce of %d uint32 bins)" % hh.size if world > 1 else "single rank: no exchange",
+                          "exchange_ms": c1.elapsed_time(c2), "steps_ms": c0.elapsed_time(c1),
+                          "nccl_version": int(lib_handle().pg_comm_nccl_version())}
+        del cpipe
+
+    # ---- sustained rate: the same step back to back for >= sustained_seconds (clocks settle under the power cap)
+    if args.sustained_seconds > 0 and not cfg5:
+        n_sus = max(50, int(args.sustained_seconds / (ms / args.steps * 1e-3)))
+        sus_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in pipes]
+        sampler2 = ClockSampler(local_rank)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        sampler2.start()
+        s0.record(stream)
+        for i in range(n_sus):
+            step(sus_ev if (i == n_sus - 1 and not args.tiler_only and not graphs) else None)
+        s1.record(stream)
+        torch.cuda.synchronize()
+        sus_clocks = sampler2.stop()
+        sus_ms = s0.elapsed_time(s1) / n_sus
+        sus = {"steps": n_sus, "seconds": s0.elapsed_time(s1) * 1e-3, "ms_per_step": sus_ms,
+               "pages_per_s": ppg * world * 1e3 / sus_ms if world == 1 else None, "clocks": sus_clocks}
+        if not args.tiler_only and not graphs:
+            t_ms = sum(a.elapsed_time(b) for (a, b) in sus_ev)
+            sus.update({"tiler_ms_last_step": t_ms, "frac": tiler_bytes / (t_ms * 1e-3) / 1e9 / peak})
+        else:
+            sus["frac"] = tiler_bytes / (sus_ms * 1e-3) / 1e9 / peak if args.tiler_only else None
+        roofline["sustained"] = sus
+
+    # ---- e2e: same metric end to end through host buffers.  Default: the scans cross PCIe as what they are on disk —
+    # JPEG files — and are decoded on the device (pipeline.ScanPipeline: H2D -> D1-D8 decode -> one-channel tiler ->
+    # box stages -> D2H), double-buffered so that the copy of the next step runs under the kernels of this one.
+    if not args.no_e2e and not args.tiler_only and args.e2e_input == "jpeg" and args.workload in ("cfg3", "cfg5"):
+        from multimodal_embeddings_b200.pipeline import ScanPipeline
+        plan0, pipe0, _, _, dets0 = pipes[0]
+        n_e = min(args.e2e_pages, pipe0.n_pages)
+        del pipes[:]
+        torch.cuda.empty_cache()
+        distinct = min(n_e, 8)
+        files = [e2e_scan_file(plan0.page_w, plan0.page_h, first_page + j) for j in range(distinct)]
+        files = [files[j % distinct] for j in range(n_e)]
+        blob, file_off = ops.pack_files(files)
+        sp = ScanPipeline(plan0.page_w, plan0.page_h, n_e, [(rows, cols)], 20.0, overlap=not args.no_overlap)
+        probe = PagePipeline(sp.plan, n_e)
+        ehost = probe.set_detections(dets0[:n_e])
+        del probe
+        for _ in range(3):
+            k = sp.submit(blob, file_off, ehost)
+        res = sp.results(k)
+        torch.cuda.synchronize()
+        dec_status = sp.slots[0]["dec"].status()
+        e2e_steps = max(4, min(args.steps, 12))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter()
+        for _ in range(e2e_steps):
+            k = sp.submit(blob, file_off, ehost)
+        sp.drain()
+        e_ms = (time.perf_counter() - t_wall) * 1e3
+        for kk in range(k - sp.depth + 1, k + 1):
+            res = sp.results(kk)  # status words of the last steps of every slot
+        if world > 1:
+            t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        line["e2e"] = {"value": n_e * world * e2e_steps / (e_ms * 1e-3), "unit": UNIT,
+                       "h2d_bytes_per_step": sp.h2d_bytes, "d2h_bytes_per_step": sp.d2h_bytes,
+                       "pages_per_step": n_e * world, "steps": e2e_steps,
+                       "h2d_gb_per_s_per_gpu": sp.h2d_bytes * e2e_steps / (e_ms * 1e-3) / 1e9,
+                       "input": f"{n_e} greyscale JPEG files per step ({distinct} distinct pages, quality {E2E_JPEG_QUALITY}, "
+                                f"{sum(len(f) for f in files) / n_e / 1e6:.1f} MB each instead of 144 MB as the BGR array cv2.imread returns)",
+                       "jpeg_decoder": {"chunk_bytes": sp.slots[0]["dec"].chunk_bytes, **{k2: int(v) for k2, v in dec_status.items()}},
+                       "kernels_per_step": KERNELS_PER_STEP + 9 + sp.slots[0]["dec"].sync_rounds,
+                       "kept_boxes_last_step": int(res["n_kept2"].sum()),
+                       **({"host": numa_note} if numa_note else {}),
+                       "timed": "wall clock around submit x steps + drain (host parse of the JPEG headers included), max over ranks",
+                       "note": "pinned host JPEG files + detections -> H2D -> device decode -> one-channel tiler -> box "
+                               "stages -> D2H of kept indices/medians/columns, two steps in flight (copy under compute); "
+                               "fp16 tiles stay in HBM for the detector"}
+        line["gpu_launches"] += (KERNELS_PER_STEP + 9 + sp.slots[0]["dec"].sync_rounds) * (e2e_steps + 3)
+        del sp
+        torch.cuda.empty_cache()
+    elif not args.no_e2e and not args.tiler_only:
         plan, pipe0, pages0, host0, dets0 = pipes[0]
         n_e = min(args.e2e_pages, pipe0.n_pages)
         if is_batch(plan):
@@ -522,14 +671,14 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        del pipes
+        del pipes[:]
         torch.cuda.empty_cache()
         r = run_cpu_arm(workload_spec("cfg3") if args.workload == "cfg3" else spec, steps=2, warmup=1, budget_s=40.0)
         line["cpu_baseline"] = {
             "value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
             "sample": f"2 timed steps of {r['pages_per_step']} page(s), one page per worker process on {r['cores']} cores; "
-                      f"oracle port of the reference at function level (cv2 tiles, edge filter, pure-Python NMS, median, "
-                      f"columns); {r['single_page_s']:.1f} s per page per core"}
+                      f"oracle port of the reference at function level (cv2.imdecode of the page's JPEG, cv2 tiles, edge "
+                      f"filter, pure-Python NMS, median, columns); {r['single_page_s']:.1f} s per page per core"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -167,7 +167,8 @@ int pg_nms_merge_ex(const double* boxes, const double* scores, const double* cla
                     size_t workspace_bytes, void* stream);
 /* After the stream has been synchronised: status word + counters the merge left in
  * its workspace. stats[0]=status (PG_OK/PG_ERR_*), [1]=candidate block pairs,
- * [2]=resolve rounds (max over pages), [3]=box pairs tested. */
+ * [2]=resolve rounds (max over pages), [3]=box pairs that went through the prefilter test (counted in the
+ * kernel: runs of J skipped by their bounds are not in it). */
 int pg_nms_stats(const void* workspace /*dev*/, int64_t stats[4]);
 
 /* ------------------------------------------------------------------ K4 width median
@@ -355,8 +356,8 @@ double pg_hostcheck_density_weight(int32_t bin, int32_t left, int32_t right, int
  * form used by the density kernel differs from the true divide (must be 0) */
 int64_t pg_hostcheck_density_rcp_mismatches(int32_t max_span, int32_t max_n);
 /* the decoder's inline code (csrc/pg_jpeg.h) evaluated on the host, chunk by chunk in the kernels' order: one
- * greyscale file -> out[height, pitch] (out NULL: header only).  stats: [0] sync rounds that changed a state,
- * [1] states replaced in round 1, [2] chunks, [3] restart markers */
+ * greyscale file -> out[height, pitch].  stats: [0] sync rounds that changed a state, [1] states replaced in
+ * round 1, [2] chunks, [3] restart markers.  out NULL: header only (width, height; stats[3] = components). */
 int pg_hostcheck_jpeg_decode(const uint8_t* file, int64_t len, int32_t chunk_bytes, int32_t max_rounds, uint8_t* out,
                              int64_t pitch, int32_t* width, int32_t* height, int64_t stats[4]);
 int pg_hostcheck_resize_row(const uint8_t* row0, const uint8_t* row1, int32_t src_w, int32_t src_h,

@@ -175,6 +175,7 @@ def _take(values, keep):
 
 
 def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
+    import torch
     from . import ops, synth
     from .reference_api import nms_per_tile, parse_grid_configs, translate_coordinates_to_original
     logger = _logger("DocLayoutAnalyzer")
@@ -199,6 +200,7 @@ def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
     p.add_argument("--imgsz", type=int, default=1024)
     p.add_argument("--write_tiles", action="store_true", help="also write the tile images of 1:568 (grid_RxC/images)")
     p.add_argument("--batch_pages", type=int, default=16, help="pages tiled per launch")
+    p.add_argument("--host_decode", action="store_true", help="decode every scan with cv2 on the host, JPEG included")
     args = p.parse_args(argv)
     if args.device == "cpu":
         logger.error("--device cpu: this implementation has no CPU path (libpagegeom.so is CUDA only)")
@@ -249,30 +251,63 @@ def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
         if stop:
             break
         chunk = image_paths[b0:b0 + max(1, args.batch_pages)]
-        # decode on host threads (cv2 releases the GIL), upload through pinned staging, ONE tiler launch for every
-        # tile of every grid of every page of the chunk (pages of different sizes: PgTileBatch)
-        decoded = list(pool.map(ops.decode_page, chunk))
-        live = [(path, page) for path, page in zip(chunk, decoded) if page is not None]
-        for path, page in zip(chunk, decoded):
-            if page is None:  # detect_regions -> None -> process_image False (1:240-242, 466-482)
+        # Greyscale baseline JPEG scans cross PCIe as files and are decoded on the device (pg_jpeg_decode; one grey
+        # plane, tiled by the one-channel plans).  Everything else is decoded on host threads like the reference
+        # (cv2.imread, 1:381; cv2 releases the GIL) and uploaded as BGR through pinned staging.  Either way ONE
+        # tiler launch per kind covers every tile of every grid of every page of the chunk (PgTileBatch).
+        jpeg_bytes = {}
+        if not args.host_decode:
+            for path in chunk:
+                if os.path.splitext(path)[1].lower() in (".jpg", ".jpeg"):
+                    try:
+                        with open(path, "rb") as f:
+                            data = f.read()
+                        if ops.jpeg_probe(data) is not None:
+                            jpeg_bytes[path] = data
+                    except OSError:
+                        pass
+        host_paths = [p_ for p_ in chunk if p_ not in jpeg_bytes]
+        decoded = dict(zip(host_paths, pool.map(ops.decode_page, host_paths)))
+        for path in host_paths:
+            if decoded[path] is None:  # detect_regions -> None -> process_image False (1:240-242, 466-482)
                 logger.error(f"Error detecting regions in {os.path.basename(path)}: cannot decode image")
                 errors += 1
-        if not live:
-            continue
+        live = []  # (path, batch, index in batch, width, height, host page or None)
         try:
-            batch = ops.TileBatch([(pg.shape[1], pg.shape[0]) for _, pg in live], grids, args.overlap, args.imgsz)
-            batch.bind(ops.upload_pages_pinned([pg for _, pg in live]))
-            batch.run()
+            grey = [p_ for p_ in chunk if p_ in jpeg_bytes]
+            if grey:
+                jdec = ops.JpegDecoder()
+                blob, off = ops.pack_files([jpeg_bytes[p_] for p_ in grey])
+                sizes = jdec.set_files(blob, off)
+                pages_dev = jdec.decode(blob.to("cuda", non_blocking=True))
+                torch.cuda.current_stream().synchronize()
+                jdec.check()
+                gb = ops.TileBatch([(w_, h_) for w_, h_, _ in sizes], grids, args.overlap, args.imgsz, channels=1)
+                gb.bind(pages_dev)
+                gb.run()
+                for i, (p_, (w_, h_, _)) in enumerate(zip(grey, sizes)):
+                    host_page = None
+                    if args.write_tiles:  # the tile files need the pixels on the host
+                        g_ = pages_dev[i][:, :w_].cpu().numpy()
+                        host_page = np.repeat(g_[..., None], 3, -1)
+                    live.append((p_, gb, i, w_, h_, host_page))
+            colour = [p_ for p_ in host_paths if decoded[p_] is not None]
+            if colour:
+                cb = ops.TileBatch([(decoded[p_].shape[1], decoded[p_].shape[0]) for p_ in colour], grids, args.overlap, args.imgsz)
+                cb.bind(ops.upload_pages_pinned([decoded[p_] for p_ in colour]))
+                cb.run()
+                for i, p_ in enumerate(colour):
+                    live.append((p_, cb, i, decoded[p_].shape[1], decoded[p_].shape[0], decoded[p_]))
         except Exception as e:
-            errors += len(live)
-            logger.error(f"Error processing {os.path.basename(live[0][0])}: {str(e)}")
+            errors += len(chunk)
+            logger.error(f"Error processing {os.path.basename(chunk[0])}: {str(e)}")
             if not args.skip_errors:
                 logger.error("Stopping due to error. Use --skip_errors to continue despite errors.")
                 break
             continue
-        for pi, (image_path, page) in enumerate(live):
+        live.sort(key=lambda t: t[0])  # the reference's order: sorted paths (1:364)
+        for image_path, batch, pi, w, h, page in live:
             try:
-                h, w = page.shape[:2]
                 plan = batch.plan_of(pi)
                 base, ext = os.path.splitext(os.path.basename(image_path))
                 t0 = 0

@@ -686,6 +686,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) nms_mask_kernel(NmsWs ws, doubl
   SLite li = slite_of(bi);
   uint32_t li_ch = 0u;
   float4 bbI = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned long long runs_tested = 0;  // runs of 8 boxes of J whose prefilter chains were actually evaluated (x 256 pairs)
   for (long long u = gw; u * MASK_UNIT < total; u += nw) {
     for (int q = 0; q < MASK_UNIT; ++q) {
       const long long e = u * MASK_UNIT + q;
@@ -717,6 +718,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) nms_mask_kernel(NmsWs ws, doubl
         ghit = all_pairs || !(sb.z < bbI.x || bbI.z < sb.x || sb.w < bbI.y || bbI.w < sb.y);
       }
       const unsigned groups = __ballot_sync(0xffffffffu, ghit) & 0xFu;
+      runs_tested += (unsigned)__popc(groups);
       __syncwarp();
       // phase 1
       uint32_t cand = 0;
@@ -755,7 +757,8 @@ __global__ void __launch_bounds__(256, MIN_CTAS) nms_mask_kernel(NmsWs ws, doubl
       if (lane == 0 && !any) ws.ent_j[e] = -1;
     }
   }
-  if (gw == 0 && lane == 0) ws.stats[ST_TESTS] = total * 1024;
+  // box pairs that went through the prefilter: counted, not nominal (runs skipped by their bounds are not in it)
+  if (lane == 0 && runs_tested) atomicAdd((unsigned long long*)&ws.stats[ST_TESTS], runs_tested * 256ull);
 }
 
 // ---- E: resolve ----------------------------------------------------------------------------
@@ -1708,47 +1711,73 @@ __global__ void __launch_bounds__(COL_THREADS) column_peaks_kernel(
   }
   const int npk = npk_run;
 
-  // ---- distance selection (scipy _select_by_peak_distance), warp 0 ----
-  if (warp == 0 && npk > 0) {
-    for (int it = 0; it < npk; ++it) {
-      double bh = -DBL_MAX;
-      int bi = -1;
-      for (int j = lane; j < npk; j += 32) {
-        if (pk_keep[j] == 1) {  // kept and not yet visited
-          const double h = pk_h[j];
-          if (h > bh || (h == bh && j > bi)) { bh = h; bi = j; }
+  // ---- distance selection (scipy _select_by_peak_distance) ----
+  // scipy visits the peaks from the highest down (equal heights: the later one first) and a visited peak that is
+  // still kept removes every peak closer than `dist`.  That greedy rule has one fixed point — a peak is kept iff
+  // no KEPT peak of higher priority lies within `dist` — reached here without the serial walk: one thread per
+  // peak, rounds in which an undecided peak is removed when a higher-priority neighbour is kept and kept when
+  // none of them is undecided any more (pk_keep: 1 undecided, 3 kept, 0 removed).  A few rounds in practice.
+  for (int round = 0; round < COL_MAX_PEAKS + 1; ++round) {
+    int state = tid < npk ? pk_keep[tid] : 0;
+    if (state == 1) {
+      const int pj = pk_pos[tid];
+      const double hj = pk_h[tid];
+      bool kept_near = false, open_near = false;
+      for (int k = tid - 1; k >= 0 && pj - pk_pos[k] < dist; --k) {
+        if (pk_h[k] > hj) {  // an earlier peak outranks this one only when strictly higher
+          const int sk = pk_keep[k];
+          kept_near |= sk == 3;
+          open_near |= sk == 1;
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double oh = __shfl_xor_sync(0xffffffffu, bh, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (oi >= 0 && (bi < 0 || oh > bh || (oh == bh && oi > bi))) { bh = oh; bi = oi; }
+      for (int k = tid + 1; k < npk && pk_pos[k] - pj < dist; ++k) {
+        if (pk_h[k] >= hj) {  // a later peak of equal height is visited first
+          const int sk = pk_keep[k];
+          kept_near |= sk == 3;
+          open_near |= sk == 1;
+        }
       }
-      if (bi < 0) break;
-      __syncwarp();
-      if (lane == 0) {
-        pk_keep[bi] = 3;  // kept + visited
-        const int pj = pk_pos[bi];
-        for (int k = bi - 1; k >= 0 && pj - pk_pos[k] < dist; --k) pk_keep[k] = 0;
-        for (int k = bi + 1; k < npk && pk_pos[k] - pj < dist; ++k) pk_keep[k] = 0;
-      }
-      __syncwarp();
+      state = kept_near ? 0 : (open_near ? 1 : 3);
     }
+    __syncthreads();  // every thread has read the old states
+    if (tid < npk) pk_keep[tid] = (unsigned char)state;
+    if (!__syncthreads_or(state == 1)) break;
   }
-  __syncthreads();
 
-  // ---- prominence (wlen=None) + final ordered compaction ----
-  int fin = 0, fpos = 0;
-  if (tid < npk && pk_keep[tid]) {
-    const int pkp = pk_pos[tid];
+  // ---- prominence (wlen=None): one warp per kept peak, 32 samples per step on each side ----
+  __shared__ unsigned char pk_fin[COL_MAX_PEAKS];
+  for (int q = warp; q < npk; q += COL_THREADS / 32) {
+    if (!pk_keep[q]) { if (lane == 0) pk_fin[q] = 0; continue; }
+    const int pkp = pk_pos[q];
     const double hp = sm[pkp];
     double lmin = hp, rmin = hp;
-    for (int i = pkp; i >= 0 && sm[i] <= hp; --i) lmin = fmin(lmin, sm[i]);
-    for (int i = pkp; i < nbins && sm[i] <= hp; ++i) rmin = fmin(rmin, sm[i]);
-    const double prom = hp - fmax(lmin, rmin);
-    if (pmin <= prom) { fin = 1; fpos = pkp; }
+    for (int i0 = pkp; i0 >= 0; i0 -= 32) {  // leftwards while sm[i] <= hp
+      const int i = i0 - lane;
+      const double v = i >= 0 ? sm[i] : 0.0;
+      const unsigned stop = __ballot_sync(0xffffffffu, i < 0 || v > hp);
+      const int first = stop ? __ffs(stop) - 1 : 32;
+      if (lane < first) lmin = fmin(lmin, v);
+      if (stop) break;
+    }
+    for (int i0 = pkp; i0 < nbins; i0 += 32) {  // rightwards
+      const int i = i0 + lane;
+      const double v = i < nbins ? sm[i] : 0.0;
+      const unsigned stop = __ballot_sync(0xffffffffu, i >= nbins || v > hp);
+      const int first = stop ? __ffs(stop) - 1 : 32;
+      if (lane < first) rmin = fmin(rmin, v);
+      if (stop) break;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+      rmin = fmin(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+    }
+    if (lane == 0) pk_fin[q] = (pmin <= hp - fmax(lmin, rmin)) ? 1 : 0;
   }
+  __syncthreads();
+  // final ordered compaction
+  int fin = 0, fpos = 0;
+  if (tid < npk && pk_fin[tid]) { fin = 1; fpos = pk_pos[tid]; }
   int nfin;
   const int fex = pg_block_exscan(fin, scan_smem, &nfin);
   __syncthreads();

@@ -24,6 +24,8 @@ constexpr int CHUNK_THREADS = 128;  // entropy kernels: chunks per CTA
 constexpr int STREAM_PAD = 1024;    // readable slack behind every unstuffed stream
 constexpr int MAX_ROUNDS = 64;
 
+static_assert(sizeof(PgjImage) % 16 == 0, "PgjImage is copied into shared memory 16 bytes at a time");
+
 struct HostImage {
   PgjImage dev;
   int64_t scan_begin = 0, scan_end = 0;  // byte offsets inside the file
@@ -213,7 +215,7 @@ struct Scratch {           // device pointers into the caller's workspace
   uint8_t* compact;
   int32_t* rst_pos;
   PgjChunkState* st[2];
-  uint8_t* changed[2];
+  PgjEntry* ent;           // the entry state each chunk's stored exit was computed from
   PgjChunkState* entry;    // exclusive segmented scan: state of the decoder at each chunk's entry
   int32_t* counters;       // [MAX_ROUNDS + 2]: changes per round; [MAX_ROUNDS+1] = error flag
   int16_t* coef;
@@ -311,7 +313,7 @@ __device__ __forceinline__ void load_image(PgjImage* dst, const PgjImage* src) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(CHUNK_THREADS) jpeg_spec_kernel(Scratch s, int chunk_bits) {
+__global__ void __launch_bounds__(CHUNK_THREADS) jpeg_spec_kernel(Scratch s, int chunk_bits, int overlap_bits) {
   __shared__ __align__(16) PgjImage im;
   const int img = s.cta_img[blockIdx.x];
   load_image(&im, s.img + img);
@@ -319,15 +321,11 @@ __global__ void __launch_bounds__(CHUNK_THREADS) jpeg_spec_kernel(Scratch s, int
   const int j = s.cta_chunk0[blockIdx.x] + threadIdx.x;
   if (j >= r.n_chunks) return;
   const PgjStream sv = stream_of(s, r, img);
-  const int64_t b0 = (int64_t)j * chunk_bits, b1 = b0 + chunk_bits;
   PgjChunkState out;
-  if (b0 >= sv.n_bits) {
-    out.p = -2; out.c = 0; out.n = 0; out.anchor = -1; out.dc[0] = out.dc[1] = out.dc[2] = 0;
-  } else {
-    pgj_span(sv, im, b0, 0, b1, j == 0 ? 0 : -1, out);
-  }
+  PgjEntry en;
+  pgj_spec_chunk(sv, im, j, chunk_bits, overlap_bits, en, out);
   s.st[0][r.chunk0 + j] = out;
-  s.changed[0][r.chunk0 + j] = 1;
+  s.ent[r.chunk0 + j] = en;
 }
 
 // ---- D5: one sync round -----------------------------------------------------------------------------------
@@ -338,33 +336,23 @@ __global__ void __launch_bounds__(CHUNK_THREADS) jpeg_sync_kernel(Scratch s, int
   const int j = s.cta_chunk0[blockIdx.x] + threadIdx.x;
   const PgjChunkState* in = s.st[(round - 1) & 1];
   PgjChunkState* outv = s.st[round & 1];
-  const uint8_t* ch_in = s.changed[(round - 1) & 1];
-  uint8_t* ch_out = s.changed[round & 1];
-  // a round in which nothing can change only carries the states over (uniform per launch)
+  // a round after one in which nothing was decoded again only carries the states over (uniform per launch)
   const bool idle = round > 1 && s.counters[round - 1] == 0;
   if (!idle) load_image(&im, s.img + img);
   if (j >= r.n_chunks) return;
   const int64_t g = r.chunk0 + j;
   PgjChunkState mine = in[g];
-  uint8_t changed = 0;
-  if (!idle && j > 0 && mine.p != -2 && ch_in[g - 1]) {
+  if (!idle && j > 0 && mine.p != -2) {
     const PgjChunkState prev = in[g - 1];
-    if (prev.p >= 0) {
+    PgjEntry en = s.ent[g];
+    if (prev.p != en.p || prev.c != en.c) {  // the exit stored for this chunk was reached from another entry
       const PgjStream sv = stream_of(s, r, img);
-      const int64_t b1 = (int64_t)(j + 1) * chunk_bits;
-      PgjChunkState now;
-      if (prev.p >= b1) {  // a block spans this whole chunk
-        now.p = prev.p; now.c = prev.c; now.n = 0; now.anchor = -1; now.dc[0] = now.dc[1] = now.dc[2] = 0;
-      } else {
-        pgj_span(sv, im, prev.p, prev.c, b1, -1, now);
-      }
-      changed = (now.p != mine.p || now.c != mine.c) ? 1 : 0;
-      mine = now;
+      pgj_sync_chunk(sv, im, j, chunk_bits, prev, en, mine);
+      s.ent[g] = en;
+      atomicAdd(&s.counters[round], 1);
     }
   }
   outv[g] = mine;
-  ch_out[g] = changed;
-  if (changed) atomicAdd(&s.counters[round], 1);
 }
 
 // ---- D6: decoder state at every chunk's entry (segmented exclusive scan; one CTA per image) ------------------
@@ -574,7 +562,7 @@ extern "C" int pg_jpeg_decoder_set_files(PgJpegDecoder* d, const uint8_t* blob, 
   add((size_t)ub * 4); add((size_t)ub * 4); add((size_t)n * 8); add((size_t)n * 4);
   add((size_t)cs); add((size_t)rst * 4 + 4);
   add((size_t)chunks * sizeof(PgjChunkState)); add((size_t)chunks * sizeof(PgjChunkState));
-  add((size_t)chunks); add((size_t)chunks);
+  add((size_t)chunks * sizeof(PgjEntry));
   add((size_t)chunks * sizeof(PgjChunkState));
   add((MAX_ROUNDS + 2) * 4);
   add((size_t)coef * 2);
@@ -626,8 +614,7 @@ extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t
   sc.rst_pos = reinterpret_cast<int32_t*>(take((size_t)d->total_rst * 4 + 4));
   sc.st[0] = reinterpret_cast<PgjChunkState*>(take((size_t)d->total_chunks * sizeof(PgjChunkState)));
   sc.st[1] = reinterpret_cast<PgjChunkState*>(take((size_t)d->total_chunks * sizeof(PgjChunkState)));
-  sc.changed[0] = take((size_t)d->total_chunks);
-  sc.changed[1] = take((size_t)d->total_chunks);
+  sc.ent = reinterpret_cast<PgjEntry*>(take((size_t)d->total_chunks * sizeof(PgjEntry)));
   sc.entry = reinterpret_cast<PgjChunkState*>(take((size_t)d->total_chunks * sizeof(PgjChunkState)));
   sc.counters = reinterpret_cast<int32_t*>(take((MAX_ROUNDS + 2) * 4));
   sc.coef = reinterpret_cast<int16_t*>(take((size_t)d->coef_elems * 2));
@@ -668,7 +655,7 @@ extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t
   jpeg_unstuff_count_kernel<<<n_ub, 256, 0, s>>>(blob_dev, sc);
   jpeg_unstuff_scan_kernel<<<(unsigned)n, 1024, 0, s>>>(sc);
   jpeg_unstuff_write_kernel<<<n_ub, 256, 0, s>>>(blob_dev, sc);
-  jpeg_spec_kernel<<<n_cta, CHUNK_THREADS, 0, s>>>(sc, chunk_bits);
+  jpeg_spec_kernel<<<n_cta, CHUNK_THREADS, 0, s>>>(sc, chunk_bits, pgj_overlap_bits(chunk_bits));
   for (int r = 1; r <= d->rounds; ++r) jpeg_sync_kernel<<<n_cta, CHUNK_THREADS, 0, s>>>(sc, chunk_bits, r);
   jpeg_entry_scan_kernel<<<(unsigned)n, 1024, 0, s>>>(sc, d->rounds & 1);
   jpeg_store_kernel<<<n_cta, CHUNK_THREADS, 0, s>>>(sc, chunk_bits);
@@ -709,7 +696,10 @@ extern "C" int pg_hostcheck_jpeg_decode(const uint8_t* file, int64_t len, int32_
   const PgjImage& im = hi.dev;
   if (width) *width = im.width;
   if (height) *height = im.height;
-  if (!out) return PG_OK;
+  if (!out) {  // header only
+    if (stats) { stats[0] = stats[1] = stats[2] = 0; stats[3] = im.n_comps; }
+    return PG_OK;
+  }
   PG_REQUIRE(im.n_comps == 1 && pitch >= im.width, "greyscale only / pitch");
   // D1-D3
   const uint8_t* p = file + hi.scan_begin;
@@ -731,16 +721,10 @@ extern "C" int pg_hostcheck_jpeg_decode(const uint8_t* file, int64_t len, int32_
   const int chunk_bits = chunk_bytes * 8;
   const int n_chunks = (int)((sl + chunk_bytes - 1) / chunk_bytes);
   std::vector<PgjChunkState> st[2];
-  std::vector<uint8_t> ch[2];
-  for (int k = 0; k < 2; ++k) { st[k].resize((size_t)n_chunks); ch[k].assign((size_t)n_chunks, 0); }
-  for (int j = 0; j < n_chunks; ++j) {  // D4
-    const int64_t b0 = (int64_t)j * chunk_bits;
-    PgjChunkState o;
-    if (b0 >= sv.n_bits) { o.p = -2; o.c = 0; o.n = 0; o.anchor = -1; o.dc[0] = o.dc[1] = o.dc[2] = 0; }
-    else pgj_span(sv, im, b0, 0, b0 + chunk_bits, j == 0 ? 0 : -1, o);
-    st[0][(size_t)j] = o;
-    ch[0][(size_t)j] = 1;
-  }
+  std::vector<PgjEntry> ent((size_t)n_chunks);
+  for (int k = 0; k < 2; ++k) st[k].resize((size_t)n_chunks);
+  for (int j = 0; j < n_chunks; ++j)  // D4
+    pgj_spec_chunk(sv, im, j, chunk_bits, pgj_overlap_bits(chunk_bits), ent[(size_t)j], st[0][(size_t)j]);
   int used = 0, first_changes = 0, parity = 0;
   for (int r = 1; r <= max_rounds; ++r) {  // D5
     const auto& in = st[(r - 1) & 1];
@@ -748,21 +732,14 @@ extern "C" int pg_hostcheck_jpeg_decode(const uint8_t* file, int64_t len, int32_
     int changes = 0;
     for (int j = 0; j < n_chunks; ++j) {
       PgjChunkState mine = in[(size_t)j];
-      uint8_t changed = 0;
-      if (j > 0 && mine.p != -2 && ch[(r - 1) & 1][(size_t)j - 1]) {
+      if (j > 0 && mine.p != -2) {
         const PgjChunkState prev = in[(size_t)j - 1];
-        if (prev.p >= 0) {
-          const int64_t b1 = (int64_t)(j + 1) * chunk_bits;
-          PgjChunkState now;
-          if (prev.p >= b1) { now.p = prev.p; now.c = prev.c; now.n = 0; now.anchor = -1; now.dc[0] = now.dc[1] = now.dc[2] = 0; }
-          else pgj_span(sv, im, prev.p, prev.c, b1, -1, now);
-          changed = (now.p != mine.p || now.c != mine.c) ? 1 : 0;
-          mine = now;
+        if (prev.p != ent[(size_t)j].p || prev.c != ent[(size_t)j].c) {
+          pgj_sync_chunk(sv, im, j, chunk_bits, prev, ent[(size_t)j], mine);
+          ++changes;
         }
       }
       ov[(size_t)j] = mine;
-      ch[r & 1][(size_t)j] = changed;
-      changes += changed;
     }
     parity = r & 1;
     if (r == 1) first_changes = changes;

@@ -9,13 +9,14 @@
 // Parallel entropy decoding.  A Huffman bit stream has no index, so it is cut into fixed CHUNKS of the
 // unstuffed stream and decoded in three passes (the self-synchronising scheme of Weissenberger & Schmidt,
 // "Massively Parallel Huffman Decoding on GPUs", adapted to JPEG block structure and restart markers):
-//   1. every chunk is decoded speculatively from its first bit as if a block started there; Huffman streams
-//      resynchronise within a few code words, so most chunks END in the true decoder state.  A chunk's exit
-//      state = (bit position, block-in-MCU index) of the first block starting at or after the chunk's end;
-//   2. sync rounds: chunk j is decoded again from chunk j-1's exit state; if the exit it reaches differs from
-//      the stored one it is replaced and chunk j+1 is redone in the next round.  Chunk 0 starts in the true
-//      state, so a round without changes means every exit state is true.  Restart markers (byte-aligned, DC
-//      predictors reset) are known true states and resynchronise a wrong decoder at once;
+//   1. every chunk is decoded speculatively, starting a quarter of a chunk BEFORE its first bit as if a block
+//      started there; Huffman streams resynchronise within a few code words, so the walk has normally fallen
+//      into step by the time it enters the chunk.  A chunk's entry / exit state = (bit position, block-in-MCU
+//      index) of the first block starting at or after the chunk's first bit / end;
+//   2. sync rounds: where chunk j-1's exit differs from the entry chunk j's exit was computed from, chunk j is
+//      decoded again from that exit.  Chunk 0 starts in the true state, so a round that redoes nothing means
+//      every state is true.  Restart markers (byte-aligned, DC predictors reset) are known true states and
+//      resynchronise a wrong decoder at once;
 //   3. a segmented scan over the chunks' block counts and DC-difference sums gives every chunk the absolute
 //      block index and DC predictors at its entry; the final pass decodes again and stores coefficients.
 #pragma once
@@ -37,7 +38,7 @@ struct PgjHuff {
   uint8_t vals[256];
 };
 
-struct PgjImage {
+struct alignas(16) PgjImage {  // copied into shared memory 16 bytes at a time
   int32_t width, height, n_comps;
   int32_t mcus_w, mcus_h, bpm;                  // blocks per MCU
   int32_t blk_comp[PGJ_MAX_BLOCKS_PER_MCU];     // component of block c of an MCU
@@ -239,6 +240,50 @@ PGJ_HD void pgj_span(const PgjStream& sv, const PgjImage& im, int64_t p, int c, 
     p = pe;
   }
   out.p = p; out.c = c; out.n = n; out.anchor = anchor; out.dc[0] = d0; out.dc[1] = d1; out.dc[2] = d2;
+}
+
+// The state a chunk was entered in: bit position and block-in-MCU index of the first block starting at or after
+// the chunk's first bit.
+struct PgjEntry {
+  int64_t p;
+  int32_t c, pad_;
+};
+
+// Pass 1 for chunk j.  The walk starts `overlap_bits` BEFORE the chunk (as if a block started there): by the time
+// it crosses the chunk's first bit it has normally fallen into step, so the entry state it reaches there — and
+// with it the chunk's exit — is normally the true one, and pass 2 has nothing to redo.
+PGJ_HD int pgj_overlap_bits(int chunk_bits) { return chunk_bits / 4 < 256 ? (chunk_bits < 256 ? chunk_bits : 256) : chunk_bits / 4; }
+
+PGJ_HD void pgj_exit_from(const PgjStream& sv, const PgjImage& im, int64_t p, int c, int64_t b1, int anchor_in,
+                          PgjChunkState& out) {
+  if (p >= b1) {  // a block spans the whole chunk: nothing starts inside it
+    out.p = p; out.c = c; out.n = 0; out.anchor = anchor_in; out.dc[0] = out.dc[1] = out.dc[2] = 0;
+  } else {
+    pgj_span(sv, im, p, c, b1, anchor_in, out);
+  }
+}
+
+PGJ_HD void pgj_spec_chunk(const PgjStream& sv, const PgjImage& im, int j, int chunk_bits, int overlap_bits, PgjEntry& en,
+                           PgjChunkState& out) {
+  const int64_t b0 = (int64_t)j * chunk_bits, b1 = b0 + chunk_bits;
+  en.p = 0; en.c = 0; en.pad_ = 0;
+  if (b0 >= sv.n_bits) {
+    out.p = -2; out.c = 0; out.n = 0; out.anchor = -1; out.dc[0] = out.dc[1] = out.dc[2] = 0;
+    return;
+  }
+  if (j > 0) {
+    PgjChunkState lead;
+    pgj_span(sv, im, b0 - overlap_bits, 0, b0, -1, lead);
+    en.p = lead.p; en.c = lead.c;
+  }
+  pgj_exit_from(sv, im, en.p, en.c, b1, j == 0 ? 0 : -1, out);
+}
+
+// Pass 2 for chunk j whose predecessor's exit `prev` differs from the entry its own exit was computed from.
+PGJ_HD void pgj_sync_chunk(const PgjStream& sv, const PgjImage& im, int j, int chunk_bits, const PgjChunkState& prev,
+                           PgjEntry& en, PgjChunkState& out) {
+  en.p = prev.p; en.c = prev.c;
+  pgj_exit_from(sv, im, prev.p, prev.c, (int64_t)(j + 1) * chunk_bits, -1, out);
 }
 
 // where block `blk` (scan order) of the image keeps its 64 coefficients, in int16 elements from the image's base

@@ -326,6 +326,19 @@ class JpegDecoder:
         return st
 
 
+def jpeg_probe(data: bytes) -> Optional[Tuple[int, int]]:
+    """(width, height) when `data` is a JPEG file the device path decodes (greyscale baseline / extended
+    sequential Huffman, one scan), else None.  Host only: parses the headers (pg_hostcheck_jpeg_decode with no
+    output buffer)."""
+    b = np.frombuffer(data, np.uint8)
+    w, h, st = C.c_int32(), C.c_int32(), (C.c_int64 * 4)()
+    if lib().pg_hostcheck_jpeg_decode(b.ctypes.data, len(b), 512, 0, None, 0, C.byref(w), C.byref(h), st) != 0:
+        return None
+    if st[3] != 1:  # components
+        return None
+    return w.value, h.value
+
+
 def pack_files(files: Sequence[bytes], pinned: bool = True):
     """Files back to back, each starting on a 256-byte boundary -> (uint8 CPU tensor, int64 offsets [n+1] of the
     files' FIRST bytes plus the end of the last).  pg_jpeg_decoder_set_files takes file i as

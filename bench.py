@@ -576,7 +576,7 @@ def main():
         res = sp.results(k)
         torch.cuda.synchronize()
         dec_status = sp.slots[0]["dec"].status()
-        e2e_steps = max(4, min(args.steps, 12))
+        e2e_steps = max(8, min(2 * args.steps, 40))
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -587,6 +587,12 @@ def main():
         e_ms = (time.perf_counter() - t_wall) * 1e3
         for kk in range(k - sp.depth + 1, k + 1):
             res = sp.results(kk)  # status words of the last steps of every slot
+        # where the time of a step goes: three more steps with events around the copy and the compute part
+        sp.trace = []
+        for _ in range(3):
+            k = sp.submit(blob, file_off, ehost)
+        sp.drain()
+        timeline = sp.timeline_ms()
         if world > 1:
             t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -600,6 +606,8 @@ def main():
                        "jpeg_decoder": {"chunk_bytes": sp.slots[0]["dec"].chunk_bytes, **{k2: int(v) for k2, v in dec_status.items()}},
                        "kernels_per_step": KERNELS_PER_STEP + 9 + sp.slots[0]["dec"].sync_rounds,
                        "kept_boxes_last_step": int(res["n_kept2"].sum()),
+                       "timeline_ms": {"what": "three extra steps: [copy start, copy end, compute start, compute end] from the first copy's start",
+                                       "steps": timeline},
                        **({"host": numa_note} if numa_note else {}),
                        "timed": "wall clock around submit x steps + drain (host parse of the JPEG headers included), max over ranks",
                        "note": "pinned host JPEG files + detections -> H2D -> device decode -> one-channel tiler -> box "

@@ -20,7 +20,7 @@
 namespace {
 
 constexpr int UB_BYTES = 4096;      // unstuff: input bytes per CTA (256 threads x 16)
-constexpr int CHUNK_THREADS = 128;  // entropy kernels: chunks per CTA
+constexpr int CHUNK_THREADS = 256;  // entropy kernels: chunks per CTA
 constexpr int STREAM_PAD = 1024;    // readable slack behind every unstuffed stream
 constexpr int MAX_ROUNDS = 64;
 
@@ -42,7 +42,19 @@ int build_huff(const uint8_t* counts, const uint8_t* symbols, int n_symbols, Pgj
       if (k >= n_symbols || k >= 256) return -1;
       if (l <= PGJ_LUT_BITS) {
         const int first = code << (PGJ_LUT_BITS - l), n = 1 << (PGJ_LUT_BITS - l);
-        for (int j = 0; j < n; ++j) h.lut[first + j] = (uint16_t)((l << 8) | symbols[k]);
+        const int sym = symbols[k], run = sym >> 4, size = sym & 15;
+        for (int j = 0; j < n; ++j) {
+          h.lut[first + j] = (uint16_t)((l << 8) | sym);
+          // AC views of the same slot (unused for DC tables)
+          h.skip[first + j] = (uint16_t)((l + size) | (run << 5) | (size == 0 ? 512 : 0));
+          if (size != 0 && l + size <= PGJ_LUT_BITS) {
+            // the magnitude bits follow the code inside the 9-bit window
+            const int rest = (first + j) & ((1 << (PGJ_LUT_BITS - l)) - 1);
+            const int mag = rest >> (PGJ_LUT_BITS - l - size);
+            const int val = mag < (1 << (size - 1)) ? mag - (1 << size) + 1 : mag;
+            if (val >= -128 && val <= 127) h.fast[first + j] = (int16_t)(val * 256 + run * 16 + l + size);
+          }
+        }
       }
       h.vals[k] = symbols[k];
       ++code;
@@ -231,20 +243,35 @@ __device__ __forceinline__ PgjStream stream_of(const Scratch& s, const ImgRec& r
 }
 
 // ---- D1-D3: unstuff ---------------------------------------------------------------------------------------
-// thread t of block b looks at 16 consecutive bytes of the image's entropy-coded segment
-__device__ __forceinline__ void unstuff_masks(const uint8_t* blob, const ImgRec& r, int64_t first, uint32_t& keep, uint32_t& rst) {
+// Thread t of an unstuff block looks at 16 bytes of the file blob on an absolute 16-byte boundary (one LDG.128);
+// the bytes before the segment's first / behind its last are masked out.  The neighbouring bytes a marker test
+// needs come from the adjacent lanes.
+__device__ __forceinline__ void unstuff_masks(const uint8_t* blob, const ImgRec& r, int64_t ub_local, uint32_t& keep,
+                                              uint32_t& rst, uint4& bytes) {
+  const int64_t abs0 = (r.src_off & ~(int64_t)15) + (ub_local * 256 + threadIdx.x) * 16;  // absolute, 16-aligned
+  const int64_t rel0 = abs0 - r.src_off;                                                    // may be negative (< 16)
+  const int lane = threadIdx.x & 31;
+  const bool live = rel0 < r.src_len && rel0 > -16;
+  bytes = live ? __ldg(reinterpret_cast<const uint4*>(blob + abs0)) : make_uint4(0u, 0u, 0u, 0u);
+  uint32_t prev = __shfl_up_sync(0xffffffffu, bytes.w >> 24, 1);
+  uint32_t next = __shfl_down_sync(0xffffffffu, bytes.x & 0xFFu, 1);
+  if (lane == 0) prev = (live && abs0 > 0) ? blob[abs0 - 1] : 0u;
+  if (lane == 31) next = (live && rel0 + 16 < r.src_len) ? blob[abs0 + 16] : 0u;
   keep = 0; rst = 0;
-  if (first >= r.src_len) return;
-  const uint8_t* p = blob + r.src_off;
-  uint8_t prev = first > 0 ? p[first - 1] : 0;
-  uint8_t cur = p[first];
+  if (!live) return;
+  const uint32_t w[4] = {bytes.x, bytes.y, bytes.z, bytes.w};
+  uint8_t p = rel0 > 0 ? (uint8_t)prev : 0;  // the byte before the segment's first does not count
+#pragma unroll
   for (int k = 0; k < 16; ++k) {
-    const int64_t j = first + k;
-    if (j >= r.src_len) break;
-    const uint8_t next = j + 1 < r.src_len ? p[j + 1] : 0;
-    if (pgj_keep_byte(prev, cur, next)) keep |= 1u << k;
-    if (pgj_rst_starts(cur, next)) rst |= 1u << k;
-    prev = cur; cur = next;
+    const uint8_t cur = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+    uint8_t nx = k < 15 ? (uint8_t)(w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) : (uint8_t)next;
+    const int64_t j = rel0 + k;
+    if (j + 1 >= r.src_len) nx = 0;
+    if (j >= 0 && j < r.src_len) {
+      if (pgj_keep_byte(p, cur, nx)) keep |= 1u << k;
+      if (pgj_rst_starts(cur, nx)) rst |= 1u << k;
+    }
+    p = j >= 0 ? cur : 0;
   }
 }
 
@@ -252,9 +279,9 @@ __global__ void __launch_bounds__(256) jpeg_unstuff_count_kernel(const uint8_t* 
   __shared__ int sm[34];
   const int img = s.ub_img[blockIdx.x];
   const ImgRec r = s.rec[img];
-  const int64_t first = ((int64_t)(blockIdx.x - r.ub0) * 256 + threadIdx.x) * 16;
   uint32_t keep, rst;
-  unstuff_masks(blob, r, first, keep, rst);
+  uint4 bytes;
+  unstuff_masks(blob, r, blockIdx.x - r.ub0, keep, rst, bytes);
   int tk, tr;
   pg_block_exscan(__popc(keep), sm, &tk);
   pg_block_exscan(__popc(rst), sm, &tr);
@@ -281,27 +308,32 @@ __global__ void __launch_bounds__(1024) jpeg_unstuff_scan_kernel(Scratch s) {
 
 __global__ void __launch_bounds__(256) jpeg_unstuff_write_kernel(const uint8_t* blob, Scratch s) {
   __shared__ int sm[34];
+  __shared__ uint8_t stage[UB_BYTES];  // the block's kept bytes, packed; written out with coalesced stores
   const int img = s.ub_img[blockIdx.x];
   const ImgRec r = s.rec[img];
-  const int64_t first = ((int64_t)(blockIdx.x - r.ub0) * 256 + threadIdx.x) * 16;
   uint32_t keep, rst;
-  unstuff_masks(blob, r, first, keep, rst);
+  uint4 bytes;
+  unstuff_masks(blob, r, blockIdx.x - r.ub0, keep, rst, bytes);
   int tk, tr;
-  int ok = pg_block_exscan(__popc(keep), sm, &tk) + s.ub_kept[blockIdx.x];
+  int ok = pg_block_exscan(__popc(keep), sm, &tk);
   int orr = pg_block_exscan(__popc(rst), sm, &tr) + s.ub_rst[blockIdx.x];
-  const uint8_t* p = blob + r.src_off + first;
-  uint8_t* dst = s.compact + r.cs_off;
+  const int out0 = s.ub_kept[blockIdx.x];
+  const uint32_t w[4] = {bytes.x, bytes.y, bytes.z, bytes.w};
+#pragma unroll
   for (int k = 0; k < 16; ++k) {
     if (rst >> k & 1u) {  // restart interval (orr + 1) starts at the next byte that is kept
-      if (orr < r.rst_cap) s.rst_pos[r.rst_off + orr] = ok;
+      if (orr < r.rst_cap) s.rst_pos[r.rst_off + orr] = out0 + ok;
       ++orr;
     }
-    if (keep >> k & 1u) dst[ok++] = p[k];
+    if (keep >> k & 1u) stage[ok++] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
   }
+  __syncthreads();
+  uint8_t* dst = s.compact + r.cs_off + out0;
+  for (int i = threadIdx.x; i < tk; i += 256) dst[i] = stage[i];
   // slack behind the stream: ones, so that nothing read there looks like a code word
   if (blockIdx.x == r.ub0) {
-    const int64_t len = s.img_len[img];
-    for (int k = threadIdx.x; k < STREAM_PAD; k += 256) dst[len + k] = 0xFF;
+    uint8_t* tail = s.compact + r.cs_off + s.img_len[img];
+    for (int k = threadIdx.x; k < STREAM_PAD; k += 256) tail[k] = 0xFF;
   }
 }
 
@@ -423,8 +455,32 @@ __global__ void __launch_bounds__(1024) jpeg_entry_scan_kernel(Scratch s, int fi
 }
 
 // ---- D7: coefficient store --------------------------------------------------------------------------------
+// Every block is assembled in the thread's own 128 bytes of shared memory and leaves as one full line (eight
+// 16-byte stores): no zero-fill pass over the coefficient buffer, no two-byte scatter into global memory.
+constexpr int BLK_PITCH = 72;  // int16 per thread (64 + 8): 16-byte accesses of a quarter warp fall on distinct banks
+struct SmemBlockSink {
+  int16_t* sm;      // this thread's block
+  int16_t* base;    // the image's coefficient base
+  int pred;
+  __device__ __forceinline__ void begin(int p) {
+    pred = p;
+    uint4* z = reinterpret_cast<uint4*>(sm);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) z[k] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __device__ __forceinline__ void dc(int diff) { sm[0] = (int16_t)(pred + diff); }
+  __device__ __forceinline__ void ac(int idx, int v) { sm[idx] = (int16_t)v; }
+  __device__ __forceinline__ void end(int64_t ci) {
+    const uint4* src = reinterpret_cast<const uint4*>(sm);
+    uint4* dst = reinterpret_cast<uint4*>(base + ci);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dst[k] = src[k];
+  }
+};
+
 __global__ void __launch_bounds__(CHUNK_THREADS) jpeg_store_kernel(Scratch s, int chunk_bits) {
   __shared__ __align__(16) PgjImage im;
+  extern __shared__ __align__(16) int16_t blocks[];  // CHUNK_THREADS * BLK_PITCH (dynamic: with the tables > 48 KB)
   const int img = s.cta_img[blockIdx.x];
   load_image(&im, s.img + img);
   const ImgRec r = s.rec[img];
@@ -436,7 +492,8 @@ __global__ void __launch_bounds__(CHUNK_THREADS) jpeg_store_kernel(Scratch s, in
   const PgjChunkState e = s.entry[r.chunk0 + j];
   if (e.p < 0 || e.p >= b1) return;  // no block starts inside this chunk
   const int blk = max(e.anchor, 0) * im.restart_blocks + e.n;
-  pgj_span_store(sv, im, e.p, e.c, b1, blk, e.dc[0], e.dc[1], e.dc[2], s.coef + r.coef_off);
+  SmemBlockSink sink{blocks + threadIdx.x * BLK_PITCH, s.coef + r.coef_off, 0};
+  pgj_span_store(sv, im, e.p, e.c, b1, blk, e.dc[0], e.dc[1], e.dc[2], sink);
 }
 
 // ---- D8: inverse DCT, one thread per block, grey / luma plane ------------------------------------------------
@@ -542,7 +599,7 @@ extern "C" int pg_jpeg_decoder_set_files(PgJpegDecoder* d, const uint8_t* blob, 
     r.rst_cap = im.n_intervals;  // restart k+1 for k < n_intervals - 1; one spare slot
     rst += r.rst_cap;
     r.ub0 = (int32_t)ub;
-    r.n_ub = (int32_t)((r.src_len + UB_BYTES - 1) / UB_BYTES);
+    r.n_ub = (int32_t)(((r.src_off & 15) + r.src_len + UB_BYTES - 1) / UB_BYTES);  // blocks start on a 16-byte boundary
     for (int b = 0; b < r.n_ub; ++b) d->ub_img.push_back(i);
     ub += r.n_ub;
     r.chunk0 = chunks;
@@ -630,10 +687,17 @@ extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t
   if (!st.ev) PG_CUDA_TRY(cudaEventCreateWithFlags(&st.ev, cudaEventDisableTiming));
   else PG_CUDA_TRY(cudaEventSynchronize(st.ev));
   if (st.cap < total) {
-    if (st.host) cudaFreeHost(st.host);
-    st.host = nullptr;
-    PG_CUDA_TRY(cudaHostAlloc(&st.host, total + total / 2, cudaHostAllocDefault));
-    st.cap = total + total / 2;
+    // (re)size the whole ring at once: a pinned allocation synchronises the device, so it must not recur in a
+    // steady stream of calls
+    const size_t cap = std::max(total * 2, (size_t)1 << 20);
+    for (auto& other : d->stage) {
+      if (other.ev) PG_CUDA_TRY(cudaEventSynchronize(other.ev));
+      if (other.host) cudaFreeHost(other.host);
+      other.host = nullptr;
+      other.cap = 0;
+      PG_CUDA_TRY(cudaHostAlloc(&other.host, cap, cudaHostAllocDefault));
+      other.cap = cap;
+    }
   }
   uint8_t* hs = reinterpret_cast<uint8_t*>(st.host);
   for (int i = 0; i < n; ++i) std::memcpy(hs + o_img + (size_t)i * sizeof(PgjImage), &d->images[(size_t)i].dev, sizeof(PgjImage));
@@ -648,7 +712,6 @@ extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t
   PG_CUDA_TRY(cudaMemcpyAsync(sc.ub_img, hs + o_ub, sz_ub, cudaMemcpyHostToDevice, s));
   PG_CUDA_TRY(cudaEventRecord(st.ev, s));
   PG_CUDA_TRY(cudaMemsetAsync(sc.counters, 0, (MAX_ROUNDS + 2) * 4, s));
-  PG_CUDA_TRY(cudaMemsetAsync(sc.coef, 0, (size_t)d->coef_elems * 2, s));
 
   const int chunk_bits = d->chunk_bytes * 8;
   const unsigned n_ub = (unsigned)d->total_ub, n_cta = (unsigned)d->cta_img.size();
@@ -658,7 +721,9 @@ extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t
   jpeg_spec_kernel<<<n_cta, CHUNK_THREADS, 0, s>>>(sc, chunk_bits, pgj_overlap_bits(chunk_bits));
   for (int r = 1; r <= d->rounds; ++r) jpeg_sync_kernel<<<n_cta, CHUNK_THREADS, 0, s>>>(sc, chunk_bits, r);
   jpeg_entry_scan_kernel<<<(unsigned)n, 1024, 0, s>>>(sc, d->rounds & 1);
-  jpeg_store_kernel<<<n_cta, CHUNK_THREADS, 0, s>>>(sc, chunk_bits);
+  constexpr size_t kStoreSmem = (size_t)CHUNK_THREADS * BLK_PITCH * sizeof(int16_t);
+  PG_CUDA_TRY(cudaFuncSetAttribute(jpeg_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStoreSmem));
+  jpeg_store_kernel<<<n_cta, CHUNK_THREADS, kStoreSmem, s>>>(sc, chunk_bits);
   int max_blocks = 0;
   for (int i = 0; i < n; ++i) max_blocks = std::max(max_blocks, d->images[(size_t)i].dev.total_blocks);
   dim3 grid((unsigned)std::min(4096, (max_blocks + 127) / 128), (unsigned)n);
@@ -682,6 +747,16 @@ extern "C" int pg_jpeg_decode_status(const PgJpegDecoder* d, int64_t stats[4]) {
   stats[3] = d->total_chunks;
   return PG_OK;
 }
+
+struct HostBlockSink {
+  int16_t* base;
+  int16_t blk[64];
+  int pred;
+  void begin(int p) { pred = p; std::memset(blk, 0, sizeof(blk)); }
+  void dc(int diff) { blk[0] = (int16_t)(pred + diff); }
+  void ac(int idx, int v) { blk[idx] = (int16_t)v; }
+  void end(int64_t ci) { std::memcpy(base + ci, blk, sizeof(blk)); }
+};
 
 // ================================================================================================================
 // Host evaluation of the same inline code, chunk by chunk in the kernels' order (CPU test-suite): decodes one
@@ -754,8 +829,10 @@ extern "C" int pg_hostcheck_jpeg_decode(const uint8_t* file, int64_t len, int32_
     const int64_t b0 = (int64_t)j * chunk_bits, b1 = b0 + chunk_bits;
     const int64_t ep = j == 0 ? 0 : st[parity][(size_t)j - 1].p;
     const int ec = j == 0 ? 0 : st[parity][(size_t)j - 1].c;
-    if (b0 < sv.n_bits && ep >= 0 && ep < b1)
-      pgj_span_store(sv, im, ep, ec, b1, std::max(anchor, 0) * im.restart_blocks + n, d0, d1, d2, coef.data());
+    if (b0 < sv.n_bits && ep >= 0 && ep < b1) {
+      HostBlockSink sink{coef.data(), {0}, 0};
+      pgj_span_store(sv, im, ep, ec, b1, std::max(anchor, 0) * im.restart_blocks + n, d0, d1, d2, sink);
+    }
     if (cs.p != -2) {
       if (cs.anchor >= 0) { anchor = cs.anchor; n = cs.n; d0 = cs.dc[0]; d1 = cs.dc[1]; d2 = cs.dc[2]; }
       else { n += cs.n; d0 += cs.dc[0]; d1 += cs.dc[1]; d2 += cs.dc[2]; }

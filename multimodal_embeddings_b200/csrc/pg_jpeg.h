@@ -33,6 +33,11 @@ constexpr int PGJ_MAX_BLOCKS_PER_MCU = 10;
 
 struct PgjHuff {
   uint16_t lut[1 << PGJ_LUT_BITS];  // (length << 8) | symbol for codes of <= 9 bits; 0: longer code
+  // AC tables, same index (the next 9 bits of the stream):
+  uint16_t skip[1 << PGJ_LUT_BITS]; // passes 1-2 need no values: code length + magnitude bits (bits 0-4), run (5-8),
+                                    // bit 9 = symbol without magnitude bits (EOB / ZRL); 0: longer code
+  int16_t fast[1 << PGJ_LUT_BITS];  // pass 3: code and magnitude bits both inside the 9 bits and |value| < 128:
+                                    // (value << 8) | (run << 4) | bits; 0: take the two-step path
   int32_t maxcode[18];              // maxcode[l] = largest code of length l (-1: none); [17] = sentinel
   int32_t valoff[17];               // symbol index of the first code of length l minus that code
   uint8_t vals[256];
@@ -149,8 +154,9 @@ PGJ_HD int pgj_extend(uint32_t v, int s) { return v < (1u << (s - 1)) ? (int)v -
 // into step, so a bit pattern that is no code word costs one bit and a run that overshoots the block ends it.
 // Neither happens to a decoder in the true state on a valid stream.  `stop`: the next restart boundary / end of the
 // scan — a block that reaches it is not a block (padding, or a decoder out of step) and false is returned.
-// Emit::dc(diff) / Emit::ac(natural index, value).
-template <class Emit>
+// VALUES: Emit::dc(diff) / Emit::ac(natural index, value) receive the coefficients (pass 3); without it the AC
+// symbols are only stepped over (passes 1-2), one table look-up each.
+template <bool VALUES, class Emit>
 PGJ_HD bool pgj_block(PgjBits& br, const PgjHuff& dc, const PgjHuff& ac, int& dc_diff, Emit& emit, int64_t stop) {
   int s;
   while (true) {
@@ -166,11 +172,39 @@ PGJ_HD bool pgj_block(PgjBits& br, const PgjHuff& dc, const PgjHuff& ac, int& dc
   dc_diff = diff;
   emit.dc(diff);
   int k = 1;
-  while (k < 64) {
-    if (br.pos() >= stop) return false;
+  while (k < 64) {  // at most 63 symbols of at most 31 bits: a walk through garbage stays inside the stream's slack
     br.need32();
+    const uint32_t look = br.peek16();
+    if (!VALUES) {
+      const uint32_t e = ac.skip[look >> (16 - PGJ_LUT_BITS)];
+      if (e) {
+        if (e & 512u) {  // EOB or ZRL
+          br.skip((int)(e & 31u));
+          if (((e >> 5) & 15u) != 15u) break;
+          k += 16;
+        } else {
+          br.skip((int)(e & 31u));
+          k += (int)((e >> 5) & 15u) + 1;  // a run that overshoots ends the block (k >= 64)
+        }
+        continue;
+      }
+    } else {
+      const int f = ac.fast[look >> (16 - PGJ_LUT_BITS)];
+      if (f) {
+        k += (f >> 4) & 15;
+        br.skip(f & 15);
+        if (k > 63) break;
+        emit.ac(pgj_zigzag(k), f >> 8);
+        ++k;
+        continue;
+      }
+    }
     const int rs = pgj_symbol(br, ac);
-    if (rs < 0) { br.skip(1); continue; }
+    if (rs < 0) {
+      br.skip(1);
+      if (br.pos() >= stop) return false;
+      continue;
+    }
     const int r = rs >> 4;
     s = rs & 15;
     if (s == 0) {
@@ -224,7 +258,7 @@ PGJ_HD void pgj_span(const PgjStream& sv, const PgjImage& im, int64_t p, int c, 
   while (p < limit && p < sv.n_bits) {
     const int comp = im.blk_comp[c];
     int diff = 0;
-    const bool ok = pgj_block(br, im.huff[0][im.comp_dc[comp]], im.huff[1][im.comp_ac[comp]], diff, none, bound);
+    const bool ok = pgj_block<false>(br, im.huff[0][im.comp_dc[comp]], im.huff[1][im.comp_ac[comp]], diff, none, bound);
     const int64_t pe = br.pos();
     if (!ok || pe > bound) {
       if (bound >= sv.n_bits) { p = sv.n_bits; c = 0; break; }  // end of the scan
@@ -296,17 +330,12 @@ PGJ_HD int64_t pgj_block_coef_index(const PgjImage& im, int blk, int c, int& com
   return im.comp_coef_off[comp] + ((int64_t)by * im.comp_bw[comp] + bx) * 64;
 }
 
-struct PgjStoreEmit {
-  int16_t* dst;  // the block's 64 coefficients (zero-filled beforehand)
-  int pred;
-  PGJ_HD void dc(int diff) { if (dst) dst[0] = (int16_t)(pred + diff); }
-  PGJ_HD void ac(int idx, int v) { if (dst) dst[idx] = (int16_t)v; }
-};
-
-// Pass 3: the same walk from a TRUE state with the absolute block index and the DC predictors known; stores
-// coefficients.  Interval ends are taken from the block count here (nothing speculative is left).
+// Pass 3: the same walk from a TRUE state with the absolute block index and the DC predictors known; every block is
+// handed to `sink` (begin(pred) / dc(diff) / ac(natural index, value) / end(coefficient index)).  Interval ends are
+// taken from the block count here (nothing speculative is left).
+template <class Sink>
 PGJ_HD void pgj_span_store(const PgjStream& sv, const PgjImage& im, int64_t p, int c, int64_t limit, int blk,
-                           int pred0, int pred1, int pred2, int16_t* coef_base) {
+                           int pred0, int pred1, int pred2, Sink& sink) {
   int pred[3] = {pred0, pred1, pred2};
   if (im.restart_blocks && blk > 0 && blk % im.restart_blocks == 0) {
     // the entry lies in the padding behind a completed interval (or already on the boundary): the next block
@@ -323,9 +352,10 @@ PGJ_HD void pgj_span_store(const PgjStream& sv, const PgjImage& im, int64_t p, i
   while (p < limit && p < sv.n_bits && blk < im.total_blocks) {
     int comp;
     const int64_t ci = pgj_block_coef_index(im, blk, c, comp);
-    PgjStoreEmit emit{coef_base + ci, pred[comp]};
+    sink.begin(pred[comp]);
     int diff = 0;
-    if (!pgj_block(br, im.huff[0][im.comp_dc[comp]], im.huff[1][im.comp_ac[comp]], diff, emit, sv.n_bits + 64)) return;  // corrupt
+    if (!pgj_block<true>(br, im.huff[0][im.comp_dc[comp]], im.huff[1][im.comp_ac[comp]], diff, sink, sv.n_bits + 64)) return;  // corrupt
+    sink.end(ci);
     pred[comp] += diff;
     ++blk;
     c = c + 1 == im.bpm ? 0 : c + 1;
@@ -373,6 +403,19 @@ PGJ_HD uint8_t pgj_clamp_sample(int32_t x) {
 // coef: 64 quantised coefficients (natural order); q: quantisation table; out[8][8] samples
 PGJ_HD void pgj_idct_block(const int16_t* coef, const uint16_t* q, uint8_t out[64]) {
   int32_t ws[64];
+  {
+    // a block with nothing but its DC term (blank paper) is flat: both passes reduce to two rounding shifts
+    int any = 0;
+#pragma unroll
+    for (int k = 1; k < 64; ++k) any |= coef[k];
+    if (!any) {
+      const int32_t col = pgj_descale((int32_t)coef[0] * q[0] * 8192, 11);  // pass 1, column 0 (every row)
+      const uint8_t v = pgj_clamp_sample(pgj_descale(col * 8192, 18));      // pass 2, every sample
+#pragma unroll
+      for (int k = 0; k < 64; ++k) out[k] = v;
+      return;
+    }
+  }
 #pragma unroll
   for (int x = 0; x < 8; ++x) {  // pass 1: columns
     int32_t o[8];

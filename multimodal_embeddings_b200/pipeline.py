@@ -379,6 +379,15 @@ class ScanPipeline:
                                "busy": False})
         self.step = 0
         self.h2d_bytes = self.d2h_bytes = 0
+        self.trace = None  # set to [] to record (copy start, copy end, compute start, compute end) events per step
+
+    def timeline_ms(self):
+        """With `trace` enabled: per step, the four instants in ms from the first step's copy start."""
+        if not self.trace:
+            return []
+        torch.cuda.synchronize()
+        base = self.trace[0][0]
+        return [[round(base.elapsed_time(e), 3) for e in evs] for evs in self.trace]
 
     def submit(self, blob: torch.Tensor, file_off, host_dets: Dict[str, np.ndarray]) -> int:
         k = self.step % self.depth
@@ -402,17 +411,27 @@ class ScanPipeline:
         if sl["pin_out"] is None or sl["pin_out"]["kept2"].shape != pipe.kept2.shape:
             sl["pin_out"] = {n: torch.empty_like(getattr(pipe, n), device="cpu").pin_memory()
                              for n in ("kept2", "n_kept2", "median", "n_bins", "centers", "col_widths", "n_cols")}
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.trace is not None else None
         with torch.cuda.stream(self.s_copy):
             if sl["busy"]:
                 self.s_copy.wait_event(sl["done"])  # the slot's previous step has consumed its buffers
+            if ev:
+                ev[0].record(self.s_copy)
             sl["blob"][:blob.numel()].copy_(blob, non_blocking=True)
             box_bytes = pipe.upload_detections(host_dets, pinned=sl["pin_in"])
+            if ev:
+                ev[1].record(self.s_copy)
             sl["copied"].record(self.s_copy)
         self.s_main.wait_event(sl["copied"])
         with torch.cuda.stream(self.s_main):
+            if ev:
+                ev[2].record(self.s_main)
             dec.decode(sl["blob"], [sl["pages"][i] for i in range(self.n_pages)], stream=self.s_main)
             pipe.run(sl["pages"], stream=self.s_main)
             pipe.results_to_host(pinned=sl["pin_out"])
+            if ev:
+                ev[3].record(self.s_main)
+                self.trace.append(ev)
             sl["done"].record(self.s_main)
         sl["busy"] = True
         self.h2d_bytes = int(blob.numel() + box_bytes)

@@ -62,10 +62,11 @@ def test_decode_full_size_scan_like_pages_equals_cv2():
 
 
 def test_decode_retries_with_more_rounds_when_the_states_have_not_converged():
-    """Quality 100 on a noisy page: blocks of ~1000 bits against 64-byte chunks, one sync round configured — the
-    status word reports it and check() decodes again with more rounds until the fixed point is reached."""
-    data = _encode(_page(600, 800, 3, 40), 100)
-    dec = ops.JpegDecoder(chunk_bytes=64, sync_rounds=1)
+    """Quality 95 on a noisy page: blocks of several hundred bits against 256-byte chunks need about a dozen sync
+    rounds; with one round configured the status word reports it and check() decodes again with more rounds until the
+    fixed point is reached."""
+    data = _encode(_page(600, 800, 3, 40), 95)
+    dec = ops.JpegDecoder(chunk_bytes=256, sync_rounds=1)
     blob, off = ops.pack_files([data])
     dec.set_files(blob, off)
     pages = dec.decode(blob.cuda())

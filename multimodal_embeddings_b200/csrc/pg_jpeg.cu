@@ -211,7 +211,8 @@ struct ImgRec {            // per image, device
   int32_t n_chunks;
   int32_t pad_;
   int64_t coef_off;        // int16 elements
-  uint8_t* out;            // decoded page
+  int64_t plane_off;       // colour files: the three component planes (bytes into Scratch::planes)
+  uint8_t* out;            // decoded page: one grey plane, or BGR interleaved
   int64_t pitch;
 };
 
@@ -231,6 +232,7 @@ struct Scratch {           // device pointers into the caller's workspace
   PgjChunkState* entry;    // exclusive segmented scan: state of the decoder at each chunk's entry
   int32_t* counters;       // [MAX_ROUNDS + 2]: changes per round; [MAX_ROUNDS+1] = error flag
   int16_t* coef;
+  uint8_t* planes;         // colour files: Y, Cb, Cr after the IDCT, each comp_bw*8 x comp_bh*8
 };
 
 __device__ __forceinline__ PgjStream stream_of(const Scratch& s, const ImgRec& r, int img) {
@@ -496,14 +498,26 @@ __global__ void __launch_bounds__(CHUNK_THREADS) jpeg_store_kernel(Scratch s, in
   pgj_span_store(sv, im, e.p, e.c, b1, blk, e.dc[0], e.dc[1], e.dc[2], sink);
 }
 
-// ---- D8: inverse DCT, one thread per block, grey / luma plane ------------------------------------------------
-__global__ void __launch_bounds__(128) jpeg_idct_kernel(Scratch s, int comp) {
-  const int img = blockIdx.y;
+// ---- D8: inverse DCT, one thread per block -------------------------------------------------------------------
+// Greyscale files: straight into the page.  Colour files (blockIdx.z = component): into the component's own plane,
+// whole blocks; D9 makes the page from the three planes.
+__global__ void __launch_bounds__(128) jpeg_idct_kernel(Scratch s) {
+  const int img = blockIdx.y, comp = blockIdx.z;
   const ImgRec r = s.rec[img];
   const PgjImage* im = s.img + img;
+  if (comp >= im->n_comps) return;
   const int bw = im->comp_bw[comp], bh = im->comp_bh[comp];
   const int64_t nb = (int64_t)bw * bh;
-  const int w = im->width, h = im->height;
+  const bool grey = im->n_comps == 1;
+  const int w = grey ? im->width : bw * 8, h = grey ? im->height : bh * 8;
+  uint8_t* plane = r.out;
+  int64_t pitch = r.pitch;
+  if (!grey) {
+    int64_t off = r.plane_off;
+    for (int c = 0; c < comp; ++c) off += (int64_t)im->comp_bw[c] * im->comp_bh[c] * 64;
+    plane = s.planes + off;
+    pitch = bw * 8;
+  }
   __shared__ uint16_t q[64];
   if (threadIdx.x < 64) q[threadIdx.x] = im->qt[comp][threadIdx.x];
   __syncthreads();
@@ -521,12 +535,50 @@ __global__ void __launch_bounds__(128) jpeg_idct_kernel(Scratch s, int comp) {
 #pragma unroll
     for (int y = 0; y < 8; ++y) {
       if (y0 + y >= h) break;
-      uint8_t* dst = r.out + (int64_t)(y0 + y) * r.pitch + x0;
+      uint8_t* dst = plane + (int64_t)(y0 + y) * pitch + x0;
       if (x0 + 8 <= w) {
         *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(px + 8 * y);
       } else {
         for (int x = 0; x0 + x < w; ++x) dst[x] = px[8 * y + x];
       }
+    }
+  }
+}
+
+// ---- D9: colour files — fancy chroma upsampling + YCbCr -> BGR, four pixels (12 bytes) per thread --------------------
+__global__ void __launch_bounds__(256) jpeg_colour_kernel(Scratch s) {
+  const int img = blockIdx.y;
+  const PgjImage* im = s.img + img;
+  if (im->n_comps != 3) return;
+  const ImgRec r = s.rec[img];
+  const int w = im->width, h = im->height;
+  const int hmax = im->comp_h[0], vmax = im->comp_v[0];
+  const int p0 = im->comp_bw[0] * 8, p1 = im->comp_bw[1] * 8, p2 = im->comp_bw[2] * 8;
+  const uint8_t* yp = s.planes + r.plane_off;
+  const uint8_t* cbp = yp + (int64_t)im->comp_bw[0] * im->comp_bh[0] * 64;
+  const uint8_t* crp = cbp + (int64_t)im->comp_bw[1] * im->comp_bh[1] * 64;
+  const int fx = hmax / im->comp_h[1], fy = vmax / im->comp_v[1];
+  const int dw = (w * im->comp_h[1] + hmax - 1) / hmax, dh = (h * im->comp_v[1] + vmax - 1) / vmax;
+  const int quads = (w + 3) >> 2;
+  const int64_t total = (int64_t)quads * h;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int y = (int)(t / quads), x0 = (int)(t - (int64_t)y * quads) * 4;
+    uint8_t px[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = x0 + k < w ? x0 + k : w - 1;
+      const int yy = yp[(int64_t)y * p0 + x];
+      const int cb = pgj_upsample(cbp, p1, dw, dh, fx, fy, x, y), cr = pgj_upsample(crp, p2, dw, dh, fx, fy, x, y);
+      pgj_ycc_to_bgr(yy, cb, cr, px[3 * k], px[3 * k + 1], px[3 * k + 2]);
+    }
+    uint8_t* dst = r.out + (int64_t)y * r.pitch + 3 * x0;
+    if (x0 + 4 <= w) {
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);  // 12 * (x0 / 4) bytes into a 16-byte aligned row
+      d32[0] = px[0] | px[1] << 8 | px[2] << 16 | (uint32_t)px[3] << 24;
+      d32[1] = px[4] | px[5] << 8 | px[6] << 16 | (uint32_t)px[7] << 24;
+      d32[2] = px[8] | px[9] << 8 | px[10] << 16 | (uint32_t)px[11] << 24;
+    } else {
+      for (int k = 0; k < 3 * (w - x0); ++k) dst[k] = px[k];
     }
   }
 }
@@ -542,7 +594,8 @@ struct PgJpegDecoder {
   // layout computed by set_files
   std::vector<ImgRec> rec;
   std::vector<int32_t> cta_img, cta_chunk0, ub_img;
-  int64_t total_chunks = 0, total_ub = 0, total_rst = 0, compact_bytes = 0, coef_elems = 0;
+  int64_t total_chunks = 0, total_ub = 0, total_rst = 0, compact_bytes = 0, coef_elems = 0, plane_bytes = 0;
+  bool any_colour = false;
   size_t ws_bytes = 0;
   // pinned staging for the per-call tables (ring, so that a call may be prepared while the previous one's copy runs)
   struct Stage { void* host = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; };
@@ -583,7 +636,8 @@ extern "C" int pg_jpeg_decoder_set_files(PgJpegDecoder* d, const uint8_t* blob, 
   d->file_off.assign(file_off, file_off + n + 1);
   d->rec.assign((size_t)n, ImgRec());
   d->cta_img.clear(); d->cta_chunk0.clear(); d->ub_img.clear();
-  int64_t cs = 0, rst = 0, chunks = 0, ub = 0, coef = 0;
+  int64_t cs = 0, rst = 0, chunks = 0, ub = 0, coef = 0, planes = 0;
+  d->any_colour = false;
   for (int i = 0; i < n; ++i) {
     PG_REQUIRE(file_off[i + 1] > file_off[i], "file offsets must increase");
     const int rc = parse_jpeg(blob + file_off[i], file_off[i + 1] - file_off[i], d->images[(size_t)i]);
@@ -608,9 +662,16 @@ extern "C" int pg_jpeg_decoder_set_files(PgJpegDecoder* d, const uint8_t* blob, 
     chunks += r.n_chunks;
     r.coef_off = coef;
     coef += (int64_t)im.dev.total_blocks * 64;
+    r.plane_off = planes;
+    if (im.dev.n_comps == 3) {
+      planes += (int64_t)im.dev.total_blocks * 64;  // one byte per coefficient: the three planes after the IDCT
+      planes = (int64_t)align_up((size_t)planes, 256);
+      d->any_colour = true;
+    }
     r.out = nullptr; r.pitch = 0;
   }
   d->total_chunks = chunks; d->total_ub = ub; d->total_rst = rst; d->compact_bytes = cs; d->coef_elems = coef;
+  d->plane_bytes = planes;
   // workspace layout (sizes only; pointers are formed at decode time)
   size_t w = 0;
   auto add = [&](size_t bytes) { w = align_up(w, 256) + bytes; };
@@ -623,6 +684,7 @@ extern "C" int pg_jpeg_decoder_set_files(PgJpegDecoder* d, const uint8_t* blob, 
   add((size_t)chunks * sizeof(PgjChunkState));
   add((MAX_ROUNDS + 2) * 4);
   add((size_t)coef * 2);
+  add((size_t)planes);
   d->ws_bytes = align_up(w, 256) + 256;
   return PG_OK;
 }
@@ -648,8 +710,7 @@ extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t
   for (int i = 0; i < n; ++i) {
     const PgjImage& g = d->images[(size_t)i].dev;
     PG_REQUIRE(out_ptrs[i] != nullptr && pitches[i] >= (int64_t)g.width * (g.n_comps == 1 ? 1 : 3), "output pointer / pitch");
-    if (g.n_comps != 1) { pg_set_error("unsupported: colour JPEG on the device path (greyscale scans only)"); return PG_ERR_UNSUPPORTED; }
-    PG_REQUIRE(((uintptr_t)out_ptrs[i] & 7) == 0 && pitches[i] % 8 == 0, "output must be 8-byte aligned with pitch % 8 == 0");
+    PG_REQUIRE(((uintptr_t)out_ptrs[i] & 15) == 0 && pitches[i] % 16 == 0, "output must be 16-byte aligned with pitch % 16 == 0");
     d->rec[(size_t)i].out = out_ptrs[i];
     d->rec[(size_t)i].pitch = pitches[i];
   }
@@ -675,6 +736,7 @@ extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t
   sc.entry = reinterpret_cast<PgjChunkState*>(take((size_t)d->total_chunks * sizeof(PgjChunkState)));
   sc.counters = reinterpret_cast<int32_t*>(take((MAX_ROUNDS + 2) * 4));
   sc.coef = reinterpret_cast<int16_t*>(take((size_t)d->coef_elems * 2));
+  sc.planes = take((size_t)d->plane_bytes);
   d->last = sc;
 
   // per-call tables: one pinned staging block, one copy
@@ -726,8 +788,17 @@ extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t
   jpeg_store_kernel<<<n_cta, CHUNK_THREADS, kStoreSmem, s>>>(sc, chunk_bits);
   int max_blocks = 0;
   for (int i = 0; i < n; ++i) max_blocks = std::max(max_blocks, d->images[(size_t)i].dev.total_blocks);
-  dim3 grid((unsigned)std::min(4096, (max_blocks + 127) / 128), (unsigned)n);
-  jpeg_idct_kernel<<<grid, 128, 0, s>>>(sc, 0);
+  dim3 grid((unsigned)std::min(4096, (max_blocks + 127) / 128), (unsigned)n, d->any_colour ? 3u : 1u);
+  jpeg_idct_kernel<<<grid, 128, 0, s>>>(sc);
+  if (d->any_colour) {
+    int64_t max_quads = 0;
+    for (int i = 0; i < n; ++i) {
+      const PgjImage& g = d->images[(size_t)i].dev;
+      if (g.n_comps == 3) max_quads = std::max(max_quads, (int64_t)((g.width + 3) / 4) * g.height);
+    }
+    dim3 cgrid((unsigned)std::min<int64_t>(8192, (max_quads + 255) / 256), (unsigned)n);
+    jpeg_colour_kernel<<<cgrid, 256, 0, s>>>(sc);
+  }
   PG_LAUNCH_CHECK();
   return PG_OK;
 }
@@ -775,7 +846,7 @@ extern "C" int pg_hostcheck_jpeg_decode(const uint8_t* file, int64_t len, int32_
     if (stats) { stats[0] = stats[1] = stats[2] = 0; stats[3] = im.n_comps; }
     return PG_OK;
   }
-  PG_REQUIRE(im.n_comps == 1 && pitch >= im.width, "greyscale only / pitch");
+  PG_REQUIRE(pitch >= (int64_t)im.width * (im.n_comps == 1 ? 1 : 3), "pitch");
   // D1-D3
   const uint8_t* p = file + hi.scan_begin;
   const int64_t sl = hi.scan_end - hi.scan_begin;
@@ -838,14 +909,40 @@ extern "C" int pg_hostcheck_jpeg_decode(const uint8_t* file, int64_t len, int32_
       else { n += cs.n; d0 += cs.dc[0]; d1 += cs.dc[1]; d2 += cs.dc[2]; }
     }
   }
-  // D8
-  for (int by = 0; by < im.comp_bh[0]; ++by)
-    for (int bx = 0; bx < im.comp_bw[0]; ++bx) {
-      uint8_t px[64];
-      pgj_idct_block(coef.data() + ((size_t)by * im.comp_bw[0] + bx) * 64, im.qt[0], px);
-      for (int y = 0; y < 8 && by * 8 + y < im.height; ++y)
-        for (int x = 0; x < 8 && bx * 8 + x < im.width; ++x) out[(int64_t)(by * 8 + y) * pitch + bx * 8 + x] = px[8 * y + x];
+  // D8 (+ D9 for colour files)
+  if (im.n_comps == 1) {
+    for (int by = 0; by < im.comp_bh[0]; ++by)
+      for (int bx = 0; bx < im.comp_bw[0]; ++bx) {
+        uint8_t px[64];
+        pgj_idct_block(coef.data() + ((size_t)by * im.comp_bw[0] + bx) * 64, im.qt[0], px);
+        for (int y = 0; y < 8 && by * 8 + y < im.height; ++y)
+          for (int x = 0; x < 8 && bx * 8 + x < im.width; ++x) out[(int64_t)(by * 8 + y) * pitch + bx * 8 + x] = px[8 * y + x];
+      }
+  } else {
+    std::vector<uint8_t> plane[3];
+    for (int c = 0; c < 3; ++c) {
+      const int pw = im.comp_bw[c] * 8;
+      plane[c].resize((size_t)pw * im.comp_bh[c] * 8);
+      for (int by = 0; by < im.comp_bh[c]; ++by)
+        for (int bx = 0; bx < im.comp_bw[c]; ++bx) {
+          uint8_t px[64];
+          pgj_idct_block(coef.data() + im.comp_coef_off[c] + ((size_t)by * im.comp_bw[c] + bx) * 64, im.qt[c], px);
+          for (int y = 0; y < 8; ++y)
+            for (int x = 0; x < 8; ++x) plane[c][(size_t)(by * 8 + y) * pw + bx * 8 + x] = px[8 * y + x];
+        }
     }
+    const int hmax = im.comp_h[0], vmax = im.comp_v[0];
+    const int fx = hmax / im.comp_h[1], fy = vmax / im.comp_v[1];
+    const int dw = (im.width * im.comp_h[1] + hmax - 1) / hmax, dh = (im.height * im.comp_v[1] + vmax - 1) / vmax;
+    for (int y = 0; y < im.height; ++y)
+      for (int x = 0; x < im.width; ++x) {
+        const int yy = plane[0][(size_t)y * im.comp_bw[0] * 8 + x];
+        const int cb = pgj_upsample(plane[1].data(), im.comp_bw[1] * 8, dw, dh, fx, fy, x, y);
+        const int cr = pgj_upsample(plane[2].data(), im.comp_bw[2] * 8, dw, dh, fx, fy, x, y);
+        uint8_t* o = out + (int64_t)y * pitch + 3 * x;
+        pgj_ycc_to_bgr(yy, cb, cr, o[0], o[1], o[2]);
+      }
+  }
   if (stats) { stats[0] = used; stats[1] = first_changes; stats[2] = n_chunks; stats[3] = (int64_t)rst.size(); }
   return PG_OK;
 }

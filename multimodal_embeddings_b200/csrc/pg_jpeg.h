@@ -444,3 +444,40 @@ PGJ_HD bool pgj_keep_byte(uint8_t prev, uint8_t cur, uint8_t next) {
   return true;
 }
 PGJ_HD bool pgj_rst_starts(uint8_t cur, uint8_t next) { return cur == 0xFF && pgj_is_rst(next); }
+
+
+// ---- colour files: jdsample.c "fancy" (triangle) chroma upsampling + jdcolor.c YCbCr -> RGB ----------------------
+// One chroma sample of the full-resolution image at (x, y) from the component's own plane `p` (pitch `pp`), whose
+// real extent is dw x dh samples (the rest of the plane is block padding; libjpeg replicates the edge instead).
+// fx, fy in {1, 2}: the component's horizontal / vertical subsampling against luma.
+PGJ_HD int pgj_upsample(const uint8_t* p, int pp, int dw, int dh, int fx, int fy, int x, int y) {
+  if (fx == 1 && fy == 1) return p[(int64_t)y * pp + x];
+  if (fy == 1) {  // h2v1: 3/4 nearer + 1/4 farther column, rounding 1 / 2 alternately
+    const int cx = x >> 1;
+    int nx = (x & 1) ? cx + 1 : cx - 1;
+    nx = nx < 0 ? 0 : (nx > dw - 1 ? dw - 1 : nx);
+    const uint8_t* row = p + (int64_t)y * pp;
+    return (3 * row[cx] + row[nx] + ((x & 1) ? 2 : 1)) >> 2;
+  }
+  const int cy = y >> 1;
+  int ny = (y & 1) ? cy + 1 : cy - 1;
+  ny = ny < 0 ? 0 : (ny > dh - 1 ? dh - 1 : ny);
+  const uint8_t* r0 = p + (int64_t)cy * pp;
+  const uint8_t* r1 = p + (int64_t)ny * pp;
+  if (fx == 1) return (3 * r0[x] + r1[x] + ((y & 1) ? 2 : 1)) >> 2;  // h1v2
+  const int cx = x >> 1;  // h2v2: column sums 3 * nearer row + farther row, then the same across columns (/16)
+  int nx = (x & 1) ? cx + 1 : cx - 1;
+  nx = nx < 0 ? 0 : (nx > dw - 1 ? dw - 1 : nx);
+  const int a = 3 * r0[cx] + r1[cx], b = 3 * r0[nx] + r1[nx];
+  return (3 * a + b + ((x & 1) ? 7 : 8)) >> 4;
+}
+
+PGJ_HD uint8_t pgj_clamp8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+// jdcolor.c with SCALEBITS = 16: FIX(1.40200) = 91881, FIX(1.77200) = 116130, FIX(0.34414) = 22554, FIX(0.71414) = 46802
+PGJ_HD void pgj_ycc_to_bgr(int y, int cb, int cr, uint8_t& b, uint8_t& g, uint8_t& r) {
+  cb -= 128; cr -= 128;
+  r = pgj_clamp8(y + ((91881 * cr + 32768) >> 16));
+  b = pgj_clamp8(y + ((116130 * cb + 32768) >> 16));
+  g = pgj_clamp8(y + ((-22554 * cb - 46802 * cr + 32768) >> 16));
+}

@@ -222,8 +222,9 @@ def upload_pages_pinned(images: Sequence[np.ndarray], stream=None) -> List[torch
 # D1-D8 JPEG scans decoded on the device
 # --------------------------------------------------------------------------------------------
 class JpegDecoder:
-    """pg_jpeg_*: greyscale baseline JPEG files -> grey pages in HBM, bit for bit what cv2.imread returns
-    (in each of its three equal channels).  Usage per batch of files:
+    """pg_jpeg_*: baseline JPEG files -> pages in HBM, bit for bit what cv2.imread returns: a greyscale file gives ONE
+    grey plane [H, pitch] (cv2's three channels are equal; tile it with channels=1 plans), a colour file gives BGR
+    interleaved [H, pitch >= 3W] like cv2.  Usage per batch of files:
 
         sizes = dec.set_files(blob, file_off)        # host: headers parsed; blob = files back to back
         pages = dec.decode(blob_dev)                 # device, asynchronous; list of uint8 [H, pitch] tensors
@@ -252,7 +253,8 @@ class JpegDecoder:
 
     def set_files(self, blob, file_off) -> List[Tuple[int, int, int]]:
         """Parses the headers (host).  Returns [(width, height, channels)].  Raises PageGeomError (error 4,
-        'unsupported: ...') for anything but greyscale/colour baseline Huffman files."""
+        'unsupported: ...') for anything but baseline / extended-sequential Huffman files (progressive, arithmetic,
+        12-bit, CMYK, multi-scan, exotic sampling factors)."""
         arr = blob.numpy() if isinstance(blob, torch.Tensor) else np.asarray(blob)
         assert arr.dtype == np.uint8 and arr.ndim == 1 and arr.flags.c_contiguous
         off = np.ascontiguousarray(np.asarray(file_off, np.int64))
@@ -325,17 +327,15 @@ class JpegDecoder:
         return st
 
 
-def jpeg_probe(data: bytes) -> Optional[Tuple[int, int]]:
-    """(width, height) when `data` is a JPEG file the device path decodes (greyscale baseline / extended
-    sequential Huffman, one scan), else None.  Host only: parses the headers (pg_hostcheck_jpeg_decode with no
-    output buffer)."""
+def jpeg_probe(data: bytes) -> Optional[Tuple[int, int, int]]:
+    """(width, height, channels) when `data` is a JPEG file the device path decodes (baseline / extended sequential
+    Huffman, 8-bit, one scan; greyscale, or YCbCr with 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0 sampling), else None.  Host
+    only: parses the headers (pg_hostcheck_jpeg_decode with no output buffer)."""
     b = np.frombuffer(data, np.uint8)
     w, h, st = C.c_int32(), C.c_int32(), (C.c_int64 * 4)()
     if lib().pg_hostcheck_jpeg_decode(b.ctypes.data, len(b), 512, 0, None, 0, C.byref(w), C.byref(h), st) != 0:
         return None
-    if st[3] != 1:  # components
-        return None
-    return w.value, h.value
+    return w.value, h.value, int(st[3])
 
 
 def pack_files(files: Sequence[bytes], pinned: bool = True):
@@ -355,7 +355,7 @@ def pack_files(files: Sequence[bytes], pinned: bool = True):
 
 
 def decode_jpeg_files(files: Sequence[bytes], decoder: Optional[JpegDecoder] = None) -> List[torch.Tensor]:
-    """Convenience: greyscale JPEG files (bytes) -> grey pages on the GPU (synchronises)."""
+    """Convenience: JPEG files (bytes) -> pages on the GPU (grey plane or BGR, per file; synchronises)."""
     dec = decoder or JpegDecoder()
     blob, off = pack_files(files)
     dec.set_files(blob, off)

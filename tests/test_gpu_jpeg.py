@@ -83,11 +83,42 @@ def test_unsupported_files_are_refused_at_parse_time():
     dec = ops.JpegDecoder()
     with pytest.raises(PageGeomError, match="unsupported"):
         dec.set_files(*ops.pack_files([prog.tobytes()]))
-    colour = _encode(np.stack([g, g, 255 - g], -1))
-    blob, off = ops.pack_files([colour])
-    assert dec.set_files(blob, off) == [(64, 64, 3)]
-    with pytest.raises(PageGeomError, match="unsupported"):
-        dec.decode(blob.cuda())
+    assert ops.jpeg_probe(prog.tobytes()) is None and ops.jpeg_probe(_encode(g)) == (64, 64, 1)
+
+
+SUBSAMPLING = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+               cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440]
+
+
+def test_decode_colour_files_equals_cv2_and_feeds_the_three_channel_tiler():
+    """Colour scans (YCbCr, every common subsampling, odd sizes, restart markers) mixed with a greyscale file in one
+    batch: BGR pages bit-identical to cv2.imdecode; tiles from the device-decoded pages == tiles from cv2's pages."""
+    specs = [(517, 640), (1003, 1501), (333, 201), (64, 64), (1200, 1600), (77, 61), (900, 700), (1001, 777)]
+    files, refs = [], []
+    for i, (h, w) in enumerate(specs):
+        g = synth.newspaper_page(w, h, 40 + i)
+        c = np.stack([g, np.roll(g, 5, 1), 255 - np.roll(g, 3, 0)], -1)
+        files.append(_encode(c, (95, 75, 40)[i % 3], (0, 7)[i % 2], (cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SUBSAMPLING[i % 4])))
+    files.append(_encode(synth.newspaper_page(800, 600, 9), 95))
+    dec = ops.JpegDecoder()
+    pages = ops.decode_jpeg_files(files, dec)
+    assert [sz[2] for sz in dec.sizes] == [3] * len(specs) + [1]
+    for data, page, (w, h, c) in zip(files, pages, dec.sizes):
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        got = page[:, :c * w].cpu().numpy()
+        assert np.array_equal(got, ref.reshape(h, 3 * w) if c == 3 else ref[..., 0])
+        refs.append(ref)
+    grids = [(1, 1), (2, 2)]
+    sizes = [(w, h) for w, h, c in dec.sizes if c == 3]
+    b_dev = ops.TileBatch(sizes, grids, 20.0)
+    b_dev.bind(pages[:len(specs)])
+    b_dev.run()
+    b_ref = ops.TileBatch(sizes, grids, 20.0)
+    b_ref.bind(ops.upload_pages_pinned(refs[:len(specs)]))
+    b_ref.run()
+    torch.cuda.synchronize()
+    for a, b in zip(b_dev.outs, b_ref.outs):
+        assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("w,h,grids", [(8000, 6000, [(4, 4)]), (8000, 6000, [(1, 1), (2, 2), (3, 3), (4, 4)]),
@@ -128,3 +159,42 @@ def test_jpeg_to_tiles_equals_cv2_imread_to_tiles():
     torch.cuda.synchronize()
     for a, b in zip(b1.outs, b3.outs):
         assert torch.equal(a, b)
+
+
+def test_stage1_cli_on_jpeg_scans_equals_the_host_decode_run(tmp_path):
+    """1_doclayout_bboxes.py drop-in on a folder of .jpg scans (greyscale, colour 4:2:0, progressive) and a .png: the
+    run that decodes baseline JPEGs on the device writes the same JSON files and the same tile pixels as the run with
+    `--host_decode` (cv2.imread for every file, the reference's call)."""
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from multimodal_embeddings_b200 import cli
+    src = tmp_path / "in"
+    src.mkdir()
+    g1, g2 = synth.newspaper_page(1501, 1003, 1), synth.newspaper_page(900, 1300, 2)
+    (src / "a grey.jpg").write_bytes(_encode(g1, 95))
+    (src / "b colour.jpeg").write_bytes(_encode(np.stack([g2, np.roll(g2, 4, 1), 255 - g2], -1), 90,
+                                              extra=(cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420)))
+    (src / "c progressive.jpg").write_bytes(cv2.imencode(".jpg", g1[:800, :1000], [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])[1].tobytes())
+    cv2.imwrite(str(src / "d.png"), g2[:700, :650])
+    outs = {}
+    for mode, extra in (("device", []), ("host", ["--host_decode"])):
+        out = tmp_path / mode
+        assert cli.main_stage1(["--input_folder", str(src), "--output_folder", str(out), "--grids", "2x2", "--detector",
+                                "stub_detector:StubPlugin", "--write_tiles"] + extra) == 0
+        files = {}
+        for d, _, fs in os.walk(out):
+            for fn in fs:
+                path = os.path.join(d, fn)
+                rel = os.path.relpath(path, out)
+                if fn.endswith(".json"):
+                    files[rel] = open(path).read().replace(str(out), "<OUT>")
+                elif os.sep + "images" + os.sep in path:
+                    files[rel] = cv2.imread(path, cv2.IMREAD_UNCHANGED).tobytes() if not fn.lower().endswith((".jpg", ".jpeg")) else None
+        outs[mode] = files
+    assert sorted(outs["device"]) == sorted(outs["host"]) and len(outs["device"]) == 4 * (1 + 1 + 4) + 16
+    for rel in outs["host"]:
+        assert outs["device"][rel] == outs["host"][rel], rel
+    std = json.loads(outs["device"]["json/a grey.json"])
+    assert std["image_size"] == {"width": 1501, "height": 1003}

@@ -29,15 +29,20 @@ def _encode(img, q=95, rst=0, extra=()):
 
 
 def host_decode(data: bytes, chunk_bytes: int, max_rounds: int = 1 << 20):
+    """-> (grey [H, W] or BGR [H, W, 3], stats) through pg_hostcheck_jpeg_decode."""
     L = lib()
     w, h, st = C.c_int32(), C.c_int32(), (C.c_int64 * 4)()
     b = np.frombuffer(data, np.uint8)
     check(L.pg_hostcheck_jpeg_decode(b.ctypes.data, len(b), chunk_bytes, max_rounds, None, 0, C.byref(w), C.byref(h), st))
-    pitch = (w.value + 15) // 16 * 16
+    comps = st[3]
+    pitch = (comps * w.value + 15) // 16 * 16
     out = np.zeros((h.value, pitch), np.uint8)
     check(L.pg_hostcheck_jpeg_decode(b.ctypes.data, len(b), chunk_bytes, max_rounds, out.ctypes.data, pitch, C.byref(w),
                                      C.byref(h), st))
-    return out[:, :w.value], {"rounds": st[0], "replaced_round1": st[1], "chunks": st[2], "restarts": st[3]}
+    img = out[:, :comps * w.value]
+    if comps == 3:
+        img = img.reshape(h.value, w.value, 3)
+    return img, {"rounds": st[0], "replaced_round1": st[1], "chunks": st[2], "restarts": st[3]}
 
 
 @pytest.mark.parametrize("shape", [(64, 64), (61, 77), (8, 8), (17, 130)])
@@ -70,6 +75,23 @@ def test_chunked_decoder_inline_code_equals_cv2(shape, noise):
                 got, st = host_decode(data, chunk)
                 assert np.array_equal(got, ref[..., 0]), (shape, q, rst, chunk, st)
                 assert st["restarts"] == (0 if rst == 0 else max(0, -(-(-(-h // 8) * -(-w // 8)) // rst) - 1))
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (61, 77), (8, 8), (17, 130), (100, 33), (203, 317)])
+def test_chunked_decoder_colour_files_equal_cv2(shape):
+    """Colour files through the same inline code: interleaved MCUs (4:4:4, 4:2:2, 4:2:0, 4:4:0), fancy chroma
+    upsampling at odd sizes, YCbCr -> BGR; chunk sizes below and above an MCU, with and without restart markers."""
+    h, w = shape
+    g = _page(h, w, 9, 12)
+    c = np.stack([g, np.roll(g, 5, 1), 255 - np.roll(g, 3, 0)], -1)
+    for q in (95, 40):
+        for rst in (0, 2):
+            for ss in SUBSAMPLING.values():
+                data = _encode(c, q, rst, (cv2.IMWRITE_JPEG_SAMPLING_FACTOR, ss))
+                ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+                for chunk in (16, 256, 4096):
+                    got, st = host_decode(data, chunk)
+                    assert np.array_equal(got, ref), (shape, q, rst, ss, chunk, st)
 
 
 def test_chunk_states_converge_in_a_few_rounds_on_a_scan_like_page():

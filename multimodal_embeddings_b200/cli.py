@@ -275,8 +275,9 @@ def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
                 errors += 1
         live = []  # (path, batch, index in batch, width, height, host page or None)
         try:
+            # every page of the chunk as (path, device page [H, pitch], width, height, channels, host pixels or None)
+            staged = []
             on_device = [p_ for p_ in chunk if p_ in jpeg_bytes]
-            dev_colour = {}
             if on_device:
                 jdec = ops.JpegDecoder()
                 blob, off = ops.pack_files([jpeg_bytes[p_] for p_ in on_device])
@@ -284,32 +285,26 @@ def main_stage1(argv: Optional[Sequence[str]] = None) -> int:
                 pages_dev = jdec.decode(blob.to("cuda", non_blocking=True))
                 torch.cuda.current_stream().synchronize()
                 jdec.check()
-                grey = [i for i, sz in enumerate(sizes) if sz[2] == 1]
-                if grey:
-                    gb = ops.TileBatch([sizes[i][:2] for i in grey], grids, args.overlap, args.imgsz, channels=1)
-                    gb.bind([pages_dev[i] for i in grey])
-                    gb.run()
-                    for k_, i in enumerate(grey):
-                        w_, h_, _ = sizes[i]
-                        host_page = None
-                        if args.write_tiles:  # the tile files need the pixels on the host
-                            host_page = np.repeat(pages_dev[i][:, :w_].cpu().numpy()[..., None], 3, -1)
-                        live.append((on_device[i], gb, k_, w_, h_, host_page))
-                dev_colour = {on_device[i]: (pages_dev[i], sizes[i]) for i, sz in enumerate(sizes) if sz[2] == 3}
-            colour = [p_ for p_ in host_paths if decoded[p_] is not None]
-            if colour or dev_colour:  # BGR pages: uploaded from the host decoder, or already in HBM from the device decoder
-                uploaded = ops.upload_pages_pinned([decoded[p_] for p_ in colour]) if colour else []
-                names = colour + list(dev_colour)
-                dims = [(decoded[p_].shape[1], decoded[p_].shape[0]) for p_ in colour] + [sz[:2] for _, sz in dev_colour.values()]
-                cb = ops.TileBatch(dims, grids, args.overlap, args.imgsz)
-                cb.bind(list(uploaded) + [pg for pg, _ in dev_colour.values()])
-                cb.run()
-                for i, p_ in enumerate(names):
-                    host_page = decoded.get(p_)
-                    if host_page is None and args.write_tiles:
-                        pg, (w_, h_, _) = dev_colour[p_]
-                        host_page = pg[:, :3 * w_].cpu().numpy().reshape(h_, w_, 3)
-                    live.append((p_, cb, i, dims[i][0], dims[i][1], host_page))
+                staged += [(p_, pg, sz[0], sz[1], sz[2], None) for p_, pg, sz in zip(on_device, pages_dev, sizes)]
+            from_host = [p_ for p_ in host_paths if decoded[p_] is not None]
+            if from_host:
+                uploaded = ops.upload_pages_pinned([decoded[p_] for p_ in from_host])
+                staged += [(p_, pg, decoded[p_].shape[1], decoded[p_].shape[0], 1 if decoded[p_].ndim == 2 else 3, decoded[p_])
+                           for p_, pg in zip(from_host, uploaded)]
+            for chn in (1, 3):  # grey planes -> one-channel plans, BGR pages -> three-channel plans
+                group = [t_ for t_ in staged if t_[4] == chn]
+                if not group:
+                    continue
+                tb = ops.TileBatch([(t_[2], t_[3]) for t_ in group], grids, args.overlap, args.imgsz, channels=chn)
+                tb.bind([t_[1] for t_ in group])
+                tb.run()
+                for i, (p_, pg, w_, h_, _, host_page) in enumerate(group):
+                    if args.write_tiles:  # the tile files need the pixels on the host, as cv2.imread gives them
+                        if host_page is None:
+                            host_page = pg[:, :chn * w_].cpu().numpy().reshape(h_, w_, chn) if chn == 3 else pg[:, :w_].cpu().numpy()
+                        if host_page.ndim == 2:
+                            host_page = np.repeat(host_page[..., None], 3, -1)
+                    live.append((p_, tb, i, w_, h_, host_page))
         except Exception as e:
             errors += len(chunk)
             logger.error(f"Error processing {os.path.basename(chunk[0])}: {str(e)}")

@@ -33,6 +33,29 @@ struct HostImage {
 };
 
 // ---- marker parsing (host) ------------------------------------------------------------------------------
+// EXIF orientation (APP1 "Exif", TIFF tag 0x0112): cv2.imread turns the decoded image accordingly; a file that asks
+// for anything but the identity is left to the host decoder.  Returns the tag's value, 1 when absent / unreadable.
+int exif_orientation(const uint8_t* s, int n) {
+  if (n < 14 || std::memcmp(s, "Exif\0\0", 6) != 0) return 1;
+  const uint8_t* t = s + 6;
+  const int m = n - 6;
+  const bool le = t[0] == 'I' && t[1] == 'I', be = t[0] == 'M' && t[1] == 'M';
+  if (!le && !be) return 1;
+  auto u16 = [&](int o) { return le ? (t[o] | t[o + 1] << 8) : (t[o] << 8 | t[o + 1]); };
+  auto u32 = [&](int o) { return le ? (uint32_t)(t[o] | t[o + 1] << 8 | t[o + 2] << 16) | (uint32_t)t[o + 3] << 24
+                                    : (uint32_t)(t[o + 3] | t[o + 2] << 8 | t[o + 1] << 16) | (uint32_t)t[o] << 24; };
+  if (u16(2) != 42) return 1;
+  const uint32_t ifd = u32(4);
+  if (ifd + 2 > (uint32_t)m) return 1;
+  const int cnt = u16((int)ifd);
+  for (int i = 0; i < cnt; ++i) {
+    const uint32_t e = ifd + 2 + 12u * (uint32_t)i;
+    if (e + 12 > (uint32_t)m) return 1;
+    if (u16((int)e) == 0x0112) return u16((int)e + 8);
+  }
+  return 1;
+}
+
 int build_huff(const uint8_t* counts, const uint8_t* symbols, int n_symbols, PgjHuff& h) {
   std::memset(&h, 0, sizeof(h));
   int code = 0, k = 0;
@@ -136,6 +159,12 @@ int parse_jpeg(const uint8_t* d, int64_t n, HostImage& im) {
         if (build_huff(s + k + 1, s + k + 17, cnt, g.huff[tc][th]) != 0) { pg_set_error("unsupported: bad Huffman table"); return PG_ERR_UNSUPPORTED; }
         have_huff[tc][th] = true;
         k += 17 + cnt;
+      }
+    } else if (m == 0xE1) {
+      const int o = exif_orientation(s, sl);
+      if (o > 1 && o <= 8) {
+        pg_set_error("unsupported: EXIF orientation %d (cv2.imread would turn the image; left to the host decoder)", o);
+        return PG_ERR_UNSUPPORTED;
       }
     } else if (m == 0xDD) {
       if (sl < 2) { pg_set_error("unsupported: bad DRI"); return PG_ERR_UNSUPPORTED; }

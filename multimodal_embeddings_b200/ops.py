@@ -193,23 +193,29 @@ def upload_pages(images: Sequence[np.ndarray], plan: TilePlan, stream=None) -> t
 
 
 def decode_page(path) -> Optional[np.ndarray]:
-    """Host decode of one scan to BGR uint8 HxWx3, as the reference's cv2.imread (1_doclayout_bboxes.py:381);
-    None when the file cannot be decoded (cv2's own convention)."""
+    """Host decode of one scan, as the reference's cv2.imread (1_doclayout_bboxes.py:381): BGR uint8 HxWx3 — or, for
+    a greyscale file (where cv2.imread's three channels are equal), the single plane HxW, which crosses PCIe at a
+    third of the bytes and is tiled by the one-channel plans.  cv2.IMREAD_ANYCOLOR is IMREAD_COLOR without the
+    replication: 8-bit, EXIF orientation applied.  None when the file cannot be decoded (cv2's own convention)."""
     import cv2
-    return cv2.imread(str(path))
+    img = cv2.imread(str(path), cv2.IMREAD_ANYCOLOR)
+    if img is None or img.dtype != np.uint8 or img.ndim not in (2, 3) or (img.ndim == 3 and img.shape[2] != 3):
+        img = cv2.imread(str(path))
+    return img
 
 
 def upload_pages_pinned(images: Sequence[np.ndarray], stream=None) -> List[torch.Tensor]:
-    """Host BGR pages of any sizes -> one pitched cuda tensor [H, pitch] per page (TileBatch.bind's input).
-    All pages go through ONE pinned staging buffer and one asynchronous copy."""
+    """Host pages of any sizes — BGR HxWx3 or grey HxW, uniformly — -> one pitched cuda tensor [H, pitch] per page
+    (TileBatch.bind's input).  All pages go through ONE pinned staging buffer and one asynchronous copy."""
     _require_cuda()
-    sizes = [(img.shape[0], row_pitch(img.shape[1])) for img in images]
+    chans = [1 if img.ndim == 2 else 3 for img in images]
+    sizes = [(img.shape[0], row_pitch(img.shape[1], c)) for img, c in zip(images, chans)]
     offs = np.concatenate([[0], np.cumsum([h * p for h, p in sizes])]).astype(np.int64)
     host = torch.empty(int(offs[-1]), dtype=torch.uint8).pin_memory()
     hv = host.numpy()
-    for img, (h, p), o in zip(images, sizes, offs):
-        assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3
-        hv[o:o + h * p].reshape(h, p)[:, : 3 * img.shape[1]] = img.reshape(h, 3 * img.shape[1])
+    for img, c, (h, p), o in zip(images, chans, sizes, offs):
+        assert img.dtype == np.uint8 and (img.ndim == 2 or img.shape[2] == 3)
+        hv[o:o + h * p].reshape(h, p)[:, : c * img.shape[1]] = img.reshape(h, c * img.shape[1])
     if stream is not None:
         with torch.cuda.stream(stream):
             dev = host.to("cuda", non_blocking=True)

@@ -115,9 +115,9 @@ class TileBatch:
     """Plans only (pg_tile_plan_* is host code); no pixels are produced — the tests that use this stand-in
     plug in detectors that do not look at the tiles."""
 
-    def __init__(self, sizes, grids=((2, 2),), overlap=20.0, imgsz=1024, stride=32, auto=True):
+    def __init__(self, sizes, grids=((2, 2),), overlap=20.0, imgsz=1024, stride=32, auto=True, channels=3):
         self.sizes = [(int(w), int(h)) for w, h in sizes]
-        self.plans = {s: ops.TilePlan(s[0], s[1], grids, overlap, imgsz, stride, auto) for s in set(self.sizes)}
+        self.plans = {s: ops.TilePlan(s[0], s[1], grids, overlap, imgsz, stride, auto, channels=channels) for s in set(self.sizes)}
 
     def plan_of(self, page):
         return self.plans[self.sizes[page]]

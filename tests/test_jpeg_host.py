@@ -116,3 +116,35 @@ def test_parser_refuses_what_the_device_path_does_not_decode():
         assert rc == 4 and b"unsupported" in L.pg_last_error()  # PG_ERR_UNSUPPORTED
     with pytest.raises(PageGeomError):
         check(4)
+
+
+def test_host_decode_of_a_scan_equals_cv2_imread_and_exif_turned_files_stay_on_the_host(tmp_path):
+    """ops.decode_page: the plane of a greyscale file (PNG, JPEG, BMP) is what cv2.imread returns in each of its three
+    channels, colour files come back as cv2.imread gives them; a JPEG whose EXIF orientation asks for a rotation —
+    which cv2.imread applies — is refused by the device path's parser and decoded, turned, on the host."""
+    from PIL import Image
+    from multimodal_embeddings_b200 import ops
+    g = _page(120, 200, 4)
+    c = np.stack([g, np.roll(g, 3, 1), 255 - g], -1)
+    for name, img in (("g.png", g), ("g.jpg", g), ("g.bmp", g), ("c.png", c), ("c.jpg", c), ("g.tif", g)):
+        path = str(tmp_path / name)
+        assert cv2.imwrite(path, img)
+        ref = cv2.imread(path)
+        got = ops.decode_page(path)
+        if img.ndim == 2:
+            assert got.ndim == 2 and all(np.array_equal(got, ref[..., k]) for k in range(3)), name
+        else:
+            assert np.array_equal(got, ref), name
+    assert ops.decode_page(str(tmp_path / "missing.png")) is None
+    exif = Image.Exif()
+    exif[0x0112] = 6  # rotate 90 degrees clockwise to display
+    turned = str(tmp_path / "turned.jpg")
+    Image.fromarray(g).save(turned, quality=90, exif=exif)
+    plain = str(tmp_path / "plain.jpg")
+    Image.fromarray(g).save(plain, quality=90)
+    assert cv2.imread(turned).shape[:2] == (200, 120) and cv2.imread(plain).shape[:2] == (120, 200)
+    assert ops.jpeg_probe(open(plain, "rb").read()) == (200, 120, 1)
+    assert ops.jpeg_probe(open(turned, "rb").read()) is None
+    assert b"EXIF orientation" in lib().pg_last_error()
+    got = ops.decode_page(turned)
+    assert got.shape == (200, 120) and np.array_equal(got, cv2.imread(turned)[..., 0])

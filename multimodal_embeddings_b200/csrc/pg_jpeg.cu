@@ -238,7 +238,7 @@ struct ImgRec {            // per image, device
   int32_t ub0, n_ub;       // unstuff blocks
   int64_t chunk0;          // first chunk
   int32_t n_chunks;
-  int32_t pad_;
+  int32_t cta0;            // first entropy CTA of the image (its CTAs are consecutive)
   int64_t coef_off;        // int16 elements
   int64_t plane_off;       // colour files: the three component planes (bytes into Scratch::planes)
   uint8_t* out;            // decoded page: one grey plane, or BGR interleaved
@@ -258,7 +258,7 @@ struct Scratch {           // device pointers into the caller's workspace
   int32_t* rst_pos;
   PgjChunkState* st[2];
   PgjEntry* ent;           // the entry state each chunk's stored exit was computed from
-  PgjChunkState* entry;    // exclusive segmented scan: state of the decoder at each chunk's entry
+  PgjChunkState* cta_scan; // per entropy CTA: the segmented total of its chunks, then (in place) the state in front of it
   int32_t* counters;       // [MAX_ROUNDS + 2]: changes per round; [MAX_ROUNDS+1] = error flag
   int16_t* coef;
   uint8_t* planes;         // colour files: Y, Cb, Cr after the IDCT, each comp_bw*8 x comp_bh*8
@@ -291,18 +291,22 @@ __device__ __forceinline__ void unstuff_masks(const uint8_t* blob, const ImgRec&
   keep = 0; rst = 0;
   if (!live) return;
   const uint32_t w[4] = {bytes.x, bytes.y, bytes.z, bytes.w};
-  uint8_t p = rel0 > 0 ? (uint8_t)prev : 0;  // the byte before the segment's first does not count
+  // bytes [lo, hi) of the sixteen belong to the segment; byte k + 1 exists inside it while k + 1 < lim
+  const int lo = rel0 < 0 ? (int)-rel0 : 0;
+  const int64_t left = r.src_len - rel0;
+  const int hi = left < 16 ? (int)left : 16, lim = left < 17 ? (int)left : 17;
+  uint32_t p = rel0 > 0 ? (prev & 0xFFu) : 0u;  // the byte before the segment's first does not count
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    const uint8_t cur = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
-    uint8_t nx = k < 15 ? (uint8_t)(w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) : (uint8_t)next;
-    const int64_t j = rel0 + k;
-    if (j + 1 >= r.src_len) nx = 0;
-    if (j >= 0 && j < r.src_len) {
-      if (pgj_keep_byte(p, cur, nx)) keep |= 1u << k;
-      if (pgj_rst_starts(cur, nx)) rst |= 1u << k;
-    }
-    p = j >= 0 ? cur : 0;
+    const uint32_t cur = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+    uint32_t nx = k < 15 ? (w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xFFu : (next & 0xFFu);
+    if (k + 1 >= lim) nx = 0u;
+    const bool in = k >= lo && k < hi;
+    const bool nx_rst = (nx & 0xF8u) == 0xD0u, cur_ff = cur == 0xFFu;
+    const bool gone = (p == 0xFFu && (cur == 0u || (cur & 0xF8u) == 0xD0u)) || (cur_ff && nx_rst);  // pgj_keep_byte
+    if (in && !gone) keep |= 1u << k;
+    if (in && cur_ff && nx_rst) rst |= 1u << k;  // pgj_rst_starts
+    p = in ? cur : 0u;
   }
 }
 
@@ -418,7 +422,12 @@ __global__ void __launch_bounds__(CHUNK_THREADS) jpeg_sync_kernel(Scratch s, int
   outv[g] = mine;
 }
 
-// ---- D6: decoder state at every chunk's entry (segmented exclusive scan; one CTA per image) ------------------
+// ---- D6: decoder state at every chunk's entry ---------------------------------------------------------------
+// A segmented exclusive scan over the chunks of an image: block count and DC-difference sums accumulate, a chunk
+// that passed a restart boundary (anchor >= 0) starts a new segment.  Three steps: (a) every entropy CTA folds its
+// 256 chunks into one value; (b) one CTA per image scans those values (a few hundred) in place; (c) the store
+// kernel redoes the scan inside its CTA and adds what (b) left in front of it — the per-chunk result never
+// touches memory.
 struct ScanVal { int anchor, n, d0, d1, d2; };
 __device__ __forceinline__ ScanVal scan_op(const ScanVal& a, const ScanVal& b) {  // a then b
   if (b.anchor >= 0) return b;
@@ -429,58 +438,84 @@ __device__ __forceinline__ ScanVal shfl_up(const ScanVal& v, int d) {
                  __shfl_up_sync(0xffffffffu, v.d0, d), __shfl_up_sync(0xffffffffu, v.d1, d),
                  __shfl_up_sync(0xffffffffu, v.d2, d)};
 }
+__device__ __forceinline__ ScanVal scan_of(const PgjChunkState& cs) {
+  if (cs.p == -2) return ScanVal{-1, 0, 0, 0, 0};
+  return ScanVal{cs.anchor, cs.n, cs.dc[0], cs.dc[1], cs.dc[2]};
+}
+// Block-wide segmented scan (blockDim.x a multiple of 32, <= 1024): returns what lies in front of this thread inside
+// the block; *total = the whole block.  `sm` needs 33 ScanVal.
+__device__ __forceinline__ ScanVal block_scan(const ScanVal& v, ScanVal* sm, ScanVal* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const ScanVal ident{-1, 0, 0, 0, 0};
+  ScanVal inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const ScanVal t = shfl_up(inc, d);
+    if (lane >= d) inc = scan_op(t, inc);
+  }
+  if (lane == 31) sm[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    ScanVal w = lane < nw ? sm[lane] : ident;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const ScanVal t = shfl_up(w, d);
+      if (lane >= d) w = scan_op(t, w);
+    }
+    if (lane < nw) sm[lane] = w;  // inclusive over warps
+    if (lane == 31) sm[32] = w;   // (lanes >= nw hold the last warp's inclusive value)
+  }
+  __syncthreads();
+  ScanVal before = warp > 0 ? sm[warp - 1] : ident;
+  const ScanVal prev = shfl_up(inc, 1);
+  if (lane > 0) before = scan_op(before, prev);
+  *total = sm[32];
+  __syncthreads();
+  return before;
+}
 
-__global__ void __launch_bounds__(1024) jpeg_entry_scan_kernel(Scratch s, int final_parity) {
-  __shared__ ScanVal warp_tot[32];
+__global__ void __launch_bounds__(CHUNK_THREADS) jpeg_cta_total_kernel(Scratch s, int final_parity) {
+  __shared__ ScanVal sm[33];
+  const int img = s.cta_img[blockIdx.x];
+  const ImgRec r = s.rec[img];
+  const int j = s.cta_chunk0[blockIdx.x] + threadIdx.x;
+  ScanVal v{-1, 0, 0, 0, 0};
+  if (j < r.n_chunks) v = scan_of(s.st[final_parity][r.chunk0 + j]);
+  ScanVal total;
+  block_scan(v, sm, &total);
+  if (threadIdx.x == 0) {
+    PgjChunkState o;
+    o.p = 0; o.c = 0; o.anchor = total.anchor; o.n = total.n; o.dc[0] = total.d0; o.dc[1] = total.d1; o.dc[2] = total.d2;
+    s.cta_scan[blockIdx.x] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) jpeg_cta_carry_kernel(Scratch s) {
+  __shared__ ScanVal sm[33];
   __shared__ ScanVal carry_sm;
   const int img = blockIdx.x;
   const ImgRec r = s.rec[img];
-  const PgjChunkState* st = s.st[final_parity];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const ScanVal ident{-1, 0, 0, 0, 0};
+  const int n_cta = (r.n_chunks + CHUNK_THREADS - 1) / CHUNK_THREADS;
   if (threadIdx.x == 0) carry_sm = ScanVal{0, 0, 0, 0, 0};  // chunk 0 enters restart interval 0 at block 0
   __syncthreads();
-  for (int j0 = 0; j0 < r.n_chunks; j0 += 1024) {
-    const int j = j0 + threadIdx.x;
-    ScanVal v = ident;
-    PgjChunkState cs;
-    if (j < r.n_chunks) {
-      cs = st[r.chunk0 + j];
-      if (cs.p != -2) v = ScanVal{cs.anchor, cs.n, cs.dc[0], cs.dc[1], cs.dc[2]};
+  for (int b0 = 0; b0 < n_cta; b0 += 256) {
+    const int b = b0 + threadIdx.x;
+    ScanVal v{-1, 0, 0, 0, 0};
+    if (b < n_cta) {
+      const PgjChunkState cs = s.cta_scan[r.cta0 + b];
+      v = ScanVal{cs.anchor, cs.n, cs.dc[0], cs.dc[1], cs.dc[2]};
     }
-    ScanVal inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const ScanVal t = shfl_up(inc, d);
-      if (lane >= d) inc = scan_op(t, inc);
-    }
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      ScanVal w = warp_tot[lane];
-      ScanVal winc = w;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const ScanVal t = shfl_up(winc, d);
-        if (lane >= d) winc = scan_op(t, winc);
-      }
-      warp_tot[lane] = winc;  // inclusive over warps
-    }
-    __syncthreads();
+    ScanVal total;
+    const ScanVal before = block_scan(v, sm, &total);
     const ScanVal carry = carry_sm;
-    ScanVal before = carry;                                  // everything ahead of this tile
-    if (warp > 0) before = scan_op(before, warp_tot[warp - 1]);
-    ScanVal excl = shfl_up(inc, 1);                          // inclusive of the previous lane
-    if (lane > 0) before = scan_op(before, excl);
-    if (j < r.n_chunks) {
-      PgjChunkState e;
-      e.p = j == 0 ? 0 : st[r.chunk0 + j - 1].p;
-      e.c = j == 0 ? 0 : st[r.chunk0 + j - 1].c;
-      e.anchor = before.anchor; e.n = before.n; e.dc[0] = before.d0; e.dc[1] = before.d1; e.dc[2] = before.d2;
-      s.entry[r.chunk0 + j] = e;
+    if (b < n_cta) {
+      const ScanVal e = scan_op(carry, before);
+      PgjChunkState o;
+      o.p = 0; o.c = 0; o.anchor = e.anchor; o.n = e.n; o.dc[0] = e.d0; o.dc[1] = e.d1; o.dc[2] = e.d2;
+      s.cta_scan[r.cta0 + b] = o;
     }
     __syncthreads();
-    if (threadIdx.x == 1023) carry_sm = scan_op(carry, warp_tot[31]);
+    if (threadIdx.x == 0) carry_sm = scan_op(carry, total);
     __syncthreads();
   }
 }
@@ -509,22 +544,34 @@ struct SmemBlockSink {
   }
 };
 
-__global__ void __launch_bounds__(CHUNK_THREADS) jpeg_store_kernel(Scratch s, int chunk_bits) {
+__global__ void __launch_bounds__(CHUNK_THREADS) jpeg_store_kernel(Scratch s, int chunk_bits, int final_parity) {
   __shared__ __align__(16) PgjImage im;
+  __shared__ ScanVal scan_sm[33];
   extern __shared__ __align__(16) int16_t blocks[];  // CHUNK_THREADS * BLK_PITCH (dynamic: with the tables > 48 KB)
   const int img = s.cta_img[blockIdx.x];
   load_image(&im, s.img + img);
   const ImgRec r = s.rec[img];
   const int j = s.cta_chunk0[blockIdx.x] + threadIdx.x;
+  const PgjChunkState* st = s.st[final_parity];
+  // D6 (c): the state in front of this chunk = what lies in front of the CTA + the chunks before it inside the CTA
+  ScanVal v{-1, 0, 0, 0, 0};
+  if (j < r.n_chunks) v = scan_of(st[r.chunk0 + j]);
+  ScanVal total;
+  ScanVal before = block_scan(v, scan_sm, &total);
+  {
+    const PgjChunkState cs = s.cta_scan[blockIdx.x];
+    before = scan_op(ScanVal{cs.anchor, cs.n, cs.dc[0], cs.dc[1], cs.dc[2]}, before);
+  }
   if (j >= r.n_chunks) return;
   const PgjStream sv = stream_of(s, r, img);
   const int64_t b0 = (int64_t)j * chunk_bits, b1 = b0 + chunk_bits;
   if (b0 >= sv.n_bits) return;
-  const PgjChunkState e = s.entry[r.chunk0 + j];
-  if (e.p < 0 || e.p >= b1) return;  // no block starts inside this chunk
-  const int blk = max(e.anchor, 0) * im.restart_blocks + e.n;
+  const int64_t ep = j == 0 ? 0 : st[r.chunk0 + j - 1].p;
+  const int ec = j == 0 ? 0 : st[r.chunk0 + j - 1].c;
+  if (ep < 0 || ep >= b1) return;  // no block starts inside this chunk
+  const int blk = max(before.anchor, 0) * im.restart_blocks + before.n;
   SmemBlockSink sink{blocks + threadIdx.x * BLK_PITCH, s.coef + r.coef_off, 0};
-  pgj_span_store(sv, im, e.p, e.c, b1, blk, e.dc[0], e.dc[1], e.dc[2], sink);
+  pgj_span_store(sv, im, ep, ec, b1, blk, before.d0, before.d1, before.d2, sink);
 }
 
 // ---- D8: inverse DCT, one thread per block -------------------------------------------------------------------
@@ -687,6 +734,7 @@ extern "C" int pg_jpeg_decoder_set_files(PgJpegDecoder* d, const uint8_t* blob, 
     ub += r.n_ub;
     r.chunk0 = chunks;
     r.n_chunks = (int32_t)((r.src_len + d->chunk_bytes - 1) / d->chunk_bytes);
+    r.cta0 = (int32_t)d->cta_img.size();
     for (int c0 = 0; c0 < r.n_chunks; c0 += CHUNK_THREADS) { d->cta_img.push_back(i); d->cta_chunk0.push_back(c0); }
     chunks += r.n_chunks;
     r.coef_off = coef;
@@ -710,7 +758,7 @@ extern "C" int pg_jpeg_decoder_set_files(PgJpegDecoder* d, const uint8_t* blob, 
   add((size_t)cs); add((size_t)rst * 4 + 4);
   add((size_t)chunks * sizeof(PgjChunkState)); add((size_t)chunks * sizeof(PgjChunkState));
   add((size_t)chunks * sizeof(PgjEntry));
-  add((size_t)chunks * sizeof(PgjChunkState));
+  add(d->cta_img.size() * sizeof(PgjChunkState));
   add((MAX_ROUNDS + 2) * 4);
   add((size_t)coef * 2);
   add((size_t)planes);
@@ -762,7 +810,7 @@ extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t
   sc.st[0] = reinterpret_cast<PgjChunkState*>(take((size_t)d->total_chunks * sizeof(PgjChunkState)));
   sc.st[1] = reinterpret_cast<PgjChunkState*>(take((size_t)d->total_chunks * sizeof(PgjChunkState)));
   sc.ent = reinterpret_cast<PgjEntry*>(take((size_t)d->total_chunks * sizeof(PgjEntry)));
-  sc.entry = reinterpret_cast<PgjChunkState*>(take((size_t)d->total_chunks * sizeof(PgjChunkState)));
+  sc.cta_scan = reinterpret_cast<PgjChunkState*>(take(d->cta_img.size() * sizeof(PgjChunkState)));
   sc.counters = reinterpret_cast<int32_t*>(take((MAX_ROUNDS + 2) * 4));
   sc.coef = reinterpret_cast<int16_t*>(take((size_t)d->coef_elems * 2));
   sc.planes = take((size_t)d->plane_bytes);
@@ -811,10 +859,11 @@ extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t
   jpeg_unstuff_write_kernel<<<n_ub, 256, 0, s>>>(blob_dev, sc);
   jpeg_spec_kernel<<<n_cta, CHUNK_THREADS, 0, s>>>(sc, chunk_bits, pgj_overlap_bits(chunk_bits));
   for (int r = 1; r <= d->rounds; ++r) jpeg_sync_kernel<<<n_cta, CHUNK_THREADS, 0, s>>>(sc, chunk_bits, r);
-  jpeg_entry_scan_kernel<<<(unsigned)n, 1024, 0, s>>>(sc, d->rounds & 1);
+  jpeg_cta_total_kernel<<<n_cta, CHUNK_THREADS, 0, s>>>(sc, d->rounds & 1);
+  jpeg_cta_carry_kernel<<<(unsigned)n, 256, 0, s>>>(sc);
   constexpr size_t kStoreSmem = (size_t)CHUNK_THREADS * BLK_PITCH * sizeof(int16_t);
   PG_CUDA_TRY(cudaFuncSetAttribute(jpeg_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStoreSmem));
-  jpeg_store_kernel<<<n_cta, CHUNK_THREADS, kStoreSmem, s>>>(sc, chunk_bits);
+  jpeg_store_kernel<<<n_cta, CHUNK_THREADS, kStoreSmem, s>>>(sc, chunk_bits, d->rounds & 1);
   int max_blocks = 0;
   for (int i = 0; i < n; ++i) max_blocks = std::max(max_blocks, d->images[(size_t)i].dev.total_blocks);
   dim3 grid((unsigned)std::min(4096, (max_blocks + 127) / 128), (unsigned)n, d->any_colour ? 3u : 1u);

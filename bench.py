@@ -236,7 +236,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg2", "cfg5"])
     ap.add_argument("--total-pages", type=int, default=0, help="cfg5: corpus size (default 102400)")
     ap.add_argument("--pages-per-gpu", type=int, default=64)
-    ap.add_argument("--e2e-pages", type=int, default=16, help="pages per end-to-end step")
+    ap.add_argument("--e2e-pages", type=int, default=32, help="pages per end-to-end step")
     ap.add_argument("--e2e-input", default="jpeg", choices=["jpeg", "raw"],
                     help="what crosses PCIe in the e2e leg: the scans' JPEG files (decoded on the device) or raw BGR pages")
     ap.add_argument("--no-corpus", action="store_true", help="skip the K6 corpus sub-run (cfg5 in small)")
@@ -578,7 +578,7 @@ def main():
         res = sp.results(k)
         torch.cuda.synchronize()
         dec_status = sp.slots[0]["dec"].status()
-        e2e_steps = max(8, min(2 * args.steps, 40))
+        e2e_steps = max(8, min(args.steps, 30))
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

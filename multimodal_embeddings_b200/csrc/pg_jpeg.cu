@@ -11,6 +11,7 @@
 // D6 segmented scan, D7 coefficient store; algorithm in pg_jpeg.h), inverse DCT (D8).  No tensor cores: the
 // IDCT is 8x8 integer butterflies with libjpeg's 13-bit constants and must be bit-exact.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -380,10 +381,14 @@ __device__ __forceinline__ void load_image(PgjImage* dst, const PgjImage* src) {
   __syncthreads();
 }
 
+// TABLES_SMEM: the image's tables are staged in shared memory (default) or read where they lie (global memory through
+// L1; knob PG_JPEG_TABLES=global) — measured, see DESIGN.md.
+template <bool TABLES_SMEM>
 __global__ void __launch_bounds__(CHUNK_THREADS) jpeg_spec_kernel(Scratch s, int chunk_bits, int overlap_bits) {
-  __shared__ __align__(16) PgjImage im;
+  __shared__ __align__(16) uint8_t im_buf[TABLES_SMEM ? sizeof(PgjImage) : 16];
   const int img = s.cta_img[blockIdx.x];
-  load_image(&im, s.img + img);
+  if (TABLES_SMEM) load_image(reinterpret_cast<PgjImage*>(im_buf), s.img + img);
+  const PgjImage& im = TABLES_SMEM ? *reinterpret_cast<const PgjImage*>(im_buf) : s.img[img];
   const ImgRec r = s.rec[img];
   const int j = s.cta_chunk0[blockIdx.x] + threadIdx.x;
   if (j >= r.n_chunks) return;
@@ -544,12 +549,14 @@ struct SmemBlockSink {
   }
 };
 
+template <bool TABLES_SMEM>
 __global__ void __launch_bounds__(CHUNK_THREADS) jpeg_store_kernel(Scratch s, int chunk_bits, int final_parity) {
-  __shared__ __align__(16) PgjImage im;
+  __shared__ __align__(16) uint8_t im_buf[TABLES_SMEM ? sizeof(PgjImage) : 16];
   __shared__ ScanVal scan_sm[33];
   extern __shared__ __align__(16) int16_t blocks[];  // CHUNK_THREADS * BLK_PITCH (dynamic: with the tables > 48 KB)
   const int img = s.cta_img[blockIdx.x];
-  load_image(&im, s.img + img);
+  if (TABLES_SMEM) load_image(reinterpret_cast<PgjImage*>(im_buf), s.img + img);
+  const PgjImage& im = TABLES_SMEM ? *reinterpret_cast<const PgjImage*>(im_buf) : s.img[img];
   const ImgRec r = s.rec[img];
   const int j = s.cta_chunk0[blockIdx.x] + threadIdx.x;
   const PgjChunkState* st = s.st[final_parity];
@@ -857,13 +864,21 @@ extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t
   jpeg_unstuff_count_kernel<<<n_ub, 256, 0, s>>>(blob_dev, sc);
   jpeg_unstuff_scan_kernel<<<(unsigned)n, 1024, 0, s>>>(sc);
   jpeg_unstuff_write_kernel<<<n_ub, 256, 0, s>>>(blob_dev, sc);
-  jpeg_spec_kernel<<<n_cta, CHUNK_THREADS, 0, s>>>(sc, chunk_bits, pgj_overlap_bits(chunk_bits));
+  bool tables_smem = true;
+  if (const char* e = getenv("PG_JPEG_TABLES")) tables_smem = std::strcmp(e, "global") != 0;  // tuning knob
+  if (tables_smem) jpeg_spec_kernel<true><<<n_cta, CHUNK_THREADS, 0, s>>>(sc, chunk_bits, pgj_overlap_bits(chunk_bits));
+  else jpeg_spec_kernel<false><<<n_cta, CHUNK_THREADS, 0, s>>>(sc, chunk_bits, pgj_overlap_bits(chunk_bits));
   for (int r = 1; r <= d->rounds; ++r) jpeg_sync_kernel<<<n_cta, CHUNK_THREADS, 0, s>>>(sc, chunk_bits, r);
   jpeg_cta_total_kernel<<<n_cta, CHUNK_THREADS, 0, s>>>(sc, d->rounds & 1);
   jpeg_cta_carry_kernel<<<(unsigned)n, 256, 0, s>>>(sc);
   constexpr size_t kStoreSmem = (size_t)CHUNK_THREADS * BLK_PITCH * sizeof(int16_t);
-  PG_CUDA_TRY(cudaFuncSetAttribute(jpeg_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStoreSmem));
-  jpeg_store_kernel<<<n_cta, CHUNK_THREADS, kStoreSmem, s>>>(sc, chunk_bits, d->rounds & 1);
+  if (tables_smem) {
+    PG_CUDA_TRY(cudaFuncSetAttribute(jpeg_store_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStoreSmem));
+    jpeg_store_kernel<true><<<n_cta, CHUNK_THREADS, kStoreSmem, s>>>(sc, chunk_bits, d->rounds & 1);
+  } else {
+    PG_CUDA_TRY(cudaFuncSetAttribute(jpeg_store_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStoreSmem));
+    jpeg_store_kernel<false><<<n_cta, CHUNK_THREADS, kStoreSmem, s>>>(sc, chunk_bits, d->rounds & 1);
+  }
   int max_blocks = 0;
   for (int i = 0; i < n; ++i) max_blocks = std::max(max_blocks, d->images[(size_t)i].dev.total_blocks);
   dim3 grid((unsigned)std::min(4096, (max_blocks + 127) / 128), (unsigned)n, d->any_colour ? 3u : 1u);

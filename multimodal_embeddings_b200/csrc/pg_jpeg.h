@@ -194,7 +194,7 @@ PGJ_HD bool pgj_block(PgjBits& br, const PgjHuff& dc, const PgjHuff& ac, int& dc
         k += (f >> 4) & 15;
         br.skip(f & 15);
         if (k > 63) break;
-        emit.ac(pgj_zigzag(k), f >> 8);
+        emit.ac(k, f >> 8);
         ++k;
         continue;
       }
@@ -214,7 +214,7 @@ PGJ_HD bool pgj_block(PgjBits& br, const PgjHuff& dc, const PgjHuff& ac, int& dc
     }
     k += r;
     if (k > 63) { br.skip(s); break; }
-    emit.ac(pgj_zigzag(k), pgj_extend(br.take(s), s));
+    emit.ac(k, pgj_extend(br.take(s), s));
     ++k;
   }
   return true;
@@ -400,8 +400,21 @@ PGJ_HD uint8_t pgj_clamp_sample(int32_t x) {
   return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
 }
 
-// coef: 64 quantised coefficients (natural order); q: quantisation table; out[8][8] samples
-PGJ_HD void pgj_idct_block(const int16_t* coef, const uint16_t* q, uint8_t out[64]) {
+// zigzag position of natural index n (the inverse of the zigzag table).  Blocks are kept in ZIGZAG order between the
+// entropy pass and the IDCT: the decoder stores coefficient k where it stands in the stream (no table look-up per
+// symbol), and here every index is a compile-time constant once the loops are unrolled.
+PGJ_HD constexpr int pgj_nat2zz(int n) {
+  constexpr uint8_t t[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
+                             41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
+                             46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+  return t[n];
+}
+
+// zz: 64 quantised coefficients in zigzag order; q: quantisation table (natural order); out[8][8] samples
+PGJ_HD void pgj_idct_block(const int16_t* zz, const uint16_t* q, uint8_t out[64]) {
+  int16_t coef[64];
+#pragma unroll
+  for (int n = 0; n < 64; ++n) coef[n] = zz[pgj_nat2zz(n)];
   int32_t ws[64];
   {
     // a block with nothing but its DC term (blank paper) is flat: both passes reduce to two rounding shifts

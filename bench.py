@@ -237,6 +237,8 @@ def main():
     ap.add_argument("--total-pages", type=int, default=0, help="cfg5: corpus size (default 102400)")
     ap.add_argument("--pages-per-gpu", type=int, default=64)
     ap.add_argument("--e2e-pages", type=int, default=32, help="pages per end-to-end step")
+    ap.add_argument("--e2e-depth", type=int, default=2, help="steps in flight in the end-to-end leg")
+    ap.add_argument("--e2e-trace-all", action="store_true", help="diagnostic: events around every timed e2e step")
     ap.add_argument("--e2e-input", default="jpeg", choices=["jpeg", "raw"],
                     help="what crosses PCIe in the e2e leg: the scans' JPEG files (decoded on the device) or raw BGR pages")
     ap.add_argument("--no-corpus", action="store_true", help="skip the K6 corpus sub-run (cfg5 in small)")
@@ -569,7 +571,7 @@ def main():
         files = [e2e_scan_file(plan0.page_w, plan0.page_h, first_page + j) for j in range(distinct)]
         files = [files[j % distinct] for j in range(n_e)]
         blob, file_off = ops.pack_files(files)
-        sp = ScanPipeline(plan0.page_w, plan0.page_h, n_e, [(rows, cols)], 20.0, overlap=not args.no_overlap)
+        sp = ScanPipeline(plan0.page_w, plan0.page_h, n_e, [(rows, cols)], 20.0, depth=args.e2e_depth, overlap=not args.no_overlap)
         probe = PagePipeline(sp.plan, n_e)
         ehost = probe.set_detections(dets0[:n_e])
         del probe
@@ -582,11 +584,23 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        e_sampler = ClockSampler(local_rank)
+        e_sampler.start()
+        host_s = 0.0
+        if args.e2e_trace_all:
+            sp.trace = []
         t_wall = time.perf_counter()
         for _ in range(e2e_steps):
+            t_h = time.perf_counter()
             k = sp.submit(blob, file_off, ehost)
+            host_s += time.perf_counter() - t_h
         sp.drain()
         e_ms = (time.perf_counter() - t_wall) * 1e3
+        e_clocks = e_sampler.stop()
+        if args.e2e_trace_all:
+            tl = sp.timeline_ms()
+            print(json.dumps({"e2e_trace_all": tl}), file=sys.stderr, flush=True)
+            sp.trace = None
         for kk in range(k - sp.depth + 1, k + 1):
             res = sp.results(kk)  # status words of the last steps of every slot
         # where the time of a step goes: three more steps with events around the copy and the compute part
@@ -608,6 +622,7 @@ def main():
                        "jpeg_decoder": {"chunk_bytes": sp.slots[0]["dec"].chunk_bytes, **{k2: int(v) for k2, v in dec_status.items()}},
                        "kernels_per_step": KERNELS_PER_STEP + 9 + sp.slots[0]["dec"].sync_rounds,
                        "kept_boxes_last_step": int(res["n_kept2"].sum()),
+                       "host_ms_per_submit": host_s / e2e_steps * 1e3, "clocks": e_clocks,
                        "timeline_ms": {"what": "three extra steps: [copy start, copy end, compute start, compute end] from the first copy's start",
                                        "steps": timeline},
                        **({"host": numa_note} if numa_note else {}),

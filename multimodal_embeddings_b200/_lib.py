@@ -85,6 +85,7 @@ SIGNATURES = {
     "pg_jpeg_decoder_image_info": (C.c_int, [_P, _I32, _P, _P, _P]),
     "pg_jpeg_workspace_bytes": (_I64, [_P]),
     "pg_jpeg_decode": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P]),
+    "pg_jpeg_stage_tables": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
     "pg_jpeg_decode_status": (C.c_int, [_P, _P]),
     "pg_hostcheck_jpeg_decode": (C.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, _P, _P]),
     "pg_json_workspace_bytes": (_I64, [_I64, _I32]),

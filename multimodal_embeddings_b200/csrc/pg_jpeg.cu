@@ -684,6 +684,7 @@ struct PgJpegDecoder {
   struct Stage { void* host = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; };
   Stage stage[4];
   int next_stage = 0;
+  void* staged_ws = nullptr;  // workspace pg_jpeg_stage_tables prepared for the current files (consumed by the decode)
   Scratch last{};  // device view of the last decode (status read-back)
 };
 
@@ -716,6 +717,7 @@ extern "C" int pg_jpeg_decoder_configure(PgJpegDecoder* d, int32_t chunk_bytes, 
 extern "C" int pg_jpeg_decoder_set_files(PgJpegDecoder* d, const uint8_t* blob, const int64_t* file_off, int32_t n) {
   PG_REQUIRE(d && blob && file_off && n > 0, "set_files arguments");
   d->images.assign((size_t)n, HostImage());
+  d->staged_ws = nullptr;
   d->file_off.assign(file_off, file_off + n + 1);
   d->rec.assign((size_t)n, ImgRec());
   d->cta_img.clear(); d->cta_chunk0.clear(); d->ub_img.clear();
@@ -783,14 +785,13 @@ extern "C" int pg_jpeg_decoder_image_info(const PgJpegDecoder* d, int32_t i, int
 
 extern "C" int64_t pg_jpeg_workspace_bytes(const PgJpegDecoder* d) { return d ? (int64_t)d->ws_bytes : 0; }
 
-extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t* const* out_ptrs, const int64_t* pitches,
-                              void* workspace, int64_t workspace_bytes, void* stream) {
-  PG_REQUIRE(d && blob_dev && out_ptrs && pitches && workspace, "decode arguments");
+// Validates the outputs, carves the workspace and uploads the batch's tables on `s`.
+static int stage_tables(PgJpegDecoder* d, uint8_t* const* out_ptrs, const int64_t* pitches, void* workspace,
+                        int64_t workspace_bytes, cudaStream_t s) {
   const int n = (int)d->images.size();
   PG_REQUIRE(n > 0, "pg_jpeg_decoder_set_files first");
   if ((size_t)workspace_bytes < d->ws_bytes) { pg_set_error("workspace too small: %lld < %zu", (long long)workspace_bytes, d->ws_bytes); return PG_ERR_WORKSPACE; }
   PG_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
-  cudaStream_t s = (cudaStream_t)stream;
   for (int i = 0; i < n; ++i) {
     const PgjImage& g = d->images[(size_t)i].dev;
     PG_REQUIRE(out_ptrs[i] != nullptr && pitches[i] >= (int64_t)g.width * (g.n_comps == 1 ? 1 : 3), "output pointer / pitch");
@@ -823,7 +824,7 @@ extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t
   sc.planes = take((size_t)d->plane_bytes);
   d->last = sc;
 
-  // per-call tables: one pinned staging block, one copy
+  // per-call tables: one pinned staging block
   const size_t sz_img = (size_t)n * sizeof(PgjImage), sz_rec = (size_t)n * sizeof(ImgRec);
   const size_t sz_cta = d->cta_img.size() * 4, sz_ub = d->ub_img.size() * 4;
   const size_t o_img = 0, o_rec = align_up(o_img + sz_img, 256), o_ci = align_up(o_rec + sz_rec, 256),
@@ -857,6 +858,28 @@ extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t
   PG_CUDA_TRY(cudaMemcpyAsync(sc.cta_chunk0, hs + o_cc, sz_cta, cudaMemcpyHostToDevice, s));
   PG_CUDA_TRY(cudaMemcpyAsync(sc.ub_img, hs + o_ub, sz_ub, cudaMemcpyHostToDevice, s));
   PG_CUDA_TRY(cudaEventRecord(st.ev, s));
+  d->staged_ws = workspace;
+  return PG_OK;
+}
+
+extern "C" int pg_jpeg_stage_tables(PgJpegDecoder* d, uint8_t* const* out_ptrs, const int64_t* pitches, void* workspace,
+                                    int64_t workspace_bytes, void* copy_stream) {
+  PG_REQUIRE(d && out_ptrs && pitches && workspace, "stage arguments");
+  return stage_tables(d, out_ptrs, pitches, workspace, workspace_bytes, (cudaStream_t)copy_stream);
+}
+
+extern "C" int pg_jpeg_decode(PgJpegDecoder* d, const uint8_t* blob_dev, uint8_t* const* out_ptrs, const int64_t* pitches,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+  PG_REQUIRE(d && blob_dev && out_ptrs && pitches && workspace, "decode arguments");
+  PG_REQUIRE(((uintptr_t)blob_dev & 15) == 0, "blob_dev must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (d->staged_ws != workspace) {  // tables not uploaded by pg_jpeg_stage_tables for this batch: do it here
+    const int rc = stage_tables(d, out_ptrs, pitches, workspace, workspace_bytes, s);
+    if (rc != PG_OK) return rc;
+  }
+  d->staged_ws = nullptr;  // consumed
+  const int n = (int)d->images.size();
+  const Scratch sc = d->last;
   PG_CUDA_TRY(cudaMemsetAsync(sc.counters, 0, (MAX_ROUNDS + 2) * 4, s));
 
   const int chunk_bits = d->chunk_bytes * 8;

@@ -293,11 +293,7 @@ class JpegDecoder:
         _require_cuda()
         return [torch.empty((h, row_pitch(w, c)), dtype=torch.uint8, device="cuda") for w, h, c in self.sizes]
 
-    def decode(self, blob_dev: torch.Tensor, outs: Optional[Sequence[torch.Tensor]] = None, stream=None) -> List[torch.Tensor]:
-        _require_cuda()
-        assert blob_dev.is_cuda and blob_dev.dtype == torch.uint8 and blob_dev.is_contiguous()
-        if outs is None:
-            outs = self.alloc_pages()
+    def _call_args(self, outs):
         n = len(self.sizes)
         assert len(outs) == n
         need = int(lib().pg_jpeg_workspace_bytes(self._h))
@@ -306,6 +302,21 @@ class JpegDecoder:
         ws_ptr = self.ws.data_ptr() + ((-self.ws.data_ptr()) % 256)
         ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in outs])
         pitches = (C.c_int64 * n)(*[t.shape[1] for t in outs])
+        return ptrs, pitches, ws_ptr, need
+
+    def stage_tables(self, outs: Sequence[torch.Tensor], stream=None) -> None:
+        """pg_jpeg_stage_tables: upload the batch's tables on the stream that carries the files (see pagegeom.h); the
+        decode() that follows, ordered after it, then issues no host->device copy."""
+        _require_cuda()
+        ptrs, pitches, ws_ptr, need = self._call_args(outs)
+        check(lib().pg_jpeg_stage_tables(self._h, ptrs, pitches, ws_ptr, need, stream_ptr(stream)))
+
+    def decode(self, blob_dev: torch.Tensor, outs: Optional[Sequence[torch.Tensor]] = None, stream=None) -> List[torch.Tensor]:
+        _require_cuda()
+        assert blob_dev.is_cuda and blob_dev.dtype == torch.uint8 and blob_dev.is_contiguous()
+        if outs is None:
+            outs = self.alloc_pages()
+        ptrs, pitches, ws_ptr, need = self._call_args(outs)
         check(lib().pg_jpeg_decode(self._h, ptr(blob_dev), ptrs, pitches, ws_ptr, need, stream_ptr(stream)))
         self._last = (blob_dev, list(outs), stream)
         return list(outs)

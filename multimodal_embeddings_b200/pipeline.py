@@ -417,6 +417,8 @@ class ScanPipeline:
                 self.s_copy.wait_event(sl["done"])  # the slot's previous step has consumed its buffers
             if ev:
                 ev[0].record(self.s_copy)
+            outs = [sl["pages"][i] for i in range(self.n_pages)]
+            dec.stage_tables(outs, stream=self.s_copy)  # the decoder's tables travel in front of the files, not behind the next step's
             sl["blob"][:blob.numel()].copy_(blob, non_blocking=True)
             box_bytes = pipe.upload_detections(host_dets, pinned=sl["pin_in"])
             if ev:
@@ -426,7 +428,7 @@ class ScanPipeline:
         with torch.cuda.stream(self.s_main):
             if ev:
                 ev[2].record(self.s_main)
-            dec.decode(sl["blob"], [sl["pages"][i] for i in range(self.n_pages)], stream=self.s_main)
+            dec.decode(sl["blob"], outs, stream=self.s_main)
             pipe.run(sl["pages"], stream=self.s_main)
             pipe.results_to_host(pinned=sl["pin_out"])
             if ev:

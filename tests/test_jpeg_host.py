@@ -148,3 +148,27 @@ def test_host_decode_of_a_scan_equals_cv2_imread_and_exif_turned_files_stay_on_t
     assert b"EXIF orientation" in lib().pg_last_error()
     got = ops.decode_page(turned)
     assert got.shape == (200, 120) and np.array_equal(got, cv2.imread(turned)[..., 0])
+
+
+def test_files_from_another_encoder_with_optimised_tables(tmp_path):
+    """Pillow's encoder (libjpeg via a different front end): optimised Huffman tables (codes up to 16 bits, not the
+    standard tables), its own subsampling choices, a comment and an EXIF block without orientation, restart markers
+    counted in MCU rows."""
+    from PIL import Image
+    g = _page(233, 317, 21, 25)
+    c = np.stack([g, np.roll(g, 7, 1), 255 - np.roll(g, 5, 0)], -1)
+    exif = Image.Exif()
+    exif[0x010E] = "a scan"  # ImageDescription: an EXIF block that does not turn the image
+    cases = [(g, dict(quality=92, optimize=True)), (g, dict(quality=35, optimize=True, comment=b"hello")),
+             (c[..., ::-1], dict(quality=88, optimize=True, subsampling=2)), (c[..., ::-1], dict(quality=97, subsampling=0, exif=exif)),
+             (c[..., ::-1], dict(quality=70, optimize=True, subsampling=1, restart_marker_rows=1)),
+             (g, dict(quality=100, optimize=True, restart_marker_blocks=3))]
+    for i, (img, kw) in enumerate(cases):
+        path = str(tmp_path / f"p{i}.jpg")
+        Image.fromarray(img).save(path, **kw)
+        data = open(path, "rb").read()
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        for chunk in (32, 512):
+            got, st = host_decode(data, chunk)
+            want = ref if got.ndim == 3 else ref[..., 0]
+            assert np.array_equal(got, want), (i, kw, chunk, st)

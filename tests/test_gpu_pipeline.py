@@ -118,3 +118,51 @@ def test_pipeline_matches_oracle_and_accumulates_corpus_histograms(workload, ove
     if ref_w.sum():
         srt = np.sort(np.repeat(np.arange(PG_WIDTH_HIST_BINS), 2 * ref_w))
         assert corpus_median_width(pipe.width_hist) == (srt[(len(srt) - 1) // 2] + srt[len(srt) // 2]) / 2.0
+
+
+def test_scan_pipeline_on_jpeg_files_equals_page_pipeline_on_cv2_pages():
+    """pipeline.ScanPipeline (files + detections in host memory -> H2D -> device decode -> one-channel tiler -> box
+    stages -> D2H, double-buffered) against PagePipeline fed with what cv2.imdecode returns for the same files: same
+    tiles, same kept indices, medians and columns — for several steps in flight with different detections per step,
+    and with the decoder deliberately configured with too few sync rounds (the step is redone by results())."""
+    import cv2
+    from multimodal_embeddings_b200.pipeline import ScanPipeline
+    w, h, rows, cols, n_pages = 1504, 1000, 2, 2, 3
+    rng = np.random.default_rng(5)
+    noisy = np.clip(200 + rng.normal(0, 40, (h, w)), 0, 255).astype(np.uint8)  # long blocks: needs many sync rounds
+    greys = [synth.newspaper_page(w, h, 31), noisy, synth.newspaper_page(w, h, 33)]
+    files = [cv2.imencode(".jpg", g, [cv2.IMWRITE_JPEG_QUALITY, 95])[1].tobytes() for g in greys]
+    blob, off = ops.pack_files(files)
+    sp = ScanPipeline(w, h, n_pages, [(rows, cols)], 20.0)
+    for sl in sp.slots:
+        sl["dec"].auto_chunk, sl["dec"].chunk_bytes, sl["dec"].sync_rounds = False, 256, 1
+    plan3 = ops.TilePlan(w, h, [(rows, cols)], 20.0)
+    bgr = [cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_COLOR) for f in files]
+    pages3 = ops.upload_pages(bgr, plan3)
+    steps = []
+    for s_i in range(4):
+        dets = [synth.page_detections(w, h, rows, cols, 20.0, 700 + 50 * s_i, 900 + 10 * s_i + p) for p in range(n_pages)]
+        probe = PagePipeline(plan3, n_pages)
+        host = probe.set_detections(dets)
+        probe.run(pages3)
+        torch.cuda.synchronize()
+        probe.check_status()
+        steps.append((host, {k: v.clone() for k, v in probe.results_to_host().items()}, probe.tiles_out.clone()))
+    ids = [sp.submit(blob, off, host) for host, _, _ in steps[:2]]
+    for s_i in range(4):
+        got = sp.results(ids[s_i])
+        want = steps[s_i][1]
+        for k in ("n_kept2", "median", "n_bins", "n_cols"):
+            assert np.array_equal(got[k], want[k].numpy()), (s_i, k)
+        offp = steps[s_i][0]["page_off"]
+        for p in range(n_pages):
+            nk = int(want["n_kept2"][p])
+            assert np.array_equal(got["kept2"][offp[p]:offp[p] + nk], want["kept2"][offp[p]:offp[p] + nk].numpy())
+            nc = int(want["n_cols"][p])
+            assert np.array_equal(got["centers"][p, :nc], want["centers"][p, :nc].numpy())
+            assert np.array_equal(got["col_widths"][p, :nc], want["col_widths"][p, :nc].numpy())
+        sl = sp.slots[ids[s_i] % sp.depth]
+        assert torch.equal(sl["pipe"].tiles_out, steps[s_i][2])  # tiles from the decoded grey planes == tiles from cv2's BGR pages
+        if s_i + 2 < 4:
+            ids.append(sp.submit(blob, off, steps[s_i + 2][0]))
+    assert all(sl["dec"].sync_rounds > 1 for sl in sp.slots)  # the unconverged decodes were noticed and redone

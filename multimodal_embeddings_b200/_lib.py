@@ -115,11 +115,12 @@ def lib() -> C.CDLL:
     """Load libpagegeom.so; fail loudly if it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("PAGEGEOM_LIB") or LIB_PATH  # A/B builds of the same sources (scripts/gpu_*.sh); default: the in-tree build
+        if not os.path.exists(path):
             raise PageGeomError(
-                f"{LIB_PATH} not found: build it with `python -m multimodal_embeddings_b200.build` "
+                f"{path} not found: build it with `python -m multimodal_embeddings_b200.build` "
                 "(nvcc, sm_100a). There is no CPU fallback.")
-        handle = C.CDLL(LIB_PATH)
+        handle = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)  # AttributeError if the symbol is missing
             fn.restype = res

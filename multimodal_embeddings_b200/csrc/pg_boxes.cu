@@ -100,8 +100,10 @@ extern "C" int pg_edge_filter(const double* boxes, int32_t boxes_are_local, cons
 // through distributed shared memory): nms_resolve_cluster_kernel, nms_emit_cluster_kernel.
 // =============================================================================================
 constexpr int NMS_GY = 128;     // y cells (7-bit digit)
+constexpr int NMS_GYF = 128;    // subdivisions of a y cell (a third, finer 7-bit digit), used on crowded pages only
+constexpr int NMS_FINE_MIN_PER_CELL = 16;  // ... those with more boxes per (x strip, y cell) than this on average
 constexpr int NMS_GX_MAX = 64;  // x strips (6-bit digit), chosen per page from the mean box width
-constexpr int NMS_CLUSTER_MAX = 8;  // CTAs per page when a launch has few, large pages
+constexpr int NMS_CLUSTER_MAX = 16;  // CTAs per page when a launch has few, large pages (above 8: non-portable cluster size)
 
 struct __align__(16) SBox {  // one box in spatial order
   double x0, y0, x1, y1;
@@ -130,6 +132,7 @@ struct NmsWs {
   uint32_t* ent_mask;  // [E*32]
   int64_t nb_cap, ent_cap;
   int32_t mode;        // PG_NMS_* bits
+  int32_t fine_min;    // boxes per (x strip, y cell) above which the sub-cell digit is sorted too
 };
 // stats[] slots
 enum { ST_STATUS = 0, ST_PAIRS = 1, ST_ROUNDS = 2, ST_TESTS = 3, ST_ENT_TOTAL = 4 };
@@ -259,6 +262,22 @@ __device__ __forceinline__ void block_stable_pass(int m, int* hist, int* scan_sm
   __syncthreads();
 }
 
+// Spatial key of a box centre at grid position (fx, fy): x strip | y cell | y sub-cell, 6 + 7 + 7 bits.  Pure
+// heuristic — any ordering gives the same kept set; a tighter one gives fewer candidate block pairs.  The sub-cell
+// digit costs a third sorting pass and is used only where a (strip, cell) holds many boxes: there, 32 consecutive
+// boxes in (strip, cell) order span the whole cell and every block of a cell is a candidate of every other.
+__device__ __forceinline__ int32_t nms_cell_id(double fx, double fy, int gxn) {
+  const int gx = (fx >= 0.0) ? (fx < (double)(gxn - 1) ? (int)fx : gxn - 1) : 0;
+  const double fyc = (fy >= 0.0) ? fy : 0.0;
+  const int gy = fyc < (double)(NMS_GY - 1) ? (int)fyc : NMS_GY - 1;
+  const double sub = (fyc - (double)gy) * (double)NMS_GYF;
+  const int gyf = sub < (double)(NMS_GYF - 1) ? (int)sub : NMS_GYF - 1;
+  return (gx * NMS_GY + gy) * NMS_GYF + gyf;
+}
+__device__ __forceinline__ bool nms_fine_cells(int m, int gxn, int min_per_cell) {
+  return (int64_t)m > (int64_t)min_per_cell * NMS_GY * gxn;
+}
+
 // ---- A: bin --------------------------------------------------------------------------------
 __device__ __forceinline__ void nms_blocked_copy(const double* __restrict__ boxes, const double* __restrict__ scores,
                                                  const double* __restrict__ classes, const int32_t* __restrict__ sel_idx,
@@ -316,19 +335,25 @@ __global__ void __launch_bounds__(1024) nms_bin_kernel(const double* __restrict_
     const double2 a = *reinterpret_cast<const double2*>(boxes + 4 * gi);
     const double2 b = *reinterpret_cast<const double2*>(boxes + 4 * gi + 2);
     const double fx = ((a.x + b.x) * 0.5 - mnx) * sx, fy = ((a.y + b.y) * 0.5 - mny) * sy;
-    const int gx = (fx >= 0.0) ? (fx < (double)(gxn - 1) ? (int)fx : gxn - 1) : 0;
-    const int gy = (fy >= 0.0) ? (fy < (double)(NMS_GY - 1) ? (int)fy : NMS_GY - 1) : 0;
-    ws.cellid[sp.base + k] = gx * NMS_GY + gy;
+    ws.cellid[sp.base + k] = nms_cell_id(fx, fy, gxn);
   }
   __syncthreads();
-  // stable LSD radix sort by (x strip, y cell): pass 1 on y, pass 2 on x
+  // stable LSD radix sort by (x strip, y cell[, y sub-cell]): the finest digit first
   const int32_t* cellid = ws.cellid + sp.base;
   int32_t* tmp = ws.kpos + sp.base;
   int32_t* sorted = ws.sorted_pos + sp.base;
-  block_stable_pass<NMS_GY>(sp.m, hist, scan_smem, [](int i) { return i; },
-                            [cellid](int e) { return cellid[e] & (NMS_GY - 1); }, tmp);
+  if (nms_fine_cells(sp.m, gxn, ws.fine_min)) {
+    int32_t* tmp0 = reinterpret_cast<int32_t*>(ws.kscore + sp.base);  // free until the resolve kernel writes the kept scores
+    block_stable_pass<NMS_GYF>(sp.m, hist, scan_smem, [](int i) { return i; },
+                               [cellid](int e) { return cellid[e] & (NMS_GYF - 1); }, tmp0);
+    block_stable_pass<NMS_GY>(sp.m, hist, scan_smem, [tmp0](int i) { return tmp0[i]; },
+                              [cellid](int e) { return (cellid[e] >> 7) & (NMS_GY - 1); }, tmp);
+  } else {
+    block_stable_pass<NMS_GY>(sp.m, hist, scan_smem, [](int i) { return i; },
+                              [cellid](int e) { return (cellid[e] >> 7) & (NMS_GY - 1); }, tmp);
+  }
   block_stable_pass<NMS_GX_MAX>(sp.m, hist, scan_smem, [tmp](int i) { return tmp[i]; },
-                                [cellid](int e) { return cellid[e] >> 7; }, sorted);
+                                [cellid](int e) { return cellid[e] >> 14; }, sorted);
 
   // blocked copy + block bounding boxes
   nms_blocked_copy(boxes, scores, classes, sel_idx, sp, sorted, ws, p, warp, blockDim.x >> 5);
@@ -507,19 +532,25 @@ __global__ void __launch_bounds__(1024) nms_bin_cluster_kernel(const double* __r
     const double2 a = *reinterpret_cast<const double2*>(boxes + 4 * gi);
     const double2 b = *reinterpret_cast<const double2*>(boxes + 4 * gi + 2);
     const double fx = ((a.x + b.x) * 0.5 - mnx) * sx, fy = ((a.y + b.y) * 0.5 - mny) * sy;
-    const int gx = (fx >= 0.0) ? (fx < (double)(gxn - 1) ? (int)fx : gxn - 1) : 0;
-    const int gy = (fy >= 0.0) ? (fy < (double)(NMS_GY - 1) ? (int)fy : NMS_GY - 1) : 0;
-    ws.cellid[sp.base + k] = gx * NMS_GY + gy;
+    ws.cellid[sp.base + k] = nms_cell_id(fx, fy, gxn);
   }
   __threadfence();
   cluster.sync();  // the passes read cell ids written by other CTAs
   const int32_t* cellid = ws.cellid + sp.base;
   int32_t* tmp = ws.kpos + sp.base;
   int32_t* sorted = ws.sorted_pos + sp.base;
-  cluster_stable_pass<NMS_GY>(cluster, csize, rank, sp.m, hist, all_tot, scan_smem, [](int i) { return i; },
-                              [cellid](int e) { return cellid[e] & (NMS_GY - 1); }, tmp);
+  if (nms_fine_cells(sp.m, gxn, ws.fine_min)) {  // the same decision in every CTA of the cluster
+    int32_t* tmp0 = reinterpret_cast<int32_t*>(ws.kscore + sp.base);
+    cluster_stable_pass<NMS_GYF>(cluster, csize, rank, sp.m, hist, all_tot, scan_smem, [](int i) { return i; },
+                                 [cellid](int e) { return cellid[e] & (NMS_GYF - 1); }, tmp0);
+    cluster_stable_pass<NMS_GY>(cluster, csize, rank, sp.m, hist, all_tot, scan_smem, [tmp0](int i) { return tmp0[i]; },
+                                [cellid](int e) { return (cellid[e] >> 7) & (NMS_GY - 1); }, tmp);
+  } else {
+    cluster_stable_pass<NMS_GY>(cluster, csize, rank, sp.m, hist, all_tot, scan_smem, [](int i) { return i; },
+                                [cellid](int e) { return (cellid[e] >> 7) & (NMS_GY - 1); }, tmp);
+  }
   cluster_stable_pass<NMS_GX_MAX>(cluster, csize, rank, sp.m, hist, all_tot, scan_smem, [tmp](int i) { return tmp[i]; },
-                                  [cellid](int e) { return cellid[e] >> 7; }, sorted);
+                                  [cellid](int e) { return cellid[e] >> 14; }, sorted);
   nms_blocked_copy(boxes, scores, classes, sel_idx, sp, sorted, ws, p, rank * 32 + warp, csize * 32);
 }
 
@@ -797,6 +828,42 @@ __device__ __forceinline__ void resolve_scan_entries(const NmsWs& ws, const vola
   }
 }
 
+// One Jacobi round over the blocks first, first + stride, ... a warp owns.  A block that was final in the previous
+// round already is copied once into the other buffer and then leaves the warp's `alive` mask (bit i = i-th owned
+// block): later rounds visit only blocks that can still change.  Warps that own more than 32 blocks keep visiting
+// all of them.  Returns whether any visited block is still undecided.
+__device__ __forceinline__ int resolve_round(const NmsWs& ws, volatile uint32_t* kept, volatile uint32_t* undec, int64_t rc,
+                                             int64_t rn, const PageSpan& sp, int first, int stride, int owned, uint32_t& alive,
+                                             int lane) {
+  int pending = 0;
+  auto visit = [&](int b) -> bool {
+    const int64_t I = sp.blk0 + b;
+    const uint32_t u = undec[rc + I], k = kept[rc + I];
+    if (u == 0u) {
+      if (lane == 0) { undec[rn + I] = 0u; kept[rn + I] = k; }
+      return false;
+    }
+    const bool mine = (u >> lane) & 1u;
+    bool sup = false, wait = false;
+    resolve_scan_entries(ws, kept, undec, rc, I, mine, lane, sup, wait);
+    const unsigned bk = __ballot_sync(0xffffffffu, mine && !sup && !wait);
+    const unsigned bs = __ballot_sync(0xffffffffu, mine && sup);
+    const uint32_t un = u & ~(bk | bs);
+    if (lane == 0) { kept[rn + I] = k | bk; undec[rn + I] = un; }
+    pending |= (un != 0u);
+    return true;
+  };
+  if (owned <= 32) {
+    for (uint32_t am = alive; am; am &= am - 1u) {
+      const int i = __ffs(am) - 1;
+      if (!visit(first + i * stride)) alive &= ~(1u << i);
+    }
+  } else {
+    for (int b = first; b < sp.nb; b += stride) visit(b);
+  }
+  return pending;
+}
+
 __global__ void __launch_bounds__(1024) nms_resolve_kernel(const int64_t* __restrict__ page_off,
                                                            const int32_t* __restrict__ n_sel, NmsWs ws,
                                                            int32_t* __restrict__ n_kept) {
@@ -817,26 +884,12 @@ __global__ void __launch_bounds__(1024) nms_resolve_kernel(const int64_t* __rest
     kept[sp.blk0 + b] = 0u;
   }
   __syncthreads();
+  const int owned = warp < sp.nb ? (sp.nb - warp + nwarps - 1) / nwarps : 0;
+  uint32_t alive = owned >= 32 ? 0xffffffffu : ((1u << owned) - 1u);
   int cur = 0, rounds = 0;
   while (true) {
     const int64_t rc = (int64_t)cur * nbc, rn = (int64_t)(cur ^ 1) * nbc;
-    int pending = 0;
-    for (int b = warp; b < sp.nb; b += nwarps) {
-      const int64_t I = sp.blk0 + b;
-      const uint32_t u = undec[rc + I], k = kept[rc + I];
-      if (u == 0u) {
-        if (lane == 0) { undec[rn + I] = 0u; kept[rn + I] = k; }
-        continue;
-      }
-      const bool mine = (u >> lane) & 1u;
-      bool sup = false, wait = false;
-      resolve_scan_entries(ws, kept, undec, rc, I, mine, lane, sup, wait);
-      const unsigned bk = __ballot_sync(0xffffffffu, mine && !sup && !wait);
-      const unsigned bs = __ballot_sync(0xffffffffu, mine && sup);
-      const uint32_t un = u & ~(bk | bs);
-      if (lane == 0) { kept[rn + I] = k | bk; undec[rn + I] = un; }
-      pending |= (un != 0u);
-    }
+    const int pending = resolve_round(ws, kept, undec, rc, rn, sp, warp, nwarps, owned, alive, lane);
     cur ^= 1;
     ++rounds;
     if (!__syncthreads_or(pending)) break;
@@ -897,26 +950,13 @@ __global__ void __launch_bounds__(1024) nms_resolve_cluster_kernel(const int64_t
   }
   __threadfence();
   cluster.sync();
+  const int first = rank * nwarps + warp;
+  const int owned = first < sp.nb ? (sp.nb - first + csize * nwarps - 1) / (csize * nwarps) : 0;
+  uint32_t alive = owned >= 32 ? 0xffffffffu : ((1u << owned) - 1u);
   int cur = 0, rounds = 0;
   while (true) {
     const int64_t rc = (int64_t)cur * nbc, rn = (int64_t)(cur ^ 1) * nbc;
-    int pending = 0;
-    for (int b = rank * nwarps + warp; b < sp.nb; b += csize * nwarps) {
-      const int64_t I = sp.blk0 + b;
-      const uint32_t u = undec[rc + I], k = kept[rc + I];
-      if (u == 0u) {
-        if (lane == 0) { undec[rn + I] = 0u; kept[rn + I] = k; }
-        continue;
-      }
-      const bool mine = (u >> lane) & 1u;
-      bool sup = false, wait = false;
-      resolve_scan_entries(ws, kept, undec, rc, I, mine, lane, sup, wait);
-      const unsigned bk = __ballot_sync(0xffffffffu, mine && !sup && !wait);
-      const unsigned bs = __ballot_sync(0xffffffffu, mine && sup);
-      const uint32_t un = u & ~(bk | bs);
-      if (lane == 0) { kept[rn + I] = k | bk; undec[rn + I] = un; }
-      pending |= (un != 0u);
-    }
+    const int pending = resolve_round(ws, kept, undec, rc, rn, sp, first, csize * nwarps, owned, alive, lane);
     const int any_local = __syncthreads_or(pending);
     const int par = rounds & 1;
     if (tid < csize) *cluster.map_shared_rank(&pend_x[par][rank], tid) = any_local;
@@ -1054,7 +1094,6 @@ __global__ void __launch_bounds__(1024) nms_emit_cluster_kernel(const int32_t* _
                                                                 const int32_t* __restrict__ n_kept,
                                                                 int32_t* __restrict__ kept_idx) {
   extern __shared__ __align__(16) unsigned char emit_smem[];
-  constexpr int CH = EMIT_SMEM_ELEMS;
   cg::cluster_group cluster = cg::this_cluster();
   const int csize = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int p = blockIdx.x / csize, tid = threadIdx.x;
@@ -1064,10 +1103,10 @@ __global__ void __launch_bounds__(1024) nms_emit_cluster_kernel(const int32_t* _
   int n2 = 1;
   while (n2 < K) n2 <<= 1;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(emit_smem);
-  int32_t* idx = reinterpret_cast<int32_t*>(emit_smem + (size_t)CH * 8);
+  int32_t* idx = reinterpret_cast<int32_t*>(emit_smem + (size_t)EMIT_SMEM_ELEMS * 8);
   unsigned long long* gkeys = reinterpret_cast<unsigned long long*>(ws.kscore + base);
   int32_t* gidx = ws.kpos + base;
-  if (n2 <= CH) {  // few survivors on this page: one CTA, no cluster barrier on this path for anyone
+  if (n2 <= EMIT_SMEM_ELEMS) {  // few survivors on this page: one CTA, no cluster barrier on this path for anyone
     if (rank != 0) return;
     for (int i = tid; i < K; i += blockDim.x) { keys[i] = score_desc_key(ws.kscore[base + i]); idx[i] = ws.kpos[base + i]; }
     __syncthreads();
@@ -1078,6 +1117,8 @@ __global__ void __launch_bounds__(1024) nms_emit_cluster_kernel(const int32_t* _
     }
     return;
   }
+  int CH = EMIT_SMEM_ELEMS;  // chunk of the network that one CTA sorts in shared memory: every CTA of the cluster gets one
+  while (CH > 2048 && n2 / CH < csize) CH >>= 1;
   const int nch = n2 / CH;
   // stage 0: every chunk sorted on its own (k = 2 .. CH), scores turned into sortable keys on the way in
   for (int c = rank; c < nch; c += csize) {
@@ -1147,31 +1188,47 @@ static int nms_cluster_width(int32_t n_pages, int32_t max_boxes_per_page, int sm
   if (const char* e = getenv("PG_NMS_CLUSTER_MIN_BOXES")) min_boxes = atoi(e);  // test / tuning knob; <= 0 disables
   if (min_boxes <= 0 || max_boxes_per_page < min_boxes) return 1;
   int c = NMS_CLUSTER_MAX;
+  if (const char* e = getenv("PG_NMS_CLUSTER_MAX")) c = std::max(1, std::min(NMS_CLUSTER_MAX, atoi(e)));  // tuning knob
+  while (c & (c - 1)) c &= c - 1;
   while (c > 1 && (int64_t)n_pages * c > sms) c >>= 1;
-  if (c == 1) return 1;
-  // the device must be able to co-schedule such a cluster (1024 threads and the 96 KB emit buffer per CTA)
-  static int launchable[NMS_CLUSTER_MAX + 1] = {0};  // 0 unknown, 1 yes, -1 no
-  if (launchable[c] == 0) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)c);
-    cfg.blockDim = dim3(1024);
-    cfg.dynamicSmemBytes = (size_t)emit_smem;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    int n1 = 0, n2 = 0;
-    const cudaError_t e1 = cudaOccupancyMaxActiveClusters(&n1, nms_emit_cluster_kernel, &cfg);
-    cfg.dynamicSmemBytes = 0;
-    const cudaError_t e2 = cudaOccupancyMaxActiveClusters(&n2, nms_resolve_cluster_kernel, &cfg);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) cudaGetLastError();
-    int n3 = 0;
-    const cudaError_t e3 = cudaOccupancyMaxActiveClusters(&n3, nms_bin_cluster_kernel, &cfg);
-    if (e3 != cudaSuccess) cudaGetLastError();
-    launchable[c] = (e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess && n1 > 0 && n2 > 0 && n3 > 0) ? 1 : -1;
+  // the device must be able to co-schedule such clusters (1024 threads and the 96 KB emit buffer per CTA); above the
+  // portable width of 8 every page's cluster must be resident at once (a cluster lives inside one GPC), or the
+  // pages would queue behind each other and the wider cluster would lose what it gains
+  static int active[NMS_CLUSTER_MAX + 1] = {0};  // 0 unknown, else 1 + clusters the device keeps resident (min over the three kernels)
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(nms_bin_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(nms_resolve_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(nms_emit_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaGetLastError();
+    attr_set = true;
   }
-  return launchable[c] > 0 ? c : 1;
+  for (; c > 1; c >>= 1) {
+    if (active[c] == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(c * (sms / c)));
+      cfg.blockDim = dim3(1024);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n_min = 1 << 30;
+      cfg.dynamicSmemBytes = (size_t)emit_smem;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, nms_emit_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      n_min = std::min(n_min, n);
+      cfg.dynamicSmemBytes = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, nms_resolve_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      n_min = std::min(n_min, n);
+      if (cudaOccupancyMaxActiveClusters(&n, nms_bin_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+      n_min = std::min(n_min, n);
+      active[c] = 1 + n_min;
+    }
+    const int resident = active[c] - 1;
+    if (resident > 0 && (c <= 8 || resident >= n_pages)) return c;
+  }
+  return 1;
 }
 
 template <typename... KArgs, typename... Args>
@@ -1223,6 +1280,8 @@ extern "C" int pg_nms_merge_ex(const double* boxes, const double* scores, const 
   while (ppb > 1 && nms_layout(n_boxes, n_pages, (int32_t)ppb, nullptr, nullptr) > workspace_bytes) --ppb;
   nms_layout(n_boxes, n_pages, (int32_t)ppb, (uint8_t*)workspace, &ws);
   ws.mode = mode;
+  ws.fine_min = NMS_FINE_MIN_PER_CELL;
+  if (const char* e = getenv("PG_NMS_FINE_MIN")) ws.fine_min = atoi(e);  // tuning knob; a huge value disables the third pass
   cudaStream_t s = (cudaStream_t)stream;
   const int emit_smem = EMIT_SMEM_ELEMS * 12;
   PG_CUDA_TRY(cudaFuncSetAttribute(nms_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem));
@@ -1234,6 +1293,7 @@ extern "C" int pg_nms_merge_ex(const double* boxes, const double* scores, const 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // per-page kernels (bin, resolve, emit): one CTA per page, or one cluster per page for few large pages
   const int width = nms_cluster_width(n_pages, max_boxes_per_page, sms, emit_smem);
+  if (getenv("PG_NMS_DEBUG")) fprintf(stderr, "pg_nms_merge: %d pages, cluster width %d\n", (int)n_pages, width);
   if (width > 1) {
     PG_CUDA_TRY(launch_cluster(nms_bin_cluster_kernel, n_pages, width, 0, s, boxes, scores, classes, sel_idx, page_off,
                                n_sel, (int)n_pages, ws));

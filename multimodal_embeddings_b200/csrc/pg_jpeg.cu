@@ -296,19 +296,7 @@ __device__ __forceinline__ void unstuff_masks(const uint8_t* blob, const ImgRec&
   const int lo = rel0 < 0 ? (int)-rel0 : 0;
   const int64_t left = r.src_len - rel0;
   const int hi = left < 16 ? (int)left : 16, lim = left < 17 ? (int)left : 17;
-  uint32_t p = rel0 > 0 ? (prev & 0xFFu) : 0u;  // the byte before the segment's first does not count
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const uint32_t cur = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-    uint32_t nx = k < 15 ? (w[(k + 1) >> 2] >> (8 * ((k + 1) & 3))) & 0xFFu : (next & 0xFFu);
-    if (k + 1 >= lim) nx = 0u;
-    const bool in = k >= lo && k < hi;
-    const bool nx_rst = (nx & 0xF8u) == 0xD0u, cur_ff = cur == 0xFFu;
-    const bool gone = (p == 0xFFu && (cur == 0u || (cur & 0xF8u) == 0xD0u)) || (cur_ff && nx_rst);  // pgj_keep_byte
-    if (in && !gone) keep |= 1u << k;
-    if (in && cur_ff && nx_rst) rst |= 1u << k;  // pgj_rst_starts
-    p = in ? cur : 0u;
-  }
+  pgj_unstuff_masks16(w, rel0 > 0 ? prev : 0u, next, lo, hi, lim, keep, rst);  // the byte before the segment's first does not count
 }
 
 __global__ void __launch_bounds__(256) jpeg_unstuff_count_kernel(const uint8_t* blob, Scratch s) {
@@ -344,7 +332,7 @@ __global__ void __launch_bounds__(1024) jpeg_unstuff_scan_kernel(Scratch s) {
 
 __global__ void __launch_bounds__(256) jpeg_unstuff_write_kernel(const uint8_t* blob, Scratch s) {
   __shared__ int sm[34];
-  __shared__ uint8_t stage[UB_BYTES];  // the block's kept bytes, packed; written out with coalesced stores
+  __shared__ __align__(16) uint8_t stage[UB_BYTES + 16];  // the block's kept bytes, packed; written out with coalesced stores
   const int img = s.ub_img[blockIdx.x];
   const ImgRec r = s.rec[img];
   uint32_t keep, rst;
@@ -355,17 +343,30 @@ __global__ void __launch_bounds__(256) jpeg_unstuff_write_kernel(const uint8_t* 
   int orr = pg_block_exscan(__popc(rst), sm, &tr) + s.ub_rst[blockIdx.x];
   const int out0 = s.ub_kept[blockIdx.x];
   const uint32_t w[4] = {bytes.x, bytes.y, bytes.z, bytes.w};
+  for (uint32_t m = rst; m; m &= m - 1u) {  // rare: restart interval (orr + 1) starts at the next byte that is kept
+    const int k = __ffs(m) - 1;
+    if (orr < r.rst_cap) s.rst_pos[r.rst_off + orr] = out0 + ok + __popc(keep & ((1u << k) - 1u));
+    ++orr;
+  }
+  uint32_t sa = (uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)ok;
+  asm volatile("" : "+r"(sa));  // computed once: left alone, the compiler re-derives the shared window for every byte
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    if (rst >> k & 1u) {  // restart interval (orr + 1) starts at the next byte that is kept
-      if (orr < r.rst_cap) s.rst_pos[r.rst_off + orr] = out0 + ok;
-      ++orr;
+    if (keep >> k & 1u) {
+      asm volatile("st.shared.u8 [%0], %1;" ::"r"(sa), "r"(w[k >> 2] >> (8 * (k & 3))) : "memory");
+      ++sa;
     }
-    if (keep >> k & 1u) stage[ok++] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
   }
   __syncthreads();
+  // out: the bytes up to the first word boundary of the destination, whole words (each from two staged words), the rest
   uint8_t* dst = s.compact + r.cs_off + out0;
-  for (int i = threadIdx.x; i < tk; i += 256) dst[i] = stage[i];
+  const int head = min(tk, (int)((4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u));
+  const int nw = (tk - head) >> 2, tail0 = head + 4 * nw;
+  if ((int)threadIdx.x < head) dst[threadIdx.x] = stage[threadIdx.x];
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage);
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+  for (int i = threadIdx.x; i < nw; i += 256) dw[i] = __funnelshift_r(sw[i], sw[i + 1], 8 * head);
+  if ((int)threadIdx.x < tk - tail0) dst[tail0 + threadIdx.x] = stage[tail0 + threadIdx.x];
   // slack behind the stream: ones, so that nothing read there looks like a code word
   if (blockIdx.x == r.ub0) {
     uint8_t* tail = s.compact + r.cs_off + s.img_len[img];
@@ -973,6 +974,25 @@ extern "C" int pg_hostcheck_jpeg_decode(const uint8_t* file, int64_t len, int32_
     const uint8_t prev = j > 0 ? p[j - 1] : 0, cur = p[j], next = j + 1 < sl ? p[j + 1] : 0;
     if (pgj_rst_starts(cur, next)) rst.push_back((int32_t)compact.size());
     if (pgj_keep_byte(prev, cur, next)) compact.push_back(cur);
+  }
+  // the kernels' sixteen-bytes-at-once form of the two tests must say the same, at every alignment of the segment
+  for (int64_t g0 = -(int64_t)(hi.scan_begin & 15); g0 < sl; g0 += 16) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    for (int k = 0; k < 16; ++k)
+      if (g0 + k >= -hi.scan_begin && hi.scan_begin + g0 + k < len) w[k >> 2] |= (uint32_t)p[g0 + k] << (8 * (k & 3));
+    const int lo = g0 < 0 ? (int)-g0 : 0;
+    const int64_t left = sl - g0;
+    const int hi16 = left < 16 ? (int)left : 16, lim = left < 17 ? (int)left : 17;
+    const uint32_t before = g0 > 0 ? p[g0 - 1] : 0u, after = hi.scan_begin + g0 + 16 < len ? p[g0 + 16] : 0u;
+    uint32_t keep, rstm;
+    pgj_unstuff_masks16(w, before, after, lo, hi16, lim, keep, rstm);
+    for (int k = lo; k < hi16; ++k) {
+      const int64_t j = g0 + k;
+      const uint8_t pv = j > 0 ? p[j - 1] : 0, cur = p[j], nx = j + 1 < sl ? p[j + 1] : 0;
+      PG_REQUIRE(((keep >> k) & 1u) == (pgj_keep_byte(pv, cur, nx) ? 1u : 0u) &&
+                     ((rstm >> k) & 1u) == (pgj_rst_starts(cur, nx) ? 1u : 0u), "pgj_unstuff_masks16 disagrees with the byte tests");
+    }
+    PG_REQUIRE((keep >> hi16) == 0u && (rstm >> hi16) == 0u && (keep & ((1u << lo) - 1u)) == 0u, "pgj_unstuff_masks16 mask range");
   }
   const int64_t clen = (int64_t)compact.size();
   compact.resize((size_t)clen + STREAM_PAD, 0xFF);

@@ -458,6 +458,33 @@ PGJ_HD bool pgj_keep_byte(uint8_t prev, uint8_t cur, uint8_t next) {
 }
 PGJ_HD bool pgj_rst_starts(uint8_t cur, uint8_t next) { return cur == 0xFF && pgj_is_rst(next); }
 
+// The same two tests for sixteen bytes at once (four little-endian words), a byte to a bit: keep / rst bit k belongs to
+// byte k.  Bytes [lo, hi) of the sixteen lie inside the segment; byte k + 1 exists inside it while k + 1 < lim
+// (lim <= 17); `before` = the segment's byte in front of the sixteen (0 when there is none), `after` = the byte
+// behind them.  Byte tests run four to a word: x has a zero byte exactly where the result has 0x80, and a multiply
+// gathers the four flags into a nibble.
+PGJ_HD uint32_t pgj_zero_bytes(uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); }
+PGJ_HD uint32_t pgj_flag_nibble(uint32_t m) { return (m * 0x00204081u) >> 28; }
+PGJ_HD void pgj_unstuff_masks16(const uint32_t (&w)[4], uint32_t before, uint32_t after, int lo, int hi, int lim,
+                                uint32_t& keep, uint32_t& rst) {
+  uint32_t ff = 0u, zr = 0u, rs = 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 4; ++q) {
+    ff |= pgj_flag_nibble(pgj_zero_bytes(~w[q])) << (4 * q);
+    zr |= pgj_flag_nibble(pgj_zero_bytes(w[q])) << (4 * q);
+    rs |= pgj_flag_nibble(pgj_zero_bytes((w[q] & 0xF8F8F8F8u) ^ 0xD0D0D0D0u)) << (4 * q);
+  }
+  const uint32_t in = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+  const uint32_t nx_ok = (1u << (lim > 0 ? lim - 1 : 0)) - 1u;
+  const uint32_t rs_next = ((rs >> 1) | ((after & 0xF8u) == 0xD0u ? 0x8000u : 0u)) & nx_ok;
+  const uint32_t ff_prev = (((ff & in) << 1) | ((before & 0xFFu) == 0xFFu ? 1u : 0u)) & 0xFFFFu;
+  const uint32_t gone = (ff_prev & (zr | rs)) | (ff & rs_next);
+  keep = in & ~gone;
+  rst = in & ff & rs_next;
+}
+
 
 // ---- colour files: jdsample.c "fancy" (triangle) chroma upsampling + jdcolor.c YCbCr -> RGB ----------------------
 // One chroma sample of the full-resolution image at (x, y) from the component's own plane `p` (pitch `pp`), whose

@@ -421,21 +421,43 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 // `off` arrives packed (pack_xoff): word-aligned byte offset in the high half, bit shift in the low
 // five bits — one LEA.HI forms the address and the wrapping funnel shift takes the register as is.
 // A staged row is < 64 KB (two rows x two stages must fit 227 KB), so the offset fits 16 bits.
-__device__ __forceinline__ uint32_t pack_xoff(uint32_t off) { return ((off & ~3u) << 16) | ((off & 3u) * 8u); }
-__device__ __forceinline__ void hpass_smem(uint32_t row_addr, uint32_t off, uint32_t coef, uint32_t& hb,
-                                           uint32_t& hg, uint32_t& hr) {
-  const uint32_t a = row_addr + (off >> 16);
-  const uint32_t w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8);
-  const uint32_t sh = off;  // shf.r.wrap uses the low 5 bits only
-  const uint32_t lo = __funnelshift_r(w0, w1, sh);
-  const uint32_t hi = __funnelshift_r(w1, w2, sh);
-  const uint32_t bg = __byte_perm(lo, hi, 0x4130);  // B0 B1 G0 G1
-  const uint32_t rr = __byte_perm(lo, hi, 0x0052);  // R0 R1 . .
-  hb = __dp2a_lo(coef, bg, 0u);                     // a0*B0 + a1*B1
-  hg = __dp2a_hi(coef, bg, 0u);
-  hr = __dp2a_lo(coef, rr, 0u);
+__device__ __forceinline__ uint32_t pack_xoff(uint32_t off) {
+  // bit 5 (ignored by the wrapping shift): the pixel pair's last byte lies in the NEXT word — only for off % 4 == 3
+  // (BGR: bytes off .. off+5; grey: off, off+1), so that word's load is predicated and three lanes in four skip it
+  return ((off & ~3u) << 16) | ((off & 3u) * 8u) | ((off & 3u) == 3u ? 32u : 0u);
 }
-
+#ifndef PG_TILER_TAIL_PRED
+#define PG_TILER_TAIL_PRED 1  // 0: every lane loads the tail word (A/B builds)
+#endif
+// The aligned 8-byte windows (lo, hi) = bytes off .. off+3 and off+4 .. off+7 of both staged rows of one pixel.  The
+// word behind the second is loaded only by the lanes whose pack_xoff flag is set, INTO the register of the first
+// word once `lo` has been formed — defined on every path, so no register has to be initialised for the other lanes
+// (their `hi` takes no byte from it: shift < 24).
+__device__ __forceinline__ void lds_windows_rows(uint32_t a0, uint32_t a1, uint32_t off, uint32_t& lo0, uint32_t& hi0,
+                                                 uint32_t& lo1, uint32_t& hi1) {
+#if PG_TILER_TAIL_PRED
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 f, x0, x1, y0, y1;\n\t"
+      "and.b32 f, %6, 32;\n\t"
+      "setp.ne.u32 p, f, 0;\n\t"
+      "ld.shared.u32 x0, [%4];\n\t"
+      "ld.shared.u32 y0, [%5];\n\t"
+      "ld.shared.u32 x1, [%4+4];\n\t"
+      "ld.shared.u32 y1, [%5+4];\n\t"
+      "shf.r.wrap.b32 %0, x0, x1, %6;\n\t"
+      "shf.r.wrap.b32 %2, y0, y1, %6;\n\t"
+      "@p ld.shared.u32 x0, [%4+8];\n\t"
+      "@p ld.shared.u32 y0, [%5+8];\n\t"
+      "shf.r.wrap.b32 %1, x1, x0, %6;\n\t"
+      "shf.r.wrap.b32 %3, y1, y0, %6;\n\t}"
+      : "=&r"(lo0), "=&r"(hi0), "=&r"(lo1), "=&r"(hi1)
+      : "r"(a0), "r"(a1), "r"(off));
+#else
+  const uint32_t p0 = lds32(a0), p1 = lds32(a0 + 4), p2 = lds32(a0 + 8), q0 = lds32(a1), q1 = lds32(a1 + 4), q2 = lds32(a1 + 8);
+  lo0 = __funnelshift_r(p0, p1, off); hi0 = __funnelshift_r(p1, p2, off);
+  lo1 = __funnelshift_r(q0, q1, off); hi1 = __funnelshift_r(q1, q2, off);
+#endif
+}
 // one-channel pages: the two neighbouring source bytes of a pixel at byte offset `off` of a staged row
 __device__ __forceinline__ uint32_t hpass_smem_grey(uint32_t row_addr, uint32_t off, uint32_t coef) {
   const uint32_t a = row_addr + (off >> 16);
@@ -443,6 +465,20 @@ __device__ __forceinline__ uint32_t hpass_smem_grey(uint32_t row_addr, uint32_t 
   return __dp2a_lo(coef, __funnelshift_r(w0, w1, off), 0u);  // a0*S0 + a1*S1
 }
 
+// both source rows of one pixel at once (the predicate of the tail word is shared)
+__device__ __forceinline__ void hpass_smem_rows(uint32_t row0, uint32_t row1, uint32_t off, uint32_t coef, uint32_t (&t)[3],
+                                                uint32_t (&u)[3]) {
+  uint32_t lo0, hi0, lo1, hi1;
+  lds_windows_rows(row0 + (off >> 16), row1 + (off >> 16), off, lo0, hi0, lo1, hi1);
+  {
+    const uint32_t bg = __byte_perm(lo0, hi0, 0x4130), rr = __byte_perm(lo0, hi0, 0x0052);  // B0 B1 G0 G1 | R0 R1 . .
+    t[0] = __dp2a_lo(coef, bg, 0u); t[1] = __dp2a_hi(coef, bg, 0u); t[2] = __dp2a_lo(coef, rr, 0u);
+  }
+  {
+    const uint32_t bg = __byte_perm(lo1, hi1, 0x4130), rr = __byte_perm(lo1, hi1, 0x0052);
+    u[0] = __dp2a_lo(coef, bg, 0u); u[1] = __dp2a_hi(coef, bg, 0u); u[2] = __dp2a_lo(coef, rr, 0u);
+  }
+}
 __device__ __forceinline__ uint32_t pack_unit_half2(uint32_t va, uint32_t vb) {
   // fp16(v/255): v*(1/255) in fp32 then one RN conversion matches fp16(fp32(v)/255) for all 256 v
   const float k = 1.0f / 255.0f;
@@ -555,12 +591,11 @@ __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const ui
           ab[j] = ag[j] = ar[j] = (4u * TL_PAD_VALUE + 2u) << 16;
           bb[j] = bg[j] = br[j] = 0u;
         } else {
-          uint32_t tb, tg, tr, ub, ug, ur;
-          hpass_smem(row0, xoff[i][j], coef[i][j], tb, tg, tr);
-          hpass_smem(row1, xoff[i][j], coef[i][j], ub, ug, ur);
-          ab[j] = b0 * (tb >> 4) + 0x20000u;  bb[j] = b1 * (ub >> 4);
-          ag[j] = b0 * (tg >> 4) + 0x20000u;  bg[j] = b1 * (ug >> 4);
-          ar[j] = b0 * (tr >> 4) + 0x20000u;  br[j] = b1 * (ur >> 4);
+          uint32_t t[3], u[3];
+          hpass_smem_rows(row0, row1, xoff[i][j], coef[i][j], t, u);
+          ab[j] = b0 * (t[0] >> 4) + 0x20000u;  bb[j] = b1 * (u[0] >> 4);
+          ag[j] = b0 * (t[1] >> 4) + 0x20000u;  bg[j] = b1 * (u[1] >> 4);
+          ar[j] = b0 * (t[2] >> 4) + 0x20000u;  br[j] = b1 * (u[2] >> 4);
         }
       }
       // BGR -> RGB planes

@@ -200,32 +200,17 @@ def test_stage1_cli_on_jpeg_scans_equals_the_host_decode_run(tmp_path):
     assert std["image_size"] == {"width": 1501, "height": 1003}
 
 
-def test_decode_randomised_sweep_equals_cv2(tmp_path):
-    """Sixty files in two batches: random sizes (8 ... 900 px, mostly not multiples of 8 or 16), qualities 20-100,
-    restart intervals, greyscale and every colour subsampling, cv2's and Pillow's encoders (standard and optimised
+def test_decode_randomised_sweep_equals_cv2():
+    """Sixty files in two batches (tests/jpeg_cases.py: random sizes 8 ... 900 px, qualities 20-100, restart
+    intervals, greyscale and every colour subsampling, cv2's and Pillow's encoders with standard and optimised
     Huffman tables) — every page bit-identical to cv2.imdecode."""
-    from PIL import Image
-    rng = np.random.default_rng(2024)
-    for batch in range(2):
-        files = []
-        for i in range(30):
-            h, w = int(rng.integers(8, 900)), int(rng.integers(8, 900))
-            g = _page(h, w, int(rng.integers(1 << 30)), float(rng.choice([2.0, 8.0, 30.0])))
-            colour = rng.random() < 0.5
-            img = np.stack([g, np.roll(g, 3, 1), 255 - np.roll(g, 2, 0)], -1) if colour else g
-            q = int(rng.integers(20, 101))
-            if rng.random() < 0.3:
-                path = str(tmp_path / f"b{batch}_{i}.jpg")
-                Image.fromarray(img[..., ::-1] if colour else img).save(
-                    path, quality=q, optimize=bool(rng.random() < 0.7), subsampling=int(rng.integers(0, 3)),
-                    **({"restart_marker_blocks": int(rng.integers(1, 9))} if rng.random() < 0.4 else {}))
-                files.append(open(path, "rb").read())
-            else:
-                extra = (cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SUBSAMPLING[int(rng.integers(0, 4))]) if colour else ()
-                files.append(_encode(img, q, int(rng.choice([0, 0, 1, 5, 40])), extra))
-        dec = ops.JpegDecoder(chunk_bytes=int(rng.choice([128, 256, 1024])), sync_rounds=8)
+    import jpeg_cases
+    for batch, chunk in enumerate((128, 1024)):
+        cases = jpeg_cases.sweep_files(2024 + batch, 30)
+        files = [f for f, _ in cases]
+        dec = ops.JpegDecoder(chunk_bytes=chunk, sync_rounds=8)
         pages = ops.decode_jpeg_files(files, dec)
-        for k, (data, page, (w, h, c)) in enumerate(zip(files, pages, dec.sizes)):
+        for (data, what), page, (w, h, c) in zip(cases, pages, dec.sizes):
             ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
             got = page[:, :c * w].cpu().numpy()
-            assert np.array_equal(got, ref.reshape(h, 3 * w) if c == 3 else ref[..., 0]), (batch, k, w, h, c)
+            assert np.array_equal(got, ref.reshape(h, 3 * w) if c == 3 else ref[..., 0]), what

@@ -438,6 +438,35 @@ def test_nms_cluster_kernels_equal_single_cta_kernels(name, cfgs, dups, oracle_p
         assert n1[i] == len(ref) and np.array_equal(k1[off[i]: off[i] + n1[i]] - off[i], ref), (name, i)
 
 
+@pytest.mark.parametrize("cluster", ["0", "1"])
+def test_nms_sub_cell_digit_of_the_spatial_sort_changes_nothing(cluster, monkeypatch):
+    """The third, finer digit of the spatial sort (crowded pages; forced on every page / disabled here through
+    PG_NMS_FINE_MIN) is a pure ordering heuristic: same kept boxes in the same pick order, against the oracle, on the
+    one-CTA and on the cluster kernels; on a crowded page it must cut the pair tests."""
+    cfgs = [(8000, 6000, 4, 4, 30000, 61), (3801, 5601, 2, 2, 2000, 62), (2000, 2000, 2, 2, 1, 63), (640, 480, 1, 1, 0, 64),
+            (2778, 4187, 3, 3, 9000, 65)]
+    boxes, scores, classes, off = _pooled(cfgs, 4)
+    scores[200:260] = scores[200]
+    mx = int(np.diff(off).max())
+    monkeypatch.setenv("PG_NMS_CLUSTER_MIN_BOXES", cluster)
+    out = {}
+    for fine in ("0", "1000000000"):
+        monkeypatch.setenv("PG_NMS_FINE_MIN", fine)
+        ws = ops.NmsWorkspace(len(boxes), len(cfgs), pairs_per_block=128)
+        kept, n_kept, ws = ops.nms_merge(boxes, scores, classes, off, 0.5, max_boxes_per_page=mx, workspace=ws)
+        st = ws.stats()
+        assert st["status"] == 0
+        out[fine] = (kept.cpu().numpy(), n_kept.cpu().numpy(), st)
+    (k0, n0, st0), (k1, n1, st1) = out["0"], out["1000000000"]
+    assert np.array_equal(n0, n1)
+    for i in range(len(cfgs)):
+        sl = slice(off[i], off[i + 1])
+        assert np.array_equal(k0[off[i]: off[i] + n0[i]], k1[off[i]: off[i] + n1[i]]), i
+        ref = nms_pick_order_c(boxes[sl], scores[sl], classes[sl], 0.5)
+        assert n0[i] == len(ref) and np.array_equal(k0[off[i]: off[i] + n0[i]] - off[i], ref), i
+    assert st0["box_pairs_tested"] < st1["box_pairs_tested"]
+
+
 def test_nms_cluster_kernels_report_workspace_overflow(monkeypatch):
     monkeypatch.setenv("PG_NMS_CLUSTER_MIN_BOXES", "1")
     n = 3000

@@ -172,3 +172,13 @@ def test_files_from_another_encoder_with_optimised_tables(tmp_path):
             got, st = host_decode(data, chunk)
             want = ref if got.ndim == 3 else ref[..., 0]
             assert np.array_equal(got, want), (i, kw, chunk, st)
+
+
+def test_randomised_sweep_through_the_inline_decoder_equals_cv2():
+    """The files of the GPU sweep (tests/jpeg_cases.py, same seeds) through the same inline code on the host, chunk by chunk."""
+    import jpeg_cases
+    for seed, chunk in ((2024, 128), (2025, 1024)):
+        for data, what in jpeg_cases.sweep_files(seed, 30):
+            ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_ANYCOLOR)
+            got, _ = host_decode(data, chunk)
+            assert got.shape == ref.shape and np.array_equal(got, ref), what

@@ -47,6 +47,8 @@ extern "C" {
 
 const char* pg_last_error(void);
 int pg_version(void);
+/* 1 when the library was built with -DPG_CHECKED (device-side bounds assertions, csrc/pg_common.cuh), else 0. */
+int pg_build_checked(void);
 /* SM count / compute capability of the current device. */
 int pg_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 

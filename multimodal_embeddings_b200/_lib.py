@@ -46,6 +46,7 @@ _F64 = C.c_double
 SIGNATURES = {
     "pg_last_error": (C.c_char_p, []),
     "pg_version": (C.c_int, []),
+    "pg_build_checked": (C.c_int, []),
     "pg_device_info": (C.c_int, [_P, _P, _P]),
     "pg_tile_plan_create": (C.c_int, [_I32, _I32, _P, _P, _I32, _F64, _I32, _I32, _I32, _I32, _P]),
     "pg_tile_plan_create_ex": (C.c_int, [_I32, _I32, _I32, _P, _P, _I32, _F64, _I32, _I32, _I32, _I32, _P]),

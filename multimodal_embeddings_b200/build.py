@@ -72,5 +72,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, extra_flags) -> str:
+    """A second build of the same sources with extra nvcc flags, written to _variants/libpagegeom_<name>.so and loaded
+    through PAGEGEOM_LIB (A/B timing builds; `checked`: -DPG_CHECKED, device-side bounds assertions — pg_common.cuh)."""
+    out_dir = os.path.join(HERE, "_variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libpagegeom_{name}.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError(f"nvcc failed building {out}")
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--checked" in sys.argv:
+        print(build_variant("checked", ["-DPG_CHECKED"]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

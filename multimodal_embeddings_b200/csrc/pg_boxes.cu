@@ -256,6 +256,7 @@ __device__ __forceinline__ void block_stable_pass(int m, int* hist, int* scan_sm
       hist[warp * NDIG + d] = basepos + __popc(grp);
     }
     basepos = __shfl_sync(0xffffffffu, basepos, leader);
+    PG_DEV_ASSERT(!act || (basepos + rank >= 0 && basepos + rank < m && e >= 0 && e < m));
     if (act) dst[basepos + rank] = e;
     __syncwarp();
   }
@@ -374,6 +375,7 @@ __device__ __forceinline__ void nms_blocked_copy(const double* __restrict__ boxe
     sb.k = -1;
     if (valid) {
       const int k = sorted[pos];
+      PG_DEV_ASSERT(k >= 0 && k < sp.m);
       const int64_t gi = sel_idx ? (int64_t)sel_idx[sp.base + k] : sp.base + k;
       const double2 a = *reinterpret_cast<const double2*>(boxes + 4 * gi);
       const double2 c = *reinterpret_cast<const double2*>(boxes + 4 * gi + 2);
@@ -462,6 +464,7 @@ __device__ __forceinline__ void cluster_stable_pass(cg::cluster_group& cluster, 
       hist[warp * NDIG + d] = basepos + __popc(grp);
     }
     basepos = __shfl_sync(0xffffffffu, basepos, leader);
+    PG_DEV_ASSERT(!act || (basepos + rk >= 0 && basepos + rk < m && e >= 0 && e < m));
     if (act) dst[basepos + rk] = e;
     __syncwarp();
   }
@@ -633,6 +636,7 @@ __global__ void __launch_bounds__(256) nms_cand_kernel(const int64_t* __restrict
   cand_walk(ws, sp, p, bbI, all_pairs, lane, [&](int j, bool hit, unsigned hits) {
     if (hit) {
       const long long slot = e + __popc(hits & ((1u << lane) - 1u));
+      PG_DEV_ASSERT(slot >= 0 && slot < ws.ent_cap && j >= 0 && j < sp.nb);
       ws.ent_j[slot] = (int32_t)(sp.blk0 + j);
       ws.ent_i[slot] = (int32_t)I;
     }
@@ -723,6 +727,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) nms_mask_kernel(NmsWs ws, doubl
       const long long e = u * MASK_UNIT + q;
       if (e >= total) break;
       const int I = ws.ent_i[e], J = ws.ent_j[e];
+      PG_DEV_ASSERT(e < ws.ent_cap && I >= 0 && I < ws.nb_cap && J >= 0 && J < ws.nb_cap);
       if (I != cached) {
         bi = ws.sbox[(int64_t)I * 32 + lane];
         li = slite_of(bi);
@@ -801,9 +806,11 @@ __device__ __forceinline__ void resolve_scan_entries(const NmsWs& ws, const vola
                                                      const volatile uint32_t* undec, int64_t rc, int64_t I, bool mine,
                                                      int lane, bool& sup, bool& wait) {
   const int64_t e0 = ws.cand_off[I], e1 = e0 + ws.cand_cnt[I];
+  PG_DEV_ASSERT(e0 >= 0 && e1 <= ws.ent_cap);
   for (int64_t eb = e0; eb < e1; eb += 32) {
     const int64_t me = eb + lane;
     const int jbk = me < e1 ? ws.ent_j[me] : -1;  // global block id, -1 = no suppressor in that block
+    PG_DEV_ASSERT(jbk < ws.nb_cap);
     uint32_t kj = 0u, uj = 0u;
     if (jbk >= 0) { kj = kept[rc + jbk]; uj = undec[rc + jbk]; }
     unsigned live = __ballot_sync(0xffffffffu, (kj | uj) != 0u);
@@ -908,6 +915,7 @@ __global__ void __launch_bounds__(1024) nms_resolve_kernel(const int64_t* __rest
       const int l = __ffs(bits) - 1;
       bits &= bits - 1;
       const SBox* sb = ws.sbox + (sp.blk0 + b) * 32 + l;
+      PG_DEV_ASSERT(dst >= sp.base && dst < sp.base + sp.m);
       ws.kscore[dst] = sb->score;
       ws.kpos[dst] = (int32_t)sb->k;
       ++dst;
@@ -994,6 +1002,7 @@ __global__ void __launch_bounds__(1024) nms_resolve_cluster_kernel(const int64_t
       const int l = __ffs(bits) - 1;
       bits &= bits - 1;
       const SBox* sb = ws.sbox + (sp.blk0 + b) * 32 + l;
+      PG_DEV_ASSERT(dst >= sp.base && dst < sp.base + sp.m);
       ws.kscore[dst] = sb->score;
       ws.kpos[dst] = (int32_t)sb->k;
       ++dst;
@@ -1073,6 +1082,7 @@ __device__ __forceinline__ void emit_pass8(unsigned long long* keys, int32_t* id
     int e = base | ((r >> 2) * J) | (((r >> 1) & 1) * (J >> 1)) | ((r & 1) * q);
     if (flip && (r >> 2)) e ^= q - 1;
     at[r] = emit_slot(e);
+    PG_DEV_ASSERT(e >= 0 && at[r] < EMIT_SMEM_SLOTS);
     k[r] = keys[at[r]];
     x[r] = idx[at[r]];
   }

@@ -35,6 +35,18 @@ void pg_set_error(const char* fmt, ...);
     }                                                                           \
   } while (0)
 
+// Checked build (-DPG_CHECKED; multimodal_embeddings_b200/build.py --checked writes _variants/libpagegeom_checked.so):
+// device-side assertions on every computed index into a workspace, a staging ring or a stream.  A violation traps:
+// the launch fails with cudaErrorAssert and the caller sees PG_ERR_CUDA.  compute-sanitizer is closed on the GPU
+// pool this was developed on; the GPU test-suite is run once per round against this build instead
+// (PAGEGEOM_LIB=..., profiles/r02_checked_build.md).  The default build compiles the checks away.
+#ifdef PG_CHECKED
+#include <assert.h>
+#define PG_DEV_ASSERT(c) assert(c)
+#else
+#define PG_DEV_ASSERT(c) ((void)0)
+#endif
+
 #ifdef __CUDACC__
 __device__ __forceinline__ int pg_lane() { return threadIdx.x & 31; }
 __device__ __forceinline__ int pg_warp() { return threadIdx.x >> 5; }

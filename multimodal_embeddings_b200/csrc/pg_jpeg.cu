@@ -22,7 +22,7 @@ namespace {
 
 constexpr int UB_BYTES = 4096;      // unstuff: input bytes per CTA (256 threads x 16)
 constexpr int CHUNK_THREADS = 256;  // entropy kernels: chunks per CTA
-constexpr int STREAM_PAD = 1024;    // readable slack behind every unstuffed stream
+constexpr int STREAM_PAD = PGJ_STREAM_PAD;  // readable slack behind every unstuffed stream
 constexpr int MAX_ROUNDS = 64;
 
 static_assert(sizeof(PgjImage) % 16 == 0, "PgjImage is copied into shared memory 16 bytes at a time");
@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(256) jpeg_unstuff_write_kernel(const uint8_t* 
     if (orr < r.rst_cap) s.rst_pos[r.rst_off + orr] = out0 + ok + __popc(keep & ((1u << k) - 1u));
     ++orr;
   }
+  PG_DEV_ASSERT(ok >= 0 && ok + __popc(keep) <= UB_BYTES && tk <= UB_BYTES);
   uint32_t sa = (uint32_t)__cvta_generic_to_shared(stage) + (uint32_t)ok;
   asm volatile("" : "+r"(sa));  // computed once: left alone, the compiler re-derives the shared window for every byte
 #pragma unroll
@@ -534,6 +535,7 @@ struct SmemBlockSink {
   int16_t* sm;      // this thread's block
   int16_t* base;    // the image's coefficient base
   int pred;
+  int64_t cap;      // coefficients the image owns (checked build)
   __device__ __forceinline__ void begin(int p) {
     pred = p;
     uint4* z = reinterpret_cast<uint4*>(sm);
@@ -541,8 +543,12 @@ struct SmemBlockSink {
     for (int k = 0; k < 8; ++k) z[k] = make_uint4(0u, 0u, 0u, 0u);
   }
   __device__ __forceinline__ void dc(int diff) { sm[0] = (int16_t)(pred + diff); }
-  __device__ __forceinline__ void ac(int idx, int v) { sm[idx] = (int16_t)v; }
+  __device__ __forceinline__ void ac(int idx, int v) {
+    PG_DEV_ASSERT(idx >= 1 && idx < 64);
+    sm[idx] = (int16_t)v;
+  }
   __device__ __forceinline__ void end(int64_t ci) {
+    PG_DEV_ASSERT(ci >= 0 && ci + 64 <= cap && (ci & 63) == 0);
     const uint4* src = reinterpret_cast<const uint4*>(sm);
     uint4* dst = reinterpret_cast<uint4*>(base + ci);
 #pragma unroll
@@ -578,7 +584,10 @@ __global__ void __launch_bounds__(CHUNK_THREADS) jpeg_store_kernel(Scratch s, in
   const int ec = j == 0 ? 0 : st[r.chunk0 + j - 1].c;
   if (ep < 0 || ep >= b1) return;  // no block starts inside this chunk
   const int blk = max(before.anchor, 0) * im.restart_blocks + before.n;
-  SmemBlockSink sink{blocks + threadIdx.x * BLK_PITCH, s.coef + r.coef_off, 0};
+  int64_t cap = 0;
+  for (int c = 0; c < im.n_comps; ++c) cap += (int64_t)im.comp_bw[c] * im.comp_bh[c] * 64;
+  PG_DEV_ASSERT(blk >= 0 && ep >= 0 && ep <= sv.n_bits);
+  SmemBlockSink sink{blocks + threadIdx.x * BLK_PITCH, s.coef + r.coef_off, 0, cap};
   pgj_span_store(sv, im, ep, ec, b1, blk, before.d0, before.d1, before.d2, sink);
 }
 
@@ -620,6 +629,7 @@ __global__ void __launch_bounds__(128) jpeg_idct_kernel(Scratch s) {
     for (int y = 0; y < 8; ++y) {
       if (y0 + y >= h) break;
       uint8_t* dst = plane + (int64_t)(y0 + y) * pitch + x0;
+      PG_DEV_ASSERT(x0 + (x0 + 8 <= w ? 8 : w - x0) <= pitch);
       if (x0 + 8 <= w) {
         *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(px + 8 * y);
       } else {

@@ -91,13 +91,30 @@ PGJ_HD int pgj_zigzag(int k) {
 }
 
 // ---- bit reader over the unstuffed stream (big-endian bit order) ---------------------------------------
+#ifdef PG_CHECKED
+#include <assert.h>
+#define PGJ_ASSERT(c) assert(c)
+#else
+#define PGJ_ASSERT(c) ((void)0)
+#endif
+constexpr int PGJ_STREAM_PAD = 1024;  // readable bytes of slack (ones) behind every unstuffed stream
+
 struct PgjBits {
   const uint8_t* base;
   uint64_t buf;       // next bits, left-aligned
   int32_t avail;      // valid bits in buf
   int64_t next_word;  // index of the next 32-bit word to load
+#ifdef PG_CHECKED
+  int64_t last_word;  // last word inside the stream's slack (checked build only)
+  PGJ_HD void bound_bits(int64_t n_bits) { last_word = (n_bits + 8 * (int64_t)PGJ_STREAM_PAD) / 32 - 1; }
+#else
+  PGJ_HD void bound_bits(int64_t) {}
+#endif
 
   PGJ_HD uint32_t load_be(int64_t w) const {
+#ifdef PG_CHECKED
+    PGJ_ASSERT(w >= 0 && w <= last_word);
+#endif
     const uint32_t v = *reinterpret_cast<const uint32_t*>(base + 4 * w);  // base is 4-byte aligned
 #ifdef __CUDA_ARCH__
     return __byte_perm(v, 0u, 0x0123);
@@ -253,6 +270,7 @@ PGJ_HD void pgj_span(const PgjStream& sv, const PgjImage& im, int64_t p, int c, 
   }
   int64_t bound = r < sv.n_rst ? (int64_t)sv.rst_pos[r] * 8 : sv.n_bits;
   PgjBits br;
+  br.bound_bits(sv.n_bits);
   br.seek(sv.bytes, p);
   PgjNoEmit none;
   while (p < limit && p < sv.n_bits) {
@@ -348,6 +366,7 @@ PGJ_HD void pgj_span_store(const PgjStream& sv, const PgjImage& im, int64_t p, i
   }
   int r = pgj_next_restart(sv, p);
   PgjBits br;
+  br.bound_bits(sv.n_bits);
   br.seek(sv.bytes, p);
   while (p < limit && p < sv.n_bits && blk < im.total_blocks) {
     int comp;

@@ -44,6 +44,13 @@ void pg_set_error(const char* fmt, ...) {
 }
 extern "C" const char* pg_last_error(void) { return g_err; }
 extern "C" int pg_version(void) { return 100; }
+extern "C" int pg_build_checked(void) {
+#ifdef PG_CHECKED
+  return 1;
+#else
+  return 0;
+#endif
+}
 extern "C" int pg_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
   int dev = 0;
   PG_CUDA_TRY(cudaGetDevice(&dev));
@@ -568,6 +575,7 @@ __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const ui
             ay[j] = (4u * TL_PAD_VALUE + 2u) << 16;
             by[j] = 0u;
           } else {
+            PG_DEV_ASSERT((xoff[i][j] >> 16) + 8u <= row1 - row0);
             ay[j] = b0 * (hpass_smem_grey(row0, xoff[i][j], coef[i][j]) >> 4) + 0x20000u;
             by[j] = b1 * (hpass_smem_grey(row1, xoff[i][j], coef[i][j]) >> 4);
           }
@@ -592,6 +600,7 @@ __device__ __forceinline__ void tiler_row(uint32_t row0, uint32_t row1, const ui
           bb[j] = bg[j] = br[j] = 0u;
         } else {
           uint32_t t[3], u[3];
+          PG_DEV_ASSERT((xoff[i][j] >> 16) + 12u <= row1 - row0);  // the three words stay inside the staged row
           hpass_smem_rows(row0, row1, xoff[i][j], coef[i][j], t, u);
           ab[j] = b0 * (t[0] >> 4) + 0x20000u;  bb[j] = b1 * (u[0] >> 4);
           ag[j] = b0 * (t[1] >> 4) + 0x20000u;  bg[j] = b1 * (u[1] >> 4);
@@ -664,6 +673,8 @@ __global__ void __launch_bounds__(32 * (CW + 1), (ITER <= 2 || CW <= 4) ? 4 : 2)
         const int pad_t = t.pad_t, new_h = t.new_h, ytab_off = t.ytab_off;
         const uint8_t* src = page_src + (int64_t)t.y0 * pitch + ((CHN * t.x0) & ~15);
         const uint32_t bytes = (uint32_t)t.row_bytes;
+        PG_DEV_ASSERT(bytes <= (uint32_t)a.row_stride && (bytes & 15u) == 0u && item.x >= 0 && page >= 0 && page < a.n_pages &&
+                      (int64_t)((CHN * t.x0) & ~15) + bytes <= pitch);
         for (int oy = item.y; oy < item.y + item.z; ++oy) {
           const int ry = oy - pad_t;
           const bool pad_row = ry < 0 || ry >= new_h;

@@ -24,12 +24,15 @@ def main():
     ap.add_argument("--pages", type=int, default=32)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--only", default="", help="substring of the grid-set name to run alone (ncu captures)")
     a = ap.parse_args()
     w, h = 8000, 6000
     sets = {"full+2x2+3x3+4x4 (reference default)": [(1, 1), (2, 2), (3, 3), (4, 4)], "full page only": [(1, 1)],
             "2x2": [(2, 2)], "3x3": [(3, 3)], "4x4 (cfg3)": [(4, 4)]}
     pages = None
     for name, grids in sets.items():
+        if a.only and a.only not in name:
+            continue
         plan = ops.TilePlan(w, h, grids, 20.0)
         if pages is None:
             pages = plan.alloc_pages(a.pages)

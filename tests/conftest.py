@@ -16,6 +16,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_report_header(config):
+    """Which libpagegeom.so the run exercises (PAGEGEOM_LIB selects a variant build, e.g. the checked one)."""
+    try:
+        from multimodal_embeddings_b200 import _lib
+        path = os.environ.get("PAGEGEOM_LIB") or _lib.LIB_PATH
+        return f"libpagegeom: {path} (checked build: {bool(_lib.lib().pg_build_checked())})"
+    except Exception as e:  # not built yet: the tests themselves say so
+        return f"libpagegeom: not loadable ({e})"
+
+
 def load_golden(name):
     path = os.path.join(GOLDEN, name)
     if name.endswith(".json.gz"):

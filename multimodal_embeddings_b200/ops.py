@@ -268,7 +268,7 @@ class JpegDecoder:
         if self.auto_chunk:
             # chunk ~ 10 blocks of the batch's average block length (entropy bytes / 8x8 blocks is not known before
             # the headers are parsed, so the first pass uses the previous size and a re-parse follows only when it differs)
-            self.chunk_bytes = self.chunk_bytes or 256
+            self.chunk_bytes = self.chunk_bytes or 128
         check(lib().pg_jpeg_decoder_configure(self._h, self.chunk_bytes, self.sync_rounds))
         check(lib().pg_jpeg_decoder_set_files(self._h, arr.ctypes.data, off.ctypes.data, n))
         self.sizes = []
@@ -279,8 +279,10 @@ class JpegDecoder:
         if self.auto_chunk:
             blocks = sum(((w + 7) // 8) * ((h + 7) // 8) for w, h, _ in self.sizes)
             per_block = float(off[-1] - off[0]) / max(blocks, 1)
-            want = 256  # measured on B200: 256-byte chunks beat 1024 on scan-like pages (3.7 vs 4.1 ms per 8 pages) —
-            while want < 10 * per_block and want < 4096:  # more, shorter walks; ~10 blocks per chunk keep the redo rate ~0.1 %
+            want = 128  # measured on B200 (8 pages of 48 Mpixel): shorter chunks = more, shorter walks — 256 bytes beat 1024
+            # at quality 95 (2.8 vs 3.2 ms, 23 bytes per block), 128 beat 256 at quality 75 (2.0 vs 2.3 ms, 11 bytes
+            # per block); ~10 blocks per chunk keep the share of chunks redone in sync round 1 near 0.1 %
+            while want < 10 * per_block and want < 4096:
                 want *= 2
             if want != self.chunk_bytes:
                 self.chunk_bytes = want

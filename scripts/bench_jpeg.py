@@ -28,7 +28,7 @@ def main():
         cv2_s = time.time() - t0
         blob, off = ops.pack_files(files)
         dev = blob.cuda()
-        for chunk in ((0,) if once else (0, 256, 512, 1024, 2048)):
+        for chunk in ((0,) if once else (0, 128, 256, 512, 1024)):
             dec = ops.JpegDecoder(chunk_bytes=chunk, sync_rounds=4)
             dec.set_files(blob, off)
             outs = dec.alloc_pages()

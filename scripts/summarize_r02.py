@@ -59,7 +59,7 @@ def configs():
     out.append("## Multi-GPU (`torchrun ... bench.py --gpus N`; earlier commits of this round where noted)\n")
     out.append("| N | value (pages/s) | e2e (pages/s) | H2D per GPU (GB/s) | corpus sha | exchange |")
     out.append("|---:|---:|---:|---:|---|---|")
-    for n, f, note in ((1, "bench_default.json", ""), (2, "bench_n2.json", " (before the e2e copy-stream fix)"), (8, "bench_n8.json", "")):
+    for n, f, note in ((1, "bench_default.json", ""), (2, "bench_n2.json", ""), (8, "bench_n8.json", "")):
         path = os.path.join(G, f)
         if os.path.exists(path):
             x = last_json(path)
@@ -67,8 +67,14 @@ def configs():
                        f"{x['corpus']['hist_sha256']} | {x['corpus']['exchange']}, {x['corpus']['exchange_ms']:.3f} ms |")
             if n > 1:
                 shutil.copy(path, os.path.join(P, f"r02_{f}"))
-    out.append("\nAt N = 8 the end-to-end leg is bound by the box's aggregate host->device rate (8 x 20 GB/s = 160 GB/s against 54 GB/s"
-               " for one GPU alone): 17.3 MB per page x 9 009 pages/s = 156 GB/s.\n")
+    p8 = os.path.join(G, "bench_n8.json")
+    if os.path.exists(p8):
+        x = last_json(p8)
+        e8 = x["e2e"]
+        agg = e8["h2d_gb_per_s_per_gpu"] * 8
+        out.append(f"\nAt N = 8 the end-to-end leg is bound by the box's aggregate host->device rate (8 x {e8['h2d_gb_per_s_per_gpu']:.1f} = "
+                   f"{agg:.0f} GB/s against 51-54 GB/s for one GPU alone): 17.3 MB per page x {e8['value']:.0f} pages/s = "
+                   f"{17.3e-3 * e8['value']:.0f} GB/s.\n")
     out.append("## Command lines (`scripts/bench_cli_stage1.py`, `scripts/bench_cli_stages.py`)\n")
     c1 = json.loads(open(os.path.join(G, "cli_stage1.json")).read())
     cs = [json.loads(l) for l in open(os.path.join(G, "cli_stages.jsonl")) if l.startswith("{")]

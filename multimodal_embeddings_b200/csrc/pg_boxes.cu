@@ -21,6 +21,15 @@ namespace cg = cooperative_groups;
 // One CTA per page; order-preserving compaction by block scan.
 // =============================================================================================
 constexpr int EDGE_THREADS = 1024;
+// Threads of the one-CTA-per-page kernels whose code does not fix the width (edge filter, resolve, emit).  A CTA
+// of 1024 threads needs most of an SM's register file, so under the tiler (four resident CTAs fill it) the SM has to
+// drain before such a CTA starts; narrower CTAs slot into what one retiring tiler CTA frees.  Knob: PG_BOX_PAGE_THREADS.
+static int page_kernel_threads(int dflt) {
+  int t = dflt;
+  if (const char* e = getenv("PG_BOX_PAGE_THREADS")) t = atoi(e);
+  t = (t / 32) * 32;
+  return t < 128 ? 128 : (t > 1024 ? 1024 : t);
+}
 __global__ void __launch_bounds__(EDGE_THREADS) edge_filter_kernel(
     const double* __restrict__ boxes, int local, const int32_t* __restrict__ box_cell,
     const double* __restrict__ cells, const int32_t* __restrict__ page_wh, const int64_t* __restrict__ page_off,
@@ -66,7 +75,7 @@ extern "C" int pg_edge_filter(const double* boxes, int32_t boxes_are_local, cons
   PG_REQUIRE(n_pages >= 0, "n_pages");
   if (n_pages == 0) return PG_OK;
   PG_REQUIRE(boxes && box_cell && cells && page_wh && page_off && kept_idx && n_kept, "null device pointer");
-  edge_filter_kernel<<<n_pages, EDGE_THREADS, 0, (cudaStream_t)stream>>>(
+  edge_filter_kernel<<<n_pages, page_kernel_threads(EDGE_THREADS), 0, (cudaStream_t)stream>>>(
       boxes, boxes_are_local, box_cell, cells, page_wh, page_off, threshold, boxes_page_out, keep, kept_idx, n_kept);
   PG_LAUNCH_CHECK();
   return PG_OK;
@@ -1437,9 +1446,9 @@ extern "C" int pg_nms_merge_ex(const double* boxes, const double* scores, const 
                                (const int32_t*)n_kept, kept_idx));
     return PG_OK;
   }
-  nms_resolve_kernel<<<n_pages, 1024, 0, s>>>(page_off, n_sel, ws, n_kept);
+  nms_resolve_kernel<<<n_pages, page_kernel_threads(1024), 0, s>>>(page_off, n_sel, ws, n_kept);
   PG_LAUNCH_CHECK();
-  nms_emit_kernel<<<n_pages, 1024, emit_smem, s>>>(sel_idx, page_off, ws, n_kept, kept_idx);
+  nms_emit_kernel<<<n_pages, page_kernel_threads(1024), emit_smem, s>>>(sel_idx, page_off, ws, n_kept, kept_idx);
   PG_LAUNCH_CHECK();
   return PG_OK;
 }

@@ -53,3 +53,41 @@ def sweep_files(seed, n, max_side=900):
             extra = (cv2.IMWRITE_JPEG_SAMPLING_FACTOR, CV2_SUBSAMPLING[sub]) if colour else ()
             out.append((cv2_encode(img, q, rst, extra), f"cv2 {w}x{h} c={colour} q={q} sub={sub} rst={rst}"))
     return out
+
+
+def mutated_files(seed, n, bases=None):
+    """-> n damaged copies of a few small files: bytes flipped in the headers, anywhere, truncations, insertions."""
+    rng = np.random.default_rng(seed)
+    bases = bases or [f for f, _ in sweep_files(99, 6, max_side=200)]
+    out = []
+    for it in range(n):
+        b = bytearray(bases[it % len(bases)])
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(0, min(len(b), 700)))] = int(rng.integers(0, 256))
+        elif kind == 1:
+            b = b[: int(rng.integers(2, len(b)))]
+        elif kind == 2:
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        else:
+            at = int(rng.integers(0, len(b)))
+            b[at:at] = bytes(rng.integers(0, 256, int(rng.integers(1, 40))).tolist())
+        out.append(bytes(b))
+    return out
+
+
+def scan_damaged_files(seed, n, bases=None):
+    """-> n copies with bytes flipped only inside the entropy-coded data (headers intact: the device decodes them)."""
+    rng = np.random.default_rng(seed)
+    bases = bases or [f for f, _ in sweep_files(98, 6, max_side=300)]
+    out = []
+    for it in range(n):
+        b = bytearray(bases[it % len(bases)])
+        sos = b.rfind(b"\xff\xda")
+        lo = sos + 2 + ((b[sos + 2] << 8) | b[sos + 3])
+        for _ in range(int(rng.integers(1, 8))):
+            b[int(rng.integers(lo, len(b) - 2))] = int(rng.integers(0, 256))
+        out.append(bytes(b))
+    return out

@@ -214,3 +214,30 @@ def test_decode_randomised_sweep_equals_cv2():
             ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
             got = page[:, :c * w].cpu().numpy()
             assert np.array_equal(got, ref.reshape(h, 3 * w) if c == 3 else ref[..., 0]), what
+
+
+def test_decode_of_damaged_entropy_data_is_safe_and_leaves_the_device_usable():
+    """Files whose entropy-coded bytes were damaged (headers intact) go through the kernels: whatever pixels come out,
+    nothing may trap, hang or write outside its page (canary rows behind every page stay untouched), a batch that
+    never converges is reported (PageGeomError after 64 rounds), and a clean batch decodes bit-exactly afterwards."""
+    import jpeg_cases
+    files = jpeg_cases.scan_damaged_files(11, 48)
+    blob, off = ops.pack_files(files)
+    dec = ops.JpegDecoder(chunk_bytes=128, sync_rounds=4)
+    sizes = dec.set_files(blob, off)
+    pages = [torch.full((h + 3, ops.row_pitch(w, c)), 0xA5, dtype=torch.uint8, device="cuda") for w, h, c in sizes]
+    dec.decode(blob.cuda(), [p[:h] for p, (w, h, c) in zip(pages, sizes)])
+    torch.cuda.synchronize()
+    try:
+        dec.check()
+    except PageGeomError as e:
+        assert "converge" in str(e)
+    torch.cuda.synchronize()
+    for p, (w, h, c) in zip(pages, sizes):
+        assert bool((p[h:] == 0xA5).all())
+    clean = [f for f, _ in jpeg_cases.sweep_files(98, 6, max_side=300)]
+    for data, page in zip(clean, ops.decode_jpeg_files(clean)):
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_ANYCOLOR)
+        hh, ww = ref.shape[:2]
+        got = page[:, :(ref.size // hh)].cpu().numpy()
+        assert np.array_equal(got, ref.reshape(hh, -1))

@@ -182,3 +182,25 @@ def test_randomised_sweep_through_the_inline_decoder_equals_cv2():
             ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_ANYCOLOR)
             got, _ = host_decode(data, chunk)
             assert got.shape == ref.shape and np.array_equal(got, ref), what
+
+
+def test_damaged_files_are_refused_or_decoded_but_never_crash():
+    """600 damaged copies (tests/jpeg_cases.py: header bytes flipped, truncations, insertions, flips anywhere) through
+    the parser and the host evaluation of the decoder: an error code or some pixels, never a crash, never a size the
+    file does not declare.  scripts/fuzz_jpeg_asan.sh runs 3000 of them under AddressSanitizer."""
+    import jpeg_cases
+    L = lib()
+    seen = set()
+    for data in jpeg_cases.mutated_files(7, 600):
+        w, h, st = C.c_int32(), C.c_int32(), (C.c_int64 * 4)()
+        b = np.frombuffer(data, np.uint8)
+        rc = L.pg_hostcheck_jpeg_decode(b.ctypes.data, len(b), 256, 64, None, 0, C.byref(w), C.byref(h), st)
+        seen.add(rc)
+        if rc != 0 or w.value * h.value > 4_000_000:
+            continue
+        assert 1 <= w.value <= 65535 and 1 <= h.value <= 65535 and st[3] in (1, 3)
+        pitch = (st[3] * w.value + 15) // 16 * 16
+        out = np.zeros((h.value, pitch), np.uint8)
+        rc = L.pg_hostcheck_jpeg_decode(b.ctypes.data, len(b), 256, 64, out.ctypes.data, pitch, C.byref(w), C.byref(h), st)
+        seen.add(rc)
+    assert 0 in seen and seen - {0} and all(r in (0, 1, 4) for r in seen)  # PG_OK / PG_ERR_INVALID / PG_ERR_UNSUPPORTED

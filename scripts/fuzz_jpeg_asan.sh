@@ -26,3 +26,6 @@ for data in jpeg_cases.mutated_files(7, 3000):
     codes[rc] = codes.get(rc, 0) + 1
 print("3000 damaged files under AddressSanitizer, return codes:", codes)
 P
+# the host-side C-ABI suites (tile plans, IoU / edge predicates, Ryu formatter, number reader, JPEG host evaluation) under the same build
+ASAN_OPTIONS=detect_leaks=0:protect_shadow_gap=0 LD_PRELOAD=$(gcc -print-file-name=libasan.so) \
+PAGEGEOM_LIB=$PWD/multimodal_embeddings_b200/_variants/libpagegeom_asan.so python -m pytest tests/test_cabi_host.py tests/test_jpeg_host.py -x -q

@@ -241,6 +241,8 @@ def main():
     ap.add_argument("--e2e-trace-all", action="store_true", help="diagnostic: events around every timed e2e step")
     ap.add_argument("--e2e-input", default="jpeg", choices=["jpeg", "raw"],
                     help="what crosses PCIe in the e2e leg: the scans' JPEG files (decoded on the device) or raw BGR pages")
+    ap.add_argument("--e2e-pinned", default="default", choices=["default", "wc"],
+                    help="host staging of the scans' files: plain page-locked memory or write-combined (pg_pinned_alloc)")
     ap.add_argument("--no-corpus", action="store_true", help="skip the K6 corpus sub-run (cfg5 in small)")
     ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the sustained-rate loop (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -570,7 +572,7 @@ def main():
         distinct = min(n_e, 8)
         files = [e2e_scan_file(plan0.page_w, plan0.page_h, first_page + j) for j in range(distinct)]
         files = [files[j % distinct] for j in range(n_e)]
-        blob, file_off = ops.pack_files(files)
+        blob, file_off = ops.pack_files(files, write_combined=args.e2e_pinned == "wc")
         sp = ScanPipeline(plan0.page_w, plan0.page_h, n_e, [(rows, cols)], 20.0, depth=args.e2e_depth, overlap=not args.no_overlap)
         probe = PagePipeline(sp.plan, n_e)
         ehost = probe.set_detections(dets0[:n_e])
@@ -622,7 +624,7 @@ def main():
                        "jpeg_decoder": {"chunk_bytes": sp.slots[0]["dec"].chunk_bytes, **{k2: int(v) for k2, v in dec_status.items()}},
                        "kernels_per_step": KERNELS_PER_STEP + 9 + sp.slots[0]["dec"].sync_rounds,
                        "kept_boxes_last_step": int(res["n_kept2"].sum()),
-                       "host_ms_per_submit": host_s / e2e_steps * 1e3, "clocks": e_clocks,
+                       "host_ms_per_submit": host_s / e2e_steps * 1e3, "pinned": args.e2e_pinned, "clocks": e_clocks,
                        "timeline_ms": {"what": "three extra steps: [copy start, copy end, compute start, compute end] from the first copy's start",
                                        "steps": timeline},
                        **({"host": numa_note} if numa_note else {}),

@@ -49,6 +49,11 @@ const char* pg_last_error(void);
 int pg_version(void);
 /* 1 when the library was built with -DPG_CHECKED (device-side bounds assertions, csrc/pg_common.cuh), else 0. */
 int pg_build_checked(void);
+/* Page-locked host staging for what crosses PCIe every step (the scans' file bytes; reference: the bytes cv2.imread
+ * reads from disk, 1_doclayout_bboxes.py:381).  write_combined != 0: cudaHostAllocWriteCombined (the CPU only fills
+ * it; device reads do not snoop the CPU caches).  Free with pg_pinned_free. */
+int pg_pinned_alloc(size_t bytes, int32_t write_combined, void** out);
+int pg_pinned_free(void* p);
 /* SM count / compute capability of the current device. */
 int pg_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 

@@ -47,6 +47,8 @@ SIGNATURES = {
     "pg_last_error": (C.c_char_p, []),
     "pg_version": (C.c_int, []),
     "pg_build_checked": (C.c_int, []),
+    "pg_pinned_alloc": (C.c_int, [C.c_size_t, C.c_int32, C.POINTER(C.c_void_p)]),
+    "pg_pinned_free": (C.c_int, [C.c_void_p]),
     "pg_device_info": (C.c_int, [_P, _P, _P]),
     "pg_tile_plan_create": (C.c_int, [_I32, _I32, _P, _P, _I32, _F64, _I32, _I32, _I32, _I32, _P]),
     "pg_tile_plan_create_ex": (C.c_int, [_I32, _I32, _I32, _P, _P, _I32, _F64, _I32, _I32, _I32, _I32, _P]),

@@ -123,3 +123,19 @@ extern "C" int pg_hist_allreduce(uint32_t* hist, size_t n_bins, void* nccl_comm,
   if (rc != 0) return nccl_fail("ncclAllReduce", rc);
   return PG_OK;
 }
+
+
+// ---- pinned host staging ---------------------------------------------------------------------------------------
+// Page-locked host memory for the buffers that cross PCIe every step (the scans' file bytes).  write_combined != 0
+// asks for cudaHostAllocWriteCombined: the CPU fills it with streaming stores and never reads it back, and device
+// reads of it do not snoop the CPU caches — worth having when several GPUs pull from host memory at once.
+extern "C" int pg_pinned_alloc(size_t bytes, int32_t write_combined, void** out) {
+  PG_REQUIRE(out && bytes > 0, "pinned alloc arguments");
+  *out = nullptr;
+  PG_CUDA_TRY(cudaHostAlloc(out, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+  return PG_OK;
+}
+extern "C" int pg_pinned_free(void* p) {
+  if (p) PG_CUDA_TRY(cudaFreeHost(p));
+  return PG_OK;
+}

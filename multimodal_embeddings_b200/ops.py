@@ -357,16 +357,45 @@ def jpeg_probe(data: bytes) -> Optional[Tuple[int, int, int]]:
     return w.value, h.value, int(st[3])
 
 
-def pack_files(files: Sequence[bytes], pinned: bool = True):
+class PinnedBuffer:
+    """pg_pinned_alloc: page-locked host bytes as a uint8 CPU tensor (`.tensor`); write_combined=True for buffers the
+    CPU only fills (file bytes on their way to the GPU).  Freed when the object goes away — keep it alive while
+    copies from it are in flight."""
+
+    def __init__(self, nbytes: int, write_combined: bool = False):
+        p = C.c_void_p()
+        check(lib().pg_pinned_alloc(int(nbytes), 1 if write_combined else 0, C.byref(p)))
+        self._p, self.nbytes, self.write_combined = p, int(nbytes), bool(write_combined)
+        self.array = np.ctypeslib.as_array((C.c_uint8 * int(nbytes)).from_address(p.value))
+        self.tensor = torch.from_numpy(self.array)
+
+    def __del__(self):
+        p = getattr(self, "_p", None)
+        if p:
+            try:
+                lib().pg_pinned_free(p)
+            except Exception:
+                pass
+            self._p = None
+
+
+def pack_files(files: Sequence[bytes], pinned: bool = True, write_combined: bool = False):
     """Files back to back, each starting on a 256-byte boundary -> (uint8 CPU tensor, int64 offsets [n+1] of the
     files' FIRST bytes plus the end of the last).  pg_jpeg_decoder_set_files takes file i as
-    blob[off[i] .. off[i+1]); the alignment padding at a file's end is ignored by the parser (it lies behind EOI)."""
+    blob[off[i] .. off[i+1]); the alignment padding at a file's end is ignored by the parser (it lies behind EOI).
+    write_combined: the tensor lives in a PinnedBuffer (kept alive through `blob._pg_owner`)."""
     off = [0]
     for f in files:
         off.append(off[-1] + (len(f) + 255) // 256 * 256)
-    blob = torch.zeros(off[-1] + 256, dtype=torch.uint8)
-    if pinned and torch.cuda.is_available():
-        blob = blob.pin_memory()
+    if write_combined and pinned and torch.cuda.is_available():
+        owner = PinnedBuffer(off[-1] + 256, write_combined=True)
+        blob = owner.tensor
+        blob._pg_owner = owner
+        owner.array[off[-1]:] = 0
+    else:
+        blob = torch.zeros(off[-1] + 256, dtype=torch.uint8)
+        if pinned and torch.cuda.is_available():
+            blob = blob.pin_memory()
     view = blob.numpy()
     for f, o in zip(files, off):
         view[o:o + len(f)] = np.frombuffer(f, np.uint8)

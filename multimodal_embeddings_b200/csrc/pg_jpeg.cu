@@ -64,6 +64,7 @@ int build_huff(const uint8_t* counts, const uint8_t* symbols, int n_symbols, Pgj
     h.valoff[l] = k - code;
     for (int i = 0; i < counts[l - 1]; ++i) {
       if (k >= n_symbols || k >= 256) return -1;
+      if (code >= (1 << l)) return -1;  // more codes of this length than the code space holds (the views below index by code)
       if (l <= PGJ_LUT_BITS) {
         const int first = code << (PGJ_LUT_BITS - l), n = 1 << (PGJ_LUT_BITS - l);
         const int sym = symbols[k], run = sym >> 4, size = sym & 15;

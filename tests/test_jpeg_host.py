@@ -204,3 +204,19 @@ def test_damaged_files_are_refused_or_decoded_but_never_crash():
         rc = L.pg_hostcheck_jpeg_decode(b.ctypes.data, len(b), 256, 64, out.ctypes.data, pitch, C.byref(w), C.byref(h), st)
         seen.add(rc)
     assert 0 in seen and seen - {0} and all(r in (0, 1, 4) for r in seen)  # PG_OK / PG_ERR_INVALID / PG_ERR_UNSUPPORTED
+
+
+def test_huffman_table_with_more_codes_than_its_code_space_is_refused():
+    """A DHT whose counts claim three 1-bit codes (same number of symbols as before): the table views index by code,
+    so this has to be caught while the table is built."""
+    data = bytearray(_encode(_page(64, 64, 3)))
+    at = data.find(b"\xff\xc4")
+    counts = at + 5  # marker, length (2), class/id (1)
+    later = max(range(16), key=lambda i: data[counts + i])
+    assert data[counts + later] >= 3 and later > 0
+    data[counts + later] -= 3 - data[counts]
+    data[counts] = 3
+    w, h, st = C.c_int32(), C.c_int32(), (C.c_int64 * 4)()
+    b = np.frombuffer(bytes(data), np.uint8)
+    rc = lib().pg_hostcheck_jpeg_decode(b.ctypes.data, len(b), 256, 8, None, 0, C.byref(w), C.byref(h), st)
+    assert rc == 4 and b"Huffman" in lib().pg_last_error()

@@ -100,10 +100,11 @@ PGJ_HD int pgj_zigzag(int k) {
 constexpr int PGJ_STREAM_PAD = 1024;  // readable bytes of slack (ones) behind every unstuffed stream
 
 struct PgjBits {
-  const uint8_t* base;
-  uint64_t buf;       // next bits, left-aligned
-  int32_t avail;      // valid bits in buf
-  int64_t next_word;  // index of the next 32-bit word to load
+  const uint32_t* w0;  // the stream's first word (4-byte aligned)
+  int32_t wi;          // index of the next word to load (a stream is far below 2^31 words).  The refill is the walks'
+                       // most frequent divergent block: one address, a load, a byte swap, a shift
+  int32_t avail;       // valid bits in buf
+  uint64_t buf;        // next bits, left-aligned
 #ifdef PG_CHECKED
   int64_t last_word;  // last word inside the stream's slack (checked build only)
   PGJ_HD void bound_bits(int64_t n_bits) { last_word = (n_bits + 8 * (int64_t)PGJ_STREAM_PAD) / 32 - 1; }
@@ -111,11 +112,11 @@ struct PgjBits {
   PGJ_HD void bound_bits(int64_t) {}
 #endif
 
-  PGJ_HD uint32_t load_be(int64_t w) const {
+  PGJ_HD uint32_t load_be(int32_t w) const {
 #ifdef PG_CHECKED
-    PGJ_ASSERT(w >= 0 && w <= last_word);
+    PGJ_ASSERT(w >= 0 && (int64_t)w <= last_word);
 #endif
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(base + 4 * w);  // base is 4-byte aligned
+    const uint32_t v = w0[w];
 #ifdef __CUDA_ARCH__
     return __byte_perm(v, 0u, 0x0123);
 #else
@@ -123,21 +124,21 @@ struct PgjBits {
 #endif
   }
   PGJ_HD void seek(const uint8_t* b, int64_t p) {
-    base = b;
-    next_word = p >> 5;
-    buf = ((uint64_t)load_be(next_word) << 32) | (uint64_t)load_be(next_word + 1);
-    next_word += 2;
+    w0 = reinterpret_cast<const uint32_t*>(b);
+    wi = (int32_t)(p >> 5);
+    buf = ((uint64_t)load_be(wi) << 32) | (uint64_t)load_be(wi + 1);
+    wi += 2;
     const int sh = (int)(p & 31);
     buf <<= sh;
     avail = 64 - sh;
   }
   PGJ_HD void need32() {  // at least 32 valid bits afterwards
     if (avail < 32) {
-      buf |= (uint64_t)load_be(next_word++) << (32 - avail);
+      buf |= (uint64_t)load_be(wi++) << (32 - avail);
       avail += 32;
     }
   }
-  PGJ_HD int64_t pos() const { return next_word * 32 - avail; }
+  PGJ_HD int64_t pos() const { return (int64_t)wi * 32 - avail; }
   PGJ_HD uint32_t peek16() const { return (uint32_t)(buf >> 48); }
   PGJ_HD void skip(int n) { buf <<= n; avail -= n; }
   PGJ_HD uint32_t take(int n) {  // n in 1..16

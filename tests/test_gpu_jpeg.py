@@ -241,3 +241,19 @@ def test_decode_of_damaged_entropy_data_is_safe_and_leaves_the_device_usable():
         hh, ww = ref.shape[:2]
         got = page[:, :(ref.size // hh)].cpu().numpy()
         assert np.array_equal(got, ref.reshape(hh, -1))
+
+
+def test_files_staged_in_write_combined_pinned_memory_decode_the_same():
+    """ops.pack_files(write_combined=True): the blob lives in pg_pinned_alloc memory (the CPU only fills it; the parser
+    reads the headers back from it), the asynchronous copy and the decode give cv2's pixels."""
+    files = [_encode(_page(300, 400, 1)), _encode(_page(123, 77, 2), q=60, rst=3)]
+    blob, off = ops.pack_files(files, write_combined=True)
+    assert blob.is_pinned() and blob._pg_owner.write_combined
+    dec = ops.JpegDecoder()
+    dec.set_files(blob, off)
+    pages = dec.decode(blob.to("cuda", non_blocking=True))
+    torch.cuda.synchronize()
+    dec.check()
+    for data, page, (w, h, c) in zip(files, pages, dec.sizes):
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE)
+        assert np.array_equal(page[:, :w].cpu().numpy(), ref)

@@ -59,7 +59,7 @@ def configs():
     out.append("## Multi-GPU (`torchrun ... bench.py --gpus N`; earlier commits of this round where noted)\n")
     out.append("| N | value (pages/s) | e2e (pages/s) | H2D per GPU (GB/s) | corpus sha | exchange |")
     out.append("|---:|---:|---:|---:|---|---|")
-    for n, f, note in ((1, "bench_default.json", ""), (2, "bench_n2.json", ""), (8, "bench_n8.json", "")):
+    for n, f, note in ((1, "bench_default.json", ""), (2, "bench_n2.json", ""), (4, "bench_n4.json", ""), (8, "bench_n8.json", "")):
         path = os.path.join(G, f)
         if os.path.exists(path):
             x = last_json(path)

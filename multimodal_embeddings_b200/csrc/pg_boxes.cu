@@ -629,8 +629,19 @@ __global__ void __launch_bounds__(256) nms_cand_kernel(const int64_t* __restrict
   double bbI[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) bbI[q] = ws.bbox[4 * I + q];
+  // The counting walk also remembers the first CAND_KEEP hits of the block in shared memory: the listing below then
+  // copies them instead of walking the page's bounding boxes a second time (cfg4: 11 candidates per block on average).
+  constexpr int CAND_KEEP = 96;
+  __shared__ int32_t kept_j[8][CAND_KEEP];
   int cnt = 0;
-  cand_walk(ws, sp, p, bbI, all_pairs, lane, [&](int, bool, unsigned hits) { cnt += __popc(hits); });
+  cand_walk(ws, sp, p, bbI, all_pairs, lane, [&](int j, bool hit, unsigned hits) {
+    if (hit) {
+      const int slot = cnt + __popc(hits & ((1u << lane) - 1u));
+      if (slot < CAND_KEEP) kept_j[wib][slot] = j;
+    }
+    cnt += __popc(hits);
+  });
+  __syncwarp();
   long long off = 0;
   if (lane == 0) off = (long long)atomicAdd((unsigned long long*)&ws.stats[ST_ENT_TOTAL], (unsigned long long)cnt);
   off = __shfl_sync(0xffffffffu, off, 0);
@@ -641,6 +652,14 @@ __global__ void __launch_bounds__(256) nms_cand_kernel(const int64_t* __restrict
     if (!fits) ws.stats[ST_STATUS] = PG_ERR_WORKSPACE;  // every writer stores the same value
   }
   if (!fits) return;
+  if (cnt <= CAND_KEEP) {
+    for (int k = lane; k < cnt; k += 32) {
+      PG_DEV_ASSERT(off + k < ws.ent_cap && kept_j[wib][k] >= 0 && kept_j[wib][k] < sp.nb);
+      ws.ent_j[off + k] = (int32_t)(sp.blk0 + kept_j[wib][k]);
+      ws.ent_i[off + k] = (int32_t)I;
+    }
+    return;
+  }
   long long e = off;
   cand_walk(ws, sp, p, bbI, all_pairs, lane, [&](int j, bool hit, unsigned hits) {
     if (hit) {

@@ -251,7 +251,7 @@ def main():
     ap.add_argument("--corpus-stats", action="store_true", help="accumulate + all-reduce corpus histograms (cfg5)")
     ap.add_argument("--tiler-only", action="store_true", help="profiling helper: time the tiler alone")
     ap.add_argument("--graph", action="store_true",
-                    help="replay the step from a CUDA graph captured after warm-up (one launch per step instead of 13-17)")
+                    help="replay the step from a CUDA graph captured after warm-up (one launch per step instead of 12-16)")
     ap.add_argument("--records", action="store_true",
                     help="also lay out the stage-3 JSON records on the device every step (pg_json_combined, +4 kernels)")
     args = ap.parse_args()
@@ -692,7 +692,7 @@ def main():
                        "pages_per_step": n_e * world, "steps": e2e_steps,
                        "h2d_gb_per_s_per_gpu": (page_bytes + box_bytes) * e2e_steps / (e_ms * 1e-3) / 1e9,
                        **({"host": numa_note} if numa_note else {}),
-                       "note": "pinned host pages+detections -> H2D -> 13 kernels -> D2H kept indices/medians/columns; "
+                       "note": "pinned host pages+detections -> H2D -> 12 kernels -> D2H kept indices/medians/columns; "
                                "fp16 tiles stay in HBM for the detector; bound by the PCIe copy of the raw pages "
                                "(144 MB each; a plain pinned H2D copy reaches 55.6 GB/s on this box)"}
 

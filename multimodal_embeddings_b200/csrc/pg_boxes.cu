@@ -294,6 +294,24 @@ __device__ __forceinline__ void nms_blocked_copy(const double* __restrict__ boxe
                                                  const PageSpan& sp, const int32_t* sorted, const NmsWs& ws, int p,
                                                  int wfirst, int wstride);
 
+// Bounds of each run of 32 blocks of page p ("super-block"; page p's super-blocks start at (blk0 >> 5) + p), by the
+// warps wfirst, wfirst + wstride, ... once every block bound of the page is written and visible.
+__device__ __forceinline__ void nms_super_bounds(const PageSpan& sp, int p, const NmsWs& ws, int wfirst, int wstride) {
+  const int lane = threadIdx.x & 31;
+  const int ns = (sp.nb + 31) >> 5;
+  for (int sb = wfirst; sb < ns; sb += wstride) {
+    const int b = sb * 32 + lane;
+    const bool valid = b < sp.nb;
+    const double* bb = ws.bbox + 4 * (sp.blk0 + (valid ? b : 0));
+    const double x0 = warp_min_d(valid ? __ldcg(bb + 0) : DBL_MAX), y0 = warp_min_d(valid ? __ldcg(bb + 1) : DBL_MAX);
+    const double x1 = warp_max_d(valid ? __ldcg(bb + 2) : -DBL_MAX), y1 = warp_max_d(valid ? __ldcg(bb + 3) : -DBL_MAX);
+    if (lane == 0) {
+      double* o = ws.sbbox + 4 * ((sp.blk0 >> 5) + p + sb);
+      o[0] = x0; o[1] = y0; o[2] = x1; o[3] = y1;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(1024) nms_bin_kernel(const double* __restrict__ boxes,
                                                        const double* __restrict__ scores,
                                                        const double* __restrict__ classes,
@@ -305,6 +323,7 @@ __global__ void __launch_bounds__(1024) nms_bin_kernel(const double* __restrict_
   __shared__ int scan_smem[34];
   const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const PageSpan sp = page_span(page_off, n_sel, p);
+  if (blockIdx.x == 0 && tid < 8) ws.stats[tid] = 0;  // status / counters of this call (the first kernel of the call)
   const int64_t blk_next = (p + 1 < n_pages) ? (page_off[p + 1] >> 5) + p + 1 : ws.nb_cap;
   for (int64_t b = sp.blk0 + sp.nb + tid; b < blk_next; b += blockDim.x) ws.blk_page[b] = -1;
 
@@ -367,6 +386,9 @@ __global__ void __launch_bounds__(1024) nms_bin_kernel(const double* __restrict_
 
   // blocked copy + block bounding boxes
   nms_blocked_copy(boxes, scores, classes, sel_idx, sp, sorted, ws, p, warp, blockDim.x >> 5);
+  __threadfence_block();
+  __syncthreads();
+  nms_super_bounds(sp, p, ws, warp, blockDim.x >> 5);
 }
 
 // Blocked AoS copy of a page in spatial order + block / sub-block bounding boxes; block b is handled by the
@@ -498,6 +520,7 @@ __global__ void __launch_bounds__(1024) nms_bin_cluster_kernel(const double* __r
   const int p = blockIdx.x / csize, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ctid = rank * (int)blockDim.x + tid, cthreads = csize * (int)blockDim.x;
   const PageSpan sp = page_span(page_off, n_sel, p);
+  if (blockIdx.x == 0 && tid < 8) ws.stats[tid] = 0;  // status / counters of this call (the first kernel of the call)
   const int64_t blk_next = (p + 1 < n_pages) ? (page_off[p + 1] >> 5) + p + 1 : ws.nb_cap;
   for (int64_t b = sp.blk0 + sp.nb + ctid; b < blk_next; b += cthreads) ws.blk_page[b] = -1;
 
@@ -564,34 +587,13 @@ __global__ void __launch_bounds__(1024) nms_bin_cluster_kernel(const double* __r
   cluster_stable_pass<NMS_GX_MAX>(cluster, csize, rank, sp.m, hist, all_tot, scan_smem, [tmp](int i) { return tmp[i]; },
                                   [cellid](int e) { return cellid[e] >> 14; }, sorted);
   nms_blocked_copy(boxes, scores, classes, sel_idx, sp, sorted, ws, p, rank * 32 + warp, csize * 32);
+  __threadfence();
+  cluster.sync();  // the block bounds of the page were written by all CTAs of the cluster
+  nms_super_bounds(sp, p, ws, rank * 32 + warp, csize * 32);
 }
 
 __device__ __forceinline__ bool bbox_hit(const double* a, const double* b) {
   return !(b[2] < a[0] || a[2] < b[0] || b[3] < a[1] || a[3] < b[1]);
-}
-
-// ---- B: candidates -------------------------------------------------------------------------
-// Bounding boxes of the super-blocks (32 consecutive blocks of a page = 1024 boxes in spatial order; they
-// never span pages: page p's super-blocks start at (blk0 >> 5) + p).  One warp per block, the warps of
-// blocks that do not open a super-block leave at once.
-__global__ void __launch_bounds__(256) nms_super_kernel(const int64_t* __restrict__ page_off,
-                                                        const int32_t* __restrict__ n_sel, NmsWs ws) {
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t I = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-  if (I >= ws.nb_cap) return;
-  const int p = ws.blk_page[I];
-  if (p < 0) return;
-  const PageSpan sp = page_span(page_off, n_sel, p);
-  const int b = (int)(I - sp.blk0);
-  if (b & 31) return;
-  const bool valid = b + lane < sp.nb;
-  const double* bb = ws.bbox + 4 * (I + lane);
-  const double x0 = warp_min_d(valid ? bb[0] : DBL_MAX), y0 = warp_min_d(valid ? bb[1] : DBL_MAX);
-  const double x1 = warp_max_d(valid ? bb[2] : -DBL_MAX), y1 = warp_max_d(valid ? bb[3] : -DBL_MAX);
-  if (lane == 0) {
-    double* o = ws.sbbox + 4 * ((sp.blk0 >> 5) + p + (b >> 5));
-    o[0] = x0; o[1] = y0; o[2] = x1; o[3] = y1;
-  }
 }
 
 // One warp per block I: count the blocks J of the page whose bounding boxes intersect bbox(I),
@@ -1429,7 +1431,6 @@ extern "C" int pg_nms_merge_ex(const double* boxes, const double* scores, const 
   const int emit_smem = EMIT_SMEM_SLOTS * 12;
   PG_CUDA_TRY(cudaFuncSetAttribute(nms_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem));
   PG_CUDA_TRY(cudaFuncSetAttribute(nms_emit_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, emit_smem));
-  PG_CUDA_TRY(cudaMemsetAsync(ws.stats, 0, 8 * sizeof(int64_t), s));
   const int all_pairs = !(iou_threshold >= 0.0);  // thr < 0: disjoint boxes (IoU 0) suppress too
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -1445,8 +1446,6 @@ extern "C" int pg_nms_merge_ex(const double* boxes, const double* scores, const 
     PG_LAUNCH_CHECK();
   }
   const unsigned cand_grid = (unsigned)((ws.nb_cap + 7) / 8);
-  nms_super_kernel<<<cand_grid, 256, 0, s>>>(page_off, n_sel, ws);
-  PG_LAUNCH_CHECK();
   nms_cand_kernel<<<cand_grid, 256, 0, s>>>(page_off, n_sel, ws, all_pairs);
   PG_LAUNCH_CHECK();
   const int64_t mask_want = (ws.ent_cap + 8 * MASK_UNIT - 1) / (8 * MASK_UNIT);

@@ -20,7 +20,7 @@ from . import ops
 from ._lib import (PG_COL_HIST_BINS, PG_COL_SPAN_BYTES, PG_ERR_WORKSPACE, PG_WIDTH_HIST_BINS, check, lib, ptr,
                    stream_ptr)
 
-KERNELS_PER_STEP = 13  # tiler, edge filter, 6 NMS kernels, class flags, width median, column prep + density + peaks
+KERNELS_PER_STEP = 12  # tiler, edge filter, 5 NMS kernels, class flags, width median, column prep + density + peaks
 
 
 def shard_pages(n_pages_total: int, rank: int, world: int) -> range:

@@ -88,25 +88,30 @@ extern "C" int pg_edge_filter(const double* boxes, int32_t boxes_are_local, cons
 // Greedy NMS keeps box i iff no *kept* box j with higher priority (score desc, earlier pooled
 // position on ties, :112), same class and IoU > thr (:130) exists.  That fixed point is unique,
 // so it can be computed without replaying the sequential loop:
-//   A  bin      per page, a stable two-pass block radix sort orders the boxes by
-//               (x strip, y cell) of their centres so that runs of 32 consecutive boxes
-//               ("blocks") are spatially compact; write a blocked AoS copy + block bounding boxes;
-//   B  count    per block I, count blocks J of the same page whose bounding boxes intersect
-//               (IoU > thr >= 0 needs a non-empty intersection, the reference's own early-out);
-//   C  scan     exclusive scan of the counts -> entry offsets (workspace overflow -> status);
-//   D  fill     per candidate pair (I,J): lane i of the warp holds box i of I, the 32 boxes of J
+//   A  bin      per page, a stable block radix sort (two counting-sort passes; three on crowded pages, with a
+//               finer y digit first) orders the boxes by (x strip, y cell[, y sub-cell]) of their centres so that
+//               runs of 32 consecutive boxes ("blocks") are spatially compact; write a blocked AoS copy, the block
+//               bounding boxes, the bounds of each run of 32 blocks ("super-blocks"), and reset the call's counters;
+//   B  cand     per block I, the blocks J of the same page whose bounding boxes intersect (IoU > thr >= 0 needs
+//               a non-empty intersection, the reference's own early-out), found through the super-blocks; one
+//               atomicAdd reserves the block's entry range (workspace overflow -> status), the hits of the
+//               counting walk are kept in shared memory and copied;
+//   C  mask     per candidate pair (I,J): lane i of the warp holds box i of I, the 32 boxes of J
 //               are broadcast from shared memory; lane i accumulates a 32-bit mask of the boxes
 //               of J that would suppress it;
-//   E  resolve  per page, Jacobi rounds over two bit-words per block (kept / undecided): an
+//   D  resolve  per page, Jacobi rounds over two bit-words per block (kept / undecided): an
 //               undecided box becomes suppressed if a suppressor is kept, kept if none of its
 //               suppressors is still undecided.  Each round decides at least the best undecided
-//               box, typical depth is 3-6 rounds;
-//   F  emit     sort the kept boxes by priority (normalised bitonic network in shared memory,
-//               global-memory network for > 8192 survivors) and write global indices in pick order.
-// Pages of >= 32 768 boxes (cfg4: 100 000) would leave E and F on one CTA per page; when the pages
-// of a launch number fewer than the SMs, E and F instead run on one thread-block CLUSTER per page
-// (up to 8 CTAs, cluster barrier between rounds / network stages, flags and counts exchanged
-// through distributed shared memory): nms_resolve_cluster_kernel, nms_emit_cluster_kernel.
+//               box, typical depth is 3-8 rounds; blocks that are final leave the rounds;
+//   E  emit     sort the kept boxes by priority (normalised bitonic network, eight elements to a thread in shared
+//               memory, on the L2-resident arrays above 8192 survivors of a one-CTA page) and write global
+//               indices in pick order.
+// Five launches: nms_bin, nms_cand, nms_mask, nms_resolve, nms_emit.
+// Pages of >= 32 768 boxes (cfg4: 100 000) would leave A, D and E on one CTA per page; when the pages
+// of a launch number fewer than the SMs, they instead run on one thread-block CLUSTER per page
+// (up to 8 CTAs — 16 where every page's cluster stays resident —, cluster barrier between sort passes / rounds /
+// network stages, totals, flags and counts exchanged through distributed shared memory):
+// nms_bin_cluster_kernel, nms_resolve_cluster_kernel, nms_emit_cluster_kernel.
 // =============================================================================================
 constexpr int NMS_GY = 128;     // y cells (7-bit digit)
 constexpr int NMS_GYF = 128;    // subdivisions of a y cell (a third, finer 7-bit digit), used on crowded pages only

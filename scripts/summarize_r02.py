@@ -87,6 +87,19 @@ def configs():
         out.append(f"| {ref['reference_stage']} | {ref['seconds_per_page']} | {c['seconds_device_json'] / c['pages']:.4f} |")
     out.append(f"| 1 (decode + tiles + files, trivial detector; the reference's stage 1 cannot run without weights) | — | "
                f"{c1['seconds_device_decode'] / c1['pages']:.4f} (host decode: {c1['seconds_host_decode'] / c1['pages']:.4f}) |")
+    others = [("cfg2", "python bench.py --workload cfg2 --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --sustained-seconds 0"),
+              ("cfg5", "python bench.py --workload cfg5 --total-pages 20480 --no-cpu-baseline --no-e2e --sustained-seconds 0"),
+              ("cfg4", "python scripts/bench_merge_stress.py")]
+    if all(os.path.exists(os.path.join(G, f"r02_{n}.json")) for n, _ in others):  # scripts/gpu_r2_cfgs.sh
+        out.append("## Other BASELINE configurations at the round's last build (one B200, `scripts/gpu_r2_cfgs.sh`)\n")
+        got = {}
+        for n, cmd in others:
+            got[n] = last_json(os.path.join(G, f"r02_{n}.json"))
+            out.append(f"`{cmd}`\n\n```json\n{json.dumps(got[n])[:1500]}\n```\n")
+        out.append(f"* cfg2 (19 page sizes, heterogeneous batches): {got['cfg2']['value']:.0f} pages/s, {got['cfg2']['ms_per_step']:.3f} ms per step")
+        out.append(f"* cfg5 (corpus streamed in 64-page batches with histogram accumulation, 20 480 pages): {got['cfg5']['value']:.0f} pages/s "
+                   f"sustained, {got['cfg5']['ms_per_step']:.3f} ms per batch")
+        out.append(f"* cfg4 (8 pages x 100 000 boxes, stage 3 only): {got['cfg4']['ms_per_launch']:.3f} ms per launch\n")
     open(os.path.join(P, "r02_configs.md"), "w").write("\n".join(out) + "\n")
 
 
